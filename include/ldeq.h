@@ -1,0 +1,192 @@
+/* ldeq.h -- C ABI of libldeq.so: the B200 (sm_100a) drop-in for LatentDiffEq.jl's hot path.
+ *
+ * Every entry point replaces work that the reference does below one of its own interfaces
+ * (citations are relative to the reference tree, gabrevaya/LatentDiffEq.jl):
+ *
+ *   ldeq_solve_fwd / ldeq_solve_bwd      diffeq_layer(::Decoder{<:GOKU}, l, t)   src/models/GOKU.jl:98-130
+ *                                        (EnsembleProblem + Tsit5 per column, GOKU.jl:111-121; NaN block on
+ *                                        failure, GOKU.jl:114; (z,B,T) layout, GOKU.jl:125) and its pullback
+ *                                        (sensealg, examples/pendulum_friction-less/pendulum.jl:11)
+ *   ldeq_rhs_builtin / _from_source      the user-defined diffeq struct's f!        pendulum.jl:19-26, 65-74
+ *   ldeq_mlp_solve_fwd / _bwd            diffeq_layer(::Decoder{LatentODE}, z0, t) src/models/LatentODE.jl:61-78
+ *                                        with dudt = Chain(Dense,Dense,Dense)      examples/.../nODE.jl:14-16
+ *   ldeq_sample                          sample(mu, logvar, model)                src/models/GOKU.jl:155-173,
+ *                                                                                  src/models/LatentODE.jl:82-98
+ *   ldeq_elbo_fwd_bwd                    loss_batch + vector_kl                   examples/.../model_train.jl:225-238,
+ *                                                                                  src/utils/utils.jl:16-49
+ *   ldeq_adamw_step                      Flux.Optimise.update!(ADAMW(...))        examples/.../model_train.jl:138,201
+ *
+ * Conventions
+ *   - All array arguments are DEVICE pointers owned by the caller unless the name ends in _host.
+ *     The library never keeps a caller pointer after the call returns; a tape holds its own copies.
+ *   - Layout is the reference's column-major layout: z0 is (z,B) => element (d,b) at b*z+d;
+ *     trajectories are (z,B,T) => element (d,b,k) at (k*B+b)*z+d  (what permutedims(.,[1,3,2])
+ *     produces, GOKU.jl:125).  A contiguous torch tensor of shape [T,B,z] has the same bytes.
+ *   - Calls are asynchronous on the given CUDA stream (cudaStream_t passed as void*); functions
+ *     whose name ends in _host synchronise that stream before returning.
+ *   - Return value: 0 on success, negative ldeq_status on error (ldeq_last_error gives text).
+ *     A solver failure of one trajectory is NOT an error: its (z,T) block is filled with NaN
+ *     (GOKU.jl:114), retcode[b] says why, and its gradient contribution is zero.
+ *   - One handle per GPU and host thread; a handle is not thread-safe.
+ */
+#ifndef LDEQ_H
+#define LDEQ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDEQ_VERSION 100
+
+typedef struct ldeq_handle ldeq_handle;
+typedef struct ldeq_rhs ldeq_rhs;
+typedef struct ldeq_tape ldeq_tape;
+typedef struct ldeq_mlp_tape ldeq_mlp_tape;
+typedef void* ldeq_stream; /* cudaStream_t */
+
+enum ldeq_status {
+    LDEQ_OK = 0,
+    LDEQ_ERR_INVALID = -1,     /* bad argument */
+    LDEQ_ERR_CUDA = -2,        /* CUDA runtime error; text in ldeq_last_error */
+    LDEQ_ERR_UNSUPPORTED = -3, /* combination not built (e.g. z_dim of a compiled RHS too large) */
+    LDEQ_ERR_NOMEM = -4,
+    LDEQ_ERR_COMPILE = -5      /* NVRTC could not compile a user RHS; log in ldeq_last_error */
+};
+
+enum ldeq_dtype { LDEQ_F32 = 0, LDEQ_F64 = 1 };
+
+/* built-in right-hand sides: the reference's example diffeq structs */
+enum ldeq_rhs_kind {
+    LDEQ_RHS_PENDULUM = 0,         /* du = [y, -G/L sin x], G = 10            pendulum.jl:19-26 */
+    LDEQ_RHS_PENDULUM_FRICTION = 1 /* du = [y, -G/L sin x - (b/m) y], b=.7,m=1 pendulum.jl:65-74 */
+};
+
+/* per-trajectory return codes (SciMLBase retcodes the reference tests for at GOKU.jl:114) */
+enum ldeq_retcode {
+    LDEQ_RET_SUCCESS = 0,
+    LDEQ_RET_MAXITERS = 1,
+    LDEQ_RET_DTLESSTHANMIN = 2,
+    LDEQ_RET_UNSTABLE = 3
+};
+
+/* error-norm scope of the MLP (LatentODE) solve */
+enum ldeq_norm_mode {
+    LDEQ_NORM_GLOBAL = 0,  /* one dt for the whole (D,B) matrix state: reference semantics (LatentODE.jl:70-72) */
+    LDEQ_NORM_PER_TRAJ = 1 /* per-trajectory error control: documented deviation, no cross-CTA reduction */
+};
+
+/* arithmetic of the MLP right-hand side */
+enum ldeq_mlp_math {
+    LDEQ_MLP_MATH_FP32 = 0,    /* CUDA-core fp32 (fp64 when dtype is F64): exact-parity path */
+    LDEQ_MLP_MATH_BF16X3 = 1   /* tcgen05 tensor cores, 3-term bf16 split of fp32 operands, fp32 accumulate */
+};
+
+/* The keyword arguments the diffeq struct's `kwargs` field forwards to `solve` (pendulum.jl:11,43;
+ * GOKU.jl:108,121).  ldeq_opts_default fills OrdinaryDiffEq's defaults for Tsit5. */
+typedef struct ldeq_opts {
+    double abstol;       /* 1e-6 */
+    double reltol;       /* 1e-3 */
+    int32_t adaptive;    /* 1; 0 = fixed step `dt` */
+    int32_t controller_pow; /* 0 = DiffEqBase.fastpow (reference), 1 = exact pow */
+    double dt;           /* 0 = automatic initial step (adaptive); required when adaptive = 0 */
+    double dtmax;        /* 0 = t[T-1] - t[0] */
+    double dtmin;        /* 0 = max(eps, eps(t[0])) */
+    int64_t maxiters;    /* 1000000 */
+    double gamma;        /* 0.9 */
+    double qmin;         /* 0.2 */
+    double qmax;         /* 10 */
+    double beta1;        /* 7/50 */
+    double beta2;        /* 2/25 */
+    double qoldinit;     /* 1e-4 */
+    double qsteady_min;  /* 1 */
+    double qsteady_max;  /* 1 */
+    int32_t tape_steps;  /* accepted-step capacity per trajectory of a tape; 0 = automatic */
+    int32_t norm_mode;   /* ldeq_norm_mode, MLP solve only */
+    int32_t mlp_math;    /* ldeq_mlp_math, MLP solve only */
+    int32_t reserved;
+} ldeq_opts;
+
+int ldeq_version(void);
+void ldeq_opts_default(ldeq_opts* opts);
+
+/* ---- handle ------------------------------------------------------------------------------------ */
+int ldeq_create(ldeq_handle** out, int device);
+void ldeq_destroy(ldeq_handle* h);
+const char* ldeq_last_error(const ldeq_handle* h);
+/* number of kernels this handle has launched since creation (bench.py's gpu_launches) */
+int64_t ldeq_launch_count(const ldeq_handle* h);
+
+/* ---- right-hand sides -------------------------------------------------------------------------- */
+int ldeq_rhs_builtin(ldeq_handle* h, int kind, ldeq_rhs** out);
+/* User-defined RHS compiled with NVRTC for sm_100a.  `cuda_src` must define
+ *   template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t);
+ * It is instantiated with float, double and a forward-mode dual type (for the reverse pass). */
+int ldeq_rhs_from_source(ldeq_handle* h, const char* cuda_src, int z_dim, int p_dim, ldeq_rhs** out);
+int ldeq_rhs_dims(const ldeq_rhs* rhs, int* z_dim, int* p_dim);
+void ldeq_rhs_free(ldeq_handle* h, ldeq_rhs* rhs);
+
+/* ---- GOKU path: B independent solves ----------------------------------------------------------- */
+/* z0 (z,B), theta (p,B), t_host[T] (host, Float64 grid; t_host[0], t_host[T-1] are the tspan),
+ * traj_out (z,B,T).  retcode/naccept/nreject are optional device int32[B] outputs.
+ * If tape_out != NULL a tape of the accepted steps is recorded for ldeq_solve_bwd. */
+int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta,
+                   const double* t_host, int B, int T, const ldeq_opts* opts, void* traj_out,
+                   int32_t* retcode, int32_t* naccept, int32_t* nreject, ldeq_tape** tape_out,
+                   ldeq_stream stream);
+/* Discrete adjoint of the recorded steps: dtraj (z,B,T) -> dz0 (z,B), dtheta (p,B). */
+int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta,
+                   ldeq_stream stream);
+/* trajectories whose accepted steps exceeded the tape capacity (their gradients are NaN);
+ * synchronises the stream */
+int ldeq_tape_overflow(ldeq_handle* h, ldeq_tape* tape, int32_t* count_host, ldeq_stream stream);
+void ldeq_tape_free(ldeq_handle* h, ldeq_tape* tape, ldeq_stream stream);
+
+/* Same calls with HOST buffers (what a CPU-resident Flux model passes, GOKU.jl:102-103,128): the
+ * library stages through its own device scratch; copies are inside the call; returns after sync. */
+int ldeq_solve_fwd_host(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0_host,
+                        const void* theta_host, const double* t_host, int B, int T, const ldeq_opts* opts,
+                        void* traj_out_host, int32_t* retcode_host, int32_t* naccept_host,
+                        int32_t* nreject_host, ldeq_tape** tape_out, ldeq_stream stream);
+int ldeq_solve_bwd_host(ldeq_handle* h, ldeq_tape* tape, const void* dtraj_host, void* dz0_host,
+                        void* dtheta_host, ldeq_stream stream);
+
+/* ---- LatentODE path: one solve on the (D,B) matrix state with an MLP right-hand side ------------ */
+/* params_flat is Flux.destructure order: per layer vec(W) with W (out,in) column-major, then b.
+ * layer_dims[n_layers+1] = {D, H1, ..., D}; relu on every layer but the last (nODE.jl:14-16). */
+int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* params_flat,
+                       const int32_t* layer_dims_host, int n_layers, const double* t_host, int B, int T,
+                       const ldeq_opts* opts, void* traj_out, int32_t* retcode, int32_t* naccept,
+                       int32_t* nreject, ldeq_mlp_tape** tape_out, ldeq_stream stream);
+int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0,
+                       void* dparams_flat, ldeq_stream stream);
+void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream);
+
+/* ---- reparameterised sample: z = mu + eps * exp(logvar/2), eps ~ N(0,1) drawn on the device ---- */
+int ldeq_sample(ldeq_handle* h, const float* mu, const float* logvar, float* z_out, float* eps_out /*opt*/,
+                int64_t n, uint64_t seed, uint64_t offset, ldeq_stream stream);
+
+/* ---- ELBO: L = sum_pixels mean_{B,T}(x-xhat)^2 + beta * sum_heads (1/B) sum 0.5(e^lv + mu^2 - lv - 1)
+ * x, xhat (P,B,T); mu[h], logvar[h] (d_h,B) for n_heads heads (host arrays of device pointers).
+ * Writes loss (device float[3]: total, reconstruction, kl) and, if non-NULL, the gradients
+ * dxhat (P,B,T), dmu[h], dlogvar[h] of the TOTAL loss scaled by grad_scale. */
+int ldeq_elbo_fwd_bwd(ldeq_handle* h, const float* x, const float* xhat, const float* const* mu_host,
+                      const float* const* logvar_host, const int32_t* head_dims_host, int n_heads, float beta,
+                      int B, int T, int P, float grad_scale, float* loss, float* dxhat, float* const* dmu_host,
+                      float* const* dlogvar_host, ldeq_stream stream);
+
+/* ---- fused multi-tensor AdamW with Flux semantics:
+ * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; x -= lr * m/(1-b1^t) / (sqrt(v/(1-b2^t)) + eps) + decay * x
+ * (Flux 0.13 ADAMW = Optimiser(ADAM, WeightDecay): the decay is NOT scaled by lr).  lr, betas and eps are
+ * Float64 in Flux (the example passes eta = 1e-3), decay is the example's Float32 0.001f0; `step` is 1-based;
+ * gradients are multiplied by grad_scale first (1/world_size after a sum all-reduce). */
+int ldeq_adamw_step(ldeq_handle* h, float* params, const float* grads, float* m, float* v, int64_t n, double lr,
+                    double beta1, double beta2, double eps, float decay, int64_t step, float grad_scale,
+                    ldeq_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDEQ_H */

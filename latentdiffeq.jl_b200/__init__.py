@@ -1,0 +1,16 @@
+"""latentdiffeq.jl_b200 -- B200 (sm_100a) drop-in for the hot path of gabrevaya/LatentDiffEq.jl.
+
+The hot path is the batched latent ODE solve inside ``diffeq_layer`` of the GOKU-net and LatentODE
+models (reference ``src/models/GOKU.jl:98-130``, ``src/models/LatentODE.jl:61-78``), its reverse
+pass, the ELBO reduction and the optimiser step.  It runs in hand-written CUDA behind the C ABI of
+``include/ldeq.h`` (``lib/libldeq.so``); this package is the host-side mirror of the reference's
+model / layer / diffeq-struct API above that ABI.  The directory name contains a dot, so import it
+through the repo-root shim: ``import latentdiffeq_jl_b200 as ldeq``.
+"""
+from . import _cabi
+from ._cabi import (F32, F64, RHS_PENDULUM, RHS_PENDULUM_FRICTION, RET_SUCCESS, RET_MAXITERS, RET_DTLESSTHANMIN,
+                    RET_UNSTABLE, NORM_GLOBAL, NORM_PER_TRAJ, MLP_MATH_FP32, MLP_MATH_BF16X3, LdeqError, default_opts,
+                    handle)
+from .solve import goku_solve, goku_solve_raw, goku_bwd_raw, goku_solve_host, goku_bwd_host
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,161 @@
+// ldeq_common.cuh -- shared device code for the Tsit5 integrator kernels (sm_100a).
+//
+// Algorithm notes (what is computed, not how): OrdinaryDiffEq's Tsit5 with FSAL, RMS error norm,
+// PI step-size controller with DiffEqBase.fastpow, Hairer initial step and saveat through the
+// dense interpolant -- the semantics `solve(ens_prob, Tsit5(), EnsembleThreads(); saveat = t, ...)`
+// has at reference src/models/GOKU.jl:121.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldeq {
+
+// ---- Tsit5 tableau, rounded to the state type S at compile time --------------------------------
+template <class S> struct Tab {
+    static constexpr double c2 = 0.161, c3 = 0.327, c4 = 0.9, c5 = 0.9800255409045097;
+    static constexpr S a21 = (S)0.161;
+    static constexpr S a31 = (S)-0.008480655492356989, a32 = (S)0.335480655492357;
+    static constexpr S a41 = (S)2.8971530571054935, a42 = (S)-6.359448489975075, a43 = (S)4.3622954328695815;
+    static constexpr S a51 = (S)5.325864828439257, a52 = (S)-11.748883564062828, a53 = (S)7.4955393428898365,
+                       a54 = (S)-0.09249506636175525;
+    static constexpr S a61 = (S)5.86145544294642, a62 = (S)-12.92096931784711, a63 = (S)8.159367898576159,
+                       a64 = (S)-0.071584973281401, a65 = (S)-0.028269050394068383;
+    static constexpr S a71 = (S)0.09646076681806523, a72 = (S)0.01, a73 = (S)0.4798896504144996,
+                       a74 = (S)1.379008574103742, a75 = (S)-3.290069515436081, a76 = (S)2.324710524099774;
+    static constexpr S bt1 = (S)-0.00178001105222577714, bt2 = (S)-0.0008164344596567469,
+                       bt3 = (S)0.007880878010261995, bt4 = (S)-0.1447110071732629, bt5 = (S)0.5823571654525552,
+                       bt6 = (S)-0.45808210592918697, bt7 = (S)0.015151515151515152;
+    // dense output b_j(Theta)
+    static constexpr S r11 = (S)1.0, r12 = (S)-2.763706197274826, r13 = (S)2.9132554618219126,
+                       r14 = (S)-1.0530884977290216;
+    static constexpr S r22 = (S)0.13169999999999998, r23 = (S)-0.2234, r24 = (S)0.1017;
+    static constexpr S r32 = (S)3.9302962368947516, r33 = (S)-5.941033872131505, r34 = (S)2.490627285651253;
+    static constexpr S r42 = (S)-12.411077166933676, r43 = (S)30.33818863028232, r44 = (S)-16.548102889244902;
+    static constexpr S r52 = (S)37.50931341651104, r53 = (S)-88.1789048947664, r54 = (S)47.37952196281928;
+    static constexpr S r62 = (S)-27.896526289197286, r63 = (S)65.09189467479366, r64 = (S)-34.87065786149661;
+    static constexpr S r72 = (S)1.5, r73 = (S)-4.0, r74 = (S)2.5;
+};
+
+// dense-output weights b_1..b_7 at Theta
+template <class S> __device__ __forceinline__ void interp_weights(S th, S* bw) {
+    using Tb = Tab<S>;
+    const S th2 = th * th;
+    bw[0] = th * (Tb::r11 + th * (Tb::r12 + th * (Tb::r13 + th * Tb::r14)));
+    bw[1] = th2 * (Tb::r22 + th * (Tb::r23 + th * Tb::r24));
+    bw[2] = th2 * (Tb::r32 + th * (Tb::r33 + th * Tb::r34));
+    bw[3] = th2 * (Tb::r42 + th * (Tb::r43 + th * Tb::r44));
+    bw[4] = th2 * (Tb::r52 + th * (Tb::r53 + th * Tb::r54));
+    bw[5] = th2 * (Tb::r62 + th * (Tb::r63 + th * Tb::r64));
+    bw[6] = th2 * (Tb::r72 + th * (Tb::r73 + th * Tb::r74));
+}
+
+// ---- solver options as the kernels see them ----------------------------------------------------
+struct KOpts {
+    double abstol, reltol;
+    double dt, dtmax, dtmin;
+    double gamma, qmin, qmax, beta1, beta2, qoldinit, qsteady_min, qsteady_max;
+    long long maxiters;
+    int adaptive;
+    int controller_pow;
+};
+
+enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTLESSTHANMIN = 2, RET_UNSTABLE = 3 };
+
+// ---- DiffEqBase.fastpow: Float32 rational log2 on the significand, Float32 exp2 ------------------
+__device__ __forceinline__ float fastlog2_dev(float x) {
+    const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+    const uint32_t ux = __float_as_uint(x);
+    const int ex = (int)((ux & 0x7F800000u) >> 23);
+    const bool greater = (ux & 0x00400000u) != 0u;
+    float signif = __uint_as_float((ux & 0x007FFFFFu) | (greater ? 0x3f000000u : 0x3f800000u));
+    const float fexp = (float)(ex - (greater ? 126 : 127));
+    signif = signif - 1.0f;
+    return fexp + __fdiv_rn(__fmul_rn(signif, __fadd_rn(__fmul_rn(a, signif), b)), __fadd_rn(signif, c));
+}
+__device__ __forceinline__ double ctrl_pow(double x, double y, int exact) {
+    if (exact) return pow(x, y);
+    if (x == 0.0) return 0.0;
+    return (double)exp2f(__fmul_rn((float)y, fastlog2_dev(fabsf((float)x))));
+}
+
+// PI controller (OrdinaryDiffEq stepsize_controller!/step_accept_controller!/step_reject_controller!).
+// Returns accept; updates dt (next proposal) and qold.
+__device__ __forceinline__ bool pi_controller(const KOpts& o, double EEst, double dts, double dtmax, double& qold,
+                                              double& dt_next) {
+    double q, q11 = 1.0;
+    if (EEst == 0.0) {
+        q = 1.0 / o.qmax;
+    } else {
+        q11 = ctrl_pow(EEst, o.beta1, o.controller_pow);
+        q = q11 / ctrl_pow(qold, o.beta2, o.controller_pow);
+        q = fmax(1.0 / o.qmax, fmin(1.0 / o.qmin, q / o.gamma));
+    }
+    const bool accept = EEst <= 1.0;
+    if (accept) {
+        if (o.qsteady_min <= q && q <= o.qsteady_max) q = 1.0;
+        qold = fmax(EEst, o.qoldinit);
+        dt_next = fmin(dtmax, dts / q);
+    } else {
+        dt_next = dts / fmin(1.0 / o.qmin, q11 / o.gamma);
+    }
+    return accept;
+}
+
+// ulp(max(|a|,|b|)) for the tstop snap (fixed_t_for_floatingpoint_error!)
+__device__ __forceinline__ double ulp_of(double x) {
+    x = fabs(x);
+    return __longlong_as_double(__double_as_longlong(x) + 1) - x;
+}
+
+// ---- small typed helpers -------------------------------------------------------------------------
+template <class S> __device__ __forceinline__ S s_fma(S a, S b, S c);
+template <> __device__ __forceinline__ float s_fma<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> __device__ __forceinline__ double s_fma<double>(double a, double b, double c) { return fma(a, b, c); }
+template <class S> __device__ __forceinline__ S s_abs(S a);
+template <> __device__ __forceinline__ float s_abs<float>(float a) { return fabsf(a); }
+template <> __device__ __forceinline__ double s_abs<double>(double a) { return fabs(a); }
+template <class S> __device__ __forceinline__ S s_sqrt(S a);
+template <> __device__ __forceinline__ float s_sqrt<float>(float a) { return sqrtf(a); }
+template <> __device__ __forceinline__ double s_sqrt<double>(double a) { return sqrt(a); }
+template <class S> __device__ __forceinline__ S s_max(S a, S b);
+template <> __device__ __forceinline__ float s_max<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double s_max<double>(double a, double b) { return fmax(a, b); }
+template <class S> __device__ __forceinline__ void s_sincos(S x, S* s, S* c);
+template <> __device__ __forceinline__ void s_sincos<float>(float x, float* s, float* c) { sincosf(x, s, c); }
+template <> __device__ __forceinline__ void s_sincos<double>(double x, double* s, double* c) { sincos(x, s, c); }
+template <class S> __device__ __forceinline__ S s_sin(S x);
+template <> __device__ __forceinline__ float s_sin<float>(float x) { return sinf(x); }
+template <> __device__ __forceinline__ double s_sin<double>(double x) { return sin(x); }
+template <class S> __device__ __forceinline__ S s_nan();
+template <> __device__ __forceinline__ float s_nan<float>() { return __int_as_float(0x7fc00000); }
+template <> __device__ __forceinline__ double s_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+template <class S> __device__ __forceinline__ bool s_finite(S a);
+template <> __device__ __forceinline__ bool s_finite<float>(float a) { return isfinite(a); }
+template <> __device__ __forceinline__ bool s_finite<double>(double a) { return isfinite(a); }
+
+// vector load/store of one trajectory's ZD-vector (coalesced 8/16-byte accesses for ZD = 2)
+template <class S, int ZD> __device__ __forceinline__ void load_vec(const S* __restrict__ p, S* v) {
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) v[i] = p[i];
+}
+template <> __device__ __forceinline__ void load_vec<float, 2>(const float* __restrict__ p, float* v) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+template <> __device__ __forceinline__ void load_vec<double, 2>(const double* __restrict__ p, double* v) {
+    const double2 t = *reinterpret_cast<const double2*>(p);
+    v[0] = t.x; v[1] = t.y;
+}
+template <class S, int ZD> __device__ __forceinline__ void store_vec(S* __restrict__ p, const S* v) {
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) p[i] = v[i];
+}
+template <> __device__ __forceinline__ void store_vec<float, 2>(float* __restrict__ p, const float* v) {
+    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
+}
+template <> __device__ __forceinline__ void store_vec<double, 2>(double* __restrict__ p, const double* v) {
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+}
+
+}  // namespace ldeq

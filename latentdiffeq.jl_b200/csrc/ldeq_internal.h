@@ -1,0 +1,66 @@
+// ldeq_internal.h -- host-side objects behind the opaque C-ABI types of include/ldeq.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ldeq.h"
+#include "ldeq_common.cuh"
+
+struct ldeq_handle {
+    int device = 0;
+    std::string err;
+    int64_t launches = 0;
+    // device copy of the most recent time grid (re-uploaded only when the host grid changes)
+    double* d_tgrid = nullptr;
+    size_t d_tgrid_cap = 0;
+    std::vector<double> h_tgrid;
+    // grow-only device scratch for the *_host entry points and reductions
+    void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_cap[4] = {0, 0, 0, 0};
+    // ELBO reduction workspace
+    double* d_partials = nullptr;
+    unsigned int* d_counter = nullptr;
+    int n_partials = 0;
+    int sm_count = 148;
+};
+
+struct ldeq_rhs {
+    int kind = 0;  // ldeq_rhs_kind, or -1 for an NVRTC-compiled user RHS
+    int z_dim = 2, p_dim = 1;
+    void* module = nullptr;  // CUmodule of a user RHS
+    void* fn[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+struct ldeq_tape {
+    int dtype = 0, rhs_kind = 0, B = 0, T = 0, z_dim = 2, p_dim = 1, cap = 0;
+    const ldeq_rhs* rhs = nullptr;
+    void* base = nullptr;  // one stream-ordered allocation, carved into the arrays below
+    double* t = nullptr;
+    double* dt = nullptr;
+    void* u = nullptr;
+    void* theta = nullptr;
+    double* tgrid = nullptr;
+    int32_t* retcode = nullptr;
+    int32_t* naccept = nullptr;
+    int32_t* nreject = nullptr;
+    int32_t* overflow = nullptr;
+};
+
+namespace ldeq {
+
+int set_err(ldeq_handle* h, int code, const char* what, cudaError_t ce = cudaSuccess);
+int upload_tgrid(ldeq_handle* h, const double* t_host, int T, cudaStream_t s);
+int ensure_scratch(ldeq_handle* h, int slot, size_t bytes);
+KOpts to_kopts(const ldeq_opts* o);
+
+#define LDEQ_CUDA(call)                                                    \
+    do {                                                                   \
+        cudaError_t _e = (call);                                           \
+        if (_e != cudaSuccess) return ldeq::set_err(h, LDEQ_ERR_CUDA, #call, _e); \
+    } while (0)
+
+}  // namespace ldeq

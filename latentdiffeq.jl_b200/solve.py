@@ -1,0 +1,200 @@
+"""Torch-facing wrappers of the C-ABI solve entry points.
+
+Tensors are contiguous torch tensors whose bytes equal the reference's column-major Julia arrays:
+``z0`` is ``[B, z]`` (Julia ``(z,B)``), ``theta`` is ``[B, p]``, trajectories are ``[T, B, z]``
+(Julia ``(z,B,T)``, what ``permutedims(z, [1,3,2])`` yields at reference ``src/models/GOKU.jl:125``).
+
+PyTorch is plumbing here (device memory, streams, autograd glue); all arithmetic runs in
+``libldeq.so``.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+
+def _dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float32:
+        return _cabi.F32
+    if dt == torch.float64:
+        return _cabi.F64
+    raise TypeError(f"state dtype must be float32 or float64, got {dt}")
+
+
+def _tgrid(t) -> np.ndarray:
+    """The save grid as host Float64 (the reference's ``t`` is a Float64 range)."""
+    if isinstance(t, torch.Tensor):
+        t = t.detach().cpu().numpy()
+    t = np.ascontiguousarray(np.asarray(t, dtype=np.float64))
+    if t.ndim != 1 or t.size < 1:
+        raise ValueError("t must be a non-empty 1-D grid")
+    return t
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(x: torch.Tensor | None) -> C.c_void_p:
+    return C.c_void_p(0 if x is None else x.data_ptr())
+
+
+class _Tape:
+    """Owns an ``ldeq_tape`` (or ``ldeq_mlp_tape``); frees it stream-ordered when dropped."""
+
+    def __init__(self, h: _cabi.Handle, ptr: C.c_void_p, mlp: bool = False):
+        self.h, self.ptr, self.mlp = h, ptr, mlp
+
+    def overflow(self) -> int:
+        n = C.c_int32(0)
+        self.h.check(self.h._lib.ldeq_tape_overflow(self.h.ptr, self.ptr, C.byref(n), _stream()))
+        return int(n.value)
+
+    def free(self):
+        if self.ptr:
+            try:
+                with torch.cuda.device(self.h.device):
+                    if self.mlp:
+                        self.h._lib.ldeq_mlp_tape_free(self.h.ptr, self.ptr, _stream())
+                    else:
+                        self.h._lib.ldeq_tape_free(self.h.ptr, self.ptr, _stream())
+            finally:
+                self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class SolveStats:
+    """Per-trajectory ``retcode`` / ``naccept`` / ``nreject`` (device int32 tensors)."""
+
+    def __init__(self, retcode, naccept, nreject):
+        self.retcode, self.naccept, self.nreject = retcode, naccept, nreject
+
+
+def goku_solve_raw(z0: torch.Tensor, theta: torch.Tensor, t, rhs, opts: _cabi.Opts | None = None,
+                   want_tape: bool = False, want_stats: bool = True):
+    """One call of ``ldeq_solve_fwd``: B independent Tsit5 solves (reference GOKU.jl:111-125).
+
+    ``rhs`` is a built-in kind (``_cabi.RHS_PENDULUM`` ...) or an ``ldeq_rhs`` pointer from
+    ``Handle.rhs_from_source``.  Returns ``(traj[T,B,z], stats, tape_or_None)``.
+    """
+    if not z0.is_cuda:
+        raise RuntimeError("goku_solve_raw needs CUDA tensors; use goku_solve_host for host buffers "
+                           "(there is no CPU implementation of the hot path)")
+    h = _cabi.handle(z0.device.index or 0)
+    opts = opts or _cabi.default_opts()
+    z0 = z0.contiguous()
+    theta = theta.to(z0.dtype).contiguous()
+    tg = _tgrid(t)
+    B, Z = z0.shape
+    T = tg.shape[0]
+    rhs_ptr = h.rhs_builtin(rhs) if isinstance(rhs, int) else rhs
+    traj = torch.empty((T, B, Z), dtype=z0.dtype, device=z0.device)
+    ret = na = nr = None
+    if want_stats:
+        ret = torch.empty(B, dtype=torch.int32, device=z0.device)
+        na = torch.empty(B, dtype=torch.int32, device=z0.device)
+        nr = torch.empty(B, dtype=torch.int32, device=z0.device)
+    tape = C.c_void_p()
+    with torch.cuda.device(z0.device):
+        h.check(h._lib.ldeq_solve_fwd(h.ptr, rhs_ptr, _dtype_code(z0.dtype), _p(z0), _p(theta),
+                                      tg.ctypes.data_as(C.c_void_p), B, T, C.byref(opts), _p(traj), _p(ret), _p(na),
+                                      _p(nr), C.byref(tape) if want_tape else None, _stream()))
+    return traj, SolveStats(ret, na, nr), (_Tape(h, tape) if want_tape else None)
+
+
+def goku_bwd_raw(tape: _Tape, dtraj: torch.Tensor):
+    """One call of ``ldeq_solve_bwd``: discrete adjoint of the taped steps."""
+    h = tape.h
+    dtraj = dtraj.contiguous()
+    T, B, Z = dtraj.shape
+    dz0 = torch.empty((B, Z), dtype=dtraj.dtype, device=dtraj.device)
+    # p_dim is a property of the rhs; ask the tape's rhs through the handle-independent call
+    dth = torch.empty((B, tape.p_dim), dtype=dtraj.dtype, device=dtraj.device)
+    with torch.cuda.device(dtraj.device):
+        h.check(h._lib.ldeq_solve_bwd(h.ptr, tape.ptr, _p(dtraj), _p(dz0), _p(dth), _stream()))
+    return dz0, dth
+
+
+class _GokuSolve(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z0, theta, tg, rhs, opts, stats_out):
+        need = z0.requires_grad or theta.requires_grad
+        traj, stats, tape = goku_solve_raw(z0, theta, tg, rhs, opts, want_tape=need, want_stats=True)
+        if tape is not None:
+            tape.p_dim = theta.shape[1]
+        ctx.tape = tape
+        if stats_out is not None:
+            stats_out.append(stats)
+        return traj
+
+    @staticmethod
+    def backward(ctx, dtraj):
+        tape = ctx.tape
+        if tape is None:
+            return None, None, None, None, None, None
+        dz0, dth = goku_bwd_raw(tape, dtraj)
+        tape.free()
+        ctx.tape = None
+        return dz0, dth, None, None, None, None
+
+
+def goku_solve(z0: torch.Tensor, theta: torch.Tensor, t, rhs=_cabi.RHS_PENDULUM, opts: _cabi.Opts | None = None,
+               stats_out: list | None = None) -> torch.Tensor:
+    """Differentiable batched solve: the body of ``diffeq_layer(::Decoder{<:GOKU}, (z0, theta), t)``
+    (reference ``src/models/GOKU.jl:98-130``).  Gradients flow to ``z0`` and ``theta`` through the
+    discrete adjoint of the accepted steps."""
+    return _GokuSolve.apply(z0, theta, _tgrid(t), rhs, opts, stats_out)
+
+
+# ---- host-buffer entry points (what a CPU-resident Flux model passes, GOKU.jl:102-103,128) --------
+def goku_solve_host(z0: torch.Tensor, theta: torch.Tensor, t, rhs=_cabi.RHS_PENDULUM,
+                    opts: _cabi.Opts | None = None, device: int = 0, want_tape: bool = False,
+                    out: torch.Tensor | None = None):
+    """``ldeq_solve_fwd_host``: host tensors in, host tensor out; copies are inside the call."""
+    assert not z0.is_cuda and not theta.is_cuda
+    h = _cabi.handle(device)
+    opts = opts or _cabi.default_opts()
+    z0 = z0.contiguous()
+    theta = theta.to(z0.dtype).contiguous()
+    tg = _tgrid(t)
+    B, Z = z0.shape
+    T = tg.shape[0]
+    rhs_ptr = h.rhs_builtin(rhs) if isinstance(rhs, int) else rhs
+    if out is None:
+        out = torch.empty((T, B, Z), dtype=z0.dtype, pin_memory=True)
+    tape = C.c_void_p()
+    with torch.cuda.device(device):
+        h.check(h._lib.ldeq_solve_fwd_host(h.ptr, rhs_ptr, _dtype_code(z0.dtype), _p(z0), _p(theta),
+                                           tg.ctypes.data_as(C.c_void_p), B, T, C.byref(opts), _p(out), None, None,
+                                           None, C.byref(tape) if want_tape else None, _stream()))
+    tp = None
+    if want_tape:
+        tp = _Tape(h, tape)
+        tp.p_dim = theta.shape[1]
+    return out, tp
+
+
+def goku_bwd_host(tape: _Tape, dtraj: torch.Tensor, dz0: torch.Tensor | None = None,
+                  dtheta: torch.Tensor | None = None):
+    """``ldeq_solve_bwd_host``: host cotangent in, host gradients out."""
+    assert not dtraj.is_cuda
+    h = tape.h
+    dtraj = dtraj.contiguous()
+    T, B, Z = dtraj.shape
+    if dz0 is None:
+        dz0 = torch.empty((B, Z), dtype=dtraj.dtype, pin_memory=True)
+    if dtheta is None:
+        dtheta = torch.empty((B, tape.p_dim), dtype=dtraj.dtype, pin_memory=True)
+    with torch.cuda.device(h.device):
+        h.check(h._lib.ldeq_solve_bwd_host(h.ptr, tape.ptr, _p(dtraj), _p(dz0), _p(dtheta), _stream()))
+    return dz0, dtheta

@@ -1,0 +1,616 @@
+// ldeq_oracle.cpp -- CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE).
+//
+// A CPU restatement of the algorithm LatentDiffEq.jl runs for its GOKU hot path:
+//   diffeq_layer(::Decoder{<:GOKU}, (z0, theta), t)        reference src/models/GOKU.jl:98-130
+//     -> EnsembleProblem + EnsembleThreads, one Tsit5 solve per column   GOKU.jl:111-121
+//     -> NaN-filled (z,T) block for a failed trajectory                  GOKU.jl:114
+//     -> permutedims to (z,B,T)                                          GOKU.jl:125
+//   user RHS Pendulum / Pendulum_friction       examples/pendulum_friction-less/pendulum.jl:19-26, 65-74
+//   gradients: ForwardDiffSensitivity (1 primal + 2 dual solves)         pendulum.jl:11
+//
+// The arithmetic itself lives in un-vendored Julia packages (OrdinaryDiffEq 6.27.1,
+// DiffEqBase 6.104.3, SciMLSensitivity 7.10.0, ForwardDiff 0.10.32; pins in the reference's
+// Manifest.toml:979-983, 292-296, 1200-1204, 470-474).  What is restated here is their published
+// algorithm as summarised in SURVEY.md Appendix A: Tsit5 tableau + FSAL, RMS error norm, PI
+// controller with DiffEqBase.fastpow, Hairer initial step, saveat through the Tsit5 dense
+// interpolant, Float32 state with Float64 time (mixed precision exactly as Julia's promotion
+// rules give it), ForwardDiff dual solves whose error norm includes the partials.
+//
+// PARITY UNPINNED: the reference ships an empty test set (test/runtests.jl:4-6), no golden
+// vectors and no stored outputs, and Julia is not available in this image, so this oracle cannot
+// be checked against the reference itself.  It is pinned instead by independent checks in
+// tests/ (tableau order conditions, scipy DOP853 @1e-12, energy invariant, finite differences).
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library.  The product path (libldeq.so) never links or calls it.
+//
+// Layout contract (identical to the product C ABI): z0 is (z,B) column-major => z0[b*Z+d];
+// theta is (p,B) => theta[b*P+d]; trajectories are (z,B,T) => traj[(k*B+b)*Z+d].
+
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Tsit5 tableau (OrdinaryDiffEq Tsit5ConstantCache).  Kept in double and rounded
+// to the state type at use, which is what Tsit5ConstantCache(T, T2) does.
+// ---------------------------------------------------------------------------------------------
+constexpr double C2 = 0.161, C3 = 0.327, C4 = 0.9, C5 = 0.9800255409045097;
+constexpr double A21 = 0.161;
+constexpr double A31 = -0.008480655492356989, A32 = 0.335480655492357;
+constexpr double A41 = 2.8971530571054935, A42 = -6.359448489975075, A43 = 4.3622954328695815;
+constexpr double A51 = 5.325864828439257, A52 = -11.748883564062828, A53 = 7.4955393428898365,
+                 A54 = -0.09249506636175525;
+constexpr double A61 = 5.86145544294642, A62 = -12.92096931784711, A63 = 8.159367898576159,
+                 A64 = -0.071584973281401, A65 = -0.028269050394068383;
+constexpr double A71 = 0.09646076681806523, A72 = 0.01, A73 = 0.4798896504144996,
+                 A74 = 1.379008574103742, A75 = -3.290069515436081, A76 = 2.324710524099774;
+constexpr double BT1 = -0.00178001105222577714, BT2 = -0.0008164344596567469,
+                 BT3 = 0.007880878010261995, BT4 = -0.1447110071732629, BT5 = 0.5823571654525552,
+                 BT6 = -0.45808210592918697, BT7 = 0.015151515151515152;
+// dense-output polynomial coefficients
+constexpr double R11 = 1.0, R12 = -2.763706197274826, R13 = 2.9132554618219126,
+                 R14 = -1.0530884977290216;
+constexpr double R22 = 0.13169999999999998, R23 = -0.2234, R24 = 0.1017;
+constexpr double R32 = 3.9302962368947516, R33 = -5.941033872131505, R34 = 2.490627285651253;
+constexpr double R42 = -12.411077166933676, R43 = 30.33818863028232, R44 = -16.548102889244902;
+constexpr double R52 = 37.50931341651104, R53 = -88.1789048947664, R54 = 47.37952196281928;
+constexpr double R62 = -27.896526289197286, R63 = 65.09189467479366, R64 = -34.87065786149661;
+constexpr double R72 = 1.5, R73 = -4.0, R74 = 2.5;
+
+// ---------------------------------------------------------------------------------------------
+// DiffEqBase.fastpow: Float32 log2 by a rational fit on the significand and a
+// Float32 exp2.  x, y are demoted to Float32 and the result promoted back.
+// ---------------------------------------------------------------------------------------------
+inline float fastlog2f(float x) {
+    const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+    uint32_t ux;
+    std::memcpy(&ux, &x, 4);
+    int32_t ex = (int32_t)((ux & 0x7F800000u) >> 23);
+    uint32_t greater = ux & 0x00400000u;
+    float signif, fexp;
+    if (greater) {
+        uint32_t u2 = (ux & 0x007FFFFFu) | 0x3f000000u;
+        std::memcpy(&signif, &u2, 4);
+        fexp = (float)(ex - 126);
+    } else {
+        uint32_t u2 = (ux & 0x007FFFFFu) | 0x3f800000u;
+        std::memcpy(&signif, &u2, 4);
+        fexp = (float)(ex - 127);
+    }
+    signif = signif - 1.0f;
+    return fexp + signif * (a * signif + b) / (signif + c);
+}
+inline double fastpow(double x, double y) {
+    if (x == 0.0) return 0.0;
+    float xf = std::fabs((float)x), yf = (float)y;
+    return (double)exp2f(yf * fastlog2f(xf));
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scalar helpers: `S` is the state type (float or double); time is always double.
+// ---------------------------------------------------------------------------------------------
+template <class S> inline S fma_s(S a, S b, S c);
+template <> inline float fma_s<float>(float a, float b, float c) { return fmaf(a, b, c); }
+template <> inline double fma_s<double>(double a, double b, double c) { return fma(a, b, c); }
+
+// Forward-mode dual number with NP partials (ForwardDiff.Dual restated).  NP = 0 is a plain value.
+template <class S, int NP> struct Dual {
+    S v;
+    S d[NP > 0 ? NP : 1];
+};
+template <class S, int NP> inline Dual<S, NP> dmake(S v) {
+    Dual<S, NP> r;
+    r.v = v;
+    for (int i = 0; i < NP; ++i) r.d[i] = S(0);
+    return r;
+}
+template <class S, int NP> inline Dual<S, NP> operator+(Dual<S, NP> a, Dual<S, NP> b) {
+    a.v += b.v;
+    for (int i = 0; i < NP; ++i) a.d[i] += b.d[i];
+    return a;
+}
+template <class S, int NP> inline Dual<S, NP> operator-(Dual<S, NP> a, Dual<S, NP> b) {
+    a.v -= b.v;
+    for (int i = 0; i < NP; ++i) a.d[i] -= b.d[i];
+    return a;
+}
+template <class S, int NP> inline Dual<S, NP> operator-(Dual<S, NP> a) {
+    a.v = -a.v;
+    for (int i = 0; i < NP; ++i) a.d[i] = -a.d[i];
+    return a;
+}
+template <class S, int NP> inline Dual<S, NP> operator*(Dual<S, NP> a, Dual<S, NP> b) {
+    Dual<S, NP> r;
+    r.v = a.v * b.v;
+    for (int i = 0; i < NP; ++i) r.d[i] = a.d[i] * b.v + a.v * b.d[i];
+    return r;
+}
+template <class S, int NP> inline Dual<S, NP> operator*(S a, Dual<S, NP> b) {
+    b.v *= a;
+    for (int i = 0; i < NP; ++i) b.d[i] *= a;
+    return b;
+}
+template <class S, int NP> inline Dual<S, NP> operator/(Dual<S, NP> a, Dual<S, NP> b) {
+    Dual<S, NP> r;
+    r.v = a.v / b.v;
+    for (int i = 0; i < NP; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v;
+    return r;
+}
+template <class S, int NP> inline Dual<S, NP> dsin(Dual<S, NP> a) {
+    Dual<S, NP> r;
+    S c = std::cos(a.v);
+    r.v = std::sin(a.v);
+    for (int i = 0; i < NP; ++i) r.d[i] = c * a.d[i];
+    return r;
+}
+// s*k accumulated with an explicit fma per component: acc = s*k + acc
+template <class S, int NP> inline Dual<S, NP> dfma(S s, Dual<S, NP> k, Dual<S, NP> acc) {
+    acc.v = fma_s<S>(s, k.v, acc.v);
+    for (int i = 0; i < NP; ++i) acc.d[i] = fma_s<S>(s, k.d[i], acc.d[i]);
+    return acc;
+}
+// uprev + dt*sum with dt in Float64: promoted to double, fused, rounded back to S on the store
+// (Julia: `@.. tmp = uprev + dt*(...)` with dt::Float64 and a Float32 destination array).
+template <class S, int NP> inline Dual<S, NP> axpy_time(Dual<S, NP> uprev, double dt, Dual<S, NP> sum) {
+    Dual<S, NP> r;
+    r.v = (S)fma(dt, (double)sum.v, (double)uprev.v);
+    for (int i = 0; i < NP; ++i) r.d[i] = (S)fma(dt, (double)sum.d[i], (double)uprev.d[i]);
+    return r;
+}
+template <class S, int NP> inline Dual<S, NP> scale_time(double dt, Dual<S, NP> sum) {
+    Dual<S, NP> r;
+    r.v = (S)(dt * (double)sum.v);
+    for (int i = 0; i < NP; ++i) r.d[i] = (S)(dt * (double)sum.d[i]);
+    return r;
+}
+// sse(x::Dual) = value^2 + sum(partials^2)   (DiffEqBase forwarddiff.jl)
+template <class S, int NP> inline S sse(Dual<S, NP> a, bool with_partials) {
+    S s = a.v * a.v;
+    if (with_partials)
+        for (int i = 0; i < NP; ++i) s += a.d[i] * a.d[i];
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// User RHS (reference pendulum.jl:19-26 and :65-74).  G, b, m are Float32 literals in the
+// reference; they are rounded to S here.
+// ---------------------------------------------------------------------------------------------
+enum { RHS_PENDULUM = 0, RHS_PENDULUM_FRICTION = 1 };
+
+template <class S, int NP>
+inline void rhs_eval(int rhs, Dual<S, NP>* du, const Dual<S, NP>* u, const Dual<S, NP>* p, double /*t*/) {
+    const Dual<S, NP> x = u[0], y = u[1];
+    const Dual<S, NP> G = dmake<S, NP>((S)10.0f);
+    const Dual<S, NP> L = p[0];
+    du[0] = y;
+    if (rhs == RHS_PENDULUM) {
+        du[1] = (-G / L) * dsin(x);  // -G/L*sin(x)
+    } else {
+        const S bm = (S)0.7f / (S)1.0f;  // (b/m)
+        du[1] = (-G / L) * dsin(x) - bm * y;
+    }
+}
+
+struct Opts {
+    double abstol, reltol;
+    int adaptive;
+    double dt, dtmax, dtmin;
+    long long maxiters;
+    double gamma, qmin, qmax, beta1, beta2, qoldinit, qsteady_min, qsteady_max;
+    int controller_pow;  // 0 fastpow (reference), 1 exact pow
+};
+
+enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTLESSTHANMIN = 2, RET_UNSTABLE = 3 };
+
+constexpr int Z = 2;  // state dimension of both built-in systems
+constexpr int P = 1;
+
+// RMS norm over a residual vector (ODE_DEFAULT_NORM); with duals the partials count as entries.
+template <class S, int NP> inline S rms_norm(const Dual<S, NP>* a, int n, bool with_partials) {
+    S s = 0;
+    for (int i = 0; i < n; ++i) s += sse(a[i], with_partials);
+    int len = with_partials ? n * (1 + NP) : n;
+    return std::sqrt(s / (S)len);
+}
+template <class S, int NP> inline S abs_norm(Dual<S, NP> a, bool with_partials) {
+    return with_partials && NP > 0 ? std::sqrt(sse(a, true)) : std::fabs(a.v);
+}
+template <class S, int NP> inline Dual<S, NP> ddiv_s(Dual<S, NP> a, S s) {
+    a.v /= s;
+    for (int i = 0; i < NP; ++i) a.d[i] /= s;
+    return a;
+}
+
+template <class S, int NP> struct StepOut {
+    Dual<S, NP> k[7][Z];
+    Dual<S, NP> unew[Z];
+    double EEst;
+};
+
+// One Tsit5 step (OrdinaryDiffEq perform_step!).  k[0] must hold fsalfirst.
+template <class S, int NP>
+inline void tsit5_step(int rhs, const Dual<S, NP>* uprev, const Dual<S, NP>* p, double t, double dt,
+                       const Opts& o, bool norm_partials, StepOut<S, NP>& st) {
+    Dual<S, NP> tmp[Z], sum;
+    auto& k = st.k;
+    for (int i = 0; i < Z; ++i) {
+        sum = (S)A21 * k[0][i];
+        tmp[i] = axpy_time(uprev[i], dt, sum);
+    }
+    rhs_eval<S, NP>(rhs, k[1], tmp, p, t + C2 * dt);
+    for (int i = 0; i < Z; ++i) {
+        sum = (S)A31 * k[0][i];
+        sum = dfma((S)A32, k[1][i], sum);
+        tmp[i] = axpy_time(uprev[i], dt, sum);
+    }
+    rhs_eval<S, NP>(rhs, k[2], tmp, p, t + C3 * dt);
+    for (int i = 0; i < Z; ++i) {
+        sum = (S)A41 * k[0][i];
+        sum = dfma((S)A42, k[1][i], sum);
+        sum = dfma((S)A43, k[2][i], sum);
+        tmp[i] = axpy_time(uprev[i], dt, sum);
+    }
+    rhs_eval<S, NP>(rhs, k[3], tmp, p, t + C4 * dt);
+    for (int i = 0; i < Z; ++i) {
+        sum = (S)A51 * k[0][i];
+        sum = dfma((S)A52, k[1][i], sum);
+        sum = dfma((S)A53, k[2][i], sum);
+        sum = dfma((S)A54, k[3][i], sum);
+        tmp[i] = axpy_time(uprev[i], dt, sum);
+    }
+    rhs_eval<S, NP>(rhs, k[4], tmp, p, t + C5 * dt);
+    for (int i = 0; i < Z; ++i) {
+        sum = (S)A61 * k[0][i];
+        sum = dfma((S)A62, k[1][i], sum);
+        sum = dfma((S)A63, k[2][i], sum);
+        sum = dfma((S)A64, k[3][i], sum);
+        sum = dfma((S)A65, k[4][i], sum);
+        tmp[i] = axpy_time(uprev[i], dt, sum);
+    }
+    rhs_eval<S, NP>(rhs, k[5], tmp, p, t + dt);
+    for (int i = 0; i < Z; ++i) {
+        sum = (S)A71 * k[0][i];
+        sum = dfma((S)A72, k[1][i], sum);
+        sum = dfma((S)A73, k[2][i], sum);
+        sum = dfma((S)A74, k[3][i], sum);
+        sum = dfma((S)A75, k[4][i], sum);
+        sum = dfma((S)A76, k[5][i], sum);
+        st.unew[i] = axpy_time(uprev[i], dt, sum);
+    }
+    rhs_eval<S, NP>(rhs, k[6], st.unew, p, t + dt);
+    st.EEst = 0.0;
+    if (o.adaptive) {
+        Dual<S, NP> atmp[Z];
+        const S abstol = (S)o.abstol, reltol = (S)o.reltol;
+        for (int i = 0; i < Z; ++i) {
+            sum = (S)BT1 * k[0][i];
+            sum = dfma((S)BT2, k[1][i], sum);
+            sum = dfma((S)BT3, k[2][i], sum);
+            sum = dfma((S)BT4, k[3][i], sum);
+            sum = dfma((S)BT5, k[4][i], sum);
+            sum = dfma((S)BT6, k[5][i], sum);
+            sum = dfma((S)BT7, k[6][i], sum);
+            Dual<S, NP> utilde = scale_time(dt, sum);
+            S a0 = abs_norm(uprev[i], norm_partials), a1 = abs_norm(st.unew[i], norm_partials);
+            S sk = abstol + (a0 > a1 ? a0 : a1) * reltol;
+            atmp[i] = ddiv_s(utilde, sk);
+        }
+        st.EEst = (double)rms_norm(atmp, Z, norm_partials);
+    }
+}
+
+// Tsit5 dense output at theta in (0,1) of the step [tprev, tprev+dt].
+template <class S, int NP>
+inline void tsit5_interp(const Dual<S, NP>* uprev, const StepOut<S, NP>& st, double dt, double Theta,
+                         Dual<S, NP>* out) {
+    // the b_j(Theta) polynomials are evaluated in the time type (Theta is Float64) and then meet
+    // Float32 k's: Julia promotes the product to Float64 and rounds on the store.
+    const double T1 = Theta, T2 = Theta * Theta;
+    const double b1 = T1 * (R11 + T1 * (R12 + T1 * (R13 + T1 * R14)));
+    const double b2 = T2 * (R22 + T1 * (R23 + T1 * R24));
+    const double b3 = T2 * (R32 + T1 * (R33 + T1 * R34));
+    const double b4 = T2 * (R42 + T1 * (R43 + T1 * R44));
+    const double b5 = T2 * (R52 + T1 * (R53 + T1 * R54));
+    const double b6 = T2 * (R62 + T1 * (R63 + T1 * R64));
+    const double b7 = T2 * (R72 + T1 * (R73 + T1 * R74));
+    const double bb[7] = {b1, b2, b3, b4, b5, b6, b7};
+    for (int i = 0; i < Z; ++i) {
+        double sv = 0.0, sd[NP > 0 ? NP : 1] = {0};
+        for (int j = 0; j < 7; ++j) {
+            sv = fma(bb[j], (double)st.k[j][i].v, sv);
+            for (int q = 0; q < NP; ++q) sd[q] = fma(bb[j], (double)st.k[j][i].d[q], sd[q]);
+        }
+        out[i].v = (S)fma(dt, sv, (double)uprev[i].v);
+        for (int q = 0; q < NP; ++q) out[i].d[q] = (S)fma(dt, sd[q], (double)uprev[i].d[q]);
+    }
+}
+
+// Hairer initial step (ode_determine_initdt); f0 is supplied by the caller.
+template <class S, int NP>
+inline double initdt(int rhs, const Dual<S, NP>* u0, const Dual<S, NP>* p, const Dual<S, NP>* f0,
+                     double t0, double dtmax, double dtmin, const Opts& o, bool norm_partials) {
+    const S abstol = (S)o.abstol, reltol = (S)o.reltol;
+    S sk[Z];
+    Dual<S, NP> tmp[Z];
+    for (int i = 0; i < Z; ++i) {
+        sk[i] = abstol + abs_norm(u0[i], norm_partials) * reltol;
+        tmp[i] = ddiv_s(u0[i], sk[i]);
+    }
+    double d0 = (double)rms_norm(tmp, Z, norm_partials);
+    for (int i = 0; i < Z; ++i) tmp[i] = ddiv_s(f0[i], sk[i]);
+    double d1 = (double)rms_norm(tmp, Z, norm_partials);
+    double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+    dt0 = std::fmin(dt0, dtmax);
+    if (dt0 < 10.0 * std::numeric_limits<double>::epsilon()) return std::fmax(1e-6, dtmin);
+    Dual<S, NP> u1[Z], f1[Z];
+    for (int i = 0; i < Z; ++i) u1[i] = axpy_time(u0[i], dt0, f0[i]);
+    rhs_eval<S, NP>(rhs, f1, u1, p, t0 + dt0);
+    for (int i = 0; i < Z; ++i) tmp[i] = ddiv_s(f1[i] - f0[i], sk[i]);
+    double d2 = (double)rms_norm(tmp, Z, norm_partials) / dt0;
+    double m = std::fmax(d1, d2);
+    double dt1 = (m <= 1e-15) ? std::fmax(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2.0 + std::log10(m)) / 5.0);
+    return std::fmax(dtmin, std::fmin(100.0 * dt0, std::fmin(dt1, dtmax)));
+}
+
+struct StepRecord {  // optional tape of accepted steps, for tests that replay them
+    std::vector<double> t, dt;
+};
+
+// One trajectory.  u0/p are duals (NP = 0 for a primal solve).  out is [T][Z] duals.
+// Follows OrdinaryDiffEq's solve loop: attempt step -> EEst -> PI controller -> accept/reject ->
+// emit every pending saveat time <= t.
+template <class S, int NP>
+int solve_one(int rhs, const Dual<S, NP>* u0, const Dual<S, NP>* p, const double* tg, int T, const Opts& o,
+              bool norm_partials, Dual<S, NP>* out, int* naccept, int* nreject, StepRecord* rec) {
+    const double t0 = tg[0], tend = tg[T - 1];
+    const double dtmax = o.dtmax > 0 ? o.dtmax : (tend - t0);
+    // DiffEqBase.prob2dtmin: max(eps(Float64), eps(t0))
+    const double ulp0 = std::nextafter(std::fabs(t0), std::numeric_limits<double>::infinity()) - std::fabs(t0);
+    const double dtmin = o.dtmin > 0 ? o.dtmin : std::fmax(std::numeric_limits<double>::epsilon(), ulp0);
+    Dual<S, NP> u[Z];
+    StepOut<S, NP> st;
+    for (int i = 0; i < Z; ++i) u[i] = u0[i];
+    rhs_eval<S, NP>(rhs, st.k[0], u, p, t0);  // fsalfirst
+    double t = t0, dt;
+    if (o.adaptive)
+        dt = o.dt > 0 ? o.dt : initdt<S, NP>(rhs, u, p, st.k[0], t0, dtmax, dtmin, o, norm_partials);
+    else
+        dt = o.dt;
+    double qold = o.qoldinit;
+    int na = 0, nr = 0, ksave = 0;
+    for (int i = 0; i < Z; ++i) out[0 * Z + i] = u[i];  // t[1] == tspan[1] is stored exactly
+    ksave = 1;
+    long long iters = 0;
+    int ret = RET_SUCCESS;
+    if (!(dt > 0) || !std::isfinite(dt)) ret = RET_DTLESSTHANMIN;
+    while (ksave < T && ret == RET_SUCCESS) {
+        if (iters >= o.maxiters) { ret = RET_MAXITERS; break; }
+        ++iters;
+        // tstop handling (OrdinaryDiffEq modify_dt_for_tstops! + fixed_t_for_floatingpoint_error!):
+        // dt is clamped so the step cannot pass tend; the new time snaps onto tend when it is
+        // within 100 eps(max(t, tend)) of it.
+        const double dts = std::fmin(dt, tend - t);
+        double tnew = t + dts;
+        const double tmx = std::fmax(std::fabs(t), std::fabs(tend));
+        const double ulp = std::nextafter(tmx, std::numeric_limits<double>::infinity()) - tmx;
+        const bool last = std::fabs(tnew - tend) < 100.0 * ulp;
+        if (last) tnew = tend;
+        tsit5_step<S, NP>(rhs, u, p, t, dts, o, norm_partials, st);
+        bool finite = true;
+        for (int i = 0; i < Z; ++i) finite = finite && std::isfinite((double)st.unew[i].v);
+        if (!finite || std::isnan(st.EEst)) { ret = RET_UNSTABLE; break; }
+        bool accept = true;
+        double q = 1.0, q11 = 1.0;
+        if (o.adaptive) {
+            const double EEst = st.EEst;
+            if (EEst == 0.0) {
+                q = 1.0 / o.qmax;
+            } else {
+                if (o.controller_pow == 0) {
+                    q11 = fastpow(EEst, o.beta1);
+                    q = q11 / fastpow(qold, o.beta2);
+                } else {
+                    q11 = std::pow(EEst, o.beta1);
+                    q = q11 / std::pow(qold, o.beta2);
+                }
+                q = std::fmax(1.0 / o.qmax, std::fmin(1.0 / o.qmin, q / o.gamma));
+            }
+            accept = EEst <= 1.0;
+            if (accept) {
+                if (o.qsteady_min <= q && q <= o.qsteady_max) q = 1.0;
+                qold = std::fmax(EEst, o.qoldinit);
+            }
+        }
+        if (accept) {
+            const double tprev = t;
+            if (rec) { rec->t.push_back(t); rec->dt.push_back(dts); }
+            t = tnew;
+            ++na;
+            // saveat: every pending time <= t
+            while (ksave < T && tg[ksave] <= t) {
+                if (tg[ksave] == t) {
+                    for (int i = 0; i < Z; ++i) out[ksave * Z + i] = st.unew[i];
+                } else {
+                    const double Theta = (tg[ksave] - tprev) / dts;
+                    tsit5_interp<S, NP>(u, st, dts, Theta, out + ksave * Z);
+                }
+                ++ksave;
+            }
+            for (int i = 0; i < Z; ++i) { u[i] = st.unew[i]; st.k[0][i] = st.k[6][i]; }  // FSAL
+            if (o.adaptive) dt = std::fmin(dtmax, dts / q);
+        } else {
+            ++nr;
+            dt = dts / std::fmin(1.0 / o.qmin, q11 / o.gamma);
+        }
+        if (ksave < T && o.adaptive && (!(std::fabs(dt) > dtmin) || !std::isfinite(dt))) { ret = RET_DTLESSTHANMIN; break; }
+    }
+    *naccept = na;
+    *nreject = nr;
+    return ret;
+}
+
+template <class S> inline S nan_s() { return std::numeric_limits<S>::quiet_NaN(); }
+
+// B independent primal solves (EnsembleThreads => omp parallel for).
+template <class S>
+void goku_solve(int rhs, const S* z0, const S* theta, const double* tg, int B, int T, const Opts& o, S* traj,
+                int32_t* retcode, int32_t* naccept, int32_t* nreject, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        std::vector<Dual<S, 0>> out((size_t)T * Z);
+#pragma omp for schedule(dynamic, 64)
+        for (int b = 0; b < B; ++b) {
+            Dual<S, 0> u0[Z], p[P];
+            for (int i = 0; i < Z; ++i) u0[i] = dmake<S, 0>(z0[(size_t)b * Z + i]);
+            for (int i = 0; i < P; ++i) p[i] = dmake<S, 0>(theta[(size_t)b * P + i]);
+            int na = 0, nr = 0;
+            int ret = solve_one<S, 0>(rhs, u0, p, tg, T, o, false, out.data(), &na, &nr, nullptr);
+            for (int k = 0; k < T; ++k)
+                for (int i = 0; i < Z; ++i)
+                    traj[((size_t)k * B + b) * Z + i] = ret == RET_SUCCESS ? out[k * Z + i].v : nan_s<S>();
+            if (retcode) retcode[b] = ret;
+            if (naccept) naccept[b] = na;
+            if (nreject) nreject[b] = nr;
+        }
+    }
+}
+
+// Reference gradient semantics: per trajectory one dual solve seeded on p, one
+// seeded on u0; d* = sum_k J_k^T Delta_k.  norm_partials = 1 is what ForwardDiff does (partials
+// enter the error norm, so each dual solve has its own step sequence); norm_partials = 0 freezes
+// the primal step sequence, i.e. the exact derivative of the primal discretisation.
+template <class S>
+void goku_grad_fwdsens(int rhs, const S* z0, const S* theta, const double* tg, int B, int T, const Opts& o,
+                       int norm_partials, const S* dtraj, S* dz0, S* dtheta, int nthreads) {
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+    {
+        std::vector<Dual<S, P>> outp((size_t)T * Z);
+        std::vector<Dual<S, Z>> outu((size_t)T * Z);
+#pragma omp for schedule(dynamic, 64)
+        for (int b = 0; b < B; ++b) {
+            int na, nr;
+            // --- p seeded
+            {
+                Dual<S, P> u0[Z], p[P];
+                for (int i = 0; i < Z; ++i) u0[i] = dmake<S, P>(z0[(size_t)b * Z + i]);
+                for (int i = 0; i < P; ++i) { p[i] = dmake<S, P>(theta[(size_t)b * P + i]); p[i].d[i] = S(1); }
+                int ret = solve_one<S, P>(rhs, u0, p, tg, T, o, norm_partials != 0, outp.data(), &na, &nr, nullptr);
+                for (int q = 0; q < P; ++q) {
+                    double acc = 0.0;
+                    if (ret == RET_SUCCESS)
+                        for (int k = 0; k < T; ++k)
+                            for (int i = 0; i < Z; ++i)
+                                acc += (double)outp[k * Z + i].d[q] * (double)dtraj[((size_t)k * B + b) * Z + i];
+                    dtheta[(size_t)b * P + q] = (S)acc;
+                }
+            }
+            // --- u0 seeded
+            {
+                Dual<S, Z> u0[Z], p[P];
+                for (int i = 0; i < Z; ++i) { u0[i] = dmake<S, Z>(z0[(size_t)b * Z + i]); u0[i].d[i] = S(1); }
+                for (int i = 0; i < P; ++i) p[i] = dmake<S, Z>(theta[(size_t)b * P + i]);
+                int ret = solve_one<S, Z>(rhs, u0, p, tg, T, o, norm_partials != 0, outu.data(), &na, &nr, nullptr);
+                for (int q = 0; q < Z; ++q) {
+                    double acc = 0.0;
+                    if (ret == RET_SUCCESS)
+                        for (int k = 0; k < T; ++k)
+                            for (int i = 0; i < Z; ++i)
+                                acc += (double)outu[k * Z + i].d[q] * (double)dtraj[((size_t)k * B + b) * Z + i];
+                    dz0[(size_t)b * Z + q] = (S)acc;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+struct oracle_opts {
+    double abstol, reltol;
+    int adaptive;
+    double dt, dtmax, dtmin;
+    long long maxiters;
+    double gamma, qmin, qmax, beta1, beta2, qoldinit, qsteady_min, qsteady_max;
+    int controller_pow;
+};
+
+// OrdinaryDiffEq defaults for Tsit5
+void oracle_opts_default(oracle_opts* o) {
+    o->abstol = 1e-6; o->reltol = 1e-3; o->adaptive = 1; o->dt = 0.0; o->dtmax = 0.0; o->dtmin = 0.0;
+    o->maxiters = 1000000; o->gamma = 0.9; o->qmin = 0.2; o->qmax = 10.0; o->beta1 = 7.0 / 50.0;
+    o->beta2 = 2.0 / 25.0; o->qoldinit = 1e-4; o->qsteady_min = 1.0; o->qsteady_max = 1.0;
+    o->controller_pow = 0;
+}
+
+static Opts cvt(const oracle_opts* o) {
+    Opts r;
+    r.abstol = o->abstol; r.reltol = o->reltol; r.adaptive = o->adaptive; r.dt = o->dt; r.dtmax = o->dtmax;
+    r.dtmin = o->dtmin; r.maxiters = o->maxiters; r.gamma = o->gamma; r.qmin = o->qmin; r.qmax = o->qmax;
+    r.beta1 = o->beta1; r.beta2 = o->beta2; r.qoldinit = o->qoldinit; r.qsteady_min = o->qsteady_min;
+    r.qsteady_max = o->qsteady_max; r.controller_pow = o->controller_pow;
+    return r;
+}
+
+void oracle_goku_solve_f32(int rhs, const float* z0, const float* theta, const double* t, int B, int T,
+                           const oracle_opts* o, float* traj, int32_t* retcode, int32_t* naccept, int32_t* nreject,
+                           int nthreads) {
+    goku_solve<float>(rhs, z0, theta, t, B, T, cvt(o), traj, retcode, naccept, nreject, nthreads);
+}
+void oracle_goku_solve_f64(int rhs, const double* z0, const double* theta, const double* t, int B, int T,
+                           const oracle_opts* o, double* traj, int32_t* retcode, int32_t* naccept, int32_t* nreject,
+                           int nthreads) {
+    goku_solve<double>(rhs, z0, theta, t, B, T, cvt(o), traj, retcode, naccept, nreject, nthreads);
+}
+void oracle_goku_grad_f32(int rhs, const float* z0, const float* theta, const double* t, int B, int T,
+                          const oracle_opts* o, int norm_partials, const float* dtraj, float* dz0, float* dtheta,
+                          int nthreads) {
+    goku_grad_fwdsens<float>(rhs, z0, theta, t, B, T, cvt(o), norm_partials, dtraj, dz0, dtheta, nthreads);
+}
+void oracle_goku_grad_f64(int rhs, const double* z0, const double* theta, const double* t, int B, int T,
+                          const oracle_opts* o, int norm_partials, const double* dtraj, double* dz0, double* dtheta,
+                          int nthreads) {
+    goku_grad_fwdsens<double>(rhs, z0, theta, t, B, T, cvt(o), norm_partials, dtraj, dz0, dtheta, nthreads);
+}
+
+// accepted-step tape of one trajectory (tests use it to compare step sequences)
+int oracle_goku_steps_f64(int rhs, const double* z0, const double* theta, const double* t, int T,
+                          const oracle_opts* o, double* t_steps, double* dt_steps, int cap) {
+    Dual<double, 0> u0[Z], p[P];
+    for (int i = 0; i < Z; ++i) u0[i] = dmake<double, 0>(z0[i]);
+    for (int i = 0; i < P; ++i) p[i] = dmake<double, 0>(theta[i]);
+    std::vector<Dual<double, 0>> out((size_t)T * Z);
+    StepRecord rec;
+    int na, nr;
+    solve_one<double, 0>(rhs, u0, p, t, T, cvt(o), false, out.data(), &na, &nr, &rec);
+    int n = (int)rec.t.size();
+    for (int i = 0; i < n && i < cap; ++i) { t_steps[i] = rec.t[i]; dt_steps[i] = rec.dt[i]; }
+    return n;
+}
+
+double oracle_fastpow(double x, double y) { return fastpow(x, y); }
+
+int oracle_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"
