@@ -103,7 +103,8 @@ typedef struct ldeq_opts {
     double qoldinit;     /* 1e-4 */
     double qsteady_min;  /* 1 */
     double qsteady_max;  /* 1 */
-    int32_t tape_steps;  /* accepted-step capacity per trajectory of a tape; 0 = automatic */
+    int32_t tape_steps;  /* accepted-step capacity per trajectory of a tape; 0 = automatic: max(64, T) and
+                            what earlier solves on this handle needed (a too-small tape heals itself) */
     int32_t norm_mode;   /* ldeq_norm_mode, MLP solve only */
     int32_t mlp_math;    /* ldeq_mlp_math, MLP solve only */
     int32_t reserved;
@@ -130,7 +131,8 @@ void ldeq_rhs_free(ldeq_handle* h, ldeq_rhs* rhs);
 
 /* ---- GOKU path: B independent solves ----------------------------------------------------------- */
 /* z0 (z,B), theta (p,B), t_host[T] (host, Float64 grid; t_host[0], t_host[T-1] are the tspan),
- * traj_out (z,B,T).  retcode/naccept/nreject are optional device int32[B] outputs.
+ * traj_out (z,B,T), or NULL when only the tape / statistics are wanted.  retcode/naccept/nreject are
+ * optional device int32[B] outputs.
  * If tape_out != NULL a tape of the accepted steps is recorded for ldeq_solve_bwd. */
 int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta,
                    const double* t_host, int B, int T, const ldeq_opts* opts, void* traj_out,
@@ -139,8 +141,10 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
 /* Discrete adjoint of the recorded steps: dtraj (z,B,T) -> dz0 (z,B), dtheta (p,B). */
 int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta,
                    ldeq_stream stream);
-/* trajectories whose accepted steps exceeded the tape capacity (their gradients are NaN);
- * synchronises the stream */
+/* Trajectories whose accepted steps exceeded the tape capacity.  ldeq_solve_bwd heals such a tape by
+ * replaying the forward solve into a larger one (it waits for the forward kernel to learn this), so
+ * gradients are always exact; this call only reports how many trajectories needed that.  Waits for the
+ * forward kernel. */
 int ldeq_tape_overflow(ldeq_handle* h, ldeq_tape* tape, int32_t* count_host, ldeq_stream stream);
 void ldeq_tape_free(ldeq_handle* h, ldeq_tape* tape, ldeq_stream stream);
 

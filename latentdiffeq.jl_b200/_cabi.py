@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libldeq.so")
+LIB_PATH = os.environ.get("LDEQ_LIB") or os.path.join(_HERE, "lib", "libldeq.so")  # LDEQ_LIB: tuning builds
 
 # enums of include/ldeq.h
 F32, F64 = 0, 1

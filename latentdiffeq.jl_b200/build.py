@@ -40,15 +40,17 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, extra: list[str] | None = None, out: str | None = None) -> str:
+    """``extra``/``out`` build a tuning variant (other -D flags) next to the product library."""
+    LIB = out or globals()["LIB"]
+    if not force and not out and not _stale():
         return LIB
-    os.makedirs(LIB_DIR, exist_ok=True)
-    objdir = os.path.join(HERE, "build")
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)
+    objdir = os.path.join(HERE, "build", os.path.basename(LIB))
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     common = [nvcc, *ARCH, *_host_cxx(), "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-I", os.path.join(HERE, "..", "include"), "-I", CSRC]
+              "-I", os.path.join(HERE, "..", "include"), "-I", CSRC, *(extra or [])]
     if verbose:
         common += ["-Xptxas", "-v"]
     procs = []

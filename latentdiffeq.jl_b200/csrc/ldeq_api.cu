@@ -70,24 +70,118 @@ static cudaError_t launch_fwd(const void* z0, const void* theta, const double* t
                               void* traj, int32_t* ret, int32_t* na, int32_t* nr, const ldeq_tape* tape,
                               cudaStream_t s) {
     TapeView<S> tv{nullptr, nullptr, nullptr, nullptr, 0};
-    if (TAPE) tv = TapeView<S>{tape->t, tape->dt, (S*)tape->u, tape->overflow, tape->cap};
+    if (TAPE) tv = TapeView<S>{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap};
     const int grid = (B + LDEQ_FWD_THREADS - 1) / LDEQ_FWD_THREADS;
-    tsit5_fwd_kernel<PendulumRHS<S, FRICTION>, S, TAPE><<<grid, LDEQ_FWD_THREADS, 0, s>>>(
+    const size_t smem = Ring<S, 2>::bytes(LDEQ_FWD_THREADS) + (T <= LDEQ_TGRID_SMEM_MAX ? (size_t)T * sizeof(double) : 0);
+    tsit5_fwd_kernel<PendulumRHS<S, FRICTION>, S, TAPE><<<grid, LDEQ_FWD_THREADS, smem, s>>>(
         (const S*)z0, (const S*)theta, tg, B, T, ko, (S*)traj, ret, na, nr, tv);
     return cudaGetLastError();
 }
 
 template <class S, bool FRICTION>
 static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
-    TapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->overflow, tape->cap};
+    TapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap};
     const int grid = (tape->B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
-    tsit5_bwd_kernel<PendulumRHS<S, FRICTION>, S><<<grid, LDEQ_BWD_THREADS, 0, s>>>(
+    const size_t smem =
+        Ring<S, 2>::bytes(LDEQ_BWD_THREADS) + (tape->T <= LDEQ_TGRID_SMEM_MAX ? (size_t)tape->T * sizeof(double) : 0);
+    tsit5_bwd_kernel<PendulumRHS<S, FRICTION>, S><<<grid, LDEQ_BWD_THREADS, smem, s>>>(
         (const S*)tape->theta, tape->tgrid, tape->B, tape->T, (const S*)dtraj, tv, tape->retcode, tape->naccept,
         (S*)dz0, (S*)dtheta);
     return cudaGetLastError();
 }
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static bool slot_get(ldeq_handle* h, ldeq_tape* tape) {
+    if (h->free_slots.empty()) {
+        const int n = 64;
+        int32_t* blk = nullptr;
+        if (cudaMallocHost((void**)&blk, n * 2 * sizeof(int32_t)) != cudaSuccess) return false;
+        h->pinned_blocks.push_back(blk);
+        for (int i = 0; i < n; ++i) {
+            cudaEvent_t ev;
+            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+            h->free_slots.push_back({blk + 2 * i, ev});
+        }
+    }
+    ldeq_handle::Slot sl = h->free_slots.back();
+    h->free_slots.pop_back();
+    tape->h_info = sl.h_info;
+    tape->ready = sl.ev;
+    return true;
+}
+static void slot_put(ldeq_handle* h, ldeq_tape* tape) {
+    if (tape->h_info && tape->ready) {
+        cudaEventSynchronize(tape->ready);  // the async copy into the slot must have landed before reuse
+        if (h) h->free_slots.push_back({tape->h_info, tape->ready});
+    }
+    tape->h_info = nullptr;
+    tape->ready = nullptr;
+}
+
+// Carve the step arrays of a tape with capacity `cap` out of one stream-ordered allocation.
+static int tape_alloc(ldeq_handle* h, ldeq_tape* tape, int cap, cudaStream_t s) {
+    const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
+    const size_t nB = (size_t)tape->B, c = (size_t)cap, ZD = tape->z_dim, PD = tape->p_dim;
+    size_t off = 0;
+    const size_t o_t = off;   off += align_up(c * nB * 8);
+    const size_t o_dt = off;  off += align_up(c * nB * 8);
+    const size_t o_u = off;   off += align_up(c * nB * ZD * es);
+    const size_t o_th = off;  off += align_up(nB * PD * es);
+    const size_t o_tg = off;  off += align_up((size_t)tape->T * 8);
+    const size_t o_ret = off; off += align_up(nB * 4);
+    const size_t o_na = off;  off += align_up(nB * 4);
+    const size_t o_nr = off;  off += align_up(nB * 4);
+    const size_t o_info = off; off += 256;
+    void* base = nullptr;
+    cudaError_t e = cudaMallocAsync(&base, off, s);
+    if (e != cudaSuccess) return set_err(h, LDEQ_ERR_NOMEM, "cudaMallocAsync(tape)", e);
+    char* bp = (char*)base;
+    tape->base = base; tape->cap = cap;
+    tape->t = (double*)(bp + o_t); tape->dt = (double*)(bp + o_dt); tape->u = bp + o_u;
+    tape->theta = bp + o_th; tape->tgrid = (double*)(bp + o_tg); tape->retcode = (int32_t*)(bp + o_ret);
+    tape->naccept = (int32_t*)(bp + o_na); tape->nreject = (int32_t*)(bp + o_nr);
+    tape->info = (int32_t*)(bp + o_info);
+    cudaMemsetAsync(tape->info, 0, 8, s);
+    return LDEQ_OK;
+}
+
+static cudaError_t dispatch_fwd(int dtype, bool friction, const void* z0, const void* theta, const double* tg, int B,
+                                int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
+                                const ldeq_tape* tape, cudaStream_t s) {
+#define LDEQ_DISPATCH_FWD(S)                                                                              \
+    (tape ? (friction ? launch_fwd<S, true, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s)    \
+                      : launch_fwd<S, false, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s))  \
+          : (friction ? launch_fwd<S, true, false>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s)   \
+                      : launch_fwd<S, false, false>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s)))
+    return dtype == LDEQ_F32 ? LDEQ_DISPATCH_FWD(float) : LDEQ_DISPATCH_FWD(double);
+#undef LDEQ_DISPATCH_FWD
+}
+
+// A tape whose capacity turned out too small heals itself before the backward pass: the forward
+// solve is replayed (same inputs, same arithmetic, hence the same steps) into a tape sized by the
+// largest accepted-step count the first pass reported.  Costs one extra forward kernel, only then.
+static int tape_heal(ldeq_handle* h, ldeq_tape* tape, cudaStream_t s) {
+    if (tape->checked) return LDEQ_OK;
+    LDEQ_CUDA(cudaEventSynchronize(tape->ready));
+    tape->checked = true;
+    if (tape->h_info[1] > h->tape_hint) h->tape_hint = tape->h_info[1];
+    if (tape->h_info[0] == 0) return LDEQ_OK;
+    ldeq_tape old = *tape;
+    int rc = tape_alloc(h, tape, old.h_info[1], s);
+    if (rc) { *tape = old; return rc; }
+    const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
+    cudaMemcpyAsync(tape->theta, old.theta, (size_t)tape->B * tape->p_dim * es, cudaMemcpyDeviceToDevice, s);
+    cudaMemcpyAsync(tape->tgrid, old.tgrid, (size_t)tape->T * 8, cudaMemcpyDeviceToDevice, s);
+    // step 0 of the old tape holds u0 for every trajectory (capacity is always >= 1)
+    cudaError_t e = dispatch_fwd(tape->dtype, tape->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION, old.u, tape->theta,
+                                 tape->tgrid, tape->B, tape->T, tape->kopts, nullptr, tape->retcode, tape->naccept,
+                                 tape->nreject, tape, s);
+    h->launches += 1;
+    cudaFreeAsync(old.base, s);
+    if (e != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwd_kernel (tape replay) launch", e);
+    return LDEQ_OK;
+}
 
 }  // namespace ldeq
 
@@ -133,6 +227,8 @@ void ldeq_destroy(ldeq_handle* h) {
         if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_counter) cudaFree(h->d_counter);
+    for (auto& sl : h->free_slots) cudaEventDestroy(sl.ev);
+    for (auto* blk : h->pinned_blocks) cudaFreeHost(blk);
     delete h;
 }
 
@@ -163,7 +259,8 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
                    int32_t* naccept, int32_t* nreject, ldeq_tape** tape_out, ldeq_stream stream) {
     if (!h) return LDEQ_ERR_INVALID;
     if (tape_out) *tape_out = nullptr;
-    if (!rhs || !z0 || !theta || !t_host || !traj_out || !opts) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    if (!rhs || !z0 || !theta || !t_host || !opts) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    if (!traj_out && !tape_out && !naccept) return set_err(h, LDEQ_ERR_INVALID, "nothing to compute: traj_out, tape_out and naccept are all null");
     if (B < 0 || T < 1) return set_err(h, LDEQ_ERR_INVALID, "B must be >= 0 and T >= 1");
     if (dtype != LDEQ_F32 && dtype != LDEQ_F64) return set_err(h, LDEQ_ERR_INVALID, "dtype");
     if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
@@ -183,63 +280,45 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
     if (tape_out) {
         tape = new ldeq_tape();
         tape->dtype = dtype; tape->rhs_kind = rhs->kind; tape->rhs = rhs; tape->B = B; tape->T = T;
-        tape->z_dim = ZD; tape->p_dim = PD;
+        tape->z_dim = ZD; tape->p_dim = PD; tape->kopts = ko;
         long long cap = opts->tape_steps;
         if (cap <= 0) {
             if (opts->adaptive) {
-                cap = 2LL * T > 64 ? 2LL * T : 64;
+                cap = T > 64 ? T : 64;
+                if (cap < (long long)h->tape_hint + h->tape_hint / 4) cap = (long long)h->tape_hint + h->tape_hint / 4;
             } else {
                 cap = (long long)((t_host[T - 1] - t_host[0]) / opts->dt) + 3;
             }
         }
         if (cap > opts->maxiters) cap = opts->maxiters;
         if (cap > (1 << 24)) cap = 1 << 24;
-        tape->cap = (int)cap;
-        const size_t nB = (size_t)B, c = (size_t)cap;
-        size_t off = 0, o_t = off;   off += align_up(c * nB * 8);
-        size_t o_dt = off;           off += align_up(c * nB * 8);
-        size_t o_u = off;            off += align_up(c * nB * ZD * es);
-        size_t o_th = off;           off += align_up(nB * PD * es);
-        size_t o_tg = off;           off += align_up((size_t)T * 8);
-        size_t o_ret = off;          off += align_up(nB * 4);
-        size_t o_na = off;           off += align_up(nB * 4);
-        size_t o_nr = off;           off += align_up(nB * 4);
-        size_t o_ov = off;           off += 256;
-        cudaError_t e = cudaMallocAsync(&tape->base, off, s);
-        if (e != cudaSuccess) {
+        if (cap < 1) cap = 1;
+        rc = tape_alloc(h, tape, (int)cap, s);
+        if (rc) { delete tape; return rc; }
+        if (!slot_get(h, tape)) {
+            cudaFreeAsync(tape->base, s);
             delete tape;
-            return set_err(h, LDEQ_ERR_NOMEM, "cudaMallocAsync(tape)", e);
+            return set_err(h, LDEQ_ERR_NOMEM, "tape host mirror");
         }
-        char* bp = (char*)tape->base;
-        tape->t = (double*)(bp + o_t); tape->dt = (double*)(bp + o_dt); tape->u = bp + o_u;
-        tape->theta = bp + o_th; tape->tgrid = (double*)(bp + o_tg); tape->retcode = (int32_t*)(bp + o_ret);
-        tape->naccept = (int32_t*)(bp + o_na); tape->nreject = (int32_t*)(bp + o_nr);
-        tape->overflow = (int32_t*)(bp + o_ov);
-        cudaMemcpyAsync(tape->theta, theta, nB * PD * es, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(tape->theta, theta, (size_t)B * PD * es, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(tape->tgrid, h->d_tgrid, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);
-        cudaMemsetAsync(tape->overflow, 0, 4, s);
     }
     int32_t* d_ret = tape ? tape->retcode : retcode;
     int32_t* d_na = tape ? tape->naccept : naccept;
     int32_t* d_nr = tape ? tape->nreject : nreject;
     const bool fr = rhs->kind == LDEQ_RHS_PENDULUM_FRICTION;
-    cudaError_t e;
-#define LDEQ_DISPATCH_FWD(S)                                                                                         \
-    (tape ? (fr ? launch_fwd<S, true, true>(z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s)  \
-                : launch_fwd<S, false, true>(z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s)) \
-          : (fr ? launch_fwd<S, true, false>(z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s) \
-                : launch_fwd<S, false, false>(z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s)))
-    e = dtype == LDEQ_F32 ? LDEQ_DISPATCH_FWD(float) : LDEQ_DISPATCH_FWD(double);
-#undef LDEQ_DISPATCH_FWD
+    cudaError_t e = dispatch_fwd(dtype, fr, z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s);
     h->launches += 1;
     if (e != cudaSuccess) {
-        if (tape) { cudaFreeAsync(tape->base, s); delete tape; }
+        if (tape) { cudaFreeAsync(tape->base, s); cudaEventRecord(tape->ready, s); slot_put(h, tape); delete tape; }
         return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwd_kernel launch", e);
     }
     if (tape) {
         if (retcode) cudaMemcpyAsync(retcode, tape->retcode, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
         if (naccept) cudaMemcpyAsync(naccept, tape->naccept, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
         if (nreject) cudaMemcpyAsync(nreject, tape->nreject, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(tape->h_info, tape->info, 8, cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(tape->ready, s);
         *tape_out = tape;
     }
     return LDEQ_OK;
@@ -250,6 +329,8 @@ int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0
     if (!tape || !dtraj || !dz0 || !dtheta) return set_err(h, LDEQ_ERR_INVALID, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
+    int rc = tape_heal(h, tape, s);
+    if (rc) return rc;
     const bool fr = tape->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION;
     cudaError_t e;
     if (tape->dtype == LDEQ_F32)
@@ -261,11 +342,10 @@ int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0
     return LDEQ_OK;
 }
 
-int ldeq_tape_overflow(ldeq_handle* h, ldeq_tape* tape, int32_t* count_host, ldeq_stream stream) {
+int ldeq_tape_overflow(ldeq_handle* h, ldeq_tape* tape, int32_t* count_host, ldeq_stream) {
     if (!h || !tape || !count_host) return LDEQ_ERR_INVALID;
-    cudaStream_t s = (cudaStream_t)stream;
-    LDEQ_CUDA(cudaMemcpyAsync(count_host, tape->overflow, 4, cudaMemcpyDeviceToHost, s));
-    LDEQ_CUDA(cudaStreamSynchronize(s));
+    LDEQ_CUDA(cudaEventSynchronize(tape->ready));
+    *count_host = tape->checked && tape->h_info[0] > 0 && tape->cap >= tape->h_info[1] ? 0 : tape->h_info[0];
     return LDEQ_OK;
 }
 
@@ -273,6 +353,7 @@ void ldeq_tape_free(ldeq_handle* h, ldeq_tape* tape, ldeq_stream stream) {
     if (!tape) return;
     if (h) cudaSetDevice(h->device);
     if (tape->base) cudaFreeAsync(tape->base, (cudaStream_t)stream);
+    slot_put(h, tape);
     delete tape;
 }
 

@@ -73,31 +73,35 @@ __device__ __forceinline__ float fastlog2_dev(float x) {
     signif = signif - 1.0f;
     return fexp + __fdiv_rn(__fmul_rn(signif, __fadd_rn(__fmul_rn(a, signif), b)), __fadd_rn(signif, c));
 }
-__device__ __forceinline__ double ctrl_pow(double x, double y, int exact) {
-    if (exact) return pow(x, y);
-    if (x == 0.0) return 0.0;
-    return (double)exp2f(__fmul_rn((float)y, fastlog2_dev(fabsf((float)x))));
+// DiffEqBase.fastpow(x, y) for Float64 arguments: demote to Float32, exp2(y * fastlog2(x))
+__device__ __forceinline__ float ctrl_powf(double x, float y, int exact) {
+    if (exact) return (float)pow(x, (double)y);
+    if (x == 0.0) return 0.0f;
+    return exp2f(__fmul_rn(y, fastlog2_dev(fabsf((float)x))));
 }
 
 // PI controller (OrdinaryDiffEq stepsize_controller!/step_accept_controller!/step_reject_controller!).
-// Returns accept; updates dt (next proposal) and qold.
+// Returns accept; updates qold and the next step-size proposal.  The two fastpow factors are Float32 by
+// construction; their quotient and the final 1/q are taken in Float32 as well (a relative 1e-7 on the
+// proposed dt, far below anything the error control can see) so that no Float64 division is issued.
 __device__ __forceinline__ bool pi_controller(const KOpts& o, double EEst, double dts, double dtmax, double& qold,
                                               double& dt_next) {
-    double q, q11 = 1.0;
+    float q, q11 = 1.0f;
+    const float inv_gamma = (float)(1.0 / o.gamma), qlo = (float)(1.0 / o.qmax), qhi = (float)(1.0 / o.qmin);
     if (EEst == 0.0) {
-        q = 1.0 / o.qmax;
+        q = qlo;
     } else {
-        q11 = ctrl_pow(EEst, o.beta1, o.controller_pow);
-        q = q11 / ctrl_pow(qold, o.beta2, o.controller_pow);
-        q = fmax(1.0 / o.qmax, fmin(1.0 / o.qmin, q / o.gamma));
+        q11 = ctrl_powf(EEst, (float)o.beta1, o.controller_pow);
+        q = __fdiv_rn(q11, ctrl_powf(qold, (float)o.beta2, o.controller_pow));
+        q = fmaxf(qlo, fminf(qhi, q * inv_gamma));
     }
     const bool accept = EEst <= 1.0;
     if (accept) {
-        if (o.qsteady_min <= q && q <= o.qsteady_max) q = 1.0;
+        if ((float)o.qsteady_min <= q && q <= (float)o.qsteady_max) q = 1.0f;
         qold = fmax(EEst, o.qoldinit);
-        dt_next = fmin(dtmax, dts / q);
+        dt_next = fmin(dtmax, dts * (double)__frcp_rn(q));
     } else {
-        dt_next = dts / fmin(1.0 / o.qmin, q11 / o.gamma);
+        dt_next = dts * (double)__frcp_rn(fminf(qhi, q11 * inv_gamma));
     }
     return accept;
 }

@@ -26,6 +26,11 @@ struct ldeq_handle {
     unsigned int* d_counter = nullptr;
     int n_partials = 0;
     int sm_count = 148;
+    int tape_hint = 0;  // largest accepted-step count seen so far: sizes the next automatic tape
+    // recycled {pinned info slot, event} pairs for tapes (cudaMallocHost / cudaEventCreate are slow)
+    struct Slot { int32_t* h_info; cudaEvent_t ev; };
+    std::vector<Slot> free_slots;
+    std::vector<int32_t*> pinned_blocks;
 };
 
 struct ldeq_rhs {
@@ -47,7 +52,11 @@ struct ldeq_tape {
     int32_t* retcode = nullptr;
     int32_t* naccept = nullptr;
     int32_t* nreject = nullptr;
-    int32_t* overflow = nullptr;
+    int32_t* info = nullptr;     // device {overflow count, max naccept}
+    int32_t* h_info = nullptr;   // pinned host mirror of info, valid once `ready` has completed
+    cudaEvent_t ready = nullptr;
+    bool checked = false;
+    ldeq::KOpts kopts;
 };
 
 namespace ldeq {

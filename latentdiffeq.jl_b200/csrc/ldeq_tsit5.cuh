@@ -19,6 +19,12 @@ namespace ldeq {
 
 #define LDEQ_FWD_THREADS 128
 #define LDEQ_BWD_THREADS 128
+#ifndef LDEQ_FWD_MINBLOCKS
+#define LDEQ_FWD_MINBLOCKS 4
+#endif
+#ifndef LDEQ_BWD_MINBLOCKS
+#define LDEQ_BWD_MINBLOCKS 4
+#endif
 
 // Accepted-step tape, step-major so that a warp reading/writing step n touches contiguous memory:
 //   t[n*B + b], dt[n*B + b], u[(n*B + b)*ZD + d]
@@ -26,7 +32,7 @@ template <class S> struct TapeView {
     double* t;
     double* dt;
     S* u;
-    int* overflow;  // device counter of trajectories that ran past `cap`
+    int* info;  // info[0]: trajectories that ran past `cap`; info[1]: largest accepted-step count
     int cap;
 };
 
@@ -149,107 +155,252 @@ __device__ double tsit5_initdt(const S* u0, const S* p, const S* f0, double t0, 
     return fmax(dtmin, fmin(100.0 * dt0, fmin(dt1, dtmax)));
 }
 
+// ---- dense output in Horner form -------------------------------------------------------------------
+// sum_j b_j(Theta) k_j = Theta (c1 + Theta (c2 + Theta (c3 + Theta c4))) with c_m = sum_j r_jm k_j, so a step
+// pays 21 FMAs per component once and every save point inside it only 5.
+template <class S, int ZD>
+__device__ __forceinline__ void interp_coeffs(S (*k)[ZD], S (*c)[ZD]) {
+    using Tb = Tab<S>;
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) {
+        c[0][i] = k[0][i];  // r11 = 1
+        c[1][i] = s_fma<S>(Tb::r72, k[6][i], s_fma<S>(Tb::r62, k[5][i], s_fma<S>(Tb::r52, k[4][i],
+                  s_fma<S>(Tb::r42, k[3][i], s_fma<S>(Tb::r32, k[2][i], s_fma<S>(Tb::r22, k[1][i], Tb::r12 * k[0][i]))))));
+        c[2][i] = s_fma<S>(Tb::r73, k[6][i], s_fma<S>(Tb::r63, k[5][i], s_fma<S>(Tb::r53, k[4][i],
+                  s_fma<S>(Tb::r43, k[3][i], s_fma<S>(Tb::r33, k[2][i], s_fma<S>(Tb::r23, k[1][i], Tb::r13 * k[0][i]))))));
+        c[3][i] = s_fma<S>(Tb::r74, k[6][i], s_fma<S>(Tb::r64, k[5][i], s_fma<S>(Tb::r54, k[4][i],
+                  s_fma<S>(Tb::r44, k[3][i], s_fma<S>(Tb::r34, k[2][i], s_fma<S>(Tb::r24, k[1][i], Tb::r14 * k[0][i]))))));
+    }
+}
+// adjoint of interp_coeffs: kbar_j += sum_m r_jm cbar_m
+template <class S, int ZD>
+__device__ __forceinline__ void interp_coeffs_adj(S (*cb)[ZD], S (*kbar)[ZD]) {
+    using Tb = Tab<S>;
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) {
+        const S c1 = cb[0][i], c2 = cb[1][i], c3 = cb[2][i], c4 = cb[3][i];
+        kbar[0][i] += s_fma<S>(Tb::r14, c4, s_fma<S>(Tb::r13, c3, s_fma<S>(Tb::r12, c2, c1)));
+        kbar[1][i] += s_fma<S>(Tb::r24, c4, s_fma<S>(Tb::r23, c3, Tb::r22 * c2));
+        kbar[2][i] += s_fma<S>(Tb::r34, c4, s_fma<S>(Tb::r33, c3, Tb::r32 * c2));
+        kbar[3][i] += s_fma<S>(Tb::r44, c4, s_fma<S>(Tb::r43, c3, Tb::r42 * c2));
+        kbar[4][i] += s_fma<S>(Tb::r54, c4, s_fma<S>(Tb::r53, c3, Tb::r52 * c2));
+        kbar[5][i] += s_fma<S>(Tb::r64, c4, s_fma<S>(Tb::r63, c3, Tb::r62 * c2));
+        kbar[6][i] += s_fma<S>(Tb::r74, c4, s_fma<S>(Tb::r73, c3, Tb::r72 * c2));
+    }
+}
+
+// The save grid is staged in shared memory (explicit LDS, not a generic load); grids too long for
+// that are read through the global pointer.
+#define LDEQ_TGRID_SMEM_MAX 2048
+struct TGrid {
+    const double* __restrict__ g;
+    const double* s;
+    bool in_smem;
+    __device__ __forceinline__ double operator[](int i) const { return in_smem ? s[i] : g[i]; }
+};
+__device__ __forceinline__ TGrid stage_tgrid(const double* __restrict__ tg, int T, double* s_tg) {
+    TGrid r{tg, s_tg, T <= LDEQ_TGRID_SMEM_MAX};
+    if (r.in_smem) {
+        for (int i = threadIdx.x; i < T; i += blockDim.x) s_tg[i] = tg[i];
+        __syncthreads();
+    }
+    return r;
+}
+#define LDEQ_TINF __longlong_as_double(0x7ff0000000000000LL)
+
+// ---- per-lane save-point ring ----------------------------------------------------------------------
+// With adaptive steps the lanes of a warp reach a given save index k at different times, so a
+// thread-per-trajectory kernel that stores straight to the (z,B,T) array issues 8-byte stores to 32
+// different rows per instruction (ncu: 8.7 of 32 bytes per sector used, the store queue backs up and
+// the kernel runs 1.7x slower than with the stores removed).  Instead every lane owns one COLUMN of a
+// shared-memory ring of LDEQ_RING_BYTES per lane; it parks its save points there, and the warp moves
+// complete ROWS (all 32 lanes, same k) to global memory together: full 32-byte sectors, one
+// 256-byte coalesced store per row.  A lane that gets LDEQ ring rows ahead of the slowest lane of
+// its warp waits for it; the warp's iteration count is set by its slowest lane either way.
+// The backward kernel uses the same ring the other way round (rows of the cotangent are fetched
+// with cp.async, coalesced, ahead of use).
+#ifndef LDEQ_RING_BYTES
+#define LDEQ_RING_BYTES 256
+#endif
+template <class S, int ZD> struct Ring {
+    static constexpr int R = LDEQ_RING_BYTES / (ZD * (int)sizeof(S)) >= 4 ? LDEQ_RING_BYTES / (ZD * (int)sizeof(S)) : 4;
+    static_assert((R & (R - 1)) == 0, "ring rows must be a power of two");
+    S* col;      // this lane's column
+    int stride;  // elements between consecutive rows
+    __device__ __forceinline__ S* at(int k) const { return col + (size_t)(k & (R - 1)) * stride; }
+    __host__ __device__ static constexpr size_t bytes(int threads) { return (size_t)R * threads * ZD * sizeof(S); }
+};
+
+__device__ __forceinline__ int warp_min_i(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_max_i(int v) { return __reduce_max_sync(0xffffffffu, v); }
+
+template <int BYTES> __device__ __forceinline__ void cp_async_vec(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gsrc), "n"(BYTES));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
 // ---- forward ------------------------------------------------------------------------------------
 template <class RHS, class S, bool TAPE>
-__global__ void __launch_bounds__(LDEQ_FWD_THREADS)
-tsit5_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, int T,
-                 KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
+__global__ void __launch_bounds__(LDEQ_FWD_THREADS, LDEQ_FWD_MINBLOCKS)
+tsit5_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
+                 int T, KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
                  int* __restrict__ nreject, TapeView<S> tape) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
+    using RingT = Ring<S, ZD>;
+    constexpr int R = RingT::R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RingT ring{reinterpret_cast<S*>(smem_raw) + threadIdx.x * ZD, (int)blockDim.x * ZD};
+    const TGrid tg = stage_tgrid(tg_global, T, reinterpret_cast<double*>(smem_raw + RingT::bytes(blockDim.x)));
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const bool live = b < B;
+    const int bb = live ? b : B - 1;  // dead lanes of the last warp shadow a valid trajectory and store nothing
 
     S u[ZD], un[ZD], p[PD], k[7][ZD];
-    load_vec<S, ZD>(z0 + (size_t)b * ZD, u);
+    load_vec<S, ZD>(z0 + (size_t)bb * ZD, u);
 #pragma unroll
-    for (int i = 0; i < PD; ++i) p[i] = theta[(size_t)b * PD + i];
+    for (int i = 0; i < PD; ++i) p[i] = theta[(size_t)bb * PD + i];
 
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
     const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
     const S abstol = (S)o.abstol, reltol = (S)o.reltol;
+    const double abs_tend = fabs(tend);
 
     RHS::f(k[0], u, p, t0);  // fsalfirst
     double t = t0;
     double dt = (o.adaptive && !(o.dt > 0.0)) ? tsit5_initdt<RHS, S>(u, p, k[0], t0, dtmax, dtmin, o) : o.dt;
     double qold = o.qoldinit;
-    int na = 0, nr = 0, ks = 1, ret = RET_SUCCESS;
+    int na = 0, nr = 0, ret = RET_SUCCESS;
     long long iters = 0;
 
-    store_vec<S, ZD>(traj + (size_t)b * ZD, u);  // t[1] == tspan[1]: stored exactly
-    double tsave = T > 1 ? tg[1] : 0.0;
+    if (traj && live) store_vec<S, ZD>(traj + (size_t)b * ZD, u);  // t[1] == tspan[1]: stored exactly
+    // pending save time and the two after it (loaded two iterations ahead so the loop never waits)
+    double tsave = T > 1 ? tg[1] : LDEQ_TINF;
+    double tsave2 = T > 2 ? tg[2] : LDEQ_TINF;
+    double tsave3 = T > 3 ? tg[3] : LDEQ_TINF;
     if (!(dt > 0.0) || !isfinite(dt)) ret = RET_DTLESSTHANMIN;
 
-    while (ks < T && ret == RET_SUCCESS) {
-        if (iters >= o.maxiters) { ret = RET_MAXITERS; break; }
-        ++iters;
-        // tstop handling: never step past tend; snap onto it within 100 ulp
-        const double dts = fmin(dt, tend - t);
-        double tnew = t + dts;
-        if (fabs(tnew - tend) < 100.0 * ulp_of(fmax(fabs(t), fabs(tend)))) tnew = tend;
+    int ks = live ? 1 : T;  // next save index this lane emits
+    int kflush = 1;         // warp-uniform: rows below it are in global memory
+    bool active = live && T > 1 && ret == RET_SUCCESS;  // still has steps to take
+    bool pending = false;   // an accepted step whose save points are not all parked yet
+    double dts = 0.0, tnew = t0;
 
-        tsit5_stages<RHS, S, false>(u, p, t, dts, k, un, nullptr, nullptr);
+    while (kflush < T) {
+        if (active && !pending) {
+            if (iters >= o.maxiters) {
+                ret = RET_MAXITERS;
+                active = false;
+            } else {
+                ++iters;
+                // tstop handling: never step past tend; snap onto it within 100 ulp
+                dts = fmin(dt, tend - t);
+                tnew = t + dts;
+                if (fabs(tnew - tend) < 100.0 * ulp_of(fmax(fabs(t), abs_tend))) tnew = tend;
 
-        bool finite = true;
+                tsit5_stages<RHS, S, false>(u, p, t, dts, k, un, nullptr, nullptr);
+
+                bool finite = true;
 #pragma unroll
-        for (int i = 0; i < ZD; ++i) finite = finite && s_finite<S>(un[i]);
-        bool accept = true;
-        double dt_next = dt;
-        if (o.adaptive) {
-            const double EEst = tsit5_eest<S, ZD>(u, un, k, dts, abstol, reltol);
-            if (EEst != EEst) finite = false;
-            accept = pi_controller(o, EEst, dts, dtmax, qold, dt_next);
-        }
-        if (!finite) { ret = RET_UNSTABLE; break; }
-
-        if (accept) {
-            if (TAPE) {
-                if (na < tape.cap) {
-                    const size_t r = (size_t)na * B + b;
-                    tape.t[r] = t;
-                    tape.dt[r] = dts;
-                    store_vec<S, ZD>(tape.u + r * ZD, u);
-                } else if (na == tape.cap) {
-                    atomicAdd(tape.overflow, 1);
+                for (int i = 0; i < ZD; ++i) finite = finite && s_finite<S>(un[i]);
+                bool accept = true;
+                double dt_next = dt;
+                if (o.adaptive) {
+                    const double EEst = tsit5_eest<S, ZD>(u, un, k, dts, abstol, reltol);
+                    if (EEst != EEst) finite = false;
+                    accept = pi_controller(o, EEst, dts, dtmax, qold, dt_next);
+                }
+                if (!finite) {
+                    ret = RET_UNSTABLE;
+                    active = false;
+                } else {
+                    if (accept) {
+                        if (TAPE) {
+                            if (na < tape.cap) {
+                                const size_t r = (size_t)na * B + b;
+                                tape.t[r] = t;
+                                tape.dt[r] = dts;
+                                store_vec<S, ZD>(tape.u + r * ZD, u);
+                            }
+                        }
+                        ++na;
+                        pending = true;
+                    } else {
+                        ++nr;
+                    }
+                    dt = dt_next;
+                    if (o.adaptive && !(accept && tnew == tend) && (!(fabs(dt) > dtmin) || !isfinite(dt))) {
+                        ret = RET_DTLESSTHANMIN;
+                        active = false;
+                        pending = false;
+                    }
                 }
             }
-            ++na;
-            // saveat: every pending grid time <= tnew, through the dense interpolant of this step
-            if (tsave <= tnew) {
+        }
+        if (pending) {
+            // saveat: every pending grid time <= tnew; interior points through the dense interpolant of this
+            // step (Horner form), a grid time that coincides with the step end stores u_{n+1} itself
+            if (tsave < tnew && ks < kflush + R) {
+                S c[4][ZD];
+                interp_coeffs<S, ZD>(k, c);
                 const S h = (S)dts;
                 const double inv = 1.0 / dts;
                 do {
+                    const double tpre = ks + 3 < T ? tg[ks + 3] : LDEQ_TINF;  // consumed two iterations from now
                     S out[ZD];
-                    if (tsave == tnew) {
+                    const S th = (S)((tsave - t) * inv);
+                    const S hth = h * th;
 #pragma unroll
-                        for (int i = 0; i < ZD; ++i) out[i] = un[i];
-                    } else {
-                        S bw[7];
-                        interp_weights<S>((S)((tsave - t) * inv), bw);
-#pragma unroll
-                        for (int i = 0; i < ZD; ++i) {
-                            S s = bw[0] * k[0][i];
-#pragma unroll
-                            for (int j = 1; j < 7; ++j) s = s_fma<S>(bw[j], k[j][i], s);
-                            out[i] = s_fma<S>(h, s, u[i]);
-                        }
+                    for (int i = 0; i < ZD; ++i) {
+                        const S poly = s_fma<S>(th, s_fma<S>(th, s_fma<S>(th, c[3][i], c[2][i]), c[1][i]), c[0][i]);
+                        out[i] = s_fma<S>(hth, poly, u[i]);
                     }
-                    store_vec<S, ZD>(traj + ((size_t)ks * B + b) * ZD, out);
+                    store_vec<S, ZD>(ring.at(ks), out);
                     ++ks;
-                    tsave = ks < T ? tg[ks] : 0.0;
-                } while (ks < T && tsave <= tnew);
+                    tsave = tsave2;
+                    tsave2 = tsave3;
+                    tsave3 = tpre;
+                } while (tsave < tnew && ks < kflush + R);
             }
-            t = tnew;
+            if (tsave == tnew && ks < kflush + R) {
+                store_vec<S, ZD>(ring.at(ks), un);
+                const double tpre = ks + 3 < T ? tg[ks + 3] : LDEQ_TINF;
+                ++ks;
+                tsave = tsave2;
+                tsave2 = tsave3;
+                tsave3 = tpre;
+            }
+            if (!(tsave <= tnew)) {  // all save points of this step are parked: commit it
+                t = tnew;
 #pragma unroll
-            for (int i = 0; i < ZD; ++i) { u[i] = un[i]; k[0][i] = k[6][i]; }  // FSAL
-        } else {
-            ++nr;
+                for (int i = 0; i < ZD; ++i) { u[i] = un[i]; k[0][i] = k[6][i]; }  // FSAL
+                pending = false;
+                if (ks >= T) active = false;
+            }
         }
-        dt = dt_next;
-        if (ks < T && o.adaptive && (!(fabs(dt) > dtmin) || !isfinite(dt))) { ret = RET_DTLESSTHANMIN; break; }
+        // move the rows every lane of the warp has passed to global memory, coalesced
+        const int kmin = warp_min_i((active || pending) ? ks : T);
+        if (traj && live) {
+            int r = kflush;
+            for (; r + 1 < kmin; r += 2) {
+                S v0[ZD], v1[ZD];
+                load_vec<S, ZD>(ring.at(r), v0);
+                load_vec<S, ZD>(ring.at(r + 1), v1);
+                store_vec<S, ZD>(traj + ((size_t)r * B + b) * ZD, v0);
+                store_vec<S, ZD>(traj + ((size_t)(r + 1) * B + b) * ZD, v1);
+            }
+            if (r < kmin) {
+                S v0[ZD];
+                load_vec<S, ZD>(ring.at(r), v0);
+                store_vec<S, ZD>(traj + ((size_t)r * B + b) * ZD, v0);
+            }
+        }
+        kflush = kmin;
     }
 
-    if (ret != RET_SUCCESS) {  // GOKU.jl:114: the whole (z,T) block of a failed solve is NaN
+    if (!live) return;
+    if (ret != RET_SUCCESS && traj) {  // GOKU.jl:114: the whole (z,T) block of a failed solve is NaN
         S nanv[ZD];
 #pragma unroll
         for (int i = 0; i < ZD; ++i) nanv[i] = s_nan<S>();
@@ -258,164 +409,206 @@ tsit5_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const do
     if (retcode) retcode[b] = ret;
     if (naccept) naccept[b] = na;
     if (nreject) nreject[b] = nr;
+    if (TAPE) {
+        // tape.info = {trajectories that ran past the capacity, largest accepted-step count}; one atomic per warp
+        const unsigned am = __activemask();
+        const int wmax = __reduce_max_sync(am, ret == RET_SUCCESS ? na : 0);
+        const int wover = __reduce_add_sync(am, na > tape.cap ? 1 : 0);
+        if ((threadIdx.x & 31) == (__ffs(am) - 1)) {
+            if (wover) atomicAdd(tape.info, wover);
+            atomicMax(tape.info + 1, wmax);
+        }
+    }
 }
 
 // ---- backward: discrete adjoint of the taped steps ----------------------------------------------
 // dtraj (z,B,T) -> dz0 (z,B), dtheta (p,B).  Step sizes are constants of the differentiation, as in
 // the reference's ForwardDiffSensitivity where tspan/dt stay plain Float64.
 template <class RHS, class S>
-__global__ void __launch_bounds__(LDEQ_BWD_THREADS)
-tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg, int B, int T,
+__global__ void __launch_bounds__(LDEQ_BWD_THREADS, LDEQ_BWD_MINBLOCKS)
+tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
                  const S* __restrict__ dtraj, TapeView<S> tape, const int* __restrict__ retcode,
                  const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ dtheta) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
     using Tb = Tab<S>;
+    using RingT = Ring<S, ZD>;
+    constexpr int R = RingT::R;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RingT ring{reinterpret_cast<S*>(smem_raw) + threadIdx.x * ZD, (int)blockDim.x * ZD};
+    const TGrid tg = stage_tgrid(tg_global, T, reinterpret_cast<double*>(smem_raw + RingT::bytes(blockDim.x)));
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = b < B;
+    const int bb = live ? b : B - 1;  // dead lanes of the last warp read a valid column and write nothing
 
-    int na = 0, ret = RET_SUCCESS;
     S p[PD], pbar[PD], ubn[ZD];
 #pragma unroll
-    for (int i = 0; i < PD; ++i) { p[i] = (S)1; pbar[i] = (S)0; }
+    for (int i = 0; i < PD; ++i) pbar[i] = (S)0;
 #pragma unroll
     for (int i = 0; i < ZD; ++i) ubn[i] = (S)0;
-    if (live) {
-        na = naccept[b];
-        ret = retcode[b];
+    int na = naccept[bb];
+    const int ret = retcode[bb];
 #pragma unroll
-        for (int i = 0; i < PD; ++i) p[i] = theta[(size_t)b * PD + i];
-    }
+    for (int i = 0; i < PD; ++i) p[i] = theta[(size_t)bb * PD + i];
     const bool overflow = na > tape.cap;
     if (!live || ret != RET_SUCCESS || overflow) na = 0;
 
-    // warp-uniform step index so that the tape rows are read coalesced
-    int nmax = na;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, off));
+    // rows 1..T-1 of the cotangent travel through the ring: [kload, T) has been fetched so far
+    int kload = T;
+    auto refill = [&](int ks_max) {
+        int klo = ks_max - R + 1;
+        klo = klo < 1 ? 1 : klo;
+        for (int r = kload - 1; r >= klo; --r)
+            cp_async_vec<ZD * (int)sizeof(S)>(ring.at(r), dtraj + ((size_t)r * B + bb) * ZD);
+        kload = klo < kload ? klo : kload;
+    };
 
-    int ks = T - 1;
+    int n = na - 1;        // next taped step of this lane
+    int ks = T - 1;        // next save point of this lane (descending); row 0 is handled at the end
+    bool holding = false;  // a step whose stages are recomputed and whose save points are being consumed
     double tnext = tg[T - 1];  // time after step n; the forward pass ended exactly on tend
-    for (int n = nmax - 1; n >= 0; --n) {
-        if (n >= na) continue;
-        const size_t r = (size_t)n * B + b;
-        const double tn = tape.t[r], dtn = tape.dt[r];
-        S u[ZD], un[ZD], k[7][ZD], g[7][ZD], kbar[7][ZD], ub[ZD];
-        typename RHS::Aux aux[7];
-        load_vec<S, ZD>(tape.u + r * ZD, u);
-        tsit5_stages<RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
-#pragma unroll
-        for (int j = 0; j < 7; ++j)
-#pragma unroll
-            for (int i = 0; i < ZD; ++i) kbar[j][i] = (S)0;
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) ub[i] = (S)0;
-        const S h = (S)dtn;
-        const double inv = 1.0 / dtn;
+    double ts = ks >= 1 ? tg[ks] : -LDEQ_TINF;
+    double tn = 0.0, dtn = 0.0;
+    S g[7][ZD], kbar[7][ZD], cb[4][ZD], ub[ZD];
+    typename RHS::Aux aux[7];
 
-        // cotangents of the save points that lie in (t_n, t_{n+1}]
-        while (ks >= 1) {
-            const double ts = tg[ks];
-            if (!(ts > tn)) break;
-            S d[ZD];
-            load_vec<S, ZD>(dtraj + ((size_t)ks * B + b) * ZD, d);
-            if (ts == tnext) {
+    refill(warp_max_i(n >= 0 ? ks : 0));
+    // runs until every lane of the warp has swept its step 0 (early steps may hold no save point at all)
+    while (__any_sync(0xffffffffu, holding || n >= 0)) {
+        if (!holding && n >= 0) {
+            const size_t r = (size_t)n * B + b;
+            tn = tape.t[r];
+            dtn = tape.dt[r];
+            S u[ZD], un[ZD], k[7][ZD];
+            load_vec<S, ZD>(tape.u + r * ZD, u);
+            tsit5_stages<RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
 #pragma unroll
-                for (int i = 0; i < ZD; ++i) ubn[i] += d[i];
-            } else {
-                S bw[7];
-                interp_weights<S>((S)((ts - tn) * inv), bw);
+            for (int j = 0; j < 7; ++j)
 #pragma unroll
-                for (int j = 0; j < 7; ++j) {
-                    const S w = h * bw[j];
+                for (int i = 0; i < ZD; ++i) kbar[j][i] = (S)0;
 #pragma unroll
-                    for (int i = 0; i < ZD; ++i) kbar[j][i] = s_fma<S>(w, d[i], kbar[j][i]);
+            for (int m = 0; m < 4; ++m)
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) cb[m][i] = (S)0;
+#pragma unroll
+            for (int i = 0; i < ZD; ++i) ub[i] = (S)0;
+            holding = true;
+        }
+        cp_async_wait_all();  // rows fetched at the end of the previous iteration have landed by now
+        if (holding) {
+            const S h = (S)dtn;
+            const double inv = 1.0 / dtn;
+            // cotangents of the save points that lie in (t_n, t_{n+1}]
+            while (ts > tn && ks >= kload) {
+                S d[ZD];
+                load_vec<S, ZD>(ring.at(ks), d);
+                if (ts == tnext) {
+#pragma unroll
+                    for (int i = 0; i < ZD; ++i) ubn[i] += d[i];
+                } else {
+                    const S th = (S)((ts - tn) * inv);
+                    const S w1 = h * th, w2 = w1 * th, w3 = w2 * th, w4 = w3 * th;
+#pragma unroll
+                    for (int i = 0; i < ZD; ++i) {
+                        cb[0][i] = s_fma<S>(w1, d[i], cb[0][i]);
+                        cb[1][i] = s_fma<S>(w2, d[i], cb[1][i]);
+                        cb[2][i] = s_fma<S>(w3, d[i], cb[2][i]);
+                        cb[3][i] = s_fma<S>(w4, d[i], cb[3][i]);
+                        ub[i] += d[i];
+                    }
                 }
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) ub[i] += d[i];
+                --ks;
+                ts = ks >= 1 ? tg[ks] : -LDEQ_TINF;
             }
-            --ks;
+            if (!(ts > tn)) {
+                // every save point of this step has been consumed: reverse sweep through the stages
+                interp_coeffs_adj<S, ZD>(cb, kbar);
+                // k7 = f(u_{n+1}) (it is also next step's k1, whose adjoint was already folded into ubn)
+                RHS::vjp(ubn, pbar, g[6], p, tn + dtn, kbar[6], aux[6]);
+                // u_{n+1} = u_n + h sum_j a7j k_j
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) {
+                    const S v = h * ubn[i];
+                    ub[i] += ubn[i];
+                    kbar[0][i] = s_fma<S>(Tb::a71, v, kbar[0][i]);
+                    kbar[1][i] = s_fma<S>(Tb::a72, v, kbar[1][i]);
+                    kbar[2][i] = s_fma<S>(Tb::a73, v, kbar[2][i]);
+                    kbar[3][i] = s_fma<S>(Tb::a74, v, kbar[3][i]);
+                    kbar[4][i] = s_fma<S>(Tb::a75, v, kbar[4][i]);
+                    kbar[5][i] = s_fma<S>(Tb::a76, v, kbar[5][i]);
+                }
+                S gb[ZD];
+                // stage 6: g6 = u + h (a61 k1 + ... + a65 k5)
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+                RHS::vjp(gb, pbar, g[5], p, tn + dtn, kbar[5], aux[5]);
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) {
+                    const S v = h * gb[i];
+                    ub[i] += gb[i];
+                    kbar[0][i] = s_fma<S>(Tb::a61, v, kbar[0][i]);
+                    kbar[1][i] = s_fma<S>(Tb::a62, v, kbar[1][i]);
+                    kbar[2][i] = s_fma<S>(Tb::a63, v, kbar[2][i]);
+                    kbar[3][i] = s_fma<S>(Tb::a64, v, kbar[3][i]);
+                    kbar[4][i] = s_fma<S>(Tb::a65, v, kbar[4][i]);
+                }
+                // stage 5
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+                RHS::vjp(gb, pbar, g[4], p, tn + Tb::c5 * dtn, kbar[4], aux[4]);
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) {
+                    const S v = h * gb[i];
+                    ub[i] += gb[i];
+                    kbar[0][i] = s_fma<S>(Tb::a51, v, kbar[0][i]);
+                    kbar[1][i] = s_fma<S>(Tb::a52, v, kbar[1][i]);
+                    kbar[2][i] = s_fma<S>(Tb::a53, v, kbar[2][i]);
+                    kbar[3][i] = s_fma<S>(Tb::a54, v, kbar[3][i]);
+                }
+                // stage 4
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+                RHS::vjp(gb, pbar, g[3], p, tn + Tb::c4 * dtn, kbar[3], aux[3]);
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) {
+                    const S v = h * gb[i];
+                    ub[i] += gb[i];
+                    kbar[0][i] = s_fma<S>(Tb::a41, v, kbar[0][i]);
+                    kbar[1][i] = s_fma<S>(Tb::a42, v, kbar[1][i]);
+                    kbar[2][i] = s_fma<S>(Tb::a43, v, kbar[2][i]);
+                }
+                // stage 3
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+                RHS::vjp(gb, pbar, g[2], p, tn + Tb::c3 * dtn, kbar[2], aux[2]);
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) {
+                    const S v = h * gb[i];
+                    ub[i] += gb[i];
+                    kbar[0][i] = s_fma<S>(Tb::a31, v, kbar[0][i]);
+                    kbar[1][i] = s_fma<S>(Tb::a32, v, kbar[1][i]);
+                }
+                // stage 2
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+                RHS::vjp(gb, pbar, g[1], p, tn + Tb::c2 * dtn, kbar[1], aux[1]);
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) {
+                    ub[i] += gb[i];
+                    kbar[0][i] = s_fma<S>(Tb::a21, h * gb[i], kbar[0][i]);
+                }
+                // stage 1: k1 = f(u_n)
+                RHS::vjp(ub, pbar, g[0], p, tn, kbar[0], aux[0]);
+#pragma unroll
+                for (int i = 0; i < ZD; ++i) ubn[i] = ub[i];
+                tnext = tn;
+                --n;
+                holding = false;
+            }
         }
-
-        // k7 = f(u_{n+1}) (it is also next step's k1, whose adjoint was already folded into ubn)
-        RHS::vjp(ubn, pbar, g[6], p, tn + dtn, kbar[6], aux[6]);
-        // u_{n+1} = u_n + h sum_j a7j k_j
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) {
-            const S v = h * ubn[i];
-            ub[i] += ubn[i];
-            kbar[0][i] = s_fma<S>(Tb::a71, v, kbar[0][i]);
-            kbar[1][i] = s_fma<S>(Tb::a72, v, kbar[1][i]);
-            kbar[2][i] = s_fma<S>(Tb::a73, v, kbar[2][i]);
-            kbar[3][i] = s_fma<S>(Tb::a74, v, kbar[3][i]);
-            kbar[4][i] = s_fma<S>(Tb::a75, v, kbar[4][i]);
-            kbar[5][i] = s_fma<S>(Tb::a76, v, kbar[5][i]);
-        }
-        S gb[ZD];
-        // stage 6: g6 = u + h (a61 k1 + ... + a65 k5)
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-        RHS::vjp(gb, pbar, g[5], p, tn + dtn, kbar[5], aux[5]);
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) {
-            const S v = h * gb[i];
-            ub[i] += gb[i];
-            kbar[0][i] = s_fma<S>(Tb::a61, v, kbar[0][i]);
-            kbar[1][i] = s_fma<S>(Tb::a62, v, kbar[1][i]);
-            kbar[2][i] = s_fma<S>(Tb::a63, v, kbar[2][i]);
-            kbar[3][i] = s_fma<S>(Tb::a64, v, kbar[3][i]);
-            kbar[4][i] = s_fma<S>(Tb::a65, v, kbar[4][i]);
-        }
-        // stage 5
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-        RHS::vjp(gb, pbar, g[4], p, tn + Tb::c5 * dtn, kbar[4], aux[4]);
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) {
-            const S v = h * gb[i];
-            ub[i] += gb[i];
-            kbar[0][i] = s_fma<S>(Tb::a51, v, kbar[0][i]);
-            kbar[1][i] = s_fma<S>(Tb::a52, v, kbar[1][i]);
-            kbar[2][i] = s_fma<S>(Tb::a53, v, kbar[2][i]);
-            kbar[3][i] = s_fma<S>(Tb::a54, v, kbar[3][i]);
-        }
-        // stage 4
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-        RHS::vjp(gb, pbar, g[3], p, tn + Tb::c4 * dtn, kbar[3], aux[3]);
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) {
-            const S v = h * gb[i];
-            ub[i] += gb[i];
-            kbar[0][i] = s_fma<S>(Tb::a41, v, kbar[0][i]);
-            kbar[1][i] = s_fma<S>(Tb::a42, v, kbar[1][i]);
-            kbar[2][i] = s_fma<S>(Tb::a43, v, kbar[2][i]);
-        }
-        // stage 3
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-        RHS::vjp(gb, pbar, g[2], p, tn + Tb::c3 * dtn, kbar[2], aux[2]);
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) {
-            const S v = h * gb[i];
-            ub[i] += gb[i];
-            kbar[0][i] = s_fma<S>(Tb::a31, v, kbar[0][i]);
-            kbar[1][i] = s_fma<S>(Tb::a32, v, kbar[1][i]);
-        }
-        // stage 2
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-        RHS::vjp(gb, pbar, g[1], p, tn + Tb::c2 * dtn, kbar[1], aux[1]);
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) {
-            ub[i] += gb[i];
-            kbar[0][i] = s_fma<S>(Tb::a21, h * gb[i], kbar[0][i]);
-        }
-        // stage 1: k1 = f(u_n)
-        RHS::vjp(ub, pbar, g[0], p, tn, kbar[0], aux[0]);
-#pragma unroll
-        for (int i = 0; i < ZD; ++i) ubn[i] = ub[i];
-        tnext = tn;
+        // fetch the rows the slowest lane of the warp will need next, coalesced, ahead of use
+        refill(warp_max_i((holding || n >= 0) ? ks : 0));
     }
+    cp_async_wait_all();
 
     if (!live) return;
     if (ret == RET_SUCCESS && !overflow) {

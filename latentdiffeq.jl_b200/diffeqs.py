@@ -1,0 +1,141 @@
+"""The user-defined ``diffeq`` structs of the reference's examples, same field names.
+
+GOKU reads ``prob`` (``length(prob.u0)``, ``length(prob.p)``), ``solver``, ``sensealg`` and ``kwargs``
+from the struct (reference ``src/models/GOKU.jl:105-108, 207-208``); LatentODE reads ``dudt``,
+``solver``, ``neural_model``, ``augment_dim``, ``kwargs`` and ``latent_dim_in/out``
+(``src/models/LatentODE.jl:62-66, 105-106``).  The structs here carry the same fields; ``prob.f``
+names the right-hand side the CUDA integrator is instantiated with (a built-in kind, or CUDA C
+source compiled by NVRTC for a user-defined system).
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _cabi
+
+
+class Tsit5:
+    """``OrdinaryDiffEq.Tsit5()`` -- the only solver the hot path implements (pendulum.jl:11)."""
+
+    def __repr__(self):
+        return "Tsit5()"
+
+
+class ForwardDiffSensitivity:
+    """Sensitivity request of the reference's diffeq structs (pendulum.jl:11).
+
+    The CUDA path always differentiates with the discrete adjoint of the accepted steps, which in
+    fixed-step mode is the same derivative ForwardDiff computes and otherwise agrees with it to the
+    solver tolerance (DESIGN.md "Gradients")."""
+
+    def __repr__(self):
+        return "ForwardDiffSensitivity()"
+
+
+class InterpolatingAdjoint:
+    """Accepted for API compatibility (DiffEqFlux's NeuralODE default); see ForwardDiffSensitivity."""
+
+    def __repr__(self):
+        return "InterpolatingAdjoint()"
+
+
+class ODEProblem:
+    """``ODEProblem(f, u0, tspan, p)``.  ``f`` is a built-in RHS kind or a :class:`CudaRHS`."""
+
+    def __init__(self, f, u0, tspan, p):
+        self.f = f
+        self.u0 = np.asarray(u0, dtype=np.float32)
+        self.tspan = tuple(tspan)
+        self.p = np.asarray(p, dtype=np.float32)
+
+
+class CudaRHS:
+    """A user-defined right-hand side as CUDA C source, compiled once per handle with NVRTC.
+
+    ``source`` must define
+    ``template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t);``
+    """
+
+    def __init__(self, source: str, z_dim: int, p_dim: int):
+        self.source, self.z_dim, self.p_dim = source, int(z_dim), int(p_dim)
+
+    def resolve(self, h: _cabi.Handle):
+        return h.rhs_from_source(self.source, self.z_dim, self.p_dim)
+
+
+class _GokuDiffEq:
+    _kind = None
+
+    def __init__(self, solver=None, sensalg=None, **kwargs):
+        # Parameters and initial conditions only used to initialise the ODE problem (pendulum.jl:12-16)
+        self.prob = ODEProblem(self._kind, [1.0, 1.0], (0.0, 1.0), [1.0])
+        self.solver = solver or Tsit5()
+        self.sensealg = sensalg or ForwardDiffSensitivity()
+        self.kwargs = dict(kwargs)
+
+
+class Pendulum(_GokuDiffEq):
+    """Friction-less pendulum ``du = [y, -G/L sin x]``, G = 10 (pendulum.jl:4-46)."""
+    _kind = _cabi.RHS_PENDULUM
+
+
+class Pendulum_friction(_GokuDiffEq):
+    """Pendulum with friction ``du = [y, -G/L sin x - (b/m) y]``, b = 0.7, m = 1 (pendulum.jl:51-91)."""
+    _kind = _cabi.RHS_PENDULUM_FRICTION
+
+
+class UserDiffEq(_GokuDiffEq):
+    """A user-defined system for the GOKU path: same struct fields, RHS given as CUDA source."""
+
+    def __init__(self, source: str, u0, p, solver=None, sensalg=None, **kwargs):
+        self.prob = ODEProblem(CudaRHS(source, len(u0), len(p)), u0, (0.0, 1.0), p)
+        self.solver = solver or Tsit5()
+        self.sensealg = sensalg or ForwardDiffSensitivity()
+        self.kwargs = dict(kwargs)
+
+
+def glorot_uniform_(w: torch.Tensor):
+    """Flux.glorot_uniform (the default ``Dense`` init, used by nODE.jl:14-16)."""
+    fan_out, fan_in = w.shape
+    lim = math.sqrt(6.0 / (fan_in + fan_out))
+    with torch.no_grad():
+        w.uniform_(-lim, lim)
+    return w
+
+
+class NODE(nn.Module):
+    """Neural-ODE diffeq struct (nODE.jl:3-33): ``dudt = Chain(Dense(D+aug,H,relu), Dense(H,H,relu),
+    Dense(H,D+aug))``, ``Tsit5()``, ``neural_model = NeuralODE``.
+
+    Unlike the reference struct (which is not a ``@functor`` and therefore never trains, SURVEY.md
+    Appendix C.2) the MLP weights are registered parameters here and receive gradients.
+    """
+
+    def __init__(self, latent_dim_in: int, hidden_dim: int = 200, augment_dim: int = 0, **kwargs):
+        super().__init__()
+        d = latent_dim_in + augment_dim
+        self.dims = [d, hidden_dim, hidden_dim, d]
+        self.weights = nn.ParameterList()
+        self.biases = nn.ParameterList()
+        for i in range(3):
+            w = torch.empty(self.dims[i + 1], self.dims[i])
+            self.weights.append(nn.Parameter(glorot_uniform_(w)))
+            self.biases.append(nn.Parameter(torch.zeros(self.dims[i + 1])))
+        self.solver = Tsit5()
+        self.neural_model = "NeuralODE"
+        self.latent_dim_in = latent_dim_in
+        self.latent_dim_out = latent_dim_in + augment_dim
+        self.augment_dim = augment_dim
+        self.kwargs = dict(kwargs)
+
+    @property
+    def dudt(self):
+        return list(zip(self.weights, self.biases))
+
+    def flat_params(self) -> torch.Tensor:
+        """``Flux.destructure(dudt)`` order: per layer ``vec(W)`` (column-major, W is (out,in)) then ``b``."""
+        return torch.cat([torch.cat([w.t().reshape(-1), b.reshape(-1)]) for w, b in self.dudt])
