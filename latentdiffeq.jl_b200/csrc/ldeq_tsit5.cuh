@@ -472,14 +472,32 @@ tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_glob
     typename RHS::Aux aux[7];
 
     refill(warp_max_i(n >= 0 ? ks : 0));
+    // the record of the step a lane will need next is fetched one step ahead (its latency hides behind
+    // the stage recomputation of the current step)
+    double tn_pre = 0.0, dtn_pre = 0.0;
+    S u_pre[ZD];
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) u_pre[i] = (S)0;
+    if (n >= 0) {
+        const size_t r = (size_t)n * B + b;
+        tn_pre = tape.t[r];
+        dtn_pre = tape.dt[r];
+        load_vec<S, ZD>(tape.u + r * ZD, u_pre);
+    }
     // runs until every lane of the warp has swept its step 0 (early steps may hold no save point at all)
     while (__any_sync(0xffffffffu, holding || n >= 0)) {
         if (!holding && n >= 0) {
-            const size_t r = (size_t)n * B + b;
-            tn = tape.t[r];
-            dtn = tape.dt[r];
+            tn = tn_pre;
+            dtn = dtn_pre;
             S u[ZD], un[ZD], k[7][ZD];
-            load_vec<S, ZD>(tape.u + r * ZD, u);
+#pragma unroll
+            for (int i = 0; i < ZD; ++i) u[i] = u_pre[i];
+            if (n >= 1) {
+                const size_t r = (size_t)(n - 1) * B + b;
+                tn_pre = tape.t[r];
+                dtn_pre = tape.dt[r];
+                load_vec<S, ZD>(tape.u + r * ZD, u_pre);
+            }
             tsit5_stages<RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
 #pragma unroll
             for (int j = 0; j < 7; ++j)
