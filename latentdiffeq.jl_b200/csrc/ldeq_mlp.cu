@@ -1,13 +1,951 @@
-// ldeq_mlp.cu -- LatentODE path (placeholder until the MLP integrator lands in this round).
+// ldeq_mlp.cu -- LatentODE hot path: Tsit5 on the (D,B) matrix state with an MLP right-hand side.
+//
+// Drop-in for the body of diffeq_layer(::Decoder{LatentODE}, z0, t) (reference src/models/LatentODE.jl:61-78):
+//   nODE = NeuralODE(dudt, (t[1], t[end]), Tsit5(); saveat = t, kwargs...);  z = Array(nODE(z0))
+// with dudt = Chain(Dense(D,H,relu), Dense(H,H,relu), Dense(H,D)) (examples/pendulum_friction-less/nODE.jl:14-16)
+// and parameters in Flux.destructure order (per layer vec(W) column-major with W (out,in), then b).
+//
+// This file holds the exact-arithmetic path (CUDA cores, fp32 or fp64): one persistent CTA integrates a
+// tile of TB trajectories for the whole time span.  Stage vectors, hidden activations and the
+// per-trajectory controller state live in shared memory; the weights are read through L1 (187 kB for the
+// default 16-200-200-16 network).  Two error-norm scopes:
+//   LDEQ_NORM_GLOBAL    one dt for the whole batch, RMS over all D*B entries (reference semantics); the CTAs
+//                       meet at a cooperative grid barrier once per attempted step to sum the error norm;
+//   LDEQ_NORM_PER_TRAJ  every trajectory has its own dt / accept-reject sequence (documented deviation).
+// The backward kernel is the discrete adjoint of the accepted steps (the reference's InterpolatingAdjoint is a
+// continuous adjoint that agrees with it to the solver tolerance).
+#include <cooperative_groups.h>
+
 #include "ldeq_internal.h"
+
+namespace cg = cooperative_groups;
+
+namespace ldeq {
+
+#define MLP_THREADS 256
+#define MLP_MAX_LAYERS 8
+
+struct MlpNet {
+    int n_layers;
+    int dims[MLP_MAX_LAYERS + 1];
+    int w_off[MLP_MAX_LAYERS];  // offset of vec(W_l) in the flat parameter vector
+    int b_off[MLP_MAX_LAYERS];
+    int n_params;
+    int max_width;  // widest layer input/output
+};
+
+template <class S> struct MlpTapeView {
+    double* t;   // [cap][B]
+    double* dt;  // [cap][B]
+    S* u;        // [cap][B][D]
+    int cap;
+};
+
+// ---- dense layers on a tile ------------------------------------------------------------------------
+// Activations are stored feature-major per tile: x[k*TB + b].  W is (N,K) column-major: W[k*N + n].
+// Thread w handles output neuron n = w % N over the k-slice s = w / N; slices are summed through `red`.
+template <class S, int TB>
+__device__ void dense_fwd(const S* __restrict__ W, const S* __restrict__ bias, const S* __restrict__ x, S* __restrict__ y,
+                          S* __restrict__ red, int K, int N, bool relu) {
+    int SL = 1;
+    while (SL * 2 * N <= MLP_THREADS && SL < 16 && SL * 2 <= K) SL *= 2;
+    const int kper = (K + SL - 1) / SL;
+    for (int w = threadIdx.x; w < N * SL; w += MLP_THREADS) {
+        const int s = w / N, n = w - s * N;
+        const int k0 = s * kper, k1 = min(K, k0 + kper);
+        S acc[TB];
+        const S b0 = s == 0 ? bias[n] : (S)0;
+#pragma unroll
+        for (int b = 0; b < TB; ++b) acc[b] = b0;
+#pragma unroll 4
+        for (int k = k0; k < k1; ++k) {
+            const S wv = W[(size_t)k * N + n];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) acc[b] = s_fma<S>(wv, x[k * TB + b], acc[b]);
+        }
+        if (SL == 1) {
+#pragma unroll
+            for (int b = 0; b < TB; ++b) y[n * TB + b] = relu ? s_max<S>(acc[b], (S)0) : acc[b];
+        } else {
+#pragma unroll
+            for (int b = 0; b < TB; ++b) red[(s * N + n) * TB + b] = acc[b];
+        }
+    }
+    if (SL > 1) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < N * TB; i += MLP_THREADS) {
+            S a = (S)0;
+            for (int s = 0; s < SL; ++s) a += red[s * N * TB + i];
+            y[i] = relu ? s_max<S>(a, (S)0) : a;
+        }
+    }
+    __syncthreads();
+}
+
+// MLP forward on a tile: x (dims[0] x TB) -> y (dims[L] x TB).  hid: two ping-pong buffers of max_width*TB.
+// With KEEP the post-activation outputs of every hidden layer are left in act[l] (for the VJP).
+template <class S, int TB>
+__device__ void mlp_fwd(const MlpNet& net, const S* __restrict__ P, const S* x, S* y, S* hid0, S* hid1, S* red) {
+    const S* in = x;
+    for (int l = 0; l < net.n_layers; ++l) {
+        const bool last = l + 1 == net.n_layers;
+        S* out = last ? y : ((l & 1) ? hid1 : hid0);
+        dense_fwd<S, TB>(P + net.w_off[l], P + net.b_off[l], in, out, red, net.dims[l], net.dims[l + 1], !last);
+        in = out;
+    }
+}
+
+template <class S> __device__ __forceinline__ S tab_a(int j, int i) {
+    using Tb = Tab<S>;
+    switch (j * 8 + i) {
+        case 1 * 8 + 0: return Tb::a21;
+        case 2 * 8 + 0: return Tb::a31; case 2 * 8 + 1: return Tb::a32;
+        case 3 * 8 + 0: return Tb::a41; case 3 * 8 + 1: return Tb::a42; case 3 * 8 + 2: return Tb::a43;
+        case 4 * 8 + 0: return Tb::a51; case 4 * 8 + 1: return Tb::a52; case 4 * 8 + 2: return Tb::a53; case 4 * 8 + 3: return Tb::a54;
+        case 5 * 8 + 0: return Tb::a61; case 5 * 8 + 1: return Tb::a62; case 5 * 8 + 2: return Tb::a63; case 5 * 8 + 3: return Tb::a64;
+        case 5 * 8 + 4: return Tb::a65;
+        case 6 * 8 + 0: return Tb::a71; case 6 * 8 + 1: return Tb::a72; case 6 * 8 + 2: return Tb::a73; case 6 * 8 + 3: return Tb::a74;
+        case 6 * 8 + 4: return Tb::a75; case 6 * 8 + 5: return Tb::a76;
+    }
+    return (S)0;
+}
+template <class S> __device__ __forceinline__ S tab_bt(int i) {
+    using Tb = Tab<S>;
+    switch (i) {
+        case 0: return Tb::bt1; case 1: return Tb::bt2; case 2: return Tb::bt3; case 3: return Tb::bt4;
+        case 4: return Tb::bt5; case 5: return Tb::bt6; case 6: return Tb::bt7;
+    }
+    return (S)0;
+}
+__device__ __constant__ double c_stage[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+
+// Per-trajectory controller / bookkeeping state of a tile (shared memory)
+template <int TB> struct TileState {
+    double t[TB], dt[TB], dts[TB], tnew[TB], qold[TB], esum[TB], dt_next[TB];
+    long long iters[TB];
+    int ks[TB], na[TB], nr[TB], ret[TB];
+    int accept[TB], active[TB], nsave[TB];
+};
+
+// grid-wide deterministic sum: every CTA publishes its partial, all meet, all add in the same order
+__device__ double grid_sum(double part, double* partials, cg::grid_group& grid) {
+    if (threadIdx.x == 0) partials[blockIdx.x] = part;
+    grid.sync();
+    double r = 0.0;
+    for (int i = 0; i < (int)gridDim.x; ++i) r += __ldcg(partials + i);
+    grid.sync();  // partials may be overwritten by the next reduction only after everyone has read them
+    return r;
+}
+
+// ---- forward ------------------------------------------------------------------------------------------
+template <class S, int TB, bool GLOBAL>
+__global__ void __launch_bounds__(MLP_THREADS)
+mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, const double* __restrict__ tg, int B, int T,
+               KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
+               int* __restrict__ nreject, MlpTapeView<S> tape, double* __restrict__ partials) {
+    cg::grid_group grid = cg::this_grid();
+    const int D = net.dims[0];
+    const int HW = net.max_width;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S* U = reinterpret_cast<S*>(smem_raw);  // [D][TB]
+    S* G = U + D * TB;                      // stage input
+    S* UN = G + D * TB;                     // u_{n+1}
+    S* Kst = UN + D * TB;                   // [7][D][TB]
+    S* hid0 = Kst + 7 * D * TB;
+    S* hid1 = hid0 + HW * TB;
+    S* red = hid1 + HW * TB;                // [MLP_THREADS][TB]
+    const size_t s_bytes = (((size_t)(10 * D + 2 * HW + MLP_THREADS) * TB * sizeof(S)) + 15) & ~(size_t)15;
+    TileState<TB>* ts = reinterpret_cast<TileState<TB>*>(smem_raw + s_bytes);
+    __shared__ int s_any;
+
+    const double t0 = tg[0], tend = tg[T - 1];
+    const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
+    const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
+    const S abstol = (S)o.abstol, reltol = (S)o.reltol;
+    const int ntiles = (B + TB - 1) / TB;
+    const int DT = D * TB;
+
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        // GLOBAL mode runs exactly one tile per CTA (the host sizes the grid so): all CTAs then take the same
+        // steps (one dt for the batch) and meet at the same grid reductions
+        const int b0 = tile * TB;
+        // ---- load the tile, k1 = f(u0), initial step ---------------------------------------------------
+        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+            const int d = i / TB, b = i - d * TB;
+            const int gb = b0 + b;
+            U[i] = gb < B ? z0[(size_t)gb * D + d] : (S)0;
+        }
+        if (threadIdx.x < TB) {
+            const int b = threadIdx.x;
+            ts->t[b] = t0; ts->qold[b] = o.qoldinit; ts->iters[b] = 0; ts->ks[b] = 1; ts->na[b] = 0; ts->nr[b] = 0;
+            ts->ret[b] = RET_SUCCESS; ts->active[b] = (b0 + b < B) && T > 1; ts->dt[b] = o.dt;
+        }
+        __syncthreads();
+        mlp_fwd<S, TB>(net, P, U, Kst, hid0, hid1, red);  // fsalfirst
+        // save point 0 is u0 itself
+        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+            const int d = i / TB, b = i - d * TB;
+            if (b0 + b < B) traj[(size_t)(b0 + b) * D + d] = U[i];
+        }
+        if (o.adaptive && !(o.dt > 0.0)) {
+            // Hairer initial step; norms per trajectory or over the whole batch.
+            // column sums: thread b adds the D entries of its trajectory (D is small)
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                double a0 = 0.0, a1 = 0.0;
+                if (b0 + b < B)
+                    for (int d = 0; d < D; ++d) {
+                        const S sk = s_fma<S>(s_abs<S>(U[d * TB + b]), reltol, abstol);
+                        const S a = U[d * TB + b] / sk, c = Kst[d * TB + b] / sk;
+                        a0 += (double)(a * a);
+                        a1 += (double)(c * c);
+                    }
+                ts->esum[b] = a0;
+                ts->dt_next[b] = a1;
+            }
+            __syncthreads();
+            double d0[TB], d1[TB];
+            if (GLOBAL) {
+                double s0 = 0.0, s1 = 0.0;
+                for (int b = 0; b < TB; ++b) { s0 += ts->esum[b]; s1 += ts->dt_next[b]; }
+                const double n = (double)D * (double)B;
+                s0 = grid_sum(s0, partials, grid);
+                s1 = grid_sum(s1, partials, grid);
+                for (int b = 0; b < TB; ++b) { d0[b] = (double)s_sqrt<S>((S)(s0 / n)); d1[b] = (double)s_sqrt<S>((S)(s1 / n)); }
+            } else {
+                for (int b = 0; b < TB; ++b) {
+                    d0[b] = (double)s_sqrt<S>((S)(ts->esum[b] / D));
+                    d1[b] = (double)s_sqrt<S>((S)(ts->dt_next[b] / D));
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                const double dt0 = (d0[b] < 1e-5 || d1[b] < 1e-5) ? 1e-6 : 0.01 * (d0[b] / d1[b]);
+                ts->dts[b] = fmin(dt0, dtmax);
+            }
+            __syncthreads();
+            // u1 = u0 + dt0 f0, f1 = f(u1)
+            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) G[i] = s_fma<S>((S)ts->dts[i % TB], Kst[i], U[i]);
+            __syncthreads();
+            mlp_fwd<S, TB>(net, P, G, UN, hid0, hid1, red);  // f1 in UN
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                double a2 = 0.0;
+                if (b0 + b < B)
+                    for (int d = 0; d < D; ++d) {
+                        const S sk = s_fma<S>(s_abs<S>(U[d * TB + b]), reltol, abstol);
+                        const S a = (UN[d * TB + b] - Kst[d * TB + b]) / sk;
+                        a2 += (double)(a * a);
+                    }
+                ts->esum[b] = a2;
+            }
+            __syncthreads();
+            double s2 = 0.0;
+            if (GLOBAL) {
+                for (int b = 0; b < TB; ++b) s2 += ts->esum[b];
+                s2 = grid_sum(s2, partials, grid);
+            }
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                const double dt0 = ts->dts[b];
+                const double d2 = (double)s_sqrt<S>((S)(GLOBAL ? s2 / ((double)D * (double)B) : ts->esum[b] / D)) / dt0;
+                double dtv;
+                if (dt0 < 10.0 * 2.220446049250313e-16) {
+                    dtv = fmax(1e-6, dtmin);
+                } else {
+                    const double m = fmax(d1[b], d2);
+                    const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(m)) / 5.0);
+                    dtv = fmax(dtmin, fmin(100.0 * dt0, fmin(dt1, dtmax)));
+                }
+                ts->dt[b] = dtv;
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x < TB) {
+            const int b = threadIdx.x;
+            if (ts->active[b] && (!(ts->dt[b] > 0.0) || !isfinite(ts->dt[b]))) { ts->ret[b] = RET_DTLESSTHANMIN; ts->active[b] = 0; }
+        }
+        __syncthreads();
+
+        // ---- step loop ----------------------------------------------------------------------------------
+        for (;;) {
+            if (threadIdx.x == 0) s_any = 0;
+            __syncthreads();
+            if (threadIdx.x < TB && ts->active[threadIdx.x]) s_any = 1;
+            __syncthreads();
+            // GLOBAL: all trajectories share the step sequence and every tile holds at least one of them, so
+            // every CTA leaves this loop in the same iteration (no CTA is left waiting at a grid barrier)
+            if (!s_any) break;
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                if (ts->active[b]) {
+                    if (ts->iters[b] >= o.maxiters) {
+                        ts->ret[b] = RET_MAXITERS; ts->active[b] = 0;
+                    } else {
+                        ts->iters[b]++;
+                        const double t = ts->t[b];
+                        const double dts = fmin(ts->dt[b], tend - t);
+                        double tnew = t + dts;
+                        if (fabs(tnew - tend) < 100.0 * ulp_of(fmax(fabs(t), fabs(tend)))) tnew = tend;
+                        ts->dts[b] = dts; ts->tnew[b] = tnew;
+                    }
+                }
+                ts->esum[b] = 0.0;
+            }
+            __syncthreads();
+            // stages 2..7 (k1 is Kst[0] by FSAL)
+            for (int j = 1; j < 7; ++j) {
+                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                    S acc = tab_a<S>(j, 0) * Kst[i];
+                    for (int q = 1; q < j; ++q) acc = s_fma<S>(tab_a<S>(j, q), Kst[q * DT + i], acc);
+                    const S v = s_fma<S>((S)ts->dts[i % TB], acc, U[i]);
+                    G[i] = v;
+                    if (j == 6) UN[i] = v;
+                }
+                __syncthreads();
+                mlp_fwd<S, TB>(net, P, G, Kst + j * DT, hid0, hid1, red);
+            }
+            // error estimate: squared scaled residuals into G (free after the stages), then column sums
+            double part = 0.0;
+            if (o.adaptive) {
+                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                    const int b = i % TB;
+                    S acc = tab_bt<S>(0) * Kst[i];
+                    for (int q = 1; q < 7; ++q) acc = s_fma<S>(tab_bt<S>(q), Kst[q * DT + i], acc);
+                    const S ut = (S)ts->dts[b] * acc;
+                    const S sk = s_fma<S>(s_max<S>(s_abs<S>(U[i]), s_abs<S>(UN[i])), reltol, abstol);
+                    const S a = ut / sk;
+                    G[i] = a * a;
+                }
+                __syncthreads();
+                if (threadIdx.x < TB) {
+                    const int b = threadIdx.x;
+                    double e = 0.0;
+                    if (ts->active[b])
+                        for (int d = 0; d < D; ++d) e += (double)G[d * TB + b];
+                    ts->esum[b] = e;
+                }
+                __syncthreads();
+                if (GLOBAL) {
+                    for (int b = 0; b < TB; ++b) part += ts->esum[b];
+                    part = grid_sum(part, partials, grid);
+                }
+            }
+            // controller, one thread per trajectory
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                ts->accept[b] = 0;
+                if (ts->active[b]) {
+                    bool finite = true;
+                    for (int d = 0; d < D; ++d) finite = finite && s_finite<S>(UN[d * TB + b]);
+                    bool accept = true;
+                    double dt_next = ts->dt[b];
+                    if (o.adaptive) {
+                        const double e2 = GLOBAL ? part / ((double)D * (double)B) : ts->esum[b] / (double)D;
+                        const double EEst = (double)s_sqrt<S>((S)e2);
+                        if (EEst != EEst) finite = false;
+                        double q = ts->qold[b];
+                        accept = pi_controller(o, EEst, ts->dts[b], dtmax, q, dt_next);
+                        ts->qold[b] = q;
+                    }
+                    if (!finite) {
+                        ts->ret[b] = RET_UNSTABLE; ts->active[b] = 0;
+                    } else {
+                        if (accept) {
+                            const int n = ts->na[b];
+                            if (tape.cap > 0 && n < tape.cap) {
+                                tape.t[(size_t)n * B + b0 + b] = ts->t[b];
+                                tape.dt[(size_t)n * B + b0 + b] = ts->dts[b];
+                            }
+                            ts->accept[b] = 1;
+                        } else {
+                            ts->nr[b]++;
+                        }
+                        ts->dt[b] = dt_next;
+                        if (o.adaptive && !(accept && ts->tnew[b] == tend) && (!(fabs(dt_next) > dtmin) || !isfinite(dt_next))) {
+                            ts->ret[b] = RET_DTLESSTHANMIN; ts->active[b] = 0; ts->accept[b] = 0;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // tape: state at the start of the accepted step
+            if (tape.cap > 0) {
+                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                    const int d = i / TB, b = i - d * TB;
+                    if (ts->accept[b] && ts->na[b] < tape.cap)
+                        tape.u[((size_t)ts->na[b] * B + b0 + b) * D + d] = U[i];
+                }
+            }
+            // saveat through the dense interpolant; a trajectory may have several pending save points
+            for (;;) {
+                if (threadIdx.x == 0) s_any = 0;
+                __syncthreads();
+                if (threadIdx.x < TB) {
+                    const int b = threadIdx.x;
+                    const int pend = ts->accept[b] && ts->ks[b] < T && tg[ts->ks[b]] <= ts->tnew[b];
+                    ts->nsave[b] = pend;
+                    if (pend) s_any = 1;
+                }
+                __syncthreads();
+                if (!s_any) break;
+                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                    const int d = i / TB, b = i - d * TB;
+                    if (ts->nsave[b]) {
+                        const int ks = ts->ks[b];
+                        const double tsv = tg[ks];
+                        S out;
+                        if (tsv == ts->tnew[b]) {
+                            out = UN[i];
+                        } else {
+                            S bw[7];
+                            interp_weights<S>((S)((tsv - ts->t[b]) / ts->dts[b]), bw);
+                            S acc = bw[0] * Kst[i];
+#pragma unroll
+                            for (int q = 1; q < 7; ++q) acc = s_fma<S>(bw[q], Kst[q * DT + i], acc);
+                            out = s_fma<S>((S)ts->dts[b], acc, U[i]);
+                        }
+                        traj[((size_t)ks * B + b0 + b) * D + d] = out;
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x < TB && ts->nsave[threadIdx.x]) ts->ks[threadIdx.x]++;
+            }
+            // commit accepted steps
+            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                if (ts->accept[i % TB]) { U[i] = UN[i]; Kst[i] = Kst[6 * DT + i]; }
+            }
+            __syncthreads();
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                if (ts->accept[b]) {
+                    ts->t[b] = ts->tnew[b];
+                    ts->na[b]++;
+                    if (ts->ks[b] >= T) ts->active[b] = 0;
+                }
+            }
+            __syncthreads();
+        }
+        // ---- epilogue of the tile: NaN block on failure (GOKU.jl:114 convention), statistics -----------
+        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+            const int d = i / TB, b = i - d * TB;
+            if (b0 + b < B && ts->ret[b] != RET_SUCCESS)
+                for (int k = 0; k < T; ++k) traj[((size_t)k * B + b0 + b) * D + d] = s_nan<S>();
+        }
+        if (threadIdx.x < TB && b0 + threadIdx.x < B) {
+            const int b = threadIdx.x;
+            if (retcode) retcode[b0 + b] = ts->ret[b];
+            if (naccept) naccept[b0 + b] = ts->na[b];
+            if (nreject) nreject[b0 + b] = ts->nr[b];
+        }
+        __syncthreads();
+        if (GLOBAL) break;
+    }
+}
+
+// ---- backward -----------------------------------------------------------------------------------------
+// y = relu?(W x + b) on a tile, keeping the output; used to recompute hidden activations.
+// Input gradient: dx[k][b] = sum_n Wt[n*K + k] dy[n][b]  (Wt = W transposed once per call: coalesced over k)
+template <class S, int TB>
+__device__ void dense_bwd_input(const S* __restrict__ Wt, const S* __restrict__ dy, S* __restrict__ dx, S* __restrict__ red,
+                                int K, int N) {
+    // same mapping as dense_fwd with the roles of K and N swapped
+    int SL = 1;
+    while (SL * 2 * K <= MLP_THREADS && SL < 16 && SL * 2 <= N) SL *= 2;
+    const int nper = (N + SL - 1) / SL;
+    for (int w = threadIdx.x; w < K * SL; w += MLP_THREADS) {
+        const int s = w / K, k = w - s * K;
+        const int n0 = s * nper, n1 = min(N, n0 + nper);
+        S acc[TB];
+#pragma unroll
+        for (int b = 0; b < TB; ++b) acc[b] = (S)0;
+#pragma unroll 4
+        for (int n = n0; n < n1; ++n) {
+            const S wv = Wt[(size_t)n * K + k];
+#pragma unroll
+            for (int b = 0; b < TB; ++b) acc[b] = s_fma<S>(wv, dy[n * TB + b], acc[b]);
+        }
+        if (SL == 1) {
+#pragma unroll
+            for (int b = 0; b < TB; ++b) dx[k * TB + b] = acc[b];
+        } else {
+#pragma unroll
+            for (int b = 0; b < TB; ++b) red[(s * K + k) * TB + b] = acc[b];
+        }
+    }
+    if (SL > 1) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < K * TB; i += MLP_THREADS) {
+            S a = (S)0;
+            for (int s = 0; s < SL; ++s) a += red[s * K * TB + i];
+            dx[i] = a;
+        }
+    }
+    __syncthreads();
+}
+
+// Parameter gradient of one layer accumulated into this CTA's private slice of the scratch buffer:
+// gW[k*N + n] += sum_b dy[n][b] x[k][b];  gb[n] += sum_b dy[n][b]
+template <class S, int TB>
+__device__ void dense_bwd_params(S* __restrict__ gW, S* __restrict__ gb, const S* __restrict__ dy, const S* __restrict__ x,
+                                 int K, int N) {
+    for (int w = threadIdx.x; w < N * K; w += MLP_THREADS) {
+        const int k = w / N, n = w - k * N;
+        S a = (S)0;
+#pragma unroll
+        for (int b = 0; b < TB; ++b) a = s_fma<S>(dy[n * TB + b], x[k * TB + b], a);
+        gW[w] += a;
+    }
+    for (int n = threadIdx.x; n < N; n += MLP_THREADS) {
+        S a = (S)0;
+#pragma unroll
+        for (int b = 0; b < TB; ++b) a += dy[n * TB + b];
+        gb[n] += a;
+    }
+    __syncthreads();
+}
+
+// VJP of the MLP at stage input x: recompute the hidden activations (kept in `acts`), then sweep back.
+// kbar (D x TB) in, gbar (D x TB) out (overwritten), parameter gradients accumulated into gP.
+template <class S, int TB>
+__device__ void mlp_vjp(const MlpNet& net, const S* __restrict__ P, const S* __restrict__ Pt, S* __restrict__ gP, const S* x,
+                        const S* kbar, S* gbar, S* acts /*[n_layers-1][HW*TB]*/, S* dbuf0, S* dbuf1, S* ytmp, S* red,
+                        int HW) {
+    // forward, keeping every hidden activation
+    const S* in = x;
+    for (int l = 0; l < net.n_layers; ++l) {
+        const bool last = l + 1 == net.n_layers;
+        S* out = last ? ytmp : acts + (size_t)l * HW * TB;
+        dense_fwd<S, TB>(P + net.w_off[l], P + net.b_off[l], in, out, red, net.dims[l], net.dims[l + 1], !last);
+        in = out;
+    }
+    // backward
+    const S* dy = kbar;
+    for (int l = net.n_layers - 1; l >= 0; --l) {
+        const int K = net.dims[l], N = net.dims[l + 1];
+        const S* xin = l == 0 ? x : acts + (size_t)(l - 1) * HW * TB;
+        dense_bwd_params<S, TB>(gP + net.w_off[l], gP + net.b_off[l], dy, xin, K, N);
+        S* dx = l == 0 ? gbar : ((l & 1) ? dbuf1 : dbuf0);
+        dense_bwd_input<S, TB>(Pt + net.w_off[l], dy, dx, red, K, N);
+        if (l > 0) {
+            // through the relu of layer l-1: its output is xin
+            for (int i = threadIdx.x; i < K * TB; i += MLP_THREADS) dx[i] = xin[i] > (S)0 ? dx[i] : (S)0;
+            __syncthreads();
+        }
+        dy = dx;
+    }
+}
+
+template <class S, int TB>
+__global__ void __launch_bounds__(MLP_THREADS)
+mlp_bwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, const double* __restrict__ tg, int B, int T,
+               const S* __restrict__ dtraj, MlpTapeView<S> tape, const int* __restrict__ retcode,
+               const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ gscratch) {
+    const int D = net.dims[0];
+    const int HW = net.max_width;
+    const int DT = D * TB;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S* Gst = reinterpret_cast<S*>(smem_raw);   // [7][D][TB] stage inputs (Gst[0] = u_n, Gst[6] = u_{n+1})
+    S* Kst = Gst + 7 * DT;                      // [7][D][TB]
+    S* Kbar = Kst + 7 * DT;                     // [7][D][TB]
+    S* UB = Kbar + 7 * DT;                      // adjoint of u_n
+    S* UBN = UB + DT;                           // adjoint of u_{n+1}
+    S* GB = UBN + DT;                           // stage-input adjoint
+    S* ytmp = GB + DT;
+    S* acts = ytmp + DT;                        // [(L-1)][HW][TB]
+    S* dbuf0 = acts + (size_t)(net.n_layers - 1) * HW * TB;
+    S* dbuf1 = dbuf0 + HW * TB;
+    S* red = dbuf1 + HW * TB;                   // [MLP_THREADS][TB]
+    const size_t s_bytes =
+        (((size_t)(25 * D + (net.n_layers - 1) * HW + 2 * HW + MLP_THREADS) * TB * sizeof(S)) + 15) & ~(size_t)15;
+    double* tn_s = reinterpret_cast<double*>(smem_raw + s_bytes);  // [TB]
+    double* dtn_s = tn_s + TB;
+    double* tnext_s = dtn_s + TB;
+    int* n_s = reinterpret_cast<int*>(tnext_s + TB);  // [TB] current step index (-1: done)
+    int* ks_s = n_s + TB;
+    int* flag_s = ks_s + TB;
+    __shared__ int s_any;
+
+    S* gP = gscratch + (size_t)blockIdx.x * net.n_params;  // this CTA's private gradient accumulator
+    for (int i = threadIdx.x; i < net.n_params; i += MLP_THREADS) gP[i] = (S)0;
+    const int ntiles = (B + TB - 1) / TB;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int b0 = tile * TB;
+        if (threadIdx.x < TB) {
+            const int b = threadIdx.x;
+            const bool ok = b0 + b < B && retcode[b0 + b] == RET_SUCCESS && naccept[b0 + b] <= tape.cap;
+            n_s[b] = ok ? naccept[b0 + b] - 1 : -1;
+            ks_s[b] = T - 1;
+            tnext_s[b] = tg[T - 1];
+        }
+        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) UBN[i] = (S)0;
+        __syncthreads();
+        for (;;) {
+            if (threadIdx.x == 0) s_any = 0;
+            __syncthreads();
+            if (threadIdx.x < TB && n_s[threadIdx.x] >= 0) s_any = 1;
+            __syncthreads();
+            if (!s_any) break;
+            // load the step record of every live trajectory and recompute its stages
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                if (n_s[b] >= 0) {
+                    tn_s[b] = tape.t[(size_t)n_s[b] * B + b0 + b];
+                    dtn_s[b] = tape.dt[(size_t)n_s[b] * B + b0 + b];
+                } else {
+                    tn_s[b] = 0.0; dtn_s[b] = 0.0;
+                }
+            }
+            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                const int d = i / TB, b = i - d * TB;
+                Gst[i] = n_s[b] >= 0 ? tape.u[((size_t)n_s[b] * B + b0 + b) * D + d] : (S)0;
+            }
+            for (int i = threadIdx.x; i < 7 * DT; i += MLP_THREADS) Kbar[i] = (S)0;
+            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) UB[i] = (S)0;
+            __syncthreads();
+            mlp_fwd<S, TB>(net, P, Gst, Kst, dbuf0, dbuf1, red);
+            for (int j = 1; j < 7; ++j) {
+                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                    S acc = tab_a<S>(j, 0) * Kst[i];
+                    for (int q = 1; q < j; ++q) acc = s_fma<S>(tab_a<S>(j, q), Kst[q * DT + i], acc);
+                    Gst[j * DT + i] = s_fma<S>((S)dtn_s[i % TB], acc, Gst[i]);
+                }
+                __syncthreads();
+                mlp_fwd<S, TB>(net, P, Gst + j * DT, Kst + j * DT, dbuf0, dbuf1, red);
+            }
+            // cotangents of the save points in (t_n, t_{n+1}]
+            for (;;) {
+                if (threadIdx.x == 0) s_any = 0;
+                __syncthreads();
+                if (threadIdx.x < TB) {
+                    const int b = threadIdx.x;
+                    const int pend = n_s[b] >= 0 && ks_s[b] >= 1 && tg[ks_s[b]] > tn_s[b];
+                    flag_s[b] = pend;
+                    if (pend) s_any = 1;
+                }
+                __syncthreads();
+                if (!s_any) break;
+                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                    const int d = i / TB, b = i - d * TB;
+                    if (flag_s[b]) {
+                        const int ks = ks_s[b];
+                        const double tsv = tg[ks];
+                        const S dv = dtraj[((size_t)ks * B + b0 + b) * D + d];
+                        if (tsv == tnext_s[b]) {
+                            UBN[i] += dv;
+                        } else {
+                            S bw[7];
+                            interp_weights<S>((S)((tsv - tn_s[b]) / dtn_s[b]), bw);
+                            const S hd = (S)dtn_s[b] * dv;
+#pragma unroll
+                            for (int q = 0; q < 7; ++q) Kbar[q * DT + i] = s_fma<S>(bw[q], hd, Kbar[q * DT + i]);
+                            UB[i] += dv;
+                        }
+                    }
+                }
+                __syncthreads();
+                if (threadIdx.x < TB && flag_s[threadIdx.x]) ks_s[threadIdx.x]--;
+            }
+            // k7 = f(u_{n+1}): UBN += J^T kbar7
+            mlp_vjp<S, TB>(net, P, Pt, gP, Gst + 6 * DT, Kbar + 6 * DT, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                const S v = UBN[i] + GB[i];
+                UBN[i] = v;
+                UB[i] += v;
+                const S hv = (S)dtn_s[i % TB] * v;
+                for (int q = 0; q < 6; ++q) Kbar[q * DT + i] = s_fma<S>(tab_a<S>(6, q), hv, Kbar[q * DT + i]);
+            }
+            __syncthreads();
+            for (int j = 5; j >= 1; --j) {
+                mlp_vjp<S, TB>(net, P, Pt, gP, Gst + j * DT, Kbar + j * DT, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                    const S v = GB[i];
+                    UB[i] += v;
+                    const S hv = (S)dtn_s[i % TB] * v;
+                    for (int q = 0; q < j; ++q) Kbar[q * DT + i] = s_fma<S>(tab_a<S>(j, q), hv, Kbar[q * DT + i]);
+                }
+                __syncthreads();
+            }
+            mlp_vjp<S, TB>(net, P, Pt, gP, Gst, Kbar, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                const int b = i % TB;
+                if (n_s[b] >= 0) UBN[i] = UB[i] + GB[i];  // adjoint of u_n becomes "u_{n+1}" of step n-1
+            }
+            __syncthreads();
+            if (threadIdx.x < TB) {
+                const int b = threadIdx.x;
+                if (n_s[b] >= 0) { tnext_s[b] = tn_s[b]; n_s[b]--; }
+            }
+            __syncthreads();
+        }
+        // save point 0 is u0 itself; failed trajectories get a zero gradient, tape overflow NaN
+        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+            const int d = i / TB, b = i - d * TB;
+            if (b0 + b < B) {
+                const bool ok = retcode[b0 + b] == RET_SUCCESS;
+                const bool over = ok && naccept[b0 + b] > tape.cap;
+                S v = ok ? UBN[i] + dtraj[(size_t)(b0 + b) * D + d] : (S)0;
+                if (over) v = s_nan<S>();
+                dz0[(size_t)(b0 + b) * D + d] = v;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// transpose every layer's W (N,K col-major: W[k*N+n]) into Wt[n*K + k]; biases are copied
+template <class S> __global__ void mlp_transpose_kernel(MlpNet net, const S* __restrict__ P, S* __restrict__ Pt) {
+    for (int l = 0; l < net.n_layers; ++l) {
+        const int K = net.dims[l], N = net.dims[l + 1];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K * N; i += gridDim.x * blockDim.x) {
+            const int n = i / K, k = i - n * K;
+            Pt[net.w_off[l] + i] = P[net.w_off[l] + (size_t)k * N + n];
+        }
+    }
+}
+
+// dparams[i] = sum over CTAs of their private accumulators, in a fixed order (deterministic)
+template <class S> __global__ void mlp_reduce_grads_kernel(const S* __restrict__ gscratch, int n_cta, int n_params,
+                                                            S* __restrict__ dparams) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_params; i += gridDim.x * blockDim.x) {
+        double a = 0.0;
+        for (int c = 0; c < n_cta; ++c) a += (double)gscratch[(size_t)c * n_params + i];
+        dparams[i] = (S)a;
+    }
+}
+
+template <class S, int TB> static size_t fwd_smem(const MlpNet& net) {
+    const size_t D = net.dims[0], HW = net.max_width;
+    size_t n = (3 * D + 7 * D + 2 * HW + MLP_THREADS) * TB * sizeof(S);
+    n = (n + 15) & ~(size_t)15;
+    return n + sizeof(TileState<TB>) + 64;
+}
+template <class S, int TB> static size_t bwd_smem(const MlpNet& net) {
+    const size_t D = net.dims[0], HW = net.max_width;
+    size_t n = (21 * D + 4 * D + (net.n_layers - 1) * HW + 2 * HW + MLP_THREADS) * TB * sizeof(S);
+    n = (n + 15) & ~(size_t)15;
+    return n + 3 * TB * sizeof(double) + 3 * TB * sizeof(int) + 64;
+}
+
+}  // namespace ldeq
+
 using namespace ldeq;
+
+struct ldeq_mlp_tape {
+    int dtype = 0, B = 0, T = 0, cap = 0, tb = 0;
+    MlpNet net;
+    void* base = nullptr;
+    double* t = nullptr;
+    double* dt = nullptr;
+    void* u = nullptr;
+    void* params = nullptr;  // copy of the flat parameters
+    void* params_t = nullptr;
+    double* tgrid = nullptr;
+    int32_t* retcode = nullptr;
+    int32_t* naccept = nullptr;
+    int32_t* nreject = nullptr;
+};
+
+static int make_net(ldeq_handle* h, const int32_t* dims, int n_layers, MlpNet* net) {
+    if (n_layers < 1 || n_layers > MLP_MAX_LAYERS) return set_err(h, LDEQ_ERR_UNSUPPORTED, "mlp: 1..8 layers supported");
+    if (dims[0] != dims[n_layers]) return set_err(h, LDEQ_ERR_INVALID, "mlp: first and last layer width must be equal");
+    net->n_layers = n_layers;
+    int off = 0, mw = 0;
+    for (int l = 0; l <= n_layers; ++l) {
+        if (dims[l] < 1 || dims[l] > 1024) return set_err(h, LDEQ_ERR_UNSUPPORTED, "mlp: layer widths 1..1024 supported");
+        net->dims[l] = dims[l];
+        if (dims[l] > mw) mw = dims[l];
+    }
+    for (int l = 0; l < n_layers; ++l) {
+        net->w_off[l] = off; off += dims[l] * dims[l + 1];
+        net->b_off[l] = off; off += dims[l + 1];
+    }
+    net->n_params = off;
+    net->max_width = mw;
+    return LDEQ_OK;
+}
+
+static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+template <class S, int TB, bool GLOBAL>
+static int launch_mlp_fwd(ldeq_handle* h, const MlpNet& net, const void* P, const void* z0, const double* tg, int B, int T,
+                          const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr, MlpTapeView<S> tv,
+                          double* partials, int grid, cudaStream_t s) {
+    const size_t smem = fwd_smem<S, TB>(net);
+    auto kern = mlp_fwd_kernel<S, TB, GLOBAL>;
+    LDEQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MlpNet netv = net;
+    const S* Pp = (const S*)P;
+    const S* zp = (const S*)z0;
+    S* tp = (S*)traj;
+    KOpts kov = ko;
+    void* args[] = {&netv, &Pp, &zp, &tg, &B, &T, &kov, &tp, &ret, &na, &nr, &tv, &partials};
+    if (GLOBAL) {
+        LDEQ_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(MLP_THREADS), args, smem, s));
+    } else {
+        LDEQ_CUDA(cudaLaunchKernel((void*)kern, dim3(grid), dim3(MLP_THREADS), args, smem, s));
+    }
+    h->launches += 1;
+    return LDEQ_OK;
+}
+
+template <class S>
+static int mlp_fwd_dispatch(ldeq_handle* h, const MlpNet& net, const void* P, const void* z0, const double* tg, int B, int T,
+                            const KOpts& ko, int norm_mode, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
+                            ldeq_mlp_tape* tape, cudaStream_t s) {
+    MlpTapeView<S> tv{nullptr, nullptr, nullptr, 0};
+    if (tape) tv = MlpTapeView<S>{tape->t, tape->dt, (S*)tape->u, tape->cap};
+    // reduction scratch for the grid sums
+    int rc = ensure_scratch(h, 0, sizeof(double) * 4096);
+    if (rc) return rc;
+    double* partials = (double*)h->scratch[0];
+    const int sms = h->sm_count;
+    if (norm_mode == LDEQ_NORM_GLOBAL) {
+        // one tile per CTA, all CTAs co-resident (cooperative launch): pick the smallest tile that fits the chip
+        auto fits = [&](int tb, size_t smem, const void* fn) -> int {
+            int per_sm = 0;
+            cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, MLP_THREADS, smem);
+            return per_sm * sms >= (B + tb - 1) / tb;
+        };
+        if (fits(2, fwd_smem<S, 2>(net), (const void*)mlp_fwd_kernel<S, 2, true>))
+            return launch_mlp_fwd<S, 2, true>(h, net, P, z0, tg, B, T, ko, traj, ret, na, nr, tv, partials, (B + 1) / 2, s);
+        if (fits(8, fwd_smem<S, 8>(net), (const void*)mlp_fwd_kernel<S, 8, true>))
+            return launch_mlp_fwd<S, 8, true>(h, net, P, z0, tg, B, T, ko, traj, ret, na, nr, tv, partials, (B + 7) / 8, s);
+        if (fits(32, fwd_smem<S, 32>(net), (const void*)mlp_fwd_kernel<S, 32, true>))
+            return launch_mlp_fwd<S, 32, true>(h, net, P, z0, tg, B, T, ko, traj, ret, na, nr, tv, partials, (B + 31) / 32, s);
+        return set_err(h, LDEQ_ERR_UNSUPPORTED,
+                       "mlp: batch too large for the global-norm mode of the exact path (all tiles must be co-resident); "
+                       "use LDEQ_NORM_PER_TRAJ");
+    }
+    if (B <= 2 * sms * 2) {
+        const int tiles = (B + 1) / 2;
+        return launch_mlp_fwd<S, 2, false>(h, net, P, z0, tg, B, T, ko, traj, ret, na, nr, tv, partials, tiles, s);
+    }
+    const int tiles = (B + 7) / 8;
+    const int grid = tiles < 4 * sms ? tiles : 4 * sms;
+    return launch_mlp_fwd<S, 8, false>(h, net, P, z0, tg, B, T, ko, traj, ret, na, nr, tv, partials, grid, s);
+}
+
 extern "C" {
-int ldeq_mlp_solve_fwd(ldeq_handle* h, int, const void*, const void*, const int32_t*, int, const double*, int, int,
-                       const ldeq_opts*, void*, int32_t*, int32_t*, int32_t*, ldeq_mlp_tape**, ldeq_stream) {
-    return set_err(h, LDEQ_ERR_UNSUPPORTED, "ldeq_mlp_solve_fwd: not built yet");
+
+int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* params_flat, const int32_t* layer_dims_host,
+                       int n_layers, const double* t_host, int B, int T, const ldeq_opts* opts, void* traj_out,
+                       int32_t* retcode, int32_t* naccept, int32_t* nreject, ldeq_mlp_tape** tape_out,
+                       ldeq_stream stream) {
+    if (!h) return LDEQ_ERR_INVALID;
+    if (tape_out) *tape_out = nullptr;
+    if (!z0 || !params_flat || !layer_dims_host || !t_host || !opts || !traj_out) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    if (B < 1 || T < 1) return set_err(h, LDEQ_ERR_INVALID, "B and T must be >= 1");
+    if (dtype != LDEQ_F32 && dtype != LDEQ_F64) return set_err(h, LDEQ_ERR_INVALID, "dtype");
+    if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
+    for (int k = 1; k < T; ++k)
+        if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
+    if (opts->mlp_math != LDEQ_MLP_MATH_FP32) return set_err(h, LDEQ_ERR_UNSUPPORTED, "mlp_math: only the exact FP32/FP64 path is built");
+    MlpNet net;
+    int rc = make_net(h, layer_dims_host, n_layers, &net);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    if ((rc = upload_tgrid(h, t_host, T, s))) return rc;
+    KOpts ko = to_kopts(opts);
+    const size_t es = dtype == LDEQ_F32 ? 4 : 8;
+    const int D = net.dims[0];
+    ldeq_mlp_tape* tape = nullptr;
+    if (tape_out) {
+        tape = new ldeq_mlp_tape();
+        tape->dtype = dtype; tape->B = B; tape->T = T; tape->net = net;
+        long long cap = opts->tape_steps;
+        if (cap <= 0) cap = opts->adaptive ? (4LL * T > 256 ? 4LL * T : 256) : (long long)((t_host[T - 1] - t_host[0]) / opts->dt) + 3;
+        if (cap > opts->maxiters) cap = opts->maxiters;
+        tape->cap = (int)cap;
+        const size_t nB = B, c = (size_t)cap;
+        size_t off = 0;
+        const size_t o_t = off; off += al256(c * nB * 8);
+        const size_t o_dt = off; off += al256(c * nB * 8);
+        const size_t o_u = off; off += al256(c * nB * D * es);
+        const size_t o_p = off; off += al256((size_t)net.n_params * es);
+        const size_t o_pt = off; off += al256((size_t)net.n_params * es);
+        const size_t o_tg = off; off += al256((size_t)T * 8);
+        const size_t o_r = off; off += al256(nB * 4);
+        const size_t o_na = off; off += al256(nB * 4);
+        const size_t o_nr = off; off += al256(nB * 4);
+        cudaError_t e = cudaMallocAsync(&tape->base, off, s);
+        if (e != cudaSuccess) { delete tape; return set_err(h, LDEQ_ERR_NOMEM, "cudaMallocAsync(mlp tape)", e); }
+        char* bp = (char*)tape->base;
+        tape->t = (double*)(bp + o_t); tape->dt = (double*)(bp + o_dt); tape->u = bp + o_u; tape->params = bp + o_p;
+        tape->params_t = bp + o_pt; tape->tgrid = (double*)(bp + o_tg); tape->retcode = (int32_t*)(bp + o_r);
+        tape->naccept = (int32_t*)(bp + o_na); tape->nreject = (int32_t*)(bp + o_nr);
+        cudaMemcpyAsync(tape->params, params_flat, (size_t)net.n_params * es, cudaMemcpyDeviceToDevice, s);
+        cudaMemcpyAsync(tape->tgrid, h->d_tgrid, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);
+    }
+    int32_t* d_ret = tape ? tape->retcode : retcode;
+    int32_t* d_na = tape ? tape->naccept : naccept;
+    int32_t* d_nr = tape ? tape->nreject : nreject;
+    if (dtype == LDEQ_F32)
+        rc = mlp_fwd_dispatch<float>(h, net, params_flat, z0, h->d_tgrid, B, T, ko, opts->norm_mode, traj_out, d_ret, d_na, d_nr, tape, s);
+    else
+        rc = mlp_fwd_dispatch<double>(h, net, params_flat, z0, h->d_tgrid, B, T, ko, opts->norm_mode, traj_out, d_ret, d_na, d_nr, tape, s);
+    if (rc) {
+        if (tape) { cudaFreeAsync(tape->base, s); delete tape; }
+        return rc;
+    }
+    if (tape) {
+        if (retcode) cudaMemcpyAsync(retcode, tape->retcode, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
+        if (naccept) cudaMemcpyAsync(naccept, tape->naccept, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
+        if (nreject) cudaMemcpyAsync(nreject, tape->nreject, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
+        *tape_out = tape;
+    }
+    return LDEQ_OK;
 }
-int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape*, const void*, void*, void*, ldeq_stream) {
-    return set_err(h, LDEQ_ERR_UNSUPPORTED, "ldeq_mlp_solve_bwd: not built yet");
+
+}  // extern "C"
+
+template <class S, int TB>
+static int launch_mlp_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0, void* dparams, cudaStream_t s) {
+    const MlpNet& net = tape->net;
+    const int B = tape->B;
+    const int tiles = (B + TB - 1) / TB;
+    const int grid = tiles < 2 * h->sm_count ? tiles : 2 * h->sm_count;
+    int rc = ensure_scratch(h, 1, (size_t)grid * net.n_params * sizeof(S));
+    if (rc) return rc;
+    mlp_transpose_kernel<S><<<64, 256, 0, s>>>(net, (const S*)tape->params, (S*)tape->params_t);
+    // biases are not used from the transposed copy
+    const size_t smem = bwd_smem<S, TB>(net);
+    LDEQ_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<S, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MlpTapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->cap};
+    mlp_bwd_kernel<S, TB><<<grid, MLP_THREADS, smem, s>>>(net, (const S*)tape->params, (const S*)tape->params_t, tape->tgrid,
+                                                          B, tape->T, (const S*)dtraj, tv, tape->retcode, tape->naccept,
+                                                          (S*)dz0, (S*)h->scratch[1]);
+    LDEQ_CUDA(cudaGetLastError());
+    mlp_reduce_grads_kernel<S><<<(net.n_params + 255) / 256, 256, 0, s>>>((const S*)h->scratch[1], grid, net.n_params, (S*)dparams);
+    LDEQ_CUDA(cudaGetLastError());
+    h->launches += 3;
+    return LDEQ_OK;
 }
-void ldeq_mlp_tape_free(ldeq_handle*, ldeq_mlp_tape*, ldeq_stream) {}
+
+extern "C" {
+
+int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0, void* dparams_flat,
+                       ldeq_stream stream) {
+    if (!h) return LDEQ_ERR_INVALID;
+    if (!tape || !dtraj || !dz0 || !dparams_flat) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    const bool small = tape->B <= 4 * h->sm_count;
+    if (tape->dtype == LDEQ_F32)
+        return small ? launch_mlp_bwd<float, 2>(h, tape, dtraj, dz0, dparams_flat, s)
+                     : launch_mlp_bwd<float, 8>(h, tape, dtraj, dz0, dparams_flat, s);
+    return small ? launch_mlp_bwd<double, 2>(h, tape, dtraj, dz0, dparams_flat, s)
+                 : launch_mlp_bwd<double, 8>(h, tape, dtraj, dz0, dparams_flat, s);
 }
+
+void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream) {
+    if (!tape) return;
+    if (h) cudaSetDevice(h->device);
+    if (tape->base) cudaFreeAsync(tape->base, (cudaStream_t)stream);
+    delete tape;
+}
+
+}  // extern "C"

@@ -198,3 +198,171 @@ def goku_bwd_host(tape: _Tape, dtraj: torch.Tensor, dz0: torch.Tensor | None = N
     with torch.cuda.device(h.device):
         h.check(h._lib.ldeq_solve_bwd_host(h.ptr, tape.ptr, _p(dtraj), _p(dz0), _p(dtheta), _stream()))
     return dz0, dtheta
+
+
+# ---- LatentODE path: one solve on the (D,B) matrix state with an MLP right-hand side ---------------
+def mlp_solve_raw(z0: torch.Tensor, params_flat: torch.Tensor, dims: Sequence[int], t, opts: _cabi.Opts | None = None,
+                  want_tape: bool = False):
+    """One call of ``ldeq_mlp_solve_fwd`` (reference ``src/models/LatentODE.jl:61-78``).
+
+    ``z0`` is ``[B, D]``; ``params_flat`` is ``Flux.destructure`` order; ``dims = [D, H1, ..., D]``.
+    Returns ``(traj[T,B,D], stats, tape_or_None)``."""
+    if not z0.is_cuda:
+        raise RuntimeError("mlp_solve_raw needs CUDA tensors (there is no CPU implementation of the hot path)")
+    h = _cabi.handle(z0.device.index or 0)
+    opts = opts or _cabi.default_opts()
+    z0 = z0.contiguous()
+    params_flat = params_flat.to(z0.dtype).contiguous()
+    tg = _tgrid(t)
+    B, D = z0.shape
+    T = tg.shape[0]
+    dims_a = np.ascontiguousarray(np.asarray(dims, dtype=np.int32))
+    assert dims_a[0] == D and dims_a[-1] == D
+    traj = torch.empty((T, B, D), dtype=z0.dtype, device=z0.device)
+    ret = torch.empty(B, dtype=torch.int32, device=z0.device)
+    na = torch.empty(B, dtype=torch.int32, device=z0.device)
+    nr = torch.empty(B, dtype=torch.int32, device=z0.device)
+    tape = C.c_void_p()
+    with torch.cuda.device(z0.device):
+        h.check(h._lib.ldeq_mlp_solve_fwd(h.ptr, _dtype_code(z0.dtype), _p(z0), _p(params_flat),
+                                          dims_a.ctypes.data_as(C.c_void_p), len(dims_a) - 1,
+                                          tg.ctypes.data_as(C.c_void_p), B, T, C.byref(opts), _p(traj), _p(ret), _p(na),
+                                          _p(nr), C.byref(tape) if want_tape else None, _stream()))
+    tp = None
+    if want_tape:
+        tp = _Tape(h, tape, mlp=True)
+        tp.n_params = int(params_flat.numel())
+    return traj, SolveStats(ret, na, nr), tp
+
+
+def mlp_bwd_raw(tape: _Tape, dtraj: torch.Tensor):
+    """One call of ``ldeq_mlp_solve_bwd``: ``dtraj[T,B,D] -> (dz0[B,D], dparams_flat)``."""
+    h = tape.h
+    dtraj = dtraj.contiguous()
+    T, B, D = dtraj.shape
+    dz0 = torch.empty((B, D), dtype=dtraj.dtype, device=dtraj.device)
+    dp = torch.empty(tape.n_params, dtype=dtraj.dtype, device=dtraj.device)
+    with torch.cuda.device(dtraj.device):
+        h.check(h._lib.ldeq_mlp_solve_bwd(h.ptr, tape.ptr, _p(dtraj), _p(dz0), _p(dp), _stream()))
+    return dz0, dp
+
+
+class _MlpSolve(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z0, params_flat, tg, dims, opts, stats_out):
+        need = z0.requires_grad or params_flat.requires_grad
+        traj, stats, tape = mlp_solve_raw(z0, params_flat, dims, tg, opts, want_tape=need)
+        ctx.tape = tape
+        if stats_out is not None:
+            stats_out.append(stats)
+        return traj
+
+    @staticmethod
+    def backward(ctx, dtraj):
+        tape = ctx.tape
+        if tape is None:
+            return None, None, None, None, None, None
+        dz0, dp = mlp_bwd_raw(tape, dtraj)
+        tape.free()
+        ctx.tape = None
+        return dz0, dp, None, None, None, None
+
+
+def mlp_solve(z0, params_flat, dims, t, opts: _cabi.Opts | None = None, stats_out: list | None = None):
+    """Differentiable LatentODE solve: the body of ``diffeq_layer(::Decoder{LatentODE}, z0, t)``."""
+    return _MlpSolve.apply(z0, params_flat, _tgrid(t), list(dims), opts, stats_out)
+
+
+# ---- reparameterised sample, ELBO, AdamW ------------------------------------------------------------
+def sample_raw(mu: torch.Tensor, logvar: torch.Tensor, seed: int, offset: int = 0, want_eps: bool = True):
+    """``ldeq_sample``: ``z = mu + eps * exp(logvar/2)``, ``eps ~ N(0,1)`` drawn on the device (Philox4x32-10)."""
+    h = _cabi.handle(mu.device.index or 0)
+    mu = mu.contiguous().float()
+    logvar = logvar.contiguous().float()
+    z = torch.empty_like(mu)
+    eps = torch.empty_like(mu) if want_eps else None
+    with torch.cuda.device(mu.device):
+        h.check(h._lib.ldeq_sample(h.ptr, _p(mu), _p(logvar), _p(z), _p(eps), mu.numel(), C.c_uint64(seed & (2**64 - 1)),
+                                   C.c_uint64(offset & (2**64 - 1)), _stream()))
+    return z, eps
+
+
+class _Sample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mu, logvar, seed, offset):
+        z, eps = sample_raw(mu, logvar, seed, offset)
+        ctx.save_for_backward(eps, logvar)
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        eps, logvar = ctx.saved_tensors
+        return dz, dz * eps * torch.exp(logvar * 0.5) * 0.5, None, None
+
+
+def sample_reparam(mu, logvar, seed: int, offset: int = 0):
+    """Differentiable reparameterised sample (reference ``src/models/GOKU.jl:155-173``)."""
+    return _Sample.apply(mu, logvar, int(seed), int(offset))
+
+
+def elbo_raw(x: torch.Tensor, xhat: torch.Tensor, mus, logvars, beta: float, want_grad: bool = True,
+             grad_scale: float = 1.0):
+    """``ldeq_elbo_fwd_bwd``: ``x, xhat`` are ``[T, B, P]``; ``mus/logvars`` lists of ``[B, d_h]`` heads.
+    Returns ``(loss3 = [total, reconstruction, kl], dxhat, dmus, dlogvars)``."""
+    h = _cabi.handle(x.device.index or 0)
+    x = x.contiguous().float()
+    xhat = xhat.contiguous().float()
+    T, B, P = x.shape
+    mus = [m.contiguous().float() for m in mus]
+    logvars = [l.contiguous().float() for l in logvars]
+    nh = len(mus)
+    loss = torch.empty(3, dtype=torch.float32, device=x.device)
+    dxhat = torch.empty_like(xhat) if want_grad else None
+    dmus = [torch.empty_like(m) for m in mus] if want_grad else None
+    dlvs = [torch.empty_like(l) for l in logvars] if want_grad else None
+    PA = C.c_void_p * max(nh, 1)
+    mu_a = PA(*[m.data_ptr() for m in mus])
+    lv_a = PA(*[l.data_ptr() for l in logvars])
+    dmu_a = PA(*[m.data_ptr() for m in dmus]) if want_grad else None
+    dlv_a = PA(*[l.data_ptr() for l in dlvs]) if want_grad else None
+    hd = (C.c_int32 * max(nh, 1))(*[m.shape[1] for m in mus])
+    with torch.cuda.device(x.device):
+        h.check(h._lib.ldeq_elbo_fwd_bwd(h.ptr, _p(x), _p(xhat), mu_a, lv_a, hd, nh, C.c_float(beta), B, T, P,
+                                         C.c_float(grad_scale), _p(loss), _p(dxhat), dmu_a, dlv_a, _stream()))
+    return loss, dxhat, dmus, dlvs
+
+
+class _Elbo(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, xhat, beta, nh, *heads):
+        mus, lvs = list(heads[:nh]), list(heads[nh:])
+        loss, dxhat, dmus, dlvs = elbo_raw(x, xhat, mus, lvs, beta, want_grad=True)
+        ctx.save_for_backward(dxhat, *dmus, *dlvs)
+        ctx.nh = nh
+        ctx.parts = loss
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        dxhat, rest = saved[0], saved[1:]
+        return (None, g * dxhat, None, None, *[g * r for r in rest])
+
+
+def elbo_loss(x, xhat, mu, logvar, beta: float):
+    """``loss_batch``'s reduction (reference ``examples/pendulum_friction-less/model_train.jl:225-238``):
+    ``sum(mean((x - xhat)^2, dims=(2,3))) + beta * vector_kl(mu, logvar)`` as one fused forward+gradient pass."""
+    mus = list(mu) if isinstance(mu, (tuple, list)) else [mu]
+    lvs = list(logvar) if isinstance(logvar, (tuple, list)) else [logvar]
+    return _Elbo.apply(x, xhat, float(beta), len(mus), *mus, *lvs)
+
+
+def adamw_step(params: torch.Tensor, grads: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr=1e-3,
+               betas=(0.9, 0.999), eps=1e-8, decay=1e-3, grad_scale: float = 1.0):
+    """``ldeq_adamw_step`` on flat fp32 buffers: Flux ``ADAMW(eta, beta, decay)`` semantics (model_train.jl:138)."""
+    h = _cabi.handle(params.device.index or 0)
+    assert params.is_contiguous() and grads.is_contiguous() and m.is_contiguous() and v.is_contiguous()
+    with torch.cuda.device(params.device):
+        h.check(h._lib.ldeq_adamw_step(h.ptr, _p(params), _p(grads), _p(m), _p(v), params.numel(), float(lr),
+                                       float(betas[0]), float(betas[1]), float(eps), C.c_float(decay), int(step),
+                                       C.c_float(grad_scale), _stream()))

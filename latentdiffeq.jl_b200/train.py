@@ -1,0 +1,102 @@
+"""The training step of the reference's example script on the CUDA path.
+
+``loss_batch`` (``examples/pendulum_friction-less/model_train.jl:225-238``), the gradient step
+``Flux.pullback`` + ``update!(ADAMW(...))`` (``model_train.jl:138,195-201``) and, for several GPUs of
+one box, the data-parallel layout the north star asks for: every rank integrates its own slice of
+the batch, the parameter gradient lives in ONE flat fp32 bucket that is all-reduced once per step
+over NCCL, then every rank applies the same fused AdamW.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .solve import adamw_step, elbo_loss
+
+
+def loss_batch(model, x, t, beta, variational):
+    """model_train.jl:225-238.  ``x`` is ``[T, B, P]``."""
+    X_hat, mu, logvar = model(x, t, variational)
+    x_hat, z_hat, l_hat = X_hat
+    if x.is_cuda:
+        return elbo_loss(x, x_hat, mu, logvar, beta)
+    from .utils import vector_kl
+    rec = ((x - x_hat) ** 2).mean(dim=(0, 1)).sum()
+    return rec + beta * vector_kl(mu, logvar)
+
+
+def shard_bounds(n: int, rank: int, world: int):
+    """Contiguous batch slice of ``rank``: trajectories are independent (GOKU.jl:111), so the batch is
+    simply cut into ``world`` pieces; remainders go to the first ranks."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class FlatParams:
+    """All trainable parameters of a model viewed through ONE contiguous fp32 buffer (and one gradient
+    buffer): a single all-reduce and a single fused AdamW launch per step."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.params = [p for p in module.parameters() if p.requires_grad]
+        n = sum(p.numel() for p in self.params)
+        n_pad = (n + 3) // 4 * 4
+        dev = self.params[0].device
+        self.n = n
+        self.flat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            self.flat[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat[off:off + k].view_as(p)
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+
+    def zero_grad(self):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:  # autograd may have replaced .grad
+            k = p.numel()
+            p.grad = self.grad[off:off + k].view_as(p)
+            off += k
+
+
+class ADAMW:
+    """``ADAMW(eta, (b1, b2), decay)`` of the reference (model_train.jl:138) on a :class:`FlatParams`."""
+
+    def __init__(self, flat: FlatParams, eta=1e-3, beta=(0.9, 0.999), decay=1e-3, eps=1e-8):
+        self.flat, self.eta, self.beta, self.decay, self.eps = flat, eta, beta, decay, eps
+        self.step_count = 0
+
+    def step(self, grad_scale: float = 1.0):
+        self.step_count += 1
+        f = self.flat
+        if f.flat.is_cuda:
+            adamw_step(f.flat, f.grad, f.m, f.v, self.step_count, self.eta, self.beta, self.eps, self.decay, grad_scale)
+        else:
+            raise RuntimeError("the optimiser step runs in libldeq.so on a CUDA device (no CPU fallback)")
+
+
+def allreduce_grads(flat: FlatParams):
+    """One sum all-reduce of the flat gradient bucket (NCCL over NVLink on the GPU box, gloo in the CPU tests)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
+
+
+def train_step(model, flat: FlatParams, opt: ADAMW, x_local, t, beta, variational=True, global_batch=None):
+    """One data-parallel training step on this rank's slice ``x_local`` ``[T, B_local, P]``.
+
+    The loss is a mean over the GLOBAL batch: the local loss is scaled by ``B_local / B_global`` before the
+    backward pass, gradients are summed across ranks, and every rank applies the same AdamW update."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    B_local = x_local.shape[1]
+    B_global = global_batch or B_local * world
+    flat.zero_grad()
+    loss = loss_batch(model, x_local, t, beta, variational)
+    (loss * (B_local / B_global)).backward()
+    allreduce_grads(flat)
+    opt.step()
+    return loss.detach()
