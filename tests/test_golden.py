@@ -1,0 +1,86 @@
+"""Frozen golden vectors (tests/golden/*.npz, made by tests/golden/make_golden.py from the oracle).
+CPU tier: the oracle still reproduces them.  GPU tier: the CUDA path matches them through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import goku as og
+from oracle import mlp as om
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _load(name):
+    return np.load(os.path.join(G, name))
+
+
+def test_oracle_reproduces_goku_golden():
+    g = _load("c1_goku_pendulum_f32.npz")
+    tr, ret, na, nr = og.solve(og.PENDULUM, g["z0"], g["theta"], g["t"])
+    assert np.array_equal(na, g["naccept_adaptive"]) and np.allclose(tr, g["traj_adaptive"], rtol=0, atol=1e-6)
+    tr, ret, na, nr = og.solve(og.PENDULUM, g["z0"], g["theta"], g["t"], og.Opts(adaptive=False, dt=0.05))
+    assert np.array_equal(na, g["naccept_fixed"]) and np.allclose(tr, g["traj_fixed"], rtol=0, atol=1e-6)
+    gz, gp = og.grad(og.PENDULUM, g["z0"], g["theta"], g["t"], g["dtraj"], og.Opts(adaptive=False, dt=0.05))
+    assert np.allclose(gz, g["dz0_fixed"], rtol=1e-5, atol=1e-5) and np.allclose(gp, g["dtheta_fixed"], rtol=1e-5, atol=1e-5)
+    g = _load("c3_goku_friction.npz")
+    tr, _, na, _ = og.solve(og.PENDULUM_FRICTION, g["z0"], g["theta"], g["t"])
+    assert np.array_equal(na, g["naccept_f64"]) and np.allclose(tr, g["traj_f64"], rtol=0, atol=1e-12)
+
+
+def test_oracle_reproduces_latentode_golden():
+    g = _load("c2_latentode_mlp.npz")
+    dims = g["dims"].tolist()
+    tr, na, nr, _ = om.solve(g["z0"], g["params"], dims, g["t"])
+    assert na == int(g["naccept_f32"]) and np.allclose(tr, g["traj_f32_adaptive_global"], rtol=0, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_goku_golden(ldeq):
+    dev = "cuda:0"
+    g = _load("c1_goku_pendulum_f32.npz")
+    z = torch.from_numpy(g["z0"]).to(dev).requires_grad_(True)
+    p = torch.from_numpy(g["theta"]).to(dev).requires_grad_(True)
+    st = []
+    tr = ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM, ldeq.default_opts(adaptive=False, dt=0.05), st)
+    tr.backward(torch.from_numpy(g["dtraj"]).to(dev))
+    assert np.array_equal(st[0].naccept.cpu().numpy(), g["naccept_fixed"])            # identical accepted-step counts
+    assert np.abs(tr.detach().cpu().numpy() - g["traj_fixed"]).max() <= 1e-5 * np.abs(g["traj_fixed"]).max()
+    assert np.abs(z.grad.cpu().numpy() - g["dz0_fixed"]).max() <= 1e-4 * np.abs(g["dz0_fixed"]).max()
+    assert np.abs(p.grad.cpu().numpy() - g["dtheta_fixed"]).max() <= 1e-4 * np.abs(g["dtheta_fixed"]).max()
+    tr, stt, _ = ldeq.goku_solve_raw(z.detach(), p.detach(), g["t"], ldeq.RHS_PENDULUM)
+    assert np.abs(tr.cpu().numpy() - g["traj_adaptive"]).max() <= 1e-3 * np.abs(g["traj_adaptive"]).max()
+    # adaptive gradients vs the reference's ForwardDiff semantics: agreement at the solver tolerance
+    z.grad = None
+    p.grad = None
+    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM).backward(torch.from_numpy(g["dtraj"]).to(dev))
+    assert np.abs(z.grad.cpu().numpy() - g["dz0_adaptive_fwddiff"]).max() <= 2e-2 * np.abs(g["dz0_adaptive_fwddiff"]).max()
+    g = _load("c3_goku_friction.npz")
+    for dt, key, rtol in ((torch.float64, "traj_f64", 1e-5), (torch.float32, "traj_f32", 1e-3)):
+        tr, stt, _ = ldeq.goku_solve_raw(torch.from_numpy(g["z0"]).to(dev, dt), torch.from_numpy(g["theta"]).to(dev, dt),
+                                         g["t"], ldeq.RHS_PENDULUM_FRICTION)
+        assert np.abs(tr.cpu().numpy() - g[key]).max() <= rtol * np.abs(g[key]).max()
+    z = torch.from_numpy(g["z0"]).to(dev).requires_grad_(True)
+    p = torch.from_numpy(g["theta"]).to(dev).requires_grad_(True)
+    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM_FRICTION).backward(torch.from_numpy(g["dtraj"]).to(dev))
+    assert np.abs(z.grad.cpu().numpy() - g["dz0_f64_frozen"]).max() <= 1e-4 * np.abs(g["dz0_f64_frozen"]).max()
+    assert np.abs(p.grad.cpu().numpy() - g["dtheta_f64_frozen"]).max() <= 1e-4 * np.abs(g["dtheta_f64_frozen"]).max()
+
+
+@pytest.mark.gpu
+def test_cuda_matches_latentode_golden(ldeq):
+    dev = "cuda:0"
+    g = _load("c2_latentode_mlp.npz")
+    dims = g["dims"].tolist()
+    tr, st, _ = ldeq.mlp_solve_raw(torch.from_numpy(g["z0"]).to(dev), torch.from_numpy(g["params"]).to(dev), dims, g["t"])
+    assert (st.naccept.cpu().numpy() == int(g["naccept_f32"])).all()
+    ref = g["traj_f32_adaptive_global"]
+    assert np.abs(tr.cpu().numpy() - ref).max() <= 1e-3 * np.abs(ref).max()
+    z = torch.from_numpy(g["z0"]).to(dev).double().requires_grad_(True)
+    p = torch.from_numpy(g["params"]).to(dev).double().requires_grad_(True)
+    tr = ldeq.mlp_solve(z, p, dims, g["t"], ldeq.default_opts(adaptive=False, dt=0.05))
+    tr.backward(torch.from_numpy(g["dtraj"]).to(dev))
+    assert np.abs(tr.detach().cpu().numpy() - g["traj_f64_fixed"]).max() <= 1e-11 * np.abs(g["traj_f64_fixed"]).max()
+    assert np.abs(z.grad.cpu().numpy() - g["dz0_f64_fixed"]).max() <= 1e-9 * np.abs(g["dz0_f64_fixed"]).max()
+    assert np.abs(p.grad.cpu().numpy() - g["dparams_f64_fixed"]).max() <= 1e-6 * np.abs(g["dparams_f64_fixed"]).max()
