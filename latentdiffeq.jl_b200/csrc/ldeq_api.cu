@@ -92,6 +92,41 @@ static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, void* dz
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// shared memory of one CTA for a state of z_dim elements of `es` bytes: per-lane ring + staged time grid
+static size_t ring_smem(int z_dim, size_t es, int threads, int T) {
+    int rows = LDEQ_RING_BYTES / (z_dim * (int)es);
+    rows = rows >= 64 ? 64 : rows >= 32 ? 32 : rows >= 16 ? 16 : rows >= 8 ? 8 : 4;
+    return (size_t)rows * threads * z_dim * es + (T <= LDEQ_TGRID_SMEM_MAX ? (size_t)T * sizeof(double) : 0);
+}
+
+// kernels of an NVRTC-compiled user right-hand side (ldeq_user_rhs.cu): fn[] = {fwd f32, fwd f32 tape, fwd f64,
+// fwd f64 tape, bwd f32, bwd f64}; same signatures as the built-in instantiations
+static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg,
+                                   int B, int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
+                                   const ldeq_tape* tape, cudaStream_t s) {
+    TapeView<float> tv{nullptr, nullptr, nullptr, nullptr, 0};  // identical layout for float and double
+    if (tape) tv = TapeView<float>{tape->t, tape->dt, (float*)tape->u, tape->info, tape->cap};
+    KOpts kov = ko;
+    void* args[] = {&z0, &theta, &tg, &B, &T, &kov, &traj, &ret, &na, &nr, &tv};
+    const int grid = (B + LDEQ_FWD_THREADS - 1) / LDEQ_FWD_THREADS;
+    const size_t es = dtype == LDEQ_F32 ? 4 : 8;
+    void* fn = rhs->fn[(dtype == LDEQ_F32 ? 0 : 2) + (tape ? 1 : 0)];
+    return cudaLaunchKernel(fn, dim3(grid), dim3(LDEQ_FWD_THREADS), args, ring_smem(rhs->z_dim, es, LDEQ_FWD_THREADS, T), s);
+}
+static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
+    TapeView<float> tv{tape->t, tape->dt, (float*)tape->u, tape->info, tape->cap};
+    const void* theta = tape->theta;
+    const double* tg = tape->tgrid;
+    int B = tape->B, T = tape->T;
+    const int32_t* ret = tape->retcode;
+    const int32_t* na = tape->naccept;
+    void* args[] = {&theta, &tg, &B, &T, &dtraj, &tv, &ret, &na, &dz0, &dtheta};
+    const int grid = (B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
+    const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
+    void* fn = tape->rhs->fn[tape->dtype == LDEQ_F32 ? 4 : 5];
+    return cudaLaunchKernel(fn, dim3(grid), dim3(LDEQ_BWD_THREADS), args, ring_smem(tape->z_dim, es, LDEQ_BWD_THREADS, T), s);
+}
+
 static bool slot_get(ldeq_handle* h, ldeq_tape* tape) {
     if (h->free_slots.empty()) {
         const int n = 64;
@@ -146,9 +181,11 @@ static int tape_alloc(ldeq_handle* h, ldeq_tape* tape, int cap, cudaStream_t s) 
     return LDEQ_OK;
 }
 
-static cudaError_t dispatch_fwd(int dtype, bool friction, const void* z0, const void* theta, const double* tg, int B,
+static cudaError_t dispatch_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg, int B,
                                 int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
                                 const ldeq_tape* tape, cudaStream_t s) {
+    if (rhs->kind < 0) return launch_user_fwd(rhs, dtype, z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s);
+    const bool friction = rhs->kind == LDEQ_RHS_PENDULUM_FRICTION;
 #define LDEQ_DISPATCH_FWD(S)                                                                              \
     (tape ? (friction ? launch_fwd<S, true, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s)    \
                       : launch_fwd<S, false, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s))  \
@@ -174,7 +211,7 @@ static int tape_heal(ldeq_handle* h, ldeq_tape* tape, cudaStream_t s) {
     cudaMemcpyAsync(tape->theta, old.theta, (size_t)tape->B * tape->p_dim * es, cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(tape->tgrid, old.tgrid, (size_t)tape->T * 8, cudaMemcpyDeviceToDevice, s);
     // step 0 of the old tape holds u0 for every trajectory (capacity is always >= 1)
-    cudaError_t e = dispatch_fwd(tape->dtype, tape->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION, old.u, tape->theta,
+    cudaError_t e = dispatch_fwd(tape->rhs, tape->dtype, old.u, tape->theta,
                                  tape->tgrid, tape->B, tape->T, tape->kopts, nullptr, tape->retcode, tape->naccept,
                                  tape->nreject, tape, s);
     h->launches += 1;
@@ -266,7 +303,6 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
     if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
     for (int k = 1; k < T; ++k)
         if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
-    if (rhs->kind < 0) return set_err(h, LDEQ_ERR_UNSUPPORTED, "user rhs goes through ldeq_rhs_from_source path");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
     if (B == 0) return LDEQ_OK;
@@ -306,8 +342,7 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
     int32_t* d_ret = tape ? tape->retcode : retcode;
     int32_t* d_na = tape ? tape->naccept : naccept;
     int32_t* d_nr = tape ? tape->nreject : nreject;
-    const bool fr = rhs->kind == LDEQ_RHS_PENDULUM_FRICTION;
-    cudaError_t e = dispatch_fwd(dtype, fr, z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s);
+    cudaError_t e = dispatch_fwd(rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s);
     h->launches += 1;
     if (e != cudaSuccess) {
         if (tape) { cudaFreeAsync(tape->base, s); cudaEventRecord(tape->ready, s); slot_put(h, tape); delete tape; }
@@ -333,7 +368,9 @@ int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0
     if (rc) return rc;
     const bool fr = tape->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION;
     cudaError_t e;
-    if (tape->dtype == LDEQ_F32)
+    if (tape->rhs_kind < 0)
+        e = launch_user_bwd(tape, dtraj, dz0, dtheta, s);
+    else if (tape->dtype == LDEQ_F32)
         e = fr ? launch_bwd<float, true>(tape, dtraj, dz0, dtheta, s) : launch_bwd<float, false>(tape, dtraj, dz0, dtheta, s);
     else
         e = fr ? launch_bwd<double, true>(tape, dtraj, dz0, dtheta, s) : launch_bwd<double, false>(tape, dtraj, dz0, dtheta, s);

@@ -6,8 +6,13 @@
 // has at reference src/models/GOKU.jl:121.
 #pragma once
 
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+// NVRTC (user-defined right-hand sides are compiled at run time): no host headers
+typedef unsigned int uint32_t;
+#endif
 
 namespace ldeq {
 

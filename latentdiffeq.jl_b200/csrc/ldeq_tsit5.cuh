@@ -223,8 +223,8 @@ __device__ __forceinline__ TGrid stage_tgrid(const double* __restrict__ tg, int 
 #define LDEQ_RING_BYTES 256
 #endif
 template <class S, int ZD> struct Ring {
-    static constexpr int R = LDEQ_RING_BYTES / (ZD * (int)sizeof(S)) >= 4 ? LDEQ_RING_BYTES / (ZD * (int)sizeof(S)) : 4;
-    static_assert((R & (R - 1)) == 0, "ring rows must be a power of two");
+    static constexpr int floor_pow2(int x) { return x >= 64 ? 64 : x >= 32 ? 32 : x >= 16 ? 16 : x >= 8 ? 8 : 4; }
+    static constexpr int R = floor_pow2(LDEQ_RING_BYTES / (ZD * (int)sizeof(S)));
     S* col;      // this lane's column
     int stride;  // elements between consecutive rows
     __device__ __forceinline__ S* at(int k) const { return col + (size_t)(k & (R - 1)) * stride; }
@@ -238,12 +238,21 @@ template <int BYTES> __device__ __forceinline__ void cp_async_vec(void* smem_dst
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(d), "l"(gsrc), "n"(BYTES));
 }
+// one ZD-vector row: a single 8/16-byte copy when the row has that size, element-wise otherwise
+template <class S, int ZD> __device__ __forceinline__ void cp_async_row(S* smem_dst, const S* gsrc) {
+    if constexpr (ZD * sizeof(S) == 8 || ZD * sizeof(S) == 16) {
+        cp_async_vec<ZD * (int)sizeof(S)>(smem_dst, gsrc);
+    } else {
+#pragma unroll
+        for (int i = 0; i < ZD; ++i) cp_async_vec<(int)sizeof(S)>(smem_dst + i, gsrc + i);
+    }
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // ---- forward ------------------------------------------------------------------------------------
 template <class RHS, class S, bool TAPE>
-__global__ void __launch_bounds__(LDEQ_FWD_THREADS, LDEQ_FWD_MINBLOCKS)
-tsit5_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
+__device__ __forceinline__ void
+tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
                  int T, KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
                  int* __restrict__ nreject, TapeView<S> tape) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
@@ -425,8 +434,8 @@ tsit5_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const do
 // dtraj (z,B,T) -> dz0 (z,B), dtheta (p,B).  Step sizes are constants of the differentiation, as in
 // the reference's ForwardDiffSensitivity where tspan/dt stay plain Float64.
 template <class RHS, class S>
-__global__ void __launch_bounds__(LDEQ_BWD_THREADS, LDEQ_BWD_MINBLOCKS)
-tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
+__device__ __forceinline__ void
+tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
                  const S* __restrict__ dtraj, TapeView<S> tape, const int* __restrict__ retcode,
                  const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ dtheta) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
@@ -458,7 +467,7 @@ tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_glob
         int klo = ks_max - R + 1;
         klo = klo < 1 ? 1 : klo;
         for (int r = kload - 1; r >= klo; --r)
-            cp_async_vec<ZD * (int)sizeof(S)>(ring.at(r), dtraj + ((size_t)r * B + bb) * ZD);
+            cp_async_row<S, ZD>(ring.at(r), dtraj + ((size_t)r * B + bb) * ZD);
         kload = klo < kload ? klo : kload;
     };
 
@@ -644,6 +653,23 @@ tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_glob
     store_vec<S, ZD>(dz0 + (size_t)b * ZD, ubn);
 #pragma unroll
     for (int i = 0; i < PD; ++i) dtheta[(size_t)b * PD + i] = pbar[i];
+}
+
+// ---- kernel entry points ---------------------------------------------------------------------------------
+template <class RHS, class S, bool TAPE>
+__global__ void __launch_bounds__(LDEQ_FWD_THREADS, LDEQ_FWD_MINBLOCKS)
+tsit5_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
+                 int T, KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
+                 int* __restrict__ nreject, TapeView<S> tape) {
+    tsit5_fwd_body<RHS, S, TAPE>(z0, theta, tg_global, B, T, o, traj, retcode, naccept, nreject, tape);
+}
+
+template <class RHS, class S>
+__global__ void __launch_bounds__(LDEQ_BWD_THREADS, LDEQ_BWD_MINBLOCKS)
+tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
+                 const S* __restrict__ dtraj, TapeView<S> tape, const int* __restrict__ retcode,
+                 const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ dtheta) {
+    tsit5_bwd_body<RHS, S>(theta, tg_global, B, T, dtraj, tape, retcode, naccept, dz0, dtheta);
 }
 
 }  // namespace ldeq
