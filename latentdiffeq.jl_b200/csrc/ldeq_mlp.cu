@@ -732,6 +732,12 @@ template <class S, int TB> static size_t bwd_smem(const MlpNet& net) {
 
 using namespace ldeq;
 
+// ldeq_mlp_tc.cu: the tcgen05 / TMEM forward kernel (LDEQ_MLP_MATH_BF16X3)
+int ldeq_mlp_tc_forward(ldeq_handle* h, const int32_t* dims, int n_layers, const float* params, const float* z0,
+                        const double* d_tgrid, int B, int T, const KOpts& ko, int norm_mode, float* traj, int32_t* ret,
+                        int32_t* na, int32_t* nr, double* tape_t, double* tape_dt, float* tape_u, int tape_cap,
+                        cudaStream_t s);
+
 struct ldeq_mlp_tape {
     int dtype = 0, B = 0, T = 0, cap = 0, tb = 0;
     MlpNet net;
@@ -801,7 +807,7 @@ static int mlp_fwd_dispatch(ldeq_handle* h, const MlpNet& net, const void* P, co
     if (rc) return rc;
     double* partials = (double*)h->scratch[0];
     const int sms = h->sm_count;
-    if (norm_mode == LDEQ_NORM_GLOBAL) {
+    if (norm_mode == LDEQ_NORM_GLOBAL && ko.adaptive) {   // fixed-step mode computes no error norm: no grid barrier
         // one tile per CTA, all CTAs co-resident (cooperative launch): pick the smallest tile that fits the chip
         auto fits = [&](int tb, size_t smem, const void* fn) -> int {
             int per_sm = 0;
@@ -842,7 +848,9 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
     if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
     for (int k = 1; k < T; ++k)
         if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
-    if (opts->mlp_math != LDEQ_MLP_MATH_FP32) return set_err(h, LDEQ_ERR_UNSUPPORTED, "mlp_math: only the exact FP32/FP64 path is built");
+    if (opts->mlp_math != LDEQ_MLP_MATH_FP32 && opts->mlp_math != LDEQ_MLP_MATH_BF16X3) return set_err(h, LDEQ_ERR_INVALID, "mlp_math");
+    if (opts->mlp_math == LDEQ_MLP_MATH_BF16X3 && dtype != LDEQ_F32)
+        return set_err(h, LDEQ_ERR_UNSUPPORTED, "mlp_math BF16X3 (tensor cores) needs a Float32 state; Float64 runs on the exact path");
     MlpNet net;
     int rc = make_net(h, layer_dims_host, n_layers, &net);
     if (rc) return rc;
@@ -883,7 +891,11 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
     int32_t* d_ret = tape ? tape->retcode : retcode;
     int32_t* d_na = tape ? tape->naccept : naccept;
     int32_t* d_nr = tape ? tape->nreject : nreject;
-    if (dtype == LDEQ_F32)
+    if (opts->mlp_math == LDEQ_MLP_MATH_BF16X3)
+        rc = ldeq_mlp_tc_forward(h, layer_dims_host, n_layers, (const float*)params_flat, (const float*)z0, h->d_tgrid, B, T, ko,
+                                 opts->norm_mode, (float*)traj_out, d_ret, d_na, d_nr, tape ? tape->t : nullptr,
+                                 tape ? tape->dt : nullptr, tape ? (float*)tape->u : nullptr, tape ? tape->cap : 0, s);
+    else if (dtype == LDEQ_F32)
         rc = mlp_fwd_dispatch<float>(h, net, params_flat, z0, h->d_tgrid, B, T, ko, opts->norm_mode, traj_out, d_ret, d_na, d_nr, tape, s);
     else
         rc = mlp_fwd_dispatch<double>(h, net, params_flat, z0, h->d_tgrid, B, T, ko, opts->norm_mode, traj_out, d_ret, d_na, d_nr, tape, s);

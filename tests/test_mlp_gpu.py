@@ -132,3 +132,56 @@ def test_large_batch_per_trajectory(ldeq):
     otr, _, _, _ = om.solve(z0[sel], p, dims, t, norm_mode="per_traj")
     assert (ret == 0).all()
     assert np.abs(tr[:, sel] - otr).max() <= 1e-3 * np.abs(otr).max()
+
+
+# ---- tcgen05 / TMEM path (LDEQ_MLP_MATH_BF16X3) ---------------------------------------------------------------
+@pytest.mark.parametrize("B", [256, 1000, 20000])
+def test_tensor_core_path_matches_oracle_and_exact_path(ldeq, B):
+    # north star: trajectories within 1e-3 (fp32).  The bf16x3 product carries 2^-16 per term: fixed-step
+    # trajectories agree with the oracle to ~4e-6.
+    dims, p, rng = _net(bias_scale=0.1)
+    T = 50
+    z0 = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
+    t = 0.05 * np.arange(T)
+    tc, ret, na, nr = _solve(ldeq, z0, p, dims, t, adaptive=False, dt=0.05, mlp_math=ldeq.MLP_MATH_BF16X3)
+    ex, _, na_e, _ = _solve(ldeq, z0, p, dims, t, adaptive=False, dt=0.05)
+    assert (ret == 0).all() and (na == na_e).all() and (na == T - 1).all()
+    assert np.abs(tc - ex).max() <= 5e-5 * np.abs(ex).max()
+    sel = np.arange(0, B, max(1, B // 64))
+    otr, _, _, _ = om.solve(z0[sel], p, dims, t, og.Opts(adaptive=False, dt=0.05))
+    assert np.abs(tc[:, sel] - otr).max() <= 5e-5 * np.abs(otr).max()
+    # adaptive, per-trajectory control (any B) and global norm (B <= 128 * SM count)
+    tc, ret, na, nr = _solve(ldeq, z0, p, dims, t, norm_mode=ldeq.NORM_PER_TRAJ, mlp_math=ldeq.MLP_MATH_BF16X3)
+    otr, _, _, _ = om.solve(z0[sel[:16]], p, dims, t, norm_mode="per_traj")
+    assert (ret == 0).all() and np.abs(tc[:, sel[:16]] - otr).max() <= 1e-3 * np.abs(otr).max()
+    if B <= 1000:
+        tc, ret, na, nr = _solve(ldeq, z0, p, dims, t, norm_mode=ldeq.NORM_GLOBAL, mlp_math=ldeq.MLP_MATH_BF16X3)
+        otr, ona, onr, _ = om.solve(z0, p, dims, t, norm_mode="global")
+        assert (na == ona).all() and (nr == onr).all()
+        assert np.abs(tc - otr).max() <= 1e-3 * np.abs(otr).max()
+
+
+def test_tensor_core_path_gradients_through_the_exact_adjoint(ldeq):
+    # the tensor-core forward records the same tape; the (exact-arithmetic) adjoint kernel sweeps it
+    dims, p, rng = _net(bias_scale=0.1)
+    B, T = 130, 20
+    z0 = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
+    t = 0.05 * np.arange(T)
+    d = rng.standard_normal((T, B, 16)).astype(np.float32)
+    tr, gz, gp = _solve(ldeq, z0, p, dims, t, want_grad=d, adaptive=False, dt=0.05, mlp_math=ldeq.MLP_MATH_BF16X3)
+    _, _, _, tape = om.solve(z0, p, dims, t, og.Opts(adaptive=False, dt=0.05), record=True)
+    oz, op = om.discrete_adjoint(p.astype(np.float64), dims, t, tape, d)
+    assert np.abs(gz - oz).max() <= 2e-4 * np.abs(oz).max() and np.abs(gp - op).max() <= 2e-4 * np.abs(op).max()
+
+
+def test_tensor_core_path_refuses_unsupported_shapes(ldeq):
+    rng = np.random.Generator(np.random.PCG64(5))
+    dims = [16, 300, 300, 16]
+    p = np.zeros(om.n_params(dims), np.float32)
+    z0 = rng.standard_normal((8, 16)).astype(np.float32)
+    with pytest.raises(ldeq.LdeqError) as e:
+        _solve(ldeq, z0, p, dims, 0.05 * np.arange(5), mlp_math=ldeq.MLP_MATH_BF16X3)
+    assert e.value.code == -3     # LDEQ_ERR_UNSUPPORTED, never a silent fallback
+    with pytest.raises(ldeq.LdeqError):
+        _solve(ldeq, z0.astype(np.float64), np.zeros(om.n_params([16, 200, 200, 16])), [16, 200, 200, 16], 0.05 * np.arange(5),
+               mlp_math=ldeq.MLP_MATH_BF16X3)
