@@ -26,11 +26,18 @@ namespace cg = cooperative_groups;
 
 namespace ldeq {
 
-#define TC_THREADS 128
+#define TC_THREADS 256       // 8 warps: warps w and w+4 share TMEM lane quadrant w%4 and split the columns
+#define TC_ROWS 128          // trajectories per CTA (M of the MMA)
 #define TC_MAXW 208          // largest padded layer width this kernel is built for (N of one MMA, K = 13 steps)
-#define TC_COL_D 0           // accumulators: columns [0, 208)
-#define TC_COL_AHI 208       // A operand, hi half: bf16 pairs, K/2 columns: [208, 312)
-#define TC_COL_ALO 312       // A operand, lo half: [312, 416)
+// TMEM column map (512 columns): two 208-column regions used in ping-pong + the stage slopes.
+//   layer 1: A = g in R1[0:16)        -> D = R0        epilogue 1 rewrites R0 IN PLACE as the bf16 hi/lo A operand
+//   layer 2: A = R0                   -> D = R1        epilogue 2 rewrites R1 in place
+//   layer 3: A = R1                   -> D = R0[0:16)
+// In-place layout of an A operand: the 16 fp32 accumulator columns of K-step kk become 8 columns of packed bf16
+// "hi" pairs followed by 8 columns of "lo" pairs.  Because an epilogue only touches the columns it has just read,
+// it can run on one column half while the MMAs of the other half are still in flight.
+#define TC_COL_R0 0
+#define TC_COL_R1 208
 #define TC_COL_K 416         // stage slopes k1..k6: 6 x 16 columns [416, 512)
 #define TC_TMEM_COLS 512
 
@@ -125,15 +132,20 @@ __device__ __forceinline__ void tc_st8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 
-// 16 fp32 values -> bf16 hi / lo halves packed two per 32-bit TMEM column (even element in the low half)
+// 16 fp32 values -> bf16 hi / lo halves packed two per 32-bit TMEM column (even element in the low half).
+// cvt.rn.bf16x2.f32 converts a pair in one instruction; bf16 -> fp32 is a shift.
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));  // first source -> upper half
+    return r;
+}
 __device__ __forceinline__ void split_pack16(const float* x, uint32_t* hi, uint32_t* lo) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * j]), h1 = __float2bfloat16_rn(x[2 * j + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * j] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(h1));
-        hi[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lo[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        const uint32_t h = pack_bf16x2(x[2 * j], x[2 * j + 1]);
+        const float h0 = __uint_as_float(h << 16), h1 = __uint_as_float(h & 0xFFFF0000u);
+        hi[j] = h;
+        lo[j] = pack_bf16x2(x[2 * j] - h0, x[2 * j + 1] - h1);
     }
 }
 
@@ -194,6 +206,36 @@ template <class S> struct MlpTapeViewTc {
 // Phases of the single-call-site state machine (the RHS evaluation is inlined exactly once).
 enum { PH_F0 = 0, PH_INITDT = 1, PH_STAGE = 2 };
 
+// epilogue of a hidden layer on the chunks [c_lo, c_hi) of a region: accumulators -> relu(acc + bias) -> bf16 hi/lo
+// written back IN PLACE (8 hi columns + 8 lo columns per 16-column chunk) as the A operand of the next layer
+__device__ __forceinline__ void tc_epilogue_inplace(uint32_t region_addr, const float* __restrict__ bias, int c_lo, int c_hi) {
+    for (int c = c_lo; c < c_hi; c += 16) {
+        float v[16];
+        uint32_t hi[8], lo[8];
+        tc_ld16(region_addr + c, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias[c + i], 0.f);
+        split_pack16(v, hi, lo);
+        tc_st8(region_addr + c, hi);
+        tc_st8(region_addr + c + 8, lo);
+    }
+}
+
+// MMAs of one layer for the output columns [n_lo, n_lo + n) : D[:, n_lo:n_lo+n] = A (K = 16*ksteps) x W[n_lo:n_lo+n, :]^T,
+// bf16x3: hi*hi + hi*lo + lo*hi.  A operand in the in-place layout (hi at a_addr + 16*kk, lo at a_addr + 16*kk + 8).
+__device__ __forceinline__ void tc_issue_layer(uint32_t d_addr, uint32_t a_addr, uint32_t w_hi, uint32_t w_lo, uint32_t lbo, int n_lo,
+                                               int n, int ksteps) {
+    if (n <= 0) return;  // a layer narrower than 32 has no second column half
+    const uint32_t idesc = make_idesc(n);
+    const uint32_t row_off = (uint32_t)(n_lo / 8) * 128;  // SBO = 128 bytes per 8-row group
+    for (int kk = 0; kk < ksteps; ++kk) {
+        const uint64_t bh = make_b_desc(w_hi + row_off + kk * 2 * lbo, lbo), bl = make_b_desc(w_lo + row_off + kk * 2 * lbo, lbo);
+        tc_mma_ts(d_addr + n_lo, a_addr + 16 * kk, bh, idesc, kk > 0);
+        tc_mma_ts(d_addr + n_lo, a_addr + 16 * kk, bl, idesc, 1);
+        tc_mma_ts(d_addr + n_lo, a_addr + 16 * kk + 8, bh, idesc, 1);
+    }
+}
+
 template <bool GLOBAL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const float* __restrict__ z0,
@@ -201,11 +243,13 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                   int* __restrict__ naccept, int* __restrict__ nreject, MlpTapeViewTc<float> tape, double* __restrict__ partials) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(128) unsigned char smem[];
-    __shared__ uint64_t mbar;
+    __shared__ uint64_t mbar[3];  // [0] first column half, [1] second column half, [2] output layer
     __shared__ uint32_t tmem_base_s;
-    __shared__ double red_s[TC_THREADS / 32];
+    __shared__ double red_s[TC_ROWS / 32];
 
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int quad = warp & 3, hf = warp >> 2;     // TMEM lane quadrant / column half of this warp
+    const int row = quad * 32 + (tid & 31);           // trajectory (row of the tile) this thread works on
     const int D = net.d;
     // stage the weight images (and biases) once
     {
@@ -217,7 +261,9 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
     const float* bias2 = bias1 + net.n1;
     const float* bias3 = bias2 + net.n2;
     if (tid == 0) {
-        mbar_init(&mbar, 1);
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[2], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -230,26 +276,30 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);  // this warp's 32-lane quadrant
-    uint32_t parity = 0;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);  // this warp's 32-lane quadrant
+    const uint32_t R0 = lane_addr + TC_COL_R0, R1 = lane_addr + TC_COL_R1, KS = lane_addr + TC_COL_K;
+    uint32_t par_half = 0, par_out = 0;  // phase parity of the barrier this warp waits on for its half / the output layer
 
     const uint32_t lbo1 = (net.n1 / 8) * 128, lbo2 = (net.n2 / 8) * 128, lbo3 = (16 / 8) * 128;
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t id1 = make_idesc(net.n1), id2 = make_idesc(net.n2), id3 = make_idesc(16);
+    // column halves of the two hidden layers (multiples of 16)
+    const int n1a = ((net.n1 / 16 + 1) / 2) * 16, n2a = ((net.n2 / 16 + 1) / 2) * 16;
 
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
     const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
     const float abstol = (float)o.abstol, reltol = (float)o.reltol;
-    const int ntiles = (B + TC_THREADS - 1) / TC_THREADS;
+    const int ntiles = (B + TC_ROWS - 1) / TC_ROWS;
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int b = tile * TC_THREADS + tid;
+        const int b = tile * TC_ROWS + row;
         const bool live = b < B;
+        const bool writer = hf == 0;  // both column halves carry the row's state redundantly (identical arithmetic, hence
+        // identical values: TMEM stores of state are issued by both); only one half writes to global memory
         float u[16], g[16], kout[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) u[i] = (live && i < D) ? z0[(size_t)b * D + i] : 0.f;
-        if (live) {
+        if (live && writer) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
                 if (i < D) traj[(size_t)b * D + i] = u[i];  // save point 0 is u0 itself
@@ -266,9 +316,8 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
 #pragma unroll
                 for (int i = 0; i < 16; ++i) g[i] = u[i];
             } else if (phase == PH_INITDT) {
-                // g = u0 + dt0 * f0 (f0 = k1 in TMEM slot 0)
                 float k1[16];
-                tc_ld16(lane_addr + TC_COL_K, k1);
+                tc_ld16(KS, k1);  // f0 = k1
 #pragma unroll
                 for (int i = 0; i < 16; ++i) g[i] = fmaf((float)dt0, k1[i], u[i]);
             } else {
@@ -286,7 +335,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 for (int i = 0; i < 16; ++i) acc[i] = 0.f;
                 for (int q = 0; q < stage; ++q) {
                     float kq[16];
-                    tc_ld16(lane_addr + TC_COL_K + 16 * q, kq);
+                    tc_ld16(KS + 16 * q, kq);
                     const float a = c_a[stage][q];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) acc[i] = fmaf(a, kq[i], acc[i]);
@@ -297,86 +346,64 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
             }
             // ---- RHS: three GEMMs on the tensor cores, activations TMEM -> TMEM ------------------------------------
             {
-                uint32_t hi[8], lo[8];
-                split_pack16(g, hi, lo);
-                tc_st8(lane_addr + TC_COL_AHI, hi);
-                tc_st8(lane_addr + TC_COL_ALO, lo);
-                tc_wait_st();
+                {  // g -> R1[0:16) as bf16 hi (8 columns) + lo (8 columns)
+                    uint32_t hi[8], lo[8];
+                    split_pack16(g, hi, lo);
+                    tc_st8(R1, hi);
+                    tc_st8(R1 + 8, lo);
+                    tc_wait_st();
+                }
                 tc_fence_before();
                 __syncthreads();
                 if (tid == 0) {
                     tc_fence_after();
-                    const uint64_t bh = make_b_desc(sbase + net.img_off[0], lbo1), bl = make_b_desc(sbase + net.img_off[1], lbo1);
-                    tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_AHI, bh, id1, 0);
-                    tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_AHI, bl, id1, 1);
-                    tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_ALO, bh, id1, 1);
-                    tc_commit(&mbar);
+                    const uint32_t wh = sbase + net.img_off[0], wl = sbase + net.img_off[1];
+                    tc_issue_layer(tmem_base + TC_COL_R0, tmem_base + TC_COL_R1, wh, wl, lbo1, 0, n1a, 1);
+                    tc_commit(&mbar[0]);
+                    tc_issue_layer(tmem_base + TC_COL_R0, tmem_base + TC_COL_R1, wh, wl, lbo1, n1a, net.n1 - n1a, 1);
+                    tc_commit(&mbar[1]);
                 }
-                mbar_wait(&mbar, parity);
-                parity ^= 1;
+                mbar_wait(&mbar[hf], par_half);
+                par_half ^= 1;
                 tc_fence_after();
-                // epilogue 1 -> A operand of layer 2
-                for (int c = 0; c < net.n1; c += 16) {
-                    float v[16];
-                    tc_ld16(lane_addr + TC_COL_D + c, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias1[c + i], 0.f);
-                    split_pack16(v, hi, lo);
-                    tc_st8(lane_addr + TC_COL_AHI + c / 2, hi);
-                    tc_st8(lane_addr + TC_COL_ALO + c / 2, lo);
-                }
+                // epilogue 1 (this warp's column half), in place in R0 -> A operand of layer 2
+                tc_epilogue_inplace(R0, bias1, hf ? n1a : 0, hf ? net.n1 : n1a);
                 tc_wait_st();
                 tc_fence_before();
                 __syncthreads();
                 if (tid == 0) {
                     tc_fence_after();
                     const uint32_t wh = sbase + net.img_off[2], wl = sbase + net.img_off[3];
-                    for (int kk = 0; kk < net.n1 / 16; ++kk) {
-                        const uint64_t bh = make_b_desc(wh + kk * 2 * lbo2, lbo2), bl = make_b_desc(wl + kk * 2 * lbo2, lbo2);
-                        tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_AHI + 8 * kk, bh, id2, kk > 0);
-                        tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_AHI + 8 * kk, bl, id2, 1);
-                        tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_ALO + 8 * kk, bh, id2, 1);
-                    }
-                    tc_commit(&mbar);
+                    tc_issue_layer(tmem_base + TC_COL_R1, tmem_base + TC_COL_R0, wh, wl, lbo2, 0, n2a, net.n1 / 16);
+                    tc_commit(&mbar[0]);
+                    tc_issue_layer(tmem_base + TC_COL_R1, tmem_base + TC_COL_R0, wh, wl, lbo2, n2a, net.n2 - n2a, net.n1 / 16);
+                    tc_commit(&mbar[1]);
                 }
-                mbar_wait(&mbar, parity);
-                parity ^= 1;
+                mbar_wait(&mbar[hf], par_half);
+                par_half ^= 1;
                 tc_fence_after();
-                // epilogue 2 -> A operand of layer 3
-                for (int c = 0; c < net.n2; c += 16) {
-                    float v[16];
-                    tc_ld16(lane_addr + TC_COL_D + c, v);
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + bias2[c + i], 0.f);
-                    split_pack16(v, hi, lo);
-                    tc_st8(lane_addr + TC_COL_AHI + c / 2, hi);
-                    tc_st8(lane_addr + TC_COL_ALO + c / 2, lo);
-                }
+                // epilogue 2, in place in R1 -> A operand of layer 3
+                tc_epilogue_inplace(R1, bias2, hf ? n2a : 0, hf ? net.n2 : n2a);
                 tc_wait_st();
                 tc_fence_before();
                 __syncthreads();
                 if (tid == 0) {
                     tc_fence_after();
-                    const uint32_t wh = sbase + net.img_off[4], wl = sbase + net.img_off[5];
-                    for (int kk = 0; kk < net.n2 / 16; ++kk) {
-                        const uint64_t bh = make_b_desc(wh + kk * 2 * lbo3, lbo3), bl = make_b_desc(wl + kk * 2 * lbo3, lbo3);
-                        tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_AHI + 8 * kk, bh, id3, kk > 0);
-                        tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_AHI + 8 * kk, bl, id3, 1);
-                        tc_mma_ts(tmem_base + TC_COL_D, tmem_base + TC_COL_ALO + 8 * kk, bh, id3, 1);
-                    }
-                    tc_commit(&mbar);
+                    tc_issue_layer(tmem_base + TC_COL_R0, tmem_base + TC_COL_R1, sbase + net.img_off[4], sbase + net.img_off[5], lbo3, 0, 16,
+                                   net.n2 / 16);
+                    tc_commit(&mbar[2]);
                 }
-                mbar_wait(&mbar, parity);
-                parity ^= 1;
+                mbar_wait(&mbar[2], par_out);
+                par_out ^= 1;
                 tc_fence_after();
-                tc_ld16(lane_addr + TC_COL_D, kout);
+                tc_ld16(R0, kout);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) kout[i] = i < D ? kout[i] + bias3[i] : 0.f;
             }
             // ---- what the evaluation was for ---------------------------------------------------------------------
             bool all_done = false;
             if (phase == PH_F0) {
-                tc_st16(lane_addr + TC_COL_K, kout);  // k1 = f(u0)  (fsalfirst)
+                tc_st16(KS, kout);  // k1 = f(u0)  (fsalfirst)
                 tc_wait_st();
                 if (o.adaptive && !(o.dt > 0.0)) {
                     // Hairer initial step, first half
@@ -391,18 +418,18 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                         }
                     double e0 = s0, e1 = s1, n = D;
                     if (GLOBAL) {
-                        // one dt for the batch: RMS over all D*B entries
-                        double v0 = live ? e0 : 0.0, v1 = live ? e1 : 0.0;
+                        // one dt for the batch: RMS over all D*B entries (summed by the `writer` half only)
+                        double v0 = (live && writer) ? e0 : 0.0, v1 = (live && writer) ? e1 : 0.0;
                         for (int off = 16; off > 0; off >>= 1) { v0 += __shfl_xor_sync(0xffffffffu, v0, off); v1 += __shfl_xor_sync(0xffffffffu, v1, off); }
-                        if ((tid & 31) == 0) red_s[warp] = v0;
+                        if (writer && (tid & 31) == 0) red_s[quad] = v0;
                         __syncthreads();
                         double b0 = 0.0;
-                        for (int w = 0; w < TC_THREADS / 32; ++w) b0 += red_s[w];
+                        for (int w = 0; w < TC_ROWS / 32; ++w) b0 += red_s[w];
                         __syncthreads();
-                        if ((tid & 31) == 0) red_s[warp] = v1;
+                        if (writer && (tid & 31) == 0) red_s[quad] = v1;
                         __syncthreads();
                         double b1 = 0.0;
-                        for (int w = 0; w < TC_THREADS / 32; ++w) b1 += red_s[w];
+                        for (int w = 0; w < TC_ROWS / 32; ++w) b1 += red_s[w];
                         __syncthreads();
                         if (tid == 0) partials[blockIdx.x] = b0;
                         grid.sync();
@@ -428,7 +455,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 }
             } else if (phase == PH_INITDT) {
                 float k1[16];
-                tc_ld16(lane_addr + TC_COL_K, k1);
+                tc_ld16(KS, k1);
                 float s2 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -439,12 +466,12 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                     }
                 double e2 = s2, n = D;
                 if (GLOBAL) {
-                    double v = live ? e2 : 0.0;
+                    double v = (live && writer) ? e2 : 0.0;
                     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                    if ((tid & 31) == 0) red_s[warp] = v;
+                    if (writer && (tid & 31) == 0) red_s[quad] = v;
                     __syncthreads();
                     double bsum = 0.0;
-                    for (int w = 0; w < TC_THREADS / 32; ++w) bsum += red_s[w];
+                    for (int w = 0; w < TC_ROWS / 32; ++w) bsum += red_s[w];
                     __syncthreads();
                     if (tid == 0) partials[blockIdx.x] = bsum;
                     grid.sync();
@@ -465,7 +492,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 stage = 1;
                 if (active && (!(dt > 0.0) || !isfinite(dt))) { ret = RET_DTLESSTHANMIN; active = false; }
             } else if (stage < 6) {
-                tc_st16(lane_addr + TC_COL_K + 16 * stage, kout);  // k_{stage+1}
+                tc_st16(KS + 16 * stage, kout);  // k_{stage+1}
                 tc_wait_st();
                 ++stage;
             } else {
@@ -479,7 +506,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 }
                 for (int q = 0; q < 6; ++q) {
                     float kq[16];
-                    tc_ld16(lane_addr + TC_COL_K + 16 * q, kq);
+                    tc_ld16(KS + 16 * q, kq);
                     const float r2 = c_r[q][1], r3 = c_r[q][2], r4 = c_r[q][3], bt = c_bt[q];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -504,12 +531,12 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 if (o.adaptive) {
                     double e2 = e2f, n = D;
                     if (GLOBAL) {
-                        double v = active ? e2 : 0.0;
+                        double v = (active && writer) ? e2 : 0.0;
                         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                        if ((tid & 31) == 0) red_s[warp] = v;
+                        if (writer && (tid & 31) == 0) red_s[quad] = v;
                         __syncthreads();
                         double bsum = 0.0;
-                        for (int w = 0; w < TC_THREADS / 32; ++w) bsum += red_s[w];
+                        for (int w = 0; w < TC_ROWS / 32; ++w) bsum += red_s[w];
                         __syncthreads();
                         if (tid == 0) partials[blockIdx.x] = bsum;
                         grid.sync();
@@ -522,13 +549,18 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                     if (EEst != EEst) finite = false;
                     accept = pi_controller(o, EEst, dts, dtmax, qold, dt_next);
                 }
+                // every thread of the warp has read k1..k6 by now; the FSAL store below may overwrite slot 0 only
+                // after the other half has read it as well
+                tc_fence_before();
+                __syncthreads();
+                tc_fence_after();
                 if (active) {
                     if (!finite) {
                         ret = RET_UNSTABLE;
                         active = false;
                     } else {
                         if (accept) {
-                            if (tape.cap > 0 && na < tape.cap) {
+                            if (writer && tape.cap > 0 && na < tape.cap) {
                                 tape.t[(size_t)na * B + b] = t;
                                 tape.dt[(size_t)na * B + b] = dts;
 #pragma unroll
@@ -539,18 +571,20 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                             // saveat through the dense interpolant (Horner form)
                             const double inv = 1.0 / dts;
                             while (ks < T && tg[ks] <= tnew) {
-                                const double tsv = tg[ks];
-                                float* dst = traj + ((size_t)ks * B + b) * D;
-                                if (tsv == tnew) {
+                                if (writer) {
+                                    const double tsv = tg[ks];
+                                    float* dst = traj + ((size_t)ks * B + b) * D;
+                                    if (tsv == tnew) {
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i)
-                                        if (i < D) dst[i] = g[i];
-                                } else {
-                                    const float th = (float)((tsv - t) * inv);
-                                    const float hth = h * th;
+                                        for (int i = 0; i < 16; ++i)
+                                            if (i < D) dst[i] = g[i];
+                                    } else {
+                                        const float th = (float)((tsv - t) * inv);
+                                        const float hth = h * th;
 #pragma unroll
-                                    for (int i = 0; i < 16; ++i)
-                                        if (i < D) dst[i] = fmaf(hth, fmaf(th, fmaf(th, fmaf(th, c4[i], c3[i]), c2[i]), k1v[i]), u[i]);
+                                        for (int i = 0; i < 16; ++i)
+                                            if (i < D) dst[i] = fmaf(hth, fmaf(th, fmaf(th, fmaf(th, c4[i], c3[i]), c2[i]), k1v[i]), u[i]);
+                                    }
                                 }
                                 ++ks;
                             }
@@ -571,16 +605,18 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                     const bool take = accept && finite;
 #pragma unroll
                     for (int i = 0; i < 16; ++i) k1v[i] = take ? kout[i] : k1v[i];
-                    tc_st16(lane_addr + TC_COL_K, k1v);
+                    tc_st16(KS, k1v);
                     tc_wait_st();
                 }
                 stage = 1;
+                tc_fence_before();
                 all_done = __syncthreads_or(active ? 1 : 0) == 0;
+                tc_fence_after();
             }
             if (all_done) break;
             if (phase != PH_STAGE && T <= 1) break;
         }
-        if (live) {
+        if (live && writer) {
             if (ret != RET_SUCCESS) {
                 for (int k = 0; k < T; ++k)
                     for (int i = 0; i < D; ++i) traj[((size_t)k * B + b) * D + i] = __int_as_float(0x7fc00000);
@@ -629,7 +665,7 @@ int ldeq_mlp_tc_forward(ldeq_handle* h, const int32_t* dims, int n_layers, const
     unsigned char* img = (unsigned char*)h->scratch[2];
     mlp_tc_prep_kernel<<<64, 256, 0, s>>>(net, params, D, H1, H2, img);
     LDEQ_CUDA(cudaGetLastError());
-    const int tiles = (B + TC_THREADS - 1) / TC_THREADS;
+    const int tiles = (B + TC_ROWS - 1) / TC_ROWS;
     MlpTapeViewTc<float> tv{tape_t, tape_dt, tape_u, tape_cap};
     double* partials = (double*)h->scratch[0];
     KOpts kov = ko;

@@ -29,4 +29,4 @@ for B in ([256, 2048, 18944, 65536] if not only else [int(only)]):
         ms=e0.elapsed_time(e1)/n
         na=st.naccept.float().mean().item(); nr=st.nreject.float().mean().item()
         rhs = B*(6*(st.naccept+st.nreject).float().mean().item()+2)
-        print(f"B={B:6d} {name:15s}: {ms:8.3f} ms | {B*(T-1)/ms/1e3:8.1f} M traj-steps/s | naccept {na:.1f} nreject {nr:.1f} | {rhs*92800*2/ms/1e9:7.2f} TFLOP/s (fp32-equivalent MLP flops)")
+        print(f"B={B:6d} {name:15s}: {ms:8.3f} ms | {B*(T-1)/ms/1e3:8.1f} M traj-steps/s | naccept {na:.1f} nreject {nr:.1f} | {rhs*92800/ms/1e9:7.2f} TFLOP/s (algorithmic MLP flops, 92 800 per RHS)")
