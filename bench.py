@@ -391,17 +391,84 @@ def run_training(args):
         dist.destroy_process_group()
 
 
+def run_latentode(args):
+    """`--workload c2` (BASELINE.json configs[1]: LatentODE, small-MLP RHS 16-200-200-16, batch 256, T = 50) and
+    `--workload mlp` (the same network at batch 18 944 = 128 trajectories per SM: where batch x hidden is a genuine
+    dense contraction).  Forward solve, adaptive Tsit5, per-trajectory and global (reference) error norm, exact CUDA-core
+    path vs the tcgen05 path.  Unit: accepted RK steps per trajectory per second and trajectory-steps/s."""
+    import torch
+
+    import latentdiffeq_jl_b200 as ldeq
+    from oracle import mlp as om   # weights only (glorot init of nODE.jl:14-16); nothing of the oracle is timed here
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B = 256 if args.workload == "c2" else 18944
+    T, dims = 50, [16, 200, 200, 16]
+    rng = np.random.Generator(np.random.PCG64(1))
+    layers = [(om.glorot_uniform(rng, dims[i + 1], dims[i]), np.zeros(dims[i + 1], np.float32)) for i in range(3)]
+    p = torch.from_numpy(om.pack_params(layers).astype(np.float32)).to(dev)
+    z = torch.from_numpy((0.5 * rng.standard_normal((B, 16))).astype(np.float32)).to(dev)
+    t = 0.05 * np.arange(T)
+    K, W = args.steps, max(args.warmup, 3)
+    peak_bf16 = 1634.1
+    try:
+        peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        pass
+    res = {}
+    for name, kw in (("tcgen05_bf16x3_global", dict(norm_mode=0, mlp_math=1)), ("tcgen05_bf16x3_per_traj", dict(norm_mode=1, mlp_math=1)),
+                     ("exact_fp32_global", dict(norm_mode=0)), ("exact_fp32_per_traj", dict(norm_mode=1))):
+        o = ldeq.default_opts(**kw)
+        try:
+            for _ in range(W):
+                tr, st, _ = ldeq.mlp_solve_raw(z, p, dims, t, o)
+        except ldeq.LdeqError as e:
+            res[name] = {"unavailable": str(e)}
+            continue
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            tr, st, _ = ldeq.mlp_solve_raw(z, p, dims, t, o)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / K
+        att = float((st.naccept + st.nreject).float().mean())
+        rhs = B * (6 * att + 2)
+        res[name] = {"ms": ms, "traj_steps_per_s": B * (T - 1) / (ms * 1e-3), "rk_steps_per_traj_per_s": B * att / (ms * 1e-3),
+                     "naccept_mean": float(st.naccept.float().mean()), "algorithmic_tflops": rhs * 92800 / (ms * 1e-3) / 1e12}
+        if "tcgen05" in name:
+            # tensor-pipe work actually issued: padded widths (208) and three bf16 passes per product
+            issued = rhs * 3 * 2 * (16 * 208 + 208 * 208 + 208 * 16) / (ms * 1e-3) / 1e12
+            res[name]["roofline"] = {"bound": "tensor", "achieved": issued, "peak": peak_bf16, "unit": "TFLOP/s",
+                                     "frac": issued / peak_bf16, "traffic": None,
+                                     "note": "bf16 flops issued to tcgen05 (3 passes, padded widths) / measured cuBLAS bf16 peak"}
+    best = max((v["traj_steps_per_s"], k) for k, v in res.items() if "ms" in v)
+    print(json.dumps({"metric": "latent trajectory-steps/sec (LatentODE forward solve)", "value": best[0], "unit": UNIT, "n_gpus": 1,
+                      "steps": K, "warmup": W, "ms_per_step": res[best[1]]["ms"], "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": f"{'C2' if args.workload == 'c2' else 'MLP sweep'}: LatentODE, MLP RHS 16-200-200-16, batch {B}, T = 50, "
+                                             "adaptive Tsit5 abstol 1e-6 reltol 1e-3, forward solve", "best": best[1]},
+                      "variants": res}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5", "c2", "mlp"])
     ap.add_argument("--global-batch", type=int, default=65536, help="c5 only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.workload == "c5":
+    if args.workload in ("c2", "mlp"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the reference arm covers the GOKU workloads (c4/c3/c1)"}))
+        else:
+            run_latentode(args)
+    elif args.workload == "c5":
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "C5 is a training-loop workload: the reference arm "
                               "(CPU oracle) covers the hot path only (c4/c3/c1)"}))
