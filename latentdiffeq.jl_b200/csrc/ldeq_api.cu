@@ -2,6 +2,7 @@
 //
 // ldeq_solve_fwd / ldeq_solve_bwd are the drop-in for the body of
 // diffeq_layer(::Decoder{<:GOKU}, l, t) (reference src/models/GOKU.jl:98-130) and its pullback.
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 
@@ -35,6 +36,14 @@ int upload_tgrid(ldeq_handle* h, const double* t_host, int T, cudaStream_t s) {
     }
     if (h->h_tgrid.size() != (size_t)T || std::memcmp(h->h_tgrid.data(), t_host, (size_t)T * sizeof(double)) != 0) {
         h->h_tgrid.assign(t_host, t_host + T);
+        h->grid_t0 = t_host[0];
+        h->grid_h = T > 1 ? t_host[1] - t_host[0] : 0.0;
+        h->grid_uniform = T > 1;
+#ifdef LDEQ_NO_UNIFORM_GRID
+        h->grid_uniform = 0;
+#endif
+        for (int k = 0; k < T && h->grid_uniform; ++k)
+            if (std::fma((double)k, h->grid_h, h->grid_t0) != t_host[k]) h->grid_uniform = 0;
         // source is pageable host memory: the runtime stages it before returning
         LDEQ_CUDA(cudaMemcpyAsync(h->d_tgrid, t_host, (size_t)T * sizeof(double), cudaMemcpyHostToDevice, s));
     }
@@ -68,13 +77,13 @@ KOpts to_kopts(const ldeq_opts* o) {
 template <class S, bool FRICTION, bool TAPE>
 static cudaError_t launch_fwd(const void* z0, const void* theta, const double* tg, int B, int T, const KOpts& ko,
                               void* traj, int32_t* ret, int32_t* na, int32_t* nr, const ldeq_tape* tape,
-                              cudaStream_t s) {
+                              const GridInfo& gi, cudaStream_t s) {
     TapeView<S> tv{nullptr, nullptr, nullptr, nullptr, 0};
     if (TAPE) tv = TapeView<S>{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap};
     const int grid = (B + LDEQ_FWD_THREADS - 1) / LDEQ_FWD_THREADS;
     const size_t smem = Ring<S, 2>::bytes(LDEQ_FWD_THREADS) + (T <= LDEQ_TGRID_SMEM_MAX ? (size_t)T * sizeof(double) : 0);
     tsit5_fwd_kernel<PendulumRHS<S, FRICTION>, S, TAPE><<<grid, LDEQ_FWD_THREADS, smem, s>>>(
-        (const S*)z0, (const S*)theta, tg, B, T, ko, (S*)traj, ret, na, nr, tv);
+        (const S*)z0, (const S*)theta, tg, B, T, ko, (S*)traj, ret, na, nr, tv, gi);
     return cudaGetLastError();
 }
 
@@ -86,7 +95,7 @@ static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, void* dz
         Ring<S, 2>::bytes(LDEQ_BWD_THREADS) + (tape->T <= LDEQ_TGRID_SMEM_MAX ? (size_t)tape->T * sizeof(double) : 0);
     tsit5_bwd_kernel<PendulumRHS<S, FRICTION>, S><<<grid, LDEQ_BWD_THREADS, smem, s>>>(
         (const S*)tape->theta, tape->tgrid, tape->B, tape->T, (const S*)dtraj, tv, tape->retcode, tape->naccept,
-        (S*)dz0, (S*)dtheta);
+        (S*)dz0, (S*)dtheta, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform});
     return cudaGetLastError();
 }
 
@@ -103,11 +112,12 @@ static size_t ring_smem(int z_dim, size_t es, int threads, int T) {
 // fwd f64 tape, bwd f32, bwd f64}; same signatures as the built-in instantiations
 static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg,
                                    int B, int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
-                                   const ldeq_tape* tape, cudaStream_t s) {
+                                   const ldeq_tape* tape, const GridInfo& gi, cudaStream_t s) {
     TapeView<float> tv{nullptr, nullptr, nullptr, nullptr, 0};  // identical layout for float and double
     if (tape) tv = TapeView<float>{tape->t, tape->dt, (float*)tape->u, tape->info, tape->cap};
     KOpts kov = ko;
-    void* args[] = {&z0, &theta, &tg, &B, &T, &kov, &traj, &ret, &na, &nr, &tv};
+    GridInfo giv = gi;
+    void* args[] = {&z0, &theta, &tg, &B, &T, &kov, &traj, &ret, &na, &nr, &tv, &giv};
     const int grid = (B + LDEQ_FWD_THREADS - 1) / LDEQ_FWD_THREADS;
     const size_t es = dtype == LDEQ_F32 ? 4 : 8;
     void* fn = rhs->fn[(dtype == LDEQ_F32 ? 0 : 2) + (tape ? 1 : 0)];
@@ -120,7 +130,8 @@ static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, voi
     int B = tape->B, T = tape->T;
     const int32_t* ret = tape->retcode;
     const int32_t* na = tape->naccept;
-    void* args[] = {&theta, &tg, &B, &T, &dtraj, &tv, &ret, &na, &dz0, &dtheta};
+    GridInfo giv{tape->grid_t0, tape->grid_h, tape->grid_uniform};
+    void* args[] = {&theta, &tg, &B, &T, &dtraj, &tv, &ret, &na, &dz0, &dtheta, &giv};
     const int grid = (B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
     const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
     void* fn = tape->rhs->fn[tape->dtype == LDEQ_F32 ? 4 : 5];
@@ -183,14 +194,14 @@ static int tape_alloc(ldeq_handle* h, ldeq_tape* tape, int cap, cudaStream_t s) 
 
 static cudaError_t dispatch_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg, int B,
                                 int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
-                                const ldeq_tape* tape, cudaStream_t s) {
-    if (rhs->kind < 0) return launch_user_fwd(rhs, dtype, z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s);
+                                const ldeq_tape* tape, const GridInfo& gi, cudaStream_t s) {
+    if (rhs->kind < 0) return launch_user_fwd(rhs, dtype, z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s);
     const bool friction = rhs->kind == LDEQ_RHS_PENDULUM_FRICTION;
 #define LDEQ_DISPATCH_FWD(S)                                                                              \
-    (tape ? (friction ? launch_fwd<S, true, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s)    \
-                      : launch_fwd<S, false, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s))  \
-          : (friction ? launch_fwd<S, true, false>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s)   \
-                      : launch_fwd<S, false, false>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, s)))
+    (tape ? (friction ? launch_fwd<S, true, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s)    \
+                      : launch_fwd<S, false, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s))  \
+          : (friction ? launch_fwd<S, true, false>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s)   \
+                      : launch_fwd<S, false, false>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s)))
     return dtype == LDEQ_F32 ? LDEQ_DISPATCH_FWD(float) : LDEQ_DISPATCH_FWD(double);
 #undef LDEQ_DISPATCH_FWD
 }
@@ -213,7 +224,7 @@ static int tape_heal(ldeq_handle* h, ldeq_tape* tape, cudaStream_t s) {
     // step 0 of the old tape holds u0 for every trajectory (capacity is always >= 1)
     cudaError_t e = dispatch_fwd(tape->rhs, tape->dtype, old.u, tape->theta,
                                  tape->tgrid, tape->B, tape->T, tape->kopts, nullptr, tape->retcode, tape->naccept,
-                                 tape->nreject, tape, s);
+                                 tape->nreject, tape, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform}, s);
     h->launches += 1;
     cudaFreeAsync(old.base, s);
     if (e != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwd_kernel (tape replay) launch", e);
@@ -317,6 +328,7 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
         tape = new ldeq_tape();
         tape->dtype = dtype; tape->rhs_kind = rhs->kind; tape->rhs = rhs; tape->B = B; tape->T = T;
         tape->z_dim = ZD; tape->p_dim = PD; tape->kopts = ko;
+        tape->grid_t0 = h->grid_t0; tape->grid_h = h->grid_h; tape->grid_uniform = h->grid_uniform;
         long long cap = opts->tape_steps;
         if (cap <= 0) {
             if (opts->adaptive) {
@@ -342,7 +354,8 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
     int32_t* d_ret = tape ? tape->retcode : retcode;
     int32_t* d_na = tape ? tape->naccept : naccept;
     int32_t* d_nr = tape ? tape->nreject : nreject;
-    cudaError_t e = dispatch_fwd(rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape, s);
+    cudaError_t e = dispatch_fwd(rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape,
+                                 GridInfo{h->grid_t0, h->grid_h, h->grid_uniform}, s);
     h->launches += 1;
     if (e != cudaSuccess) {
         if (tape) { cudaFreeAsync(tape->base, s); cudaEventRecord(tape->ready, s); slot_put(h, tape); delete tape; }

@@ -18,6 +18,9 @@ struct ldeq_handle {
     double* d_tgrid = nullptr;
     size_t d_tgrid_cap = 0;
     std::vector<double> h_tgrid;
+    // the cached grid is t0 + k*h bit for bit (checked on upload): kernels then compute save times instead of looking them up
+    double grid_t0 = 0.0, grid_h = 0.0;
+    int grid_uniform = 0;
     // grow-only device scratch for the *_host entry points and reductions
     void* scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
@@ -57,6 +60,8 @@ struct ldeq_tape {
     cudaEvent_t ready = nullptr;
     bool checked = false;
     ldeq::KOpts kopts;
+    double grid_t0 = 0.0, grid_h = 0.0;
+    int grid_uniform = 0;
 };
 
 namespace ldeq {
