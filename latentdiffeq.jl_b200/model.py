@@ -143,6 +143,47 @@ class LSTM(nn.Module):
         return torch.stack(out, 0)
 
 
+def _fused_recurrent(chain, xs):
+    """A ``Chain`` of same-width Flux ``RNN(relu)`` or ``LSTM`` layers applied to a CUDA sequence through cuDNN's fused
+    multi-layer kernels (one launch per stack instead of ~10 per time step and layer).  Same parameters and arithmetic as
+    the per-step loops above: Flux cells have ONE bias, so cuDNN's second bias is a constant zero; the trainable initial
+    state ``state0`` is broadcast over the batch.  Returns all hidden states of the last layer ``[T, B, H]``."""
+    layers = list(chain)
+    B = xs.shape[1]
+    flat = []
+    for l in layers:
+        flat += [l.Wi, l.Wh, l.b, torch.zeros_like(l.b)]
+    if isinstance(layers[0], LSTM):
+        h0 = torch.stack([l.h0.expand(B, -1) for l in layers]).contiguous()
+        c0 = torch.stack([l.c0.expand(B, -1) for l in layers]).contiguous()
+        out, _, _ = torch._VF.lstm(xs, (h0, c0), flat, True, len(layers), 0.0, chain.training, False, False)
+    else:
+        h0 = torch.stack([l.state0.expand(B, -1) for l in layers]).contiguous()
+        out, _ = torch._VF.rnn_relu(xs, h0, flat, True, len(layers), 0.0, chain.training, False, False)
+    return out
+
+
+def _can_fuse(chain, xs):
+    if not (xs.is_cuda and isinstance(chain, nn.Sequential) and len(chain) > 0 and torch.backends.cudnn.is_available()):
+        return False
+    layers = list(chain)
+    if all(isinstance(l, LSTM) for l in layers):
+        return len({l.out for l in layers}) == 1
+    if all(isinstance(l, RNN) and l.act is F.relu for l in layers):
+        return len({l.Wh.shape[0] for l in layers}) == 1
+    return False
+
+
+def run_recurrent(chain, xs):
+    """Apply a recurrent stack to a whole sequence ``[T, B, in]`` (fused on CUDA, per-step loops otherwise)."""
+    if FUSE_RECURRENT and _can_fuse(chain, xs):
+        return _fused_recurrent(chain, xs)
+    return chain(xs)
+
+
+FUSE_RECURRENT = True
+
+
 class _Tuple(nn.Module):
     """A tuple of layers (``pattern_extractor``, ``latent_in``, ``latent_out`` are tuples in GOKU.jl:234,243,258)."""
 
@@ -177,10 +218,10 @@ def apply_pattern_extractor(encoder, fe_out):
     rev = torch.flip(fe_out, dims=[0])
     if isinstance(encoder.model_type, GOKU):
         pe_z0, pe_th_f, pe_th_b = encoder.pattern_extractor
-        z0_out = pe_z0(rev)[-1]
-        th_out = torch.cat([pe_th_f(fe_out)[-1], pe_th_b(rev)[-1]], dim=-1)
+        z0_out = run_recurrent(pe_z0, rev)[-1]
+        th_out = torch.cat([run_recurrent(pe_th_f, fe_out)[-1], run_recurrent(pe_th_b, rev)[-1]], dim=-1)
         return z0_out, th_out
-    return encoder.pattern_extractor(rev)[-1]
+    return run_recurrent(encoder.pattern_extractor, rev)[-1]
 
 
 def apply_latent_in(encoder, pe_out):

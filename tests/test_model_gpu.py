@@ -73,3 +73,30 @@ def test_latentode_step(ldeq):
 def test_cpu_tensors_are_refused(ldeq):
     with pytest.raises(RuntimeError):
         ldeq.goku_solve(torch.zeros(4, 2), torch.ones(4, 1), np.arange(5) * 0.05)
+
+
+def test_fused_recurrent_layers_equal_the_per_step_flux_loops(ldeq):
+    # the cuDNN route of the pattern extractor must be the same function (values and gradients) as the Flux-style loops
+    from importlib import import_module
+    model_mod = import_module("latentdiffeq_jl_b200.model")
+    torch.manual_seed(3)
+    torch.backends.cudnn.allow_tf32 = False
+    mt = ldeq.GOKU_basic()
+    enc, dec = ldeq.default_layers(mt, 784, ldeq.Pendulum(), device=DEV)
+    encoder = ldeq.Encoder(mt, enc)
+    for p in encoder.parameters():           # non-trivial biases / initial states
+        if p.dim() == 1:
+            p.data.add_(0.05 * torch.randn_like(p))
+    x = torch.rand(30, 16, 784, device=DEV)
+    outs = {}
+    for fuse in (True, False):
+        model_mod.FUSE_RECURRENT = fuse
+        encoder.zero_grad()
+        mu, lv = encoder(x)
+        (mu[0].square().sum() + mu[1].sum() + lv[0].sum() + lv[1].square().sum()).backward()
+        outs[fuse] = ([m.detach().clone() for m in mu + lv], [p.grad.detach().clone() for p in encoder.parameters()])
+    model_mod.FUSE_RECURRENT = True
+    for a, b in zip(outs[True][0], outs[False][0]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-6)
+    for a, b in zip(outs[True][1], outs[False][1]):
+        assert torch.allclose(a, b, rtol=2e-3, atol=1e-5)
