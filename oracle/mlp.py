@@ -293,3 +293,118 @@ def discrete_adjoint(p_flat, dims, t, tape: Tape, dtraj):
         ubn, tnext = ub, tn
     ubn = ubn + dtraj[0]
     return ubn, pack_params(gW)
+
+
+# ---- the reference's own sensitivity algorithm for the LatentODE path ------------------------------------------
+def _dense_eval(tape_full, tq):
+    """u(tq) from the forward solve's dense output (Tsit5 interpolant of the step that contains tq)."""
+    ts = tape_full["t"]
+    n = min(max(np.searchsorted(ts, tq, side="right") - 1, 0), len(ts) - 2)
+    t0, dt = ts[n], tape_full["dt"][n]
+    th = (tq - t0) / dt
+    bw = interp_weights(th)
+    acc = sum(bw[j] * tape_full["k"][n][j] for j in range(7))
+    return tape_full["u"][n] + dt * acc
+
+
+def _forward_dense(z0, p_flat, dims, t, opts):
+    """Float64 forward solve (global norm) that keeps every accepted step's (t, dt, u, k1..k7): the `dense = true`
+    solution SciMLSensitivity's InterpolatingAdjoint interpolates during the backward sweep."""
+    layers = [(W.astype(np.float64), b.astype(np.float64)) for W, b in unpack_params(p_flat, dims)]
+    f = lambda U: mlp(layers, U)  # noqa: E731
+    t = np.asarray(t, dtype=np.float64)
+    t0, tend = t[0], t[-1]
+    u = z0.astype(np.float64).copy()
+    k1 = f(u)
+    sk = opts.abstol + np.abs(u) * opts.reltol
+    d0, d1 = _norm(u / sk, "global"), _norm(k1 / sk, "global")
+    dt0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+    f1 = f(u + dt0 * k1)
+    d2 = _norm((f1 - k1) / sk, "global") / dt0
+    dt = min(100 * dt0, 10.0 ** (-(2.0 + np.log10(max(d1, d2))) / 5.0), tend - t0) if opts.adaptive and not opts.dt > 0 else opts.dt
+    rec = {"t": [], "dt": [], "u": [], "k": []}
+    tc, qold = t0, opts.qoldinit
+    while tc < tend:
+        dts = min(dt, tend - tc)
+        kk = [k1]
+        for j in range(1, 7):
+            g = u + dts * sum(A[j][i] * kk[i] for i in range(j))
+            kk.append(f(g))
+        unew = g
+        accept, q, q11 = True, 1.0, 1.0
+        if opts.adaptive:
+            ut = dts * sum(BT[i] * kk[i] for i in range(7))
+            EEst = float(_norm(ut / (opts.abstol + np.maximum(np.abs(u), np.abs(unew)) * opts.reltol), "global"))
+            q11 = EEst ** opts.beta1 if EEst > 0 else 1.0
+            q = max(1 / opts.qmax, min(1 / opts.qmin, (q11 / qold ** opts.beta2) / opts.gamma)) if EEst > 0 else 1 / opts.qmax
+            accept = EEst <= 1
+        if accept:
+            rec["t"].append(tc); rec["dt"].append(dts); rec["u"].append(u); rec["k"].append(kk)
+            if opts.adaptive:
+                qold = max(EEst, opts.qoldinit)
+                dt = min(tend - t0, dts / q)
+            tc = tend if abs(tc + dts - tend) < 1e-13 else tc + dts
+            u, k1 = unew, kk[6]
+        else:
+            dt = dts / min(1 / opts.qmin, q11 / opts.gamma)
+    rec["t"].append(tend)
+    rec["t"] = np.array(rec["t"])
+    return rec, layers
+
+
+def interpolating_adjoint(z0, p_flat, dims, t, dtraj, opts: Opts | None = None):
+    """Gradients the way the REFERENCE computes them for LatentODE: DiffEqFlux's NeuralODE default
+    ``InterpolatingAdjoint(autojacvec = ZygoteVJP())`` -- the continuous adjoint ODE
+        lambda' = -(df/du)^T lambda,   mu' = -(df/dp)^T lambda
+    integrated backwards from t_end to t_0 with adaptive Tsit5 at the solve's abstol/reltol, u(t) taken from the forward
+    solution's dense output, and a jump ``lambda += dtraj[k]`` at every save time.  Float64 throughout.
+    Returns ``(dz0[B,D], dparams_flat)``.  This is NOT what the product computes (it uses the discrete adjoint of the
+    accepted steps); the two agree to the solver tolerance, and tests quantify by how much."""
+    opts = opts or Opts()
+    rec, layers = _forward_dense(z0, p_flat, dims, t, opts)
+    t = np.asarray(t, dtype=np.float64)
+    T = len(t)
+    lam = dtraj[T - 1].astype(np.float64).copy()
+    npar = n_params(dims)
+    mu = np.zeros(npar)
+
+    def rhs(tq, lam_):
+        u = _dense_eval(rec, tq)
+        gu, gp = mlp_vjp(layers, u, lam_)
+        return -gu, -pack_params(gp)
+
+    # segments between consecutive save times, each integrated with adaptive Tsit5 (time runs backwards: s = -t)
+    for kseg in range(T - 1, 0, -1):
+        ta, tb = t[kseg], t[kseg - 1]
+        tc, y_l, y_m = ta, lam, mu
+        span = ta - tb
+        dl, dm = rhs(tc, y_l)
+        dt = min(span, 0.01 if not opts.adaptive else span / 2)
+        qold = opts.qoldinit
+        while tc > tb + 1e-15:
+            dts = min(dt, tc - tb)
+            kl, km = [dl], [dm]
+            for j in range(1, 7):
+                gl = y_l - dts * sum(A[j][i] * kl[i] for i in range(j))
+                a, b_ = rhs(tc - CS[j] * dts, gl)
+                kl.append(a); km.append(b_)
+            new_l = gl
+            new_m = y_m - dts * sum(A[6][i] * km[i] for i in range(6))
+            el = dts * sum(BT[i] * kl[i] for i in range(7))
+            em = dts * sum(BT[i] * km[i] for i in range(7))
+            res = np.concatenate([(el / (opts.abstol + np.maximum(np.abs(y_l), np.abs(new_l)) * opts.reltol)).ravel(),
+                                  em / (opts.abstol + np.maximum(np.abs(y_m), np.abs(new_m)) * opts.reltol)])
+            EEst = float(np.sqrt(np.mean(res * res)))
+            q11 = EEst ** opts.beta1 if EEst > 0 else 1.0
+            q = max(1 / opts.qmax, min(1 / opts.qmin, (q11 / qold ** opts.beta2) / opts.gamma)) if EEst > 0 else 1 / opts.qmax
+            if EEst <= 1:
+                tc = tb if tc - dts - tb < 1e-13 else tc - dts
+                y_l, y_m = new_l, new_m
+                dl, dm = kl[6], km[6]
+                qold = max(EEst, opts.qoldinit)
+                dt = min(span, dts / q)
+            else:
+                dt = dts / min(1 / opts.qmin, q11 / opts.gamma)
+        lam = y_l + dtraj[kseg - 1]
+        mu = y_m
+    return lam, mu

@@ -261,3 +261,23 @@ def test_adamw_first_step_and_decay_not_scaled_by_lr():
     # first step: m_hat = g, v_hat = g^2 -> step = lr * g / (|g| + eps); plus decay * x (NOT lr * decay * x)
     want = x - (1e-3 * g / (np.abs(g) + 1e-8) + np.float32(0.001) * x)
     assert np.allclose(x1, want, rtol=1e-6, atol=1e-9)
+
+
+def test_reference_continuous_adjoint_converges_to_the_discrete_adjoint():
+    # Row a13: the reference differentiates LatentODE with the continuous InterpolatingAdjoint; the product computes the
+    # discrete adjoint of the accepted steps.  They are two discretisations of the same derivative: the gap closes as the
+    # tolerance tightens (slowly, the relu right-hand side is only piecewise smooth).
+    dims, layers, p, rng = _net(seed=2, dims=(6, 24, 24, 6))
+    z0 = 0.5 * rng.standard_normal((5, 6))
+    t = 0.05 * np.arange(20)
+    d = rng.standard_normal((20, 5, 6))
+    gaps = []
+    for tol in (1e-3, 1e-6, 1e-9):
+        o = og.Opts(abstol=tol * 1e-3, reltol=tol, controller_pow=1)
+        _, _, _, tape = om.solve(z0, p, dims, t, o, record=True)
+        gz, gp = om.discrete_adjoint(p, dims, t, tape, d)
+        cz, cp = om.interpolating_adjoint(z0, p, dims, t, d, o)
+        gaps.append((np.abs(gz - cz).max() / np.abs(gz).max(), np.abs(gp - cp).max() / np.abs(gp).max()))
+    assert gaps[0][0] > gaps[1][0] > gaps[2][0] and gaps[0][1] > gaps[1][1] > gaps[2][1]
+    assert gaps[0][0] < 5e-2 and gaps[0][1] < 2e-1          # default tolerance: O(reltol^(1/3)) apart
+    assert gaps[2][0] < 1e-3 and gaps[2][1] < 5e-3
