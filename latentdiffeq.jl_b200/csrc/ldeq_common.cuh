@@ -86,24 +86,42 @@ __device__ __forceinline__ float ctrl_powf(double x, float y, int exact) {
 }
 
 // PI controller (OrdinaryDiffEq stepsize_controller!/step_accept_controller!/step_reject_controller!).
-// Returns accept; updates qold and the next step-size proposal.  The two fastpow factors are Float32 by
-// construction; their quotient and the final 1/q are taken in Float32 as well (a relative 1e-7 on the
+// Returns accept; updates the controller memory and the next step-size proposal.  The two fastpow factors are
+// Float32 by construction; their quotient and the final 1/q are taken in Float32 as well (a relative 1e-7 on the
 // proposed dt, far below anything the error control can see) so that no Float64 division is issued.
-__device__ __forceinline__ bool pi_controller(const KOpts& o, double EEst, double dts, double dtmax, double& qold,
+// The memory is kept as qold_pow = fastpow(qold, beta2): after an accepted step qold = max(EEst, qoldinit), so the
+// next step's denominator is exp2(beta2 * fastlog2(EEst)) from the SAME logarithm as this step's numerator
+// (bit-identical to evaluating fastpow(qold, beta2) then, one logarithm per step instead of two).
+struct PiState {
+    float qold_pow;  // fastpow(qold, beta2)
+};
+__device__ __forceinline__ PiState pi_init(const KOpts& o) { return PiState{ctrl_powf(o.qoldinit, (float)o.beta2, o.controller_pow)}; }
+__device__ __forceinline__ bool pi_controller(const KOpts& o, double EEst, double dts, double dtmax, PiState& st,
                                               double& dt_next) {
-    float q, q11 = 1.0f;
+    float q, q11 = 1.0f, q22_next = st.qold_pow;
     const float inv_gamma = (float)(1.0 / o.gamma), qlo = (float)(1.0 / o.qmax), qhi = (float)(1.0 / o.qmin);
     if (EEst == 0.0) {
         q = qlo;
+        q22_next = ctrl_powf(o.qoldinit, (float)o.beta2, o.controller_pow);
     } else {
-        q11 = ctrl_powf(EEst, (float)o.beta1, o.controller_pow);
-        q = __fdiv_rn(q11, ctrl_powf(qold, (float)o.beta2, o.controller_pow));
+        if (o.controller_pow) {
+            q11 = (float)pow(EEst, o.beta1);
+            q22_next = (float)pow(fmax(EEst, o.qoldinit), o.beta2);
+        } else {
+            const float ef = fabsf((float)EEst);
+            const float lg = fastlog2_dev(ef);
+            q11 = exp2f(__fmul_rn((float)o.beta1, lg));
+            // fastpow(max(EEst, qoldinit), beta2): the Float32 demotion commutes with max
+            const float qf = (float)o.qoldinit;
+            q22_next = exp2f(__fmul_rn((float)o.beta2, ef >= qf ? lg : fastlog2_dev(qf)));
+        }
+        q = __fdiv_rn(q11, st.qold_pow);
         q = fmaxf(qlo, fminf(qhi, q * inv_gamma));
     }
     const bool accept = EEst <= 1.0;
     if (accept) {
         if ((float)o.qsteady_min <= q && q <= (float)o.qsteady_max) q = 1.0f;
-        qold = fmax(EEst, o.qoldinit);
+        st.qold_pow = q22_next;
         dt_next = fmin(dtmax, dts * (double)__frcp_rn(q));
     } else {
         dt_next = dts * (double)__frcp_rn(fminf(qhi, q11 * inv_gamma));

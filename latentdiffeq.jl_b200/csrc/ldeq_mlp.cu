@@ -177,7 +177,7 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
         }
         if (threadIdx.x < TB) {
             const int b = threadIdx.x;
-            ts->t[b] = t0; ts->qold[b] = o.qoldinit; ts->iters[b] = 0; ts->ks[b] = 1; ts->na[b] = 0; ts->nr[b] = 0;
+            ts->t[b] = t0; ts->qold[b] = (double)pi_init(o).qold_pow;  /* controller memory: fastpow(qold, beta2) */ ts->iters[b] = 0; ts->ks[b] = 1; ts->na[b] = 0; ts->nr[b] = 0;
             ts->ret[b] = RET_SUCCESS; ts->active[b] = (b0 + b < B) && T > 1; ts->dt[b] = o.dt;
         }
         __syncthreads();
@@ -345,9 +345,9 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
                         const double e2 = GLOBAL ? part / ((double)D * (double)B) : ts->esum[b] / (double)D;
                         const double EEst = (double)s_sqrt<S>((S)e2);
                         if (EEst != EEst) finite = false;
-                        double q = ts->qold[b];
-                        accept = pi_controller(o, EEst, ts->dts[b], dtmax, q, dt_next);
-                        ts->qold[b] = q;
+                        PiState pst{(float)ts->qold[b]};
+                        accept = pi_controller(o, EEst, ts->dts[b], dtmax, pst, dt_next);
+                        ts->qold[b] = (double)pst.qold_pow;
                     }
                     if (!finite) {
                         ts->ret[b] = RET_UNSTABLE; ts->active[b] = 0;

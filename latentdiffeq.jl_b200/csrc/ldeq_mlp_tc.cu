@@ -304,7 +304,8 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
             for (int i = 0; i < 16; ++i)
                 if (i < D) traj[(size_t)b * D + i] = u[i];  // save point 0 is u0 itself
         }
-        double t = t0, dt = o.dt, qold = o.qoldinit, dts = 0.0, tnew = t0, dt0 = 0.0, d1n = 0.0;
+        PiState pist = pi_init(o);
+        double t = t0, dt = o.dt, dts = 0.0, tnew = t0, dt0 = 0.0, d1n = 0.0;
         int na = 0, nr = 0, ks = 1, ret = RET_SUCCESS, stage = 0;
         long long iters = 0;
         bool active = live && T > 1;
@@ -547,7 +548,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                     }
                     const double EEst = (double)sqrtf((float)(e2 / n));
                     if (EEst != EEst) finite = false;
-                    accept = pi_controller(o, EEst, dts, dtmax, qold, dt_next);
+                    accept = pi_controller(o, EEst, dts, dtmax, pist, dt_next);
                 }
                 // every thread of the warp has read k1..k6 by now; the FSAL store below may overwrite slot 0 only
                 // after the other half has read it as well

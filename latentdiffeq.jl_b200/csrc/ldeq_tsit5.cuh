@@ -291,11 +291,12 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
     const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
     const S abstol = (S)o.abstol, reltol = (S)o.reltol;
     const double abs_tend = fabs(tend);
+    const double snap_end = 100.0 * ulp_of(abs_tend);  // 100 ulp(max(|t|, |tend|)) whenever |t| <= |tend|
 
     RHS::f(k[0], u, p, t0);  // fsalfirst
     double t = t0;
     double dt = (o.adaptive && !(o.dt > 0.0)) ? tsit5_initdt<RHS, S>(u, p, k[0], t0, dtmax, dtmin, o) : o.dt;
-    double qold = o.qoldinit;
+    PiState pist = pi_init(o);
     int na = 0, nr = 0, ret = RET_SUCCESS;
     long long iters = 0;
 
@@ -307,7 +308,6 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
     if (!(dt > 0.0) || !isfinite(dt)) ret = RET_DTLESSTHANMIN;
 
     int ks = live ? 1 : T;  // next save index this lane emits
-    double kd3 = (double)(ks + 3);  // ks + 3 as a double, for the prefetch of the uniform grid
     int kflush = 1;         // warp-uniform: rows below it are in global memory
     bool active = live && T > 1 && ret == RET_SUCCESS;  // still has steps to take
     bool pending = false;   // an accepted step whose save points are not all parked yet
@@ -323,7 +323,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                 // tstop handling: never step past tend; snap onto it within 100 ulp
                 dts = fmin(dt, tend - t);
                 tnew = t + dts;
-                if (fabs(tnew - tend) < 100.0 * ulp_of(fmax(fabs(t), abs_tend))) tnew = tend;
+                if (fabs(tnew - tend) < (fabs(t) > abs_tend ? 100.0 * ulp_of(fabs(t)) : snap_end)) tnew = tend;
 
                 tsit5_stages<RHS, S, false>(u, p, t, dts, k, un, nullptr, nullptr);
 
@@ -335,7 +335,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                 if (o.adaptive) {
                     const double EEst = tsit5_eest<S, ZD>(u, un, k, dts, abstol, reltol);
                     if (EEst != EEst) finite = false;
-                    accept = pi_controller(o, EEst, dts, dtmax, qold, dt_next);
+                    accept = pi_controller(o, EEst, dts, dtmax, pist, dt_next);
                 }
                 if (!finite) {
                     ret = RET_UNSTABLE;
@@ -367,13 +367,42 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
         if (pending) {
             // saveat: every pending grid time <= tnew; interior points through the dense interpolant of this
             // step (Horner form), a grid time that coincides with the step end stores u_{n+1} itself
+            if (tg.uniform) {
+                // save times are t0 + k h, one DFMA each: no table, no prefetch pipeline
+                if (tsave < tnew && ks < kflush + R) {
+                    S c[4][ZD];
+                    interp_coeffs<S, ZD>(k, c);
+                    const S h = (S)dts;
+                    const double inv = 1.0 / dts;
+                    double kd = (double)ks;
+                    do {
+                        S out[ZD];
+                        const S th = (S)((tsave - t) * inv);
+                        const S hth = h * th;
+#pragma unroll
+                        for (int i = 0; i < ZD; ++i) {
+                            const S poly = s_fma<S>(th, s_fma<S>(th, s_fma<S>(th, c[3][i], c[2][i]), c[1][i]), c[0][i]);
+                            out[i] = s_fma<S>(hth, poly, u[i]);
+                        }
+                        store_vec<S, ZD>(ring.at(ks), out);
+                        ++ks;
+                        kd += 1.0;
+                        tsave = ks < T ? fma(kd, tg.h, tg.t0) : LDEQ_TINF;
+                    } while (tsave < tnew && ks < kflush + R);
+                }
+                if (tsave == tnew && ks < kflush + R) {
+                    store_vec<S, ZD>(ring.at(ks), un);
+                    ++ks;
+                    tsave = ks < T ? fma((double)ks, tg.h, tg.t0) : LDEQ_TINF;
+                }
+            } else {
             if (tsave < tnew && ks < kflush + R) {
                 S c[4][ZD];
                 interp_coeffs<S, ZD>(k, c);
                 const S h = (S)dts;
                 const double inv = 1.0 / dts;
                 do {
-                    const double tpre = ks + 3 < T ? tg.at(ks + 3, kd3) : LDEQ_TINF;  // consumed two iterations from now
+                    const double tpre = ks + 3 < T ? tg[ks + 3] : LDEQ_TINF;  // consumed two iterations from now
                     S out[ZD];
                     const S th = (S)((tsave - t) * inv);
                     const S hth = h * th;
@@ -384,7 +413,6 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                     }
                     store_vec<S, ZD>(ring.at(ks), out);
                     ++ks;
-                    kd3 += 1.0;
                     tsave = tsave2;
                     tsave2 = tsave3;
                     tsave3 = tpre;
@@ -392,12 +420,12 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
             }
             if (tsave == tnew && ks < kflush + R) {
                 store_vec<S, ZD>(ring.at(ks), un);
-                const double tpre = ks + 3 < T ? tg.at(ks + 3, kd3) : LDEQ_TINF;
+                const double tpre = ks + 3 < T ? tg[ks + 3] : LDEQ_TINF;
                 ++ks;
-                kd3 += 1.0;
                 tsave = tsave2;
                 tsave2 = tsave3;
                 tsave3 = tpre;
+            }
             }
             if (!(tsave <= tnew)) {  // all save points of this step are parked: commit it
                 t = tnew;
