@@ -348,7 +348,7 @@ def run_training(args):
     mt = ldeq.GOKU_basic()
     enc, dec = ldeq.default_layers(mt, 784, ldeq.Pendulum(), device=dev)
     model = ldeq.LatentDiffEqModel(mt, enc, dec)
-    flat = ldeq.FlatParams(model)
+    flat = ldeq.FlatParams(model, symmetric=(world > 1 and not args.nccl_allreduce))
     opt = ldeq.ADAMW(flat, 1e-3, (0.9, 0.999), 1e-3)
     # synthetic data: true pendulum angles from the hot path itself, rasterised on the device
     z0n, thn = pendulum_inputs(GB, seed=1)
@@ -385,7 +385,9 @@ def run_training(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "C5: GOKU-net pendulum data-parallel training, default architecture (503 387 params), "
                                    f"global batch {GB} x 50 frames of 28x28, {B} per GPU, encoder/decoder layers stock PyTorch fp32, "
-                                   "solve + sample + ELBO + AdamW in libldeq.so, one NCCL all-reduce of the 2.0 MB flat gradient"},
+                                   "solve + sample + ELBO + AdamW in libldeq.so; gradient: " +
+                                   ("all-reduce fused with AdamW over NVLink peer memory (one kernel)" if flat.symm is not None
+                                    else "one NCCL all-reduce of the 2.0 MB flat bucket + AdamW kernel" if world > 1 else "local")},
             "gpu_launches": int(h.launch_count() - l0), "loss": float(loss)}))
     if world > 1:
         dist.destroy_process_group()
@@ -462,6 +464,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5", "c2", "mlp"])
     ap.add_argument("--global-batch", type=int, default=65536, help="c5 only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="c5: NCCL all-reduce + AdamW instead of the fused peer-memory kernel")
     args = ap.parse_args()
     if args.workload in ("c2", "mlp"):
         if args.impl == "reference":

@@ -11,7 +11,7 @@ from __future__ import annotations
 import torch
 import torch.distributed as dist
 
-from .solve import adamw_step, elbo_loss
+from .solve import adamw_step, allreduce_adamw_step, elbo_loss
 
 
 def loss_batch(model, x, t, beta, variational):
@@ -37,14 +37,23 @@ class FlatParams:
     """All trainable parameters of a model viewed through ONE contiguous fp32 buffer (and one gradient
     buffer): a single all-reduce and a single fused AdamW launch per step."""
 
-    def __init__(self, module: torch.nn.Module):
+    def __init__(self, module: torch.nn.Module, symmetric: bool = False):
+        """``symmetric=True`` (several CUDA ranks of one box): the gradient bucket is NVLink symmetric memory, every
+        rank can read every other rank's bucket, and the optimiser step fuses the all-reduce (``ADAMW.step``)."""
         self.params = [p for p in module.parameters() if p.requires_grad]
         n = sum(p.numel() for p in self.params)
         n_pad = (n + 3) // 4 * 4
         dev = self.params[0].device
         self.n = n
         self.flat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(n_pad, dtype=torch.float32, device=dev)
+        self.symm = None
+        if symmetric and dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            self.grad = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
+            self.grad.zero_()
+            self.symm = symm_mem.rendezvous(self.grad, dist.group.WORLD)
+        else:
+            self.grad = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         off = 0
@@ -72,12 +81,25 @@ class ADAMW:
         self.step_count = 0
 
     def step(self, grad_scale: float = 1.0):
+        """Local AdamW on the (already all-reduced) flat gradient."""
         self.step_count += 1
         f = self.flat
         if f.flat.is_cuda:
             adamw_step(f.flat, f.grad, f.m, f.v, self.step_count, self.eta, self.beta, self.eps, self.decay, grad_scale)
         else:
             raise RuntimeError("the optimiser step runs in libldeq.so on a CUDA device (no CPU fallback)")
+
+    def fused_allreduce_step(self, grad_scale: float = 1.0):
+        """All-reduce + AdamW in ONE kernel over NVLink peer memory (needs ``FlatParams(..., symmetric=True)``):
+        barrier (all buckets written) -> every rank sums all buckets in rank order and updates its replica -> barrier
+        (all ranks have read every bucket before the next backward pass overwrites them)."""
+        f = self.flat
+        assert f.symm is not None, "FlatParams was not built with symmetric=True"
+        self.step_count += 1
+        f.symm.barrier(channel=0)
+        allreduce_adamw_step(f.flat, list(f.symm.buffer_ptrs), f.m, f.v, self.step_count, self.eta, self.beta, self.eps,
+                             self.decay, grad_scale)
+        f.symm.barrier(channel=1)
 
 
 def allreduce_grads(flat: FlatParams):
@@ -97,6 +119,9 @@ def train_step(model, flat: FlatParams, opt: ADAMW, x_local, t, beta, variationa
     flat.zero_grad()
     loss = loss_batch(model, x_local, t, beta, variational)
     (loss * (B_local / B_global)).backward()
-    allreduce_grads(flat)
-    opt.step()
+    if flat.symm is not None:
+        opt.fused_allreduce_step()
+    else:
+        allreduce_grads(flat)
+        opt.step()
     return loss.detach()
