@@ -117,7 +117,6 @@ template <class S> __device__ __forceinline__ S tab_bt(int i) {
     }
     return (S)0;
 }
-__device__ __constant__ double c_stage[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
 
 // Per-trajectory controller / bookkeeping state of a tile (shared memory)
 template <int TB> struct TileState {
