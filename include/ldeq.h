@@ -192,12 +192,17 @@ int ldeq_adamw_step(ldeq_handle* h, float* params, const float* grads, float* m,
 
 /* ---- gradient all-reduce FUSED with AdamW over NVLink peer memory (data-parallel training, model_train.jl:195-201
  * on several GPUs).  peer_grads_host[r] is rank r's flat gradient bucket mapped into this process (symmetric memory /
- * CUDA IPC; the caller owns the mapping and the cross-GPU barriers before and after the call).  One kernel: every
- * rank reads all nranks buckets straight over NVLink, sums them in rank order (so all ranks get bit-identical sums),
- * scales by grad_scale and applies the AdamW update of ldeq_adamw_step to its own replica. */
-int ldeq_allreduce_adamw_step(ldeq_handle* h, float* params, const float* const* peer_grads_host, int nranks, float* m,
-                              float* v, int64_t n, double lr, double beta1, double beta2, double eps, float decay,
-                              int64_t step, float grad_scale, ldeq_stream stream);
+ * CUDA IPC; the caller owns the mappings and the cross-GPU barriers before and after the call).  ONE kernel:
+ *   peer_params_host == NULL  (one-shot):  every rank reads all nranks buckets over NVLink, sums them in rank order,
+ *        scales by grad_scale and applies the AdamW update of ldeq_adamw_step to its whole replica;
+ *   peer_params_host != NULL  (two-shot):  rank `rank` reduces and updates only its 1/nranks slice (its slice of m, v is
+ *        the only optimiser state it ever touches) and stores the updated parameters into every rank's replica
+ *        (peer_params_host[r] = rank r's flat parameter buffer): nranks times less NVLink traffic.
+ * Either way all replicas end up bit-identical. */
+int ldeq_allreduce_adamw_step(ldeq_handle* h, float* params, float* const* peer_params_host,
+                              const float* const* peer_grads_host, int nranks, int rank, float* m, float* v, int64_t n,
+                              double lr, double beta1, double beta2, double eps, float decay, int64_t step,
+                              float grad_scale, ldeq_stream stream);
 
 #ifdef __cplusplus
 }

@@ -92,7 +92,7 @@ def load() -> C.CDLL:
     lib.ldeq_sample.argtypes = [vp, vp, vp, vp, vp, i64, C.c_uint64, C.c_uint64, vp]
     lib.ldeq_elbo_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, flt, i32, i32, i32, flt, vp, vp, vp, vp, vp]
     lib.ldeq_adamw_step.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, flt, i64, flt, vp]
-    lib.ldeq_allreduce_adamw_step.argtypes = [vp, vp, vp, i32, vp, vp, i64, dbl, dbl, dbl, dbl, flt, i64, flt, vp]
+    lib.ldeq_allreduce_adamw_step.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i64, dbl, dbl, dbl, dbl, flt, i64, flt, vp]
     _lib = lib
     return lib
 

@@ -165,25 +165,27 @@ adamw_kernel(float* __restrict__ x, const float* __restrict__ g, float* __restri
 
 // ---- all-reduce fused with AdamW over peer memory ----------------------------------------------------------------
 #define LDEQ_MAX_PEERS 16
-struct PeerGrads {
-    const float* p[LDEQ_MAX_PEERS];
+struct PeerBufs {
+    const float* g[LDEQ_MAX_PEERS];  // gradient bucket of every rank (peer-mapped)
+    float* x[LDEQ_MAX_PEERS];        // parameter replica of every rank (two-shot mode), else null
     int n;
 };
-// Every rank pulls all gradient buckets over NVLink (plain loads on peer-mapped pointers; peer data is not cached in the
-// local L2), adds them in rank order and updates its own replica in the same pass: 2 MB per peer for the default GOKU,
-// latency-bound, so one launch instead of an NCCL all-reduce plus an optimiser kernel.
+// Plain 128-bit loads / stores on peer-mapped pointers travel over NVLink (peer data is not cached in the local L2).
+// One-shot: every rank sums all buckets (rank order) and updates its whole replica.  Two-shot: every rank sums and
+// updates its own slice [lo4, hi4) only and writes the new parameters into every replica.  2 MB per bucket for the
+// default GOKU: latency-bound either way, so ONE launch instead of an NCCL all-reduce plus an optimiser kernel.
+template <bool TWO_SHOT>
 __global__ void __launch_bounds__(256)
-allreduce_adamw_kernel(float* __restrict__ x, PeerGrads pg, float* __restrict__ m, float* __restrict__ v, size_t n, double b1,
-                       double b2, double c1, double c2, double eps, double lr, float decay, float gscale) {
-    const size_t n4 = n >> 2;
+allreduce_adamw_kernel(float* __restrict__ x, PeerBufs pb, float* __restrict__ m, float* __restrict__ v, size_t lo4, size_t hi4,
+                       double b1, double b2, double c1, double c2, double eps, double lr, float decay, float gscale) {
     float4* x4 = reinterpret_cast<float4*>(x);
     float4* m4 = reinterpret_cast<float4*>(m);
     float4* v4 = reinterpret_cast<float4*>(v);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    for (size_t i = lo4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi4; i += stride) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < pg.n; ++r) {
-            const float4 t = __ldcg(reinterpret_cast<const float4*>(pg.p[r]) + i);
+        for (int r = 0; r < pb.n; ++r) {
+            const float4 t = __ldcg(reinterpret_cast<const float4*>(pb.g[r]) + i);
             g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
         }
         float4 xx = x4[i], mm = m4[i], vv = v4[i];
@@ -191,15 +193,12 @@ allreduce_adamw_kernel(float* __restrict__ x, PeerGrads pg, float* __restrict__ 
         adamw_one(xx.y, g.y * gscale, mm.y, vv.y, b1, b2, c1, c2, eps, lr, decay);
         adamw_one(xx.z, g.z * gscale, mm.z, vv.z, b1, b2, c1, c2, eps, lr, decay);
         adamw_one(xx.w, g.w * gscale, mm.w, vv.w, b1, b2, c1, c2, eps, lr, decay);
-        x4[i] = xx; m4[i] = mm; v4[i] = vv;
-    }
-    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
-        const size_t i = (n4 << 2) + threadIdx.x;
-        float g = 0.f;
-        for (int r = 0; r < pg.n; ++r) g += __ldcg(pg.p[r] + i);
-        float xx = x[i], mm = m[i], vv = v[i];
-        adamw_one(xx, g * gscale, mm, vv, b1, b2, c1, c2, eps, lr, decay);
-        x[i] = xx; m[i] = mm; v[i] = vv;
+        m4[i] = mm; v4[i] = vv;
+        if (TWO_SHOT) {
+            for (int r = 0; r < pb.n; ++r) reinterpret_cast<float4*>(pb.x[r])[i] = xx;  // includes this rank's own replica
+        } else {
+            x4[i] = xx;
+        }
     }
 }
 
@@ -329,19 +328,25 @@ int ldeq_adamw_step(ldeq_handle* h, float* params, const float* grads, float* m,
     return LDEQ_OK;
 }
 
-int ldeq_allreduce_adamw_step(ldeq_handle* h, float* params, const float* const* peer_grads_host, int nranks, float* m,
-                              float* v, int64_t n, double lr, double beta1, double beta2, double eps, float decay,
-                              int64_t step, float grad_scale, ldeq_stream stream) {
+int ldeq_allreduce_adamw_step(ldeq_handle* h, float* params, float* const* peer_params_host,
+                              const float* const* peer_grads_host, int nranks, int rank, float* m, float* v, int64_t n,
+                              double lr, double beta1, double beta2, double eps, float decay, int64_t step,
+                              float grad_scale, ldeq_stream stream) {
     if (!h) return LDEQ_ERR_INVALID;
-    if (!params || !peer_grads_host || !m || !v || n < 0 || step < 1 || nranks < 1 || nranks > LDEQ_MAX_PEERS)
+    if (!params || !peer_grads_host || !m || !v || n < 0 || step < 1 || nranks < 1 || nranks > LDEQ_MAX_PEERS || rank < 0 ||
+        rank >= nranks)
         return set_err(h, LDEQ_ERR_INVALID, "allreduce_adamw: bad argument (1 <= nranks <= 16)");
+    if (n & 3) return set_err(h, LDEQ_ERR_INVALID, "allreduce_adamw: n must be a multiple of 4 (pad the flat buffers)");
     uintptr_t al = ((uintptr_t)params) | ((uintptr_t)m) | ((uintptr_t)v);
-    PeerGrads pg;
-    pg.n = nranks;
-    for (int r = 0; r < LDEQ_MAX_PEERS; ++r) pg.p[r] = r < nranks ? peer_grads_host[r] : nullptr;
+    PeerBufs pb;
+    pb.n = nranks;
+    for (int r = 0; r < LDEQ_MAX_PEERS; ++r) {
+        pb.g[r] = r < nranks ? peer_grads_host[r] : nullptr;
+        pb.x[r] = (r < nranks && peer_params_host) ? peer_params_host[r] : nullptr;
+    }
     for (int r = 0; r < nranks; ++r) {
-        if (!pg.p[r]) return set_err(h, LDEQ_ERR_INVALID, "allreduce_adamw: null peer pointer");
-        al |= (uintptr_t)pg.p[r];
+        if (!pb.g[r] || (peer_params_host && !pb.x[r])) return set_err(h, LDEQ_ERR_INVALID, "allreduce_adamw: null peer pointer");
+        al |= (uintptr_t)pb.g[r] | (uintptr_t)pb.x[r];
     }
     if (al & 15) return set_err(h, LDEQ_ERR_INVALID, "allreduce_adamw: buffers must be 16-byte aligned");
     if (n == 0) return LDEQ_OK;
@@ -349,9 +354,19 @@ int ldeq_allreduce_adamw_step(ldeq_handle* h, float* params, const float* const*
     LDEQ_CUDA(cudaSetDevice(h->device));
     double p1 = 1.0, p2 = 1.0;
     for (int64_t i = 0; i < step; ++i) { p1 *= beta1; p2 *= beta2; }
-    size_t want = (((size_t)n >> 2) + 255) / 256;
-    int grid = (int)(want < (size_t)h->sm_count * 4 ? (want ? want : 1) : (size_t)h->sm_count * 4);
-    allreduce_adamw_kernel<<<grid, 256, 0, s>>>(params, pg, m, v, (size_t)n, beta1, beta2, 1.0 - p1, 1.0 - p2, eps, lr, decay, grad_scale);
+    const size_t n4 = (size_t)n >> 2;
+    size_t lo4 = 0, hi4 = n4;
+    if (peer_params_host) {  // contiguous slice of this rank (remainder to the first ranks)
+        const size_t base = n4 / nranks, rem = n4 % nranks;
+        lo4 = rank * base + ((size_t)rank < rem ? rank : rem);
+        hi4 = lo4 + base + ((size_t)rank < rem ? 1 : 0);
+    }
+    const size_t want = (hi4 - lo4 + 255) / 256;
+    const int grid = (int)(want < (size_t)h->sm_count * 4 ? (want ? want : 1) : (size_t)h->sm_count * 4);
+    if (peer_params_host)
+        allreduce_adamw_kernel<true><<<grid, 256, 0, s>>>(params, pb, m, v, lo4, hi4, beta1, beta2, 1.0 - p1, 1.0 - p2, eps, lr, decay, grad_scale);
+    else
+        allreduce_adamw_kernel<false><<<grid, 256, 0, s>>>(params, pb, m, v, lo4, hi4, beta1, beta2, 1.0 - p1, 1.0 - p2, eps, lr, decay, grad_scale);
     LDEQ_CUDA(cudaGetLastError());
     h->launches += 1;
     return LDEQ_OK;

@@ -369,14 +369,18 @@ def adamw_step(params: torch.Tensor, grads: torch.Tensor, m: torch.Tensor, v: to
 
 
 def allreduce_adamw_step(params, peer_grad_ptrs, m, v, step: int, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, decay=1e-3,
-                         grad_scale: float = 1.0):
+                         grad_scale: float = 1.0, peer_param_ptrs=None, rank: int = 0):
     """``ldeq_allreduce_adamw_step``: sum the flat gradient buckets of all ranks straight over NVLink peer memory
-    (``peer_grad_ptrs[r]`` = rank r's bucket mapped into this process) and apply AdamW in the same kernel.  The caller
-    provides the cross-GPU barriers around the call."""
+    (``peer_grad_ptrs[r]`` = rank r's bucket mapped into this process) and apply AdamW in the same kernel.  With
+    ``peer_param_ptrs`` (every rank's parameter replica, peer-mapped) the kernel is two-shot: this rank reduces and
+    updates only its slice and writes the new parameters into every replica.  The caller provides the cross-GPU
+    barriers around the call."""
     h = _cabi.handle(params.device.index or 0)
-    PA = C.c_void_p * len(peer_grad_ptrs)
-    arr = PA(*[int(p) for p in peer_grad_ptrs])
+    W = len(peer_grad_ptrs)
+    PA = C.c_void_p * W
+    garr = PA(*[int(p) for p in peer_grad_ptrs])
+    parr = PA(*[int(p) for p in peer_param_ptrs]) if peer_param_ptrs is not None else None
     with torch.cuda.device(params.device):
-        h.check(h._lib.ldeq_allreduce_adamw_step(h.ptr, _p(params), arr, len(peer_grad_ptrs), _p(m), _p(v), params.numel(),
+        h.check(h._lib.ldeq_allreduce_adamw_step(h.ptr, _p(params), parr, garr, W, int(rank), _p(m), _p(v), params.numel(),
                                                  float(lr), float(betas[0]), float(betas[1]), float(eps), C.c_float(decay),
                                                  int(step), C.c_float(grad_scale), _stream()))

@@ -45,14 +45,17 @@ class FlatParams:
         n_pad = (n + 3) // 4 * 4
         dev = self.params[0].device
         self.n = n
-        self.flat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
-        self.symm = None
+        self.symm = self.symm_p = None
         if symmetric and dev.type == "cuda" and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             import torch.distributed._symmetric_memory as symm_mem
             self.grad = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)
             self.grad.zero_()
             self.symm = symm_mem.rendezvous(self.grad, dist.group.WORLD)
+            self.flat = symm_mem.empty(n_pad, dtype=torch.float32, device=dev)   # replicas are peer-writable (two-shot step)
+            self.flat.zero_()
+            self.symm_p = symm_mem.rendezvous(self.flat, dist.group.WORLD)
         else:
+            self.flat = torch.zeros(n_pad, dtype=torch.float32, device=dev)
             self.grad = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self.m = torch.zeros(n_pad, dtype=torch.float32, device=dev)
         self.v = torch.zeros(n_pad, dtype=torch.float32, device=dev)
@@ -91,14 +94,17 @@ class ADAMW:
 
     def fused_allreduce_step(self, grad_scale: float = 1.0):
         """All-reduce + AdamW in ONE kernel over NVLink peer memory (needs ``FlatParams(..., symmetric=True)``):
-        barrier (all buckets written) -> every rank sums all buckets in rank order and updates its replica -> barrier
-        (all ranks have read every bucket before the next backward pass overwrites them)."""
+        barrier (all buckets written) -> sum in rank order + AdamW -> barrier (every rank has read every bucket / written
+        every replica before the next pass).  Two ranks: one-shot (each rank reduces everything).  More: two-shot (each
+        rank reduces and updates its 1/N slice and stores the new parameters into every replica)."""
         f = self.flat
         assert f.symm is not None, "FlatParams was not built with symmetric=True"
         self.step_count += 1
+        two_shot = f.symm.world_size > 2 and f.symm_p is not None
         f.symm.barrier(channel=0)
         allreduce_adamw_step(f.flat, list(f.symm.buffer_ptrs), f.m, f.v, self.step_count, self.eta, self.beta, self.eps,
-                             self.decay, grad_scale)
+                             self.decay, grad_scale, peer_param_ptrs=list(f.symm_p.buffer_ptrs) if two_shot else None,
+                             rank=f.symm.rank)
         f.symm.barrier(channel=1)
 
 

@@ -35,7 +35,10 @@ def _worker(rank, world, port, q):
     oa, ob = ldeq.ADAMW(fa), ldeq.ADAMW(fb)
     assert fa.symm is not None and fb.symm is None
     for step in range(4):
-        g = torch.randn(fa.grad.numel(), device=dev, generator=torch.Generator(device=dev).manual_seed(100 * step + rank))
+        # gradients bounded away from zero: Adam's update is ~ lr * sign(g) early on, so a sum that is zero up to rounding
+        # would make the comparison depend on the summation order of the two all-reduce algorithms
+        g = 1.0 + 0.25 * torch.randn(fa.grad.numel(), device=dev, generator=torch.Generator(device=dev).manual_seed(100 * step + rank))
+        g = g * (1 - 2 * (torch.arange(g.numel(), device=dev) % 2))
         fa.grad.copy_(g)
         fb.grad.copy_(g)
         oa.fused_allreduce_step(grad_scale=1.0 / world)                  # ONE kernel over peer memory
@@ -47,20 +50,25 @@ def _worker(rank, world, port, q):
     dist.all_gather(gathered, fa.flat)
     same = all(torch.equal(gathered[0], x) for x in gathered)            # rank-ordered sum: bit-identical replicas
     if rank == 0:
+        print(f"world {world}: fused vs NCCL+AdamW rel err {err:.3e}, replicas identical {same}", flush=True)
         q.put((err, same))
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs of one box")
-def test_fused_allreduce_adamw_matches_nccl_plus_adamw():
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_allreduce_adamw_matches_nccl_plus_adamw(world):
+    # 2 ranks: one-shot kernel; 4 / 8 ranks: two-shot kernel (slice reduce + update, parameters written to every replica)
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
     err, same = q.get(timeout=300)
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert err < 1e-6 and same
+    assert err < 1e-5 and same
