@@ -57,7 +57,7 @@ __device__ void dense_fwd(const S* __restrict__ W, const S* __restrict__ bias, c
         const S b0 = s == 0 ? bias[n] : (S)0;
 #pragma unroll
         for (int b = 0; b < TB; ++b) acc[b] = b0;
-#pragma unroll 4
+#pragma unroll 8
         for (int k = k0; k < k1; ++k) {
             const S wv = W[(size_t)k * N + n];
 #pragma unroll
@@ -459,7 +459,7 @@ __device__ void dense_bwd_input(const S* __restrict__ Wt, const S* __restrict__ 
         S acc[TB];
 #pragma unroll
         for (int b = 0; b < TB; ++b) acc[b] = (S)0;
-#pragma unroll 4
+#pragma unroll 8
         for (int n = n0; n < n1; ++n) {
             const S wv = Wt[(size_t)n * K + k];
 #pragma unroll
@@ -489,18 +489,30 @@ __device__ void dense_bwd_input(const S* __restrict__ Wt, const S* __restrict__ 
 template <class S, int TB>
 __device__ void dense_bwd_params(S* __restrict__ gW, S* __restrict__ gb, const S* __restrict__ dy, const S* __restrict__ x,
                                  int K, int N) {
-    for (int w = threadIdx.x; w < N * K; w += MLP_THREADS) {
-        const int k = w / N, n = w - k * N;
-        S a = (S)0;
+    // thread = output neuron n x k-slice: dy[n][:] stays in registers, x[k][:] is a shared-memory broadcast, the
+    // accumulator is updated with consecutive threads on consecutive addresses (no integer division in the loop)
+    int SL = 1;
+    while (SL * 2 * N <= MLP_THREADS && SL < 16 && SL * 2 <= K) SL *= 2;
+    const int kper = (K + SL - 1) / SL;
+    for (int w = threadIdx.x; w < N * SL; w += MLP_THREADS) {
+        const int s = w / N, n = w - s * N;
+        const int k0 = s * kper, k1 = min(K, k0 + kper);
+        S d[TB];
 #pragma unroll
-        for (int b = 0; b < TB; ++b) a = s_fma<S>(dy[n * TB + b], x[k * TB + b], a);
-        gW[w] += a;
-    }
-    for (int n = threadIdx.x; n < N; n += MLP_THREADS) {
-        S a = (S)0;
+        for (int b = 0; b < TB; ++b) d[b] = dy[n * TB + b];
+#pragma unroll 8
+        for (int k = k0; k < k1; ++k) {
+            S a = (S)0;
 #pragma unroll
-        for (int b = 0; b < TB; ++b) a += dy[n * TB + b];
-        gb[n] += a;
+            for (int b = 0; b < TB; ++b) a = s_fma<S>(d[b], x[k * TB + b], a);
+            gW[(size_t)k * N + n] += a;
+        }
+        if (s == 0) {
+            S a = (S)0;
+#pragma unroll
+            for (int b = 0; b < TB; ++b) a += d[b];
+            gb[n] += a;
+        }
     }
     __syncthreads();
 }
@@ -536,7 +548,9 @@ __device__ void mlp_vjp(const MlpNet& net, const S* __restrict__ P, const S* __r
     }
 }
 
-template <class S, int TB>
+// SMEM_GRAD: the CTA's private parameter-gradient accumulator lives in shared memory (187 kB for 16-200-200-16 in fp32)
+// instead of its slice of the global scratch: the accumulation is a read-modify-write of every parameter per stage.
+template <class S, int TB, bool SMEM_GRAD>
 __global__ void __launch_bounds__(MLP_THREADS)
 mlp_bwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, const double* __restrict__ tg, int B, int T,
                const S* __restrict__ dtraj, MlpTapeView<S> tape, const int* __restrict__ retcode,
@@ -566,7 +580,9 @@ mlp_bwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, co
     int* flag_s = ks_s + TB;
     __shared__ int s_any;
 
-    S* gP = gscratch + (size_t)blockIdx.x * net.n_params;  // this CTA's private gradient accumulator
+    // this CTA's private gradient accumulator
+    S* gP = SMEM_GRAD ? reinterpret_cast<S*>(smem_raw + ((s_bytes + 3 * TB * sizeof(double) + 3 * TB * sizeof(int) + 15) & ~(size_t)15))
+                      : gscratch + (size_t)blockIdx.x * net.n_params;
     for (int i = threadIdx.x; i < net.n_params; i += MLP_THREADS) gP[i] = (S)0;
     const int ntiles = (B + TB - 1) / TB;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -690,6 +706,10 @@ mlp_bwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, co
             }
         }
         __syncthreads();
+    }
+    if (SMEM_GRAD) {
+        S* out = gscratch + (size_t)blockIdx.x * net.n_params;
+        for (int i = threadIdx.x; i < net.n_params; i += MLP_THREADS) out[i] = gP[i];
     }
 }
 
@@ -918,17 +938,29 @@ static int launch_mlp_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj
     const MlpNet& net = tape->net;
     const int B = tape->B;
     const int tiles = (B + TB - 1) / TB;
-    const int grid = tiles < 2 * h->sm_count ? tiles : 2 * h->sm_count;
+    const size_t smem_g = ((bwd_smem<S, TB>(net) + 15) & ~(size_t)15) + (size_t)net.n_params * sizeof(S);
+    // on-chip accumulator only when there is at most one tile per SM anyway (it costs the second resident CTA and the L1
+    // that otherwise holds the weights)
+    const bool smem_grad = smem_g <= 225 * 1024 && tiles <= h->sm_count;
+    const int per_sm = smem_grad ? 1 : 2;
+    const int grid = tiles < per_sm * h->sm_count ? tiles : per_sm * h->sm_count;
     int rc = ensure_scratch(h, 1, (size_t)grid * net.n_params * sizeof(S));
     if (rc) return rc;
     mlp_transpose_kernel<S><<<64, 256, 0, s>>>(net, (const S*)tape->params, (S*)tape->params_t);
     // biases are not used from the transposed copy
-    const size_t smem = bwd_smem<S, TB>(net);
-    LDEQ_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<S, TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     MlpTapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->cap};
-    mlp_bwd_kernel<S, TB><<<grid, MLP_THREADS, smem, s>>>(net, (const S*)tape->params, (const S*)tape->params_t, tape->tgrid,
-                                                          B, tape->T, (const S*)dtraj, tv, tape->retcode, tape->naccept,
-                                                          (S*)dz0, (S*)h->scratch[1]);
+    if (smem_grad) {
+        LDEQ_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<S, TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_g));
+        mlp_bwd_kernel<S, TB, true><<<grid, MLP_THREADS, smem_g, s>>>(net, (const S*)tape->params, (const S*)tape->params_t,
+                                                                      tape->tgrid, B, tape->T, (const S*)dtraj, tv, tape->retcode,
+                                                                      tape->naccept, (S*)dz0, (S*)h->scratch[1]);
+    } else {
+        const size_t smem = bwd_smem<S, TB>(net);
+        LDEQ_CUDA(cudaFuncSetAttribute(mlp_bwd_kernel<S, TB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        mlp_bwd_kernel<S, TB, false><<<grid, MLP_THREADS, smem, s>>>(net, (const S*)tape->params, (const S*)tape->params_t,
+                                                                     tape->tgrid, B, tape->T, (const S*)dtraj, tv, tape->retcode,
+                                                                     tape->naccept, (S*)dz0, (S*)h->scratch[1]);
+    }
     LDEQ_CUDA(cudaGetLastError());
     mlp_reduce_grads_kernel<S><<<(net.n_params + 255) / 256, 256, 0, s>>>((const S*)h->scratch[1], grid, net.n_params, (S*)dparams);
     LDEQ_CUDA(cudaGetLastError());
