@@ -14,434 +14,12 @@
 //   LDEQ_NORM_PER_TRAJ  every trajectory has its own dt / accept-reject sequence (documented deviation).
 // The backward kernel is the discrete adjoint of the accepted steps (the reference's InterpolatingAdjoint is a
 // continuous adjoint that agrees with it to the solver tolerance).
-#include <cooperative_groups.h>
+#include <cstdlib>
 
-#include "ldeq_internal.h"
-
-namespace cg = cooperative_groups;
+#include "ldeq_mlp_common.cuh"
 
 namespace ldeq {
 
-#define MLP_THREADS 256
-#define MLP_MAX_LAYERS 8
-
-struct MlpNet {
-    int n_layers;
-    int dims[MLP_MAX_LAYERS + 1];
-    int w_off[MLP_MAX_LAYERS];  // offset of vec(W_l) in the flat parameter vector
-    int b_off[MLP_MAX_LAYERS];
-    int n_params;
-    int max_width;  // widest layer input/output
-};
-
-template <class S> struct MlpTapeView {
-    double* t;   // [cap][B]
-    double* dt;  // [cap][B]
-    S* u;        // [cap][B][D]
-    int cap;
-};
-
-// ---- dense layers on a tile ------------------------------------------------------------------------
-// Activations are stored feature-major per tile: x[k*TB + b].  W is (N,K) column-major: W[k*N + n].
-// Thread w handles output neuron n = w % N over the k-slice s = w / N; slices are summed through `red`.
-template <class S, int TB>
-__device__ void dense_fwd(const S* __restrict__ W, const S* __restrict__ bias, const S* __restrict__ x, S* __restrict__ y,
-                          S* __restrict__ red, int K, int N, bool relu) {
-    int SL = 1;
-    while (SL * 2 * N <= MLP_THREADS && SL < 16 && SL * 2 <= K) SL *= 2;
-    const int kper = (K + SL - 1) / SL;
-    for (int w = threadIdx.x; w < N * SL; w += MLP_THREADS) {
-        const int s = w / N, n = w - s * N;
-        const int k0 = s * kper, k1 = min(K, k0 + kper);
-        S acc[TB];
-        const S b0 = s == 0 ? bias[n] : (S)0;
-#pragma unroll
-        for (int b = 0; b < TB; ++b) acc[b] = b0;
-#pragma unroll 8
-        for (int k = k0; k < k1; ++k) {
-            const S wv = W[(size_t)k * N + n];
-#pragma unroll
-            for (int b = 0; b < TB; ++b) acc[b] = s_fma<S>(wv, x[k * TB + b], acc[b]);
-        }
-        if (SL == 1) {
-#pragma unroll
-            for (int b = 0; b < TB; ++b) y[n * TB + b] = relu ? s_max<S>(acc[b], (S)0) : acc[b];
-        } else {
-#pragma unroll
-            for (int b = 0; b < TB; ++b) red[(s * N + n) * TB + b] = acc[b];
-        }
-    }
-    if (SL > 1) {
-        __syncthreads();
-        for (int i = threadIdx.x; i < N * TB; i += MLP_THREADS) {
-            S a = (S)0;
-            for (int s = 0; s < SL; ++s) a += red[s * N * TB + i];
-            y[i] = relu ? s_max<S>(a, (S)0) : a;
-        }
-    }
-    __syncthreads();
-}
-
-// MLP forward on a tile: x (dims[0] x TB) -> y (dims[L] x TB).  hid: two ping-pong buffers of max_width*TB.
-// With KEEP the post-activation outputs of every hidden layer are left in act[l] (for the VJP).
-template <class S, int TB>
-__device__ void mlp_fwd(const MlpNet& net, const S* __restrict__ P, const S* x, S* y, S* hid0, S* hid1, S* red) {
-    const S* in = x;
-    for (int l = 0; l < net.n_layers; ++l) {
-        const bool last = l + 1 == net.n_layers;
-        S* out = last ? y : ((l & 1) ? hid1 : hid0);
-        dense_fwd<S, TB>(P + net.w_off[l], P + net.b_off[l], in, out, red, net.dims[l], net.dims[l + 1], !last);
-        in = out;
-    }
-}
-
-template <class S> __device__ __forceinline__ S tab_a(int j, int i) {
-    using Tb = Tab<S>;
-    switch (j * 8 + i) {
-        case 1 * 8 + 0: return Tb::a21;
-        case 2 * 8 + 0: return Tb::a31; case 2 * 8 + 1: return Tb::a32;
-        case 3 * 8 + 0: return Tb::a41; case 3 * 8 + 1: return Tb::a42; case 3 * 8 + 2: return Tb::a43;
-        case 4 * 8 + 0: return Tb::a51; case 4 * 8 + 1: return Tb::a52; case 4 * 8 + 2: return Tb::a53; case 4 * 8 + 3: return Tb::a54;
-        case 5 * 8 + 0: return Tb::a61; case 5 * 8 + 1: return Tb::a62; case 5 * 8 + 2: return Tb::a63; case 5 * 8 + 3: return Tb::a64;
-        case 5 * 8 + 4: return Tb::a65;
-        case 6 * 8 + 0: return Tb::a71; case 6 * 8 + 1: return Tb::a72; case 6 * 8 + 2: return Tb::a73; case 6 * 8 + 3: return Tb::a74;
-        case 6 * 8 + 4: return Tb::a75; case 6 * 8 + 5: return Tb::a76;
-    }
-    return (S)0;
-}
-template <class S> __device__ __forceinline__ S tab_bt(int i) {
-    using Tb = Tab<S>;
-    switch (i) {
-        case 0: return Tb::bt1; case 1: return Tb::bt2; case 2: return Tb::bt3; case 3: return Tb::bt4;
-        case 4: return Tb::bt5; case 5: return Tb::bt6; case 6: return Tb::bt7;
-    }
-    return (S)0;
-}
-
-// Per-trajectory controller / bookkeeping state of a tile (shared memory)
-template <int TB> struct TileState {
-    double t[TB], dt[TB], dts[TB], tnew[TB], qold[TB], esum[TB], dt_next[TB];
-    long long iters[TB];
-    int ks[TB], na[TB], nr[TB], ret[TB];
-    int accept[TB], active[TB], nsave[TB];
-};
-
-// grid-wide deterministic sum: every CTA publishes its partial, all meet, all add in the same order
-__device__ double grid_sum(double part, double* partials, cg::grid_group& grid) {
-    if (threadIdx.x == 0) partials[blockIdx.x] = part;
-    grid.sync();
-    double r = 0.0;
-    for (int i = 0; i < (int)gridDim.x; ++i) r += __ldcg(partials + i);
-    grid.sync();  // partials may be overwritten by the next reduction only after everyone has read them
-    return r;
-}
-
-// ---- forward ------------------------------------------------------------------------------------------
-template <class S, int TB, bool GLOBAL>
-__global__ void __launch_bounds__(MLP_THREADS)
-mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, const double* __restrict__ tg, int B, int T,
-               KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
-               int* __restrict__ nreject, MlpTapeView<S> tape, double* __restrict__ partials) {
-    cg::grid_group grid = cg::this_grid();
-    const int D = net.dims[0];
-    const int HW = net.max_width;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    S* U = reinterpret_cast<S*>(smem_raw);  // [D][TB]
-    S* G = U + D * TB;                      // stage input
-    S* UN = G + D * TB;                     // u_{n+1}
-    S* Kst = UN + D * TB;                   // [7][D][TB]
-    S* hid0 = Kst + 7 * D * TB;
-    S* hid1 = hid0 + HW * TB;
-    S* red = hid1 + HW * TB;                // [MLP_THREADS][TB]
-    const size_t s_bytes = (((size_t)(10 * D + 2 * HW + MLP_THREADS) * TB * sizeof(S)) + 15) & ~(size_t)15;
-    TileState<TB>* ts = reinterpret_cast<TileState<TB>*>(smem_raw + s_bytes);
-    __shared__ int s_any;
-
-    const double t0 = tg[0], tend = tg[T - 1];
-    const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
-    const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
-    const S abstol = (S)o.abstol, reltol = (S)o.reltol;
-    const int ntiles = (B + TB - 1) / TB;
-    const int DT = D * TB;
-
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        // GLOBAL mode runs exactly one tile per CTA (the host sizes the grid so): all CTAs then take the same
-        // steps (one dt for the batch) and meet at the same grid reductions
-        const int b0 = tile * TB;
-        // ---- load the tile, k1 = f(u0), initial step ---------------------------------------------------
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-            const int d = i / TB, b = i - d * TB;
-            const int gb = b0 + b;
-            U[i] = gb < B ? z0[(size_t)gb * D + d] : (S)0;
-        }
-        if (threadIdx.x < TB) {
-            const int b = threadIdx.x;
-            ts->t[b] = t0; ts->qold[b] = (double)pi_init(o).qold_pow;  /* controller memory: fastpow(qold, beta2) */ ts->iters[b] = 0; ts->ks[b] = 1; ts->na[b] = 0; ts->nr[b] = 0;
-            ts->ret[b] = RET_SUCCESS; ts->active[b] = (b0 + b < B) && T > 1; ts->dt[b] = o.dt;
-        }
-        __syncthreads();
-        mlp_fwd<S, TB>(net, P, U, Kst, hid0, hid1, red);  // fsalfirst
-        // save point 0 is u0 itself
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-            const int d = i / TB, b = i - d * TB;
-            if (b0 + b < B) traj[(size_t)(b0 + b) * D + d] = U[i];
-        }
-        if (o.adaptive && !(o.dt > 0.0)) {
-            // Hairer initial step; norms per trajectory or over the whole batch.
-            // column sums: thread b adds the D entries of its trajectory (D is small)
-            if (threadIdx.x < TB) {
-                const int b = threadIdx.x;
-                double a0 = 0.0, a1 = 0.0;
-                if (b0 + b < B)
-                    for (int d = 0; d < D; ++d) {
-                        const S sk = s_fma<S>(s_abs<S>(U[d * TB + b]), reltol, abstol);
-                        const S a = U[d * TB + b] / sk, c = Kst[d * TB + b] / sk;
-                        a0 += (double)(a * a);
-                        a1 += (double)(c * c);
-                    }
-                ts->esum[b] = a0;
-                ts->dt_next[b] = a1;
-            }
-            __syncthreads();
-            double d0[TB], d1[TB];
-            if (GLOBAL) {
-                double s0 = 0.0, s1 = 0.0;
-                for (int b = 0; b < TB; ++b) { s0 += ts->esum[b]; s1 += ts->dt_next[b]; }
-                const double n = (double)D * (double)B;
-                s0 = grid_sum(s0, partials, grid);
-                s1 = grid_sum(s1, partials, grid);
-                for (int b = 0; b < TB; ++b) { d0[b] = (double)s_sqrt<S>((S)(s0 / n)); d1[b] = (double)s_sqrt<S>((S)(s1 / n)); }
-            } else {
-                for (int b = 0; b < TB; ++b) {
-                    d0[b] = (double)s_sqrt<S>((S)(ts->esum[b] / D));
-                    d1[b] = (double)s_sqrt<S>((S)(ts->dt_next[b] / D));
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x < TB) {
-                const int b = threadIdx.x;
-                const double dt0 = (d0[b] < 1e-5 || d1[b] < 1e-5) ? 1e-6 : 0.01 * (d0[b] / d1[b]);
-                ts->dts[b] = fmin(dt0, dtmax);
-            }
-            __syncthreads();
-            // u1 = u0 + dt0 f0, f1 = f(u1)
-            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) G[i] = s_fma<S>((S)ts->dts[i % TB], Kst[i], U[i]);
-            __syncthreads();
-            mlp_fwd<S, TB>(net, P, G, UN, hid0, hid1, red);  // f1 in UN
-            if (threadIdx.x < TB) {
-                const int b = threadIdx.x;
-                double a2 = 0.0;
-                if (b0 + b < B)
-                    for (int d = 0; d < D; ++d) {
-                        const S sk = s_fma<S>(s_abs<S>(U[d * TB + b]), reltol, abstol);
-                        const S a = (UN[d * TB + b] - Kst[d * TB + b]) / sk;
-                        a2 += (double)(a * a);
-                    }
-                ts->esum[b] = a2;
-            }
-            __syncthreads();
-            double s2 = 0.0;
-            if (GLOBAL) {
-                for (int b = 0; b < TB; ++b) s2 += ts->esum[b];
-                s2 = grid_sum(s2, partials, grid);
-            }
-            if (threadIdx.x < TB) {
-                const int b = threadIdx.x;
-                const double dt0 = ts->dts[b];
-                const double d2 = (double)s_sqrt<S>((S)(GLOBAL ? s2 / ((double)D * (double)B) : ts->esum[b] / D)) / dt0;
-                double dtv;
-                if (dt0 < 10.0 * 2.220446049250313e-16) {
-                    dtv = fmax(1e-6, dtmin);
-                } else {
-                    const double m = fmax(d1[b], d2);
-                    const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(m)) / 5.0);
-                    dtv = fmax(dtmin, fmin(100.0 * dt0, fmin(dt1, dtmax)));
-                }
-                ts->dt[b] = dtv;
-            }
-            __syncthreads();
-        }
-        if (threadIdx.x < TB) {
-            const int b = threadIdx.x;
-            if (ts->active[b] && (!(ts->dt[b] > 0.0) || !isfinite(ts->dt[b]))) { ts->ret[b] = RET_DTLESSTHANMIN; ts->active[b] = 0; }
-        }
-        __syncthreads();
-
-        // ---- step loop ----------------------------------------------------------------------------------
-        for (;;) {
-            if (threadIdx.x == 0) s_any = 0;
-            __syncthreads();
-            if (threadIdx.x < TB && ts->active[threadIdx.x]) s_any = 1;
-            __syncthreads();
-            // GLOBAL: all trajectories share the step sequence and every tile holds at least one of them, so
-            // every CTA leaves this loop in the same iteration (no CTA is left waiting at a grid barrier)
-            if (!s_any) break;
-            if (threadIdx.x < TB) {
-                const int b = threadIdx.x;
-                if (ts->active[b]) {
-                    if (ts->iters[b] >= o.maxiters) {
-                        ts->ret[b] = RET_MAXITERS; ts->active[b] = 0;
-                    } else {
-                        ts->iters[b]++;
-                        const double t = ts->t[b];
-                        const double dts = fmin(ts->dt[b], tend - t);
-                        double tnew = t + dts;
-                        if (fabs(tnew - tend) < 100.0 * ulp_of(fmax(fabs(t), fabs(tend)))) tnew = tend;
-                        ts->dts[b] = dts; ts->tnew[b] = tnew;
-                    }
-                }
-                ts->esum[b] = 0.0;
-            }
-            __syncthreads();
-            // stages 2..7 (k1 is Kst[0] by FSAL)
-            for (int j = 1; j < 7; ++j) {
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-                    S acc = tab_a<S>(j, 0) * Kst[i];
-                    for (int q = 1; q < j; ++q) acc = s_fma<S>(tab_a<S>(j, q), Kst[q * DT + i], acc);
-                    const S v = s_fma<S>((S)ts->dts[i % TB], acc, U[i]);
-                    G[i] = v;
-                    if (j == 6) UN[i] = v;
-                }
-                __syncthreads();
-                mlp_fwd<S, TB>(net, P, G, Kst + j * DT, hid0, hid1, red);
-            }
-            // error estimate: squared scaled residuals into G (free after the stages), then column sums
-            double part = 0.0;
-            if (o.adaptive) {
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-                    const int b = i % TB;
-                    S acc = tab_bt<S>(0) * Kst[i];
-                    for (int q = 1; q < 7; ++q) acc = s_fma<S>(tab_bt<S>(q), Kst[q * DT + i], acc);
-                    const S ut = (S)ts->dts[b] * acc;
-                    const S sk = s_fma<S>(s_max<S>(s_abs<S>(U[i]), s_abs<S>(UN[i])), reltol, abstol);
-                    const S a = ut / sk;
-                    G[i] = a * a;
-                }
-                __syncthreads();
-                if (threadIdx.x < TB) {
-                    const int b = threadIdx.x;
-                    double e = 0.0;
-                    if (ts->active[b])
-                        for (int d = 0; d < D; ++d) e += (double)G[d * TB + b];
-                    ts->esum[b] = e;
-                }
-                __syncthreads();
-                if (GLOBAL) {
-                    for (int b = 0; b < TB; ++b) part += ts->esum[b];
-                    part = grid_sum(part, partials, grid);
-                }
-            }
-            // controller, one thread per trajectory
-            if (threadIdx.x < TB) {
-                const int b = threadIdx.x;
-                ts->accept[b] = 0;
-                if (ts->active[b]) {
-                    bool finite = true;
-                    for (int d = 0; d < D; ++d) finite = finite && s_finite<S>(UN[d * TB + b]);
-                    bool accept = true;
-                    double dt_next = ts->dt[b];
-                    if (o.adaptive) {
-                        const double e2 = GLOBAL ? part / ((double)D * (double)B) : ts->esum[b] / (double)D;
-                        const double EEst = (double)s_sqrt<S>((S)e2);
-                        if (EEst != EEst) finite = false;
-                        PiState pst{(float)ts->qold[b]};
-                        accept = pi_controller(o, EEst, ts->dts[b], dtmax, pst, dt_next);
-                        ts->qold[b] = (double)pst.qold_pow;
-                    }
-                    if (!finite) {
-                        ts->ret[b] = RET_UNSTABLE; ts->active[b] = 0;
-                    } else {
-                        if (accept) {
-                            const int n = ts->na[b];
-                            if (tape.cap > 0 && n < tape.cap) {
-                                tape.t[(size_t)n * B + b0 + b] = ts->t[b];
-                                tape.dt[(size_t)n * B + b0 + b] = ts->dts[b];
-                            }
-                            ts->accept[b] = 1;
-                        } else {
-                            ts->nr[b]++;
-                        }
-                        ts->dt[b] = dt_next;
-                        if (o.adaptive && !(accept && ts->tnew[b] == tend) && (!(fabs(dt_next) > dtmin) || !isfinite(dt_next))) {
-                            ts->ret[b] = RET_DTLESSTHANMIN; ts->active[b] = 0; ts->accept[b] = 0;
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-            // tape: state at the start of the accepted step
-            if (tape.cap > 0) {
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-                    const int d = i / TB, b = i - d * TB;
-                    if (ts->accept[b] && ts->na[b] < tape.cap)
-                        tape.u[((size_t)ts->na[b] * B + b0 + b) * D + d] = U[i];
-                }
-            }
-            // saveat through the dense interpolant; a trajectory may have several pending save points
-            for (;;) {
-                if (threadIdx.x == 0) s_any = 0;
-                __syncthreads();
-                if (threadIdx.x < TB) {
-                    const int b = threadIdx.x;
-                    const int pend = ts->accept[b] && ts->ks[b] < T && tg[ts->ks[b]] <= ts->tnew[b];
-                    ts->nsave[b] = pend;
-                    if (pend) s_any = 1;
-                }
-                __syncthreads();
-                if (!s_any) break;
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-                    const int d = i / TB, b = i - d * TB;
-                    if (ts->nsave[b]) {
-                        const int ks = ts->ks[b];
-                        const double tsv = tg[ks];
-                        S out;
-                        if (tsv == ts->tnew[b]) {
-                            out = UN[i];
-                        } else {
-                            S bw[7];
-                            interp_weights<S>((S)((tsv - ts->t[b]) / ts->dts[b]), bw);
-                            S acc = bw[0] * Kst[i];
-#pragma unroll
-                            for (int q = 1; q < 7; ++q) acc = s_fma<S>(bw[q], Kst[q * DT + i], acc);
-                            out = s_fma<S>((S)ts->dts[b], acc, U[i]);
-                        }
-                        traj[((size_t)ks * B + b0 + b) * D + d] = out;
-                    }
-                }
-                __syncthreads();
-                if (threadIdx.x < TB && ts->nsave[threadIdx.x]) ts->ks[threadIdx.x]++;
-            }
-            // commit accepted steps
-            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-                if (ts->accept[i % TB]) { U[i] = UN[i]; Kst[i] = Kst[6 * DT + i]; }
-            }
-            __syncthreads();
-            if (threadIdx.x < TB) {
-                const int b = threadIdx.x;
-                if (ts->accept[b]) {
-                    ts->t[b] = ts->tnew[b];
-                    ts->na[b]++;
-                    if (ts->ks[b] >= T) ts->active[b] = 0;
-                }
-            }
-            __syncthreads();
-        }
-        // ---- epilogue of the tile: NaN block on failure (GOKU.jl:114 convention), statistics -----------
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
-            const int d = i / TB, b = i - d * TB;
-            if (b0 + b < B && ts->ret[b] != RET_SUCCESS)
-                for (int k = 0; k < T; ++k) traj[((size_t)k * B + b0 + b) * D + d] = s_nan<S>();
-        }
-        if (threadIdx.x < TB && b0 + threadIdx.x < B) {
-            const int b = threadIdx.x;
-            if (retcode) retcode[b0 + b] = ts->ret[b];
-            if (naccept) naccept[b0 + b] = ts->na[b];
-            if (nreject) nreject[b0 + b] = ts->nr[b];
-        }
-        __syncthreads();
-        if (GLOBAL) break;
-    }
-}
 
 // ---- backward -----------------------------------------------------------------------------------------
 // y = relu?(W x + b) on a tile, keeping the output; used to recompute hidden activations.
@@ -734,12 +312,6 @@ template <class S> __global__ void mlp_reduce_grads_kernel(const S* __restrict__
     }
 }
 
-template <class S, int TB> static size_t fwd_smem(const MlpNet& net) {
-    const size_t D = net.dims[0], HW = net.max_width;
-    size_t n = (3 * D + 7 * D + 2 * HW + MLP_THREADS) * TB * sizeof(S);
-    n = (n + 15) & ~(size_t)15;
-    return n + sizeof(TileState<TB>) + 64;
-}
 template <class S, int TB> static size_t bwd_smem(const MlpNet& net) {
     const size_t D = net.dims[0], HW = net.max_width;
     size_t n = (21 * D + 4 * D + (net.n_layers - 1) * HW + 2 * HW + MLP_THREADS) * TB * sizeof(S);
@@ -788,6 +360,19 @@ static int make_net(ldeq_handle* h, const int32_t* dims, int n_layers, MlpNet* n
     }
     net->n_params = off;
     net->max_width = mw;
+    // padded shared-memory image (resident path), activation slot layout, the layer with the batched gradient pass
+    int io = 0, ao = 0, lb = -1;
+    for (int l = 0; l < n_layers; ++l) {
+        net->i_ld[l] = dims[l + 1] | 1;
+        net->i_w[l] = io; io += (dims[l] * net->i_ld[l] + 3) & ~3;
+        net->i_b[l] = io; io += (dims[l + 1] + 3) & ~3;
+        net->act_off[l] = ao;
+        if (l + 1 < n_layers) ao += dims[l + 1];
+        if (l >= 1 && l + 1 < n_layers && (lb < 0 || dims[l] * dims[l + 1] > dims[lb] * dims[lb + 1])) lb = l;
+    }
+    net->n_img = io;
+    net->act_rows = ao;
+    net->lb = lb;
     return LDEQ_OK;
 }
 
@@ -826,6 +411,14 @@ static int mlp_fwd_dispatch(ldeq_handle* h, const MlpNet& net, const void* P, co
     if (rc) return rc;
     double* partials = (double*)h->scratch[0];
     const int sms = h->sm_count;
+    if constexpr (sizeof(S) == 4) {
+        // Float32 networks that fit one SM's shared memory run on the resident-weights kernels (ldeq_mlp_res.cu)
+        if (!getenv("LDEQ_MLP_NO_RESIDENT")) {
+            rc = ldeq_mlp_res_forward(h, net, (const float*)P, (const float*)z0, tg, B, T, ko, norm_mode, (float*)traj, ret, na, nr,
+                                      tv, partials, s);
+            if (rc != LDEQ_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if (norm_mode == LDEQ_NORM_GLOBAL && ko.adaptive) {   // fixed-step mode computes no error norm: no grid barrier
         // one tile per CTA, all CTAs co-resident (cooperative launch): pick the smallest tile that fits the chip
         auto fits = [&](int tb, size_t smem, const void* fn) -> int {
@@ -977,6 +570,13 @@ int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, v
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
     const bool small = tape->B <= 4 * h->sm_count;
+    if (tape->dtype == LDEQ_F32 && !getenv("LDEQ_MLP_NO_RESIDENT")) {
+        MlpTapeView<float> tv{tape->t, tape->dt, (float*)tape->u, tape->cap};
+        const int rc = ldeq_mlp_res_backward(h, tape->net, (const float*)tape->params, tape->tgrid, tape->B, tape->T,
+                                             (const float*)dtraj, tv, tape->retcode, tape->naccept, (float*)dz0,
+                                             (float*)dparams_flat, s);
+        if (rc != LDEQ_ERR_UNSUPPORTED) return rc;
+    }
     if (tape->dtype == LDEQ_F32)
         return small ? launch_mlp_bwd<float, 2>(h, tape, dtraj, dz0, dparams_flat, s)
                      : launch_mlp_bwd<float, 8>(h, tape, dtraj, dz0, dparams_flat, s);

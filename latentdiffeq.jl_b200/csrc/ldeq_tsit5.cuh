@@ -511,6 +511,7 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
     // rows 1..T-1 of the cotangent travel through the ring: [kload, T) has been fetched so far
     int kload = T;
     auto refill = [&](int ks_max) {
+        if (ks_max < 1) return;  // no lane of the warp has a row left to consume (finished, failed or overflowed)
         int klo = ks_max - R + 1;
         klo = klo < 1 ? 1 : klo;
         for (int r = kload - 1; r >= klo; --r)
