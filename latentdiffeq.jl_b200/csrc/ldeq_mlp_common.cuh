@@ -4,8 +4,7 @@
 #include <cooperative_groups.h>
 
 #include "ldeq_internal.h"
-
-namespace cg = cooperative_groups;
+#include "ldeq_gridsum.cuh"
 
 namespace ldeq {
 
@@ -34,6 +33,7 @@ struct MlpNet {
     int m_lgG[2][MLP_MAX_LAYERS], m_cper[2][MLP_MAX_LAYERS];
 };
 #define RES_THREADS 512
+#define RES_TGRID_MAX 256
 
 template <class S> struct MlpTapeView {
     double* t;   // [cap][B]
@@ -285,24 +285,15 @@ template <int TB> struct TileState {
     int accept[TB], active[TB], nsave[TB];
 };
 
-// grid-wide deterministic sum: every CTA publishes its partial, all meet, all add in the same order
-static __device__ __forceinline__ double grid_sum(double part, double* partials, cg::grid_group& grid) {
-    if (threadIdx.x == 0) partials[blockIdx.x] = part;
-    grid.sync();
-    double r = 0.0;
-    for (int i = 0; i < (int)gridDim.x; ++i) r += __ldcg(partials + i);
-    grid.sync();  // partials may be overwritten by the next reduction only after everyone has read them
-    return r;
-}
-
 // ---- forward ------------------------------------------------------------------------------------------
 // RES: Float32 weights staged once into shared memory (padded image) and read from there by NT threads
 template <class S, int TB, bool GLOBAL, bool RES = false, int NT = MLP_THREADS>
 __global__ void __launch_bounds__(NT)
-mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, const double* __restrict__ tg, int B, int T,
+mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, const double* __restrict__ tg_in, int B, int T,
                KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
                int* __restrict__ nreject, MlpTapeView<S> tape, double* __restrict__ partials) {
     cg::grid_group grid = cg::this_grid();
+    int gs_parity = 0;
     const int D = net.dims[0];
     const int HW = net.max_width;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -318,6 +309,16 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
         (((size_t)(RES ? net.n_img : 0) * sizeof(S) + (size_t)(10 * D + 2 * HW + (RES ? 0 : NT)) * TB * sizeof(S)) + 15) & ~(size_t)15;
     TileState<TB>* ts = reinterpret_cast<TileState<TB>*>(smem_raw + s_bytes);
     __shared__ int s_any;
+    const double* tg = tg_in;
+    if constexpr (RES) {
+        // the save-time lookups of the step loop are on the critical path of a latency-bound CTA: keep the grid on chip
+        __shared__ double tg_s[RES_TGRID_MAX];
+        if (T <= RES_TGRID_MAX) {
+            for (int i = threadIdx.x; i < T; i += NT) tg_s[i] = tg_in[i];
+            __syncthreads();
+            tg = tg_s;
+        }
+    }
 
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
@@ -377,8 +378,8 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
                 double s0 = 0.0, s1 = 0.0;
                 for (int b = 0; b < TB; ++b) { s0 += ts->esum[b]; s1 += ts->dt_next[b]; }
                 const double n = (double)D * (double)B;
-                s0 = grid_sum(s0, partials, grid);
-                s1 = grid_sum(s1, partials, grid);
+                s0 = grid_sum(s0, partials, grid, gs_parity);
+                s1 = grid_sum(s1, partials, grid, gs_parity);
                 for (int b = 0; b < TB; ++b) { d0[b] = (double)s_sqrt<S>((S)(s0 / n)); d1[b] = (double)s_sqrt<S>((S)(s1 / n)); }
             } else {
                 for (int b = 0; b < TB; ++b) {
@@ -412,7 +413,7 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
             double s2 = 0.0;
             if (GLOBAL) {
                 for (int b = 0; b < TB; ++b) s2 += ts->esum[b];
-                s2 = grid_sum(s2, partials, grid);
+                s2 = grid_sum(s2, partials, grid, gs_parity);
             }
             if (threadIdx.x < TB) {
                 const int b = threadIdx.x;
@@ -497,7 +498,7 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
                 __syncthreads();
                 if (GLOBAL) {
                     for (int b = 0; b < TB; ++b) part += ts->esum[b];
-                    part = grid_sum(part, partials, grid);
+                    part = grid_sum(part, partials, grid, gs_parity);
                 }
             }
             // controller, one thread per trajectory

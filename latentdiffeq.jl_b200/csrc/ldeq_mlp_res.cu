@@ -37,13 +37,13 @@ __device__ void grad_immediate(float* __restrict__ gW, float* __restrict__ gb, c
             float a = 0.f;
 #pragma unroll
             for (int b = 0; b < TB; ++b) a = fmaf(d[b], x[k * TB + b], a);
-            gW[(size_t)k * N + n] += a;
+            atomicAdd(gW + (size_t)k * N + n, a);  // RED: no round trip (the slice is private to the CTA, one add per address per pass)
         }
         if (s == 0) {
             float a = 0.f;
 #pragma unroll
             for (int b = 0; b < TB; ++b) a += d[b];
-            gb[n] += a;
+            atomicAdd(gb + n, a);
         }
     }
     __syncthreads();
@@ -73,7 +73,7 @@ __device__ void grad_batched(float* __restrict__ gW, float* __restrict__ gb, con
                 for (int j = 1; j < 7; ++j)
 #pragma unroll
                     for (int b = 0; b < TB; ++b) a = fmaf(d[j][b], acts[j * slot_stride + x_off + k * TB + b], a);
-                gW[(size_t)k * N + n] += a;
+                atomicAdd(gW + (size_t)k * N + n, a);  // RED: no round trip (the slice is private to the CTA, one add per address per pass)
             }
         } else {
             // only the merged stage (slot 6) carries a cotangent in this iteration
@@ -82,7 +82,7 @@ __device__ void grad_batched(float* __restrict__ gW, float* __restrict__ gb, con
                 float a = 0.f;
 #pragma unroll
                 for (int b = 0; b < TB; ++b) a = fmaf(d[6][b], acts[6 * slot_stride + x_off + k * TB + b], a);
-                gW[(size_t)k * N + n] += a;
+                atomicAdd(gW + (size_t)k * N + n, a);  // RED: no round trip (the slice is private to the CTA, one add per address per pass)
             }
         }
         if (s == 0) {
@@ -91,7 +91,7 @@ __device__ void grad_batched(float* __restrict__ gW, float* __restrict__ gb, con
             for (int j = 1; j < 7; ++j)
 #pragma unroll
                 for (int b = 0; b < TB; ++b) a += d[j][b];
-            gb[n] += a;
+            atomicAdd(gb + n, a);
         }
     }
     __syncthreads();
@@ -123,7 +123,7 @@ __device__ void mlp_vjp_res(const MlpNet& net, const float* img, float* __restri
 
 template <int TB>
 __global__ void __launch_bounds__(RES_THREADS)
-mlp_bwd_res_kernel(MlpNet net, const float* __restrict__ P, const double* __restrict__ tg, int B, int T,
+mlp_bwd_res_kernel(MlpNet net, const float* __restrict__ P, const double* tg, int B, int T,
                    const float* __restrict__ dtraj, MlpTapeView<float> tape, const int* __restrict__ retcode,
                    const int* __restrict__ naccept, float* __restrict__ dz0, float* __restrict__ gscratch) {
     constexpr int NT = RES_THREADS;
@@ -154,6 +154,11 @@ mlp_bwd_res_kernel(MlpNet net, const float* __restrict__ P, const double* __rest
     int* ks_s = n_s + TB;
     int* flag_s = ks_s + TB;
     __shared__ int s_any, s_live;
+    __shared__ double tg_s[RES_TGRID_MAX];
+    if (T <= RES_TGRID_MAX) {
+        for (int i = threadIdx.x; i < T; i += NT) tg_s[i] = tg[i];
+        tg = tg_s;  // every save-time lookup below is a shared-memory read
+    }
 
     stage_weight_image<NT>(net, P, Wimg);
     float* gP = gscratch + (size_t)blockIdx.x * net.n_params;  // this CTA's private gradient accumulator (L2 resident)
@@ -330,7 +335,7 @@ template <class S> __global__ void mlp_res_reduce_grads_kernel(const S* __restri
     }
 }
 
-static constexpr size_t kSmemMax = 227 * 1024;
+static constexpr size_t kSmemMax = 227 * 1024 - RES_TGRID_MAX * sizeof(double) - 64;  // dynamic part
 
 template <int TB, bool GLOBAL, int NT>
 static int launch_res_fwd(ldeq_handle* h, const MlpNet& net, const float* P, const float* z0, const double* tg, int B, int T,

@@ -17,12 +17,11 @@
 //     relative error 2^-16 per product instead of bf16's 2^-8;
 //   * the stage slopes k1..k6 live in the 96 TMEM columns left over (512 = 208 accumulator + 2*104 operand + 96).
 // TMEM column map: see the TC_COL_* constants below.
-#include <cooperative_groups.h>
+#include "ldeq_gridsum.cuh"
 #include <cuda_bf16.h>
 
 #include "ldeq_internal.h"
 
-namespace cg = cooperative_groups;
 
 namespace ldeq {
 
@@ -242,6 +241,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                   const double* __restrict__ tg, int B, int T, KOpts o, float* __restrict__ traj, int* __restrict__ retcode,
                   int* __restrict__ naccept, int* __restrict__ nreject, MlpTapeViewTc<float> tape, double* __restrict__ partials) {
     cg::grid_group grid = cg::this_grid();
+    int gs_parity = 0;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t mbar[3];  // [0] first column half, [1] second column half, [2] output layer
     __shared__ uint32_t tmem_base_s;
@@ -432,16 +432,8 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                         double b1 = 0.0;
                         for (int w = 0; w < TC_ROWS / 32; ++w) b1 += red_s[w];
                         __syncthreads();
-                        if (tid == 0) partials[blockIdx.x] = b0;
-                        grid.sync();
-                        e0 = 0.0;
-                        for (int i = 0; i < (int)gridDim.x; ++i) e0 += __ldcg(partials + i);
-                        grid.sync();
-                        if (tid == 0) partials[blockIdx.x] = b1;
-                        grid.sync();
-                        e1 = 0.0;
-                        for (int i = 0; i < (int)gridDim.x; ++i) e1 += __ldcg(partials + i);
-                        grid.sync();
+                        e0 = grid_sum(b0, partials, grid, gs_parity);
+                        e1 = grid_sum(b1, partials, grid, gs_parity);
                         n = (double)D * (double)B;
                     }
                     const double d0 = (double)sqrtf((float)(e0 / n));
@@ -474,11 +466,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                     double bsum = 0.0;
                     for (int w = 0; w < TC_ROWS / 32; ++w) bsum += red_s[w];
                     __syncthreads();
-                    if (tid == 0) partials[blockIdx.x] = bsum;
-                    grid.sync();
-                    e2 = 0.0;
-                    for (int i = 0; i < (int)gridDim.x; ++i) e2 += __ldcg(partials + i);
-                    grid.sync();
+                    e2 = grid_sum(bsum, partials, grid, gs_parity);
                     n = (double)D * (double)B;
                 }
                 const double d2 = (double)sqrtf((float)(e2 / n)) / dt0;
@@ -539,11 +527,7 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                         double bsum = 0.0;
                         for (int w = 0; w < TC_ROWS / 32; ++w) bsum += red_s[w];
                         __syncthreads();
-                        if (tid == 0) partials[blockIdx.x] = bsum;
-                        grid.sync();
-                        e2 = 0.0;
-                        for (int i = 0; i < (int)gridDim.x; ++i) e2 += __ldcg(partials + i);
-                        grid.sync();
+                        e2 = grid_sum(bsum, partials, grid, gs_parity);
                         n = (double)D * (double)B;
                     }
                     const double EEst = (double)sqrtf((float)(e2 / n));
