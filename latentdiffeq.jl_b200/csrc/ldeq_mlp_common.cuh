@@ -31,6 +31,7 @@ struct MlpNet {
     // [0][l] forward (outputs = dims[l+1]), [1][l] transposed (outputs = dims[l]); a warp covers 2^lgG output groups x
     // 32 >> lgG contraction slices of cper rows each
     int m_lgG[2][MLP_MAX_LAYERS], m_cper[2][MLP_MAX_LAYERS];
+    int g_sl[MLP_MAX_LAYERS];  // k-slices of the gradient update of layer l (thread = output neuron x slice)
 };
 #define RES_THREADS 512
 #define RES_TGRID_MAX 256
@@ -196,6 +197,12 @@ __device__ __forceinline__ void dense_res(const MlpNet& net, const float* img, i
 // shortest per-thread contraction whose output groups fit the CTA's warps
 static inline void res_plan(MlpNet& net, int NT) {
     const int warps = NT / 32;
+    for (int l = 0; l < net.n_layers; ++l) {
+        const int K = net.dims[l], N = net.dims[l + 1];
+        int SL = 1;
+        while (SL * 2 * N <= NT && SL < 32 && SL * 2 <= K) SL *= 2;
+        net.g_sl[l] = SL;
+    }
     for (int dir = 0; dir < 2; ++dir)
         for (int l = 0; l < net.n_layers; ++l) {
             const int NI = dir ? net.dims[l] : net.dims[l + 1], NC = dir ? net.dims[l + 1] : net.dims[l];

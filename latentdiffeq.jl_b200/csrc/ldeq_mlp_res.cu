@@ -21,9 +21,8 @@ namespace ldeq {
 
 // gW[k*N + n] += sum_b dy[n][b] x[k][b];  gb[n] += sum_b dy[n][b]   (small layers: per stage)
 template <int TB, int NT>
-__device__ void grad_immediate(float* __restrict__ gW, float* __restrict__ gb, const float* dy, const float* x, int K, int N) {
-    int SL = 1;
-    while (SL * 2 * N <= NT && SL < 32 && SL * 2 <= K) SL *= 2;
+__device__ void grad_immediate(float* __restrict__ gW, float* __restrict__ gb, const float* dy, const float* x, int K, int N,
+                               int SL, bool sync) {
     const int kper = (K + SL - 1) / SL;
     const int w = threadIdx.x;
     if (w < N * SL) {
@@ -46,16 +45,14 @@ __device__ void grad_immediate(float* __restrict__ gW, float* __restrict__ gb, c
             atomicAdd(gb + n, a);
         }
     }
-    __syncthreads();
+    if (sync) __syncthreads();
 }
 
 // rank-(NSLOT*TB) update of the batched layer from the activation slots [slot_lo, 7):
 // x = slot's output of layer lb-1, dy = slot's (overwritten) output of layer lb
 template <int TB, int NT>
 __device__ void grad_batched(float* __restrict__ gW, float* __restrict__ gb, const float* acts, int slot_stride, int x_off,
-                             int dy_off, int slot_lo, int K, int N) {
-    int SL = 1;
-    while (SL * 2 * N <= NT && SL < 32 && SL * 2 <= K) SL *= 2;
+                             int dy_off, int slot_lo, int K, int N, int SL) {
     const int kper = (K + SL - 1) / SL;
     for (int w = threadIdx.x; w < N * SL; w += NT) {
         const int s = w / N, n = w - s * N;
@@ -106,7 +103,10 @@ __device__ void mlp_vjp_res(const MlpNet& net, const float* img, float* __restri
     for (int l = net.n_layers - 1; l >= 0; --l) {
         const int K = net.dims[l], N = net.dims[l + 1];
         const float* xin = l == 0 ? x : slot + net.act_off[l - 1] * TB;
-        if (l != net.lb) grad_immediate<TB, NT>(gP + net.w_off[l], gP + net.b_off[l], dy, xin, K, N);
+        // the update only reads dy / xin and writes global memory: it needs a barrier before the dense layer below only
+        // when that layer overwrites xin in place
+        if (l != net.lb)
+            grad_immediate<TB, NT>(gP + net.w_off[l], gP + net.b_off[l], dy, xin, K, N, net.g_sl[l], l >= 1 && l - 1 == net.lb);
         float* dx;
         const float* mask = nullptr;
         if (l == 0) {
@@ -287,7 +287,7 @@ mlp_bwd_res_kernel(MlpNet net, const float* __restrict__ P, const double* tg, in
             // layer lb: one rank-(6 TB) update for the whole step
             if (lb >= 0)
                 grad_batched<TB, NT>(gP + net.w_off[lb], gP + net.b_off[lb], acts, ACT, net.act_off[lb - 1] * TB,
-                                     net.act_off[lb] * TB, any_active ? 1 : 6, net.dims[lb], net.dims[lb + 1]);
+                                     net.act_off[lb] * TB, any_active ? 1 : 6, net.dims[lb], net.dims[lb + 1], net.g_sl[lb]);
             // stage 1 is deferred: its cotangent and its activations (slot 0) travel to the next iteration
             for (int i = threadIdx.x; i < DT; i += NT) {
                 const int b = i % TB;
