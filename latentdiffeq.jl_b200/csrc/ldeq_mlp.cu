@@ -64,7 +64,9 @@ __device__ void dense_bwd_input(const S* __restrict__ Wt, const S* __restrict__ 
 
 // Parameter gradient of one layer accumulated into this CTA's private slice of the scratch buffer:
 // gW[k*N + n] += sum_b dy[n][b] x[k][b];  gb[n] += sum_b dy[n][b]
-template <class S, int TB>
+// RED: the accumulator is global memory -> reduction atomics (no read round trip; the slice is private to the CTA and
+// every address gets one add per pass, so the result does not depend on timing)
+template <class S, int TB, bool RED>
 __device__ void dense_bwd_params(S* __restrict__ gW, S* __restrict__ gb, const S* __restrict__ dy, const S* __restrict__ x,
                                  int K, int N) {
     // thread = output neuron n x k-slice: dy[n][:] stays in registers, x[k][:] is a shared-memory broadcast, the
@@ -83,13 +85,13 @@ __device__ void dense_bwd_params(S* __restrict__ gW, S* __restrict__ gb, const S
             S a = (S)0;
 #pragma unroll
             for (int b = 0; b < TB; ++b) a = s_fma<S>(d[b], x[k * TB + b], a);
-            gW[(size_t)k * N + n] += a;
+            if (RED) atomicAdd(gW + (size_t)k * N + n, a); else gW[(size_t)k * N + n] += a;
         }
         if (s == 0) {
             S a = (S)0;
 #pragma unroll
             for (int b = 0; b < TB; ++b) a += d[b];
-            gb[n] += a;
+            if (RED) atomicAdd(gb + n, a); else gb[n] += a;
         }
     }
     __syncthreads();
@@ -97,7 +99,7 @@ __device__ void dense_bwd_params(S* __restrict__ gW, S* __restrict__ gb, const S
 
 // VJP of the MLP at stage input x: recompute the hidden activations (kept in `acts`), then sweep back.
 // kbar (D x TB) in, gbar (D x TB) out (overwritten), parameter gradients accumulated into gP.
-template <class S, int TB>
+template <class S, int TB, bool RED>
 __device__ void mlp_vjp(const MlpNet& net, const S* __restrict__ P, const S* __restrict__ Pt, S* __restrict__ gP, const S* x,
                         const S* kbar, S* gbar, S* acts /*[n_layers-1][HW*TB]*/, S* dbuf0, S* dbuf1, S* ytmp, S* red,
                         int HW) {
@@ -114,7 +116,7 @@ __device__ void mlp_vjp(const MlpNet& net, const S* __restrict__ P, const S* __r
     for (int l = net.n_layers - 1; l >= 0; --l) {
         const int K = net.dims[l], N = net.dims[l + 1];
         const S* xin = l == 0 ? x : acts + (size_t)(l - 1) * HW * TB;
-        dense_bwd_params<S, TB>(gP + net.w_off[l], gP + net.b_off[l], dy, xin, K, N);
+        dense_bwd_params<S, TB, RED>(gP + net.w_off[l], gP + net.b_off[l], dy, xin, K, N);
         S* dx = l == 0 ? gbar : ((l & 1) ? dbuf1 : dbuf0);
         dense_bwd_input<S, TB>(Pt + net.w_off[l], dy, dx, red, K, N);
         if (l > 0) {
@@ -241,7 +243,7 @@ mlp_bwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, co
                 if (threadIdx.x < TB && flag_s[threadIdx.x]) ks_s[threadIdx.x]--;
             }
             // k7 = f(u_{n+1}): UBN += J^T kbar7
-            mlp_vjp<S, TB>(net, P, Pt, gP, Gst + 6 * DT, Kbar + 6 * DT, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+            mlp_vjp<S, TB, !SMEM_GRAD>(net, P, Pt, gP, Gst + 6 * DT, Kbar + 6 * DT, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
             for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
                 const S v = UBN[i] + GB[i];
                 UBN[i] = v;
@@ -251,7 +253,7 @@ mlp_bwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, co
             }
             __syncthreads();
             for (int j = 5; j >= 1; --j) {
-                mlp_vjp<S, TB>(net, P, Pt, gP, Gst + j * DT, Kbar + j * DT, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+                mlp_vjp<S, TB, !SMEM_GRAD>(net, P, Pt, gP, Gst + j * DT, Kbar + j * DT, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
                 for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
                     const S v = GB[i];
                     UB[i] += v;
@@ -260,7 +262,7 @@ mlp_bwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, co
                 }
                 __syncthreads();
             }
-            mlp_vjp<S, TB>(net, P, Pt, gP, Gst, Kbar, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+            mlp_vjp<S, TB, !SMEM_GRAD>(net, P, Pt, gP, Gst, Kbar, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
             for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
                 const int b = i % TB;
                 if (n_s[b] >= 0) UBN[i] = UB[i] + GB[i];  // adjoint of u_n becomes "u_{n+1}" of step n-1

@@ -134,6 +134,64 @@ def test_large_batch_per_trajectory(ldeq):
     assert np.abs(tr[:, sel] - otr).max() <= 1e-3 * np.abs(otr).max()
 
 
+# ---- resident-weights kernels (Float32 weight image in shared memory, ldeq_mlp_res.cu) ------------------------------
+@pytest.mark.parametrize("dims", [[16, 200, 200, 16], [6, 50, 30, 6], [8, 64, 64, 32, 8], [4, 36, 4], [10, 10]])
+def test_resident_path_other_shapes_match_oracle_and_general_path(ldeq, dims, monkeypatch):
+    # depth 1..4, widths that are / are not multiples of the warp tiling, an odd batch (ragged last tile); the
+    # Float32 fixed-step solve and its discrete adjoint against the oracle, and against the general kernels
+    rng = np.random.Generator(np.random.PCG64(11))
+    layers = [(om.glorot_uniform(rng, dims[i + 1], dims[i]), (0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32))
+              for i in range(len(dims) - 1)]
+    p = om.pack_params(layers).astype(np.float32)
+    B, T = 37, 12
+    z0 = (0.5 * rng.standard_normal((B, dims[0]))).astype(np.float32)
+    t = 0.05 * np.arange(T)
+    d = rng.standard_normal((T, B, dims[0])).astype(np.float32)
+    kw = dict(adaptive=False, dt=0.05)
+    monkeypatch.delenv("LDEQ_MLP_NO_RESIDENT", raising=False)
+    tr, gz, gp = _solve(ldeq, z0, p, dims, t, want_grad=d, **kw)
+    monkeypatch.setenv("LDEQ_MLP_NO_RESIDENT", "1")
+    tr2, gz2, gp2 = _solve(ldeq, z0, p, dims, t, want_grad=d, **kw)
+    monkeypatch.delenv("LDEQ_MLP_NO_RESIDENT")
+    otr, _, _, tape = om.solve(z0.astype(np.float64), p.astype(np.float64), dims, t, og.Opts(adaptive=False, dt=0.05), record=True)
+    oz, op = om.discrete_adjoint(p.astype(np.float64), dims, t, tape, d.astype(np.float64))
+    for a, b, o, tol in ((tr, tr2, otr, 2e-5), (gz, gz2, oz, 2e-4), (gp, gp2, op, 2e-4)):
+        scale = max(np.abs(o).max(), 1e-30)
+        assert np.abs(a - o).max() <= tol * scale      # resident vs fp64 oracle
+        assert np.abs(b - o).max() <= tol * scale      # general vs fp64 oracle
+        assert np.abs(a - b).max() <= 0.2 * tol * scale
+
+
+def test_resident_adjoint_adaptive_ragged_steps_and_failures(ldeq, monkeypatch):
+    # per-trajectory control: the two trajectories of a tile take different numbers of steps (one finishes early and
+    # pulls back k1 of its first step while the other still sweeps); a trajectory that fails (maxiters) must
+    # contribute nothing to the parameter gradient and get a zero dz0
+    dims, p, rng = _net(bias_scale=0.1)
+    B, T = 33, 20
+    z0 = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
+    z0[::2] *= 4.0   # larger states -> more steps on every other trajectory
+    t = 0.05 * np.arange(T)
+    d = rng.standard_normal((T, B, 16)).astype(np.float32)
+    kw = dict(norm_mode=ldeq.NORM_PER_TRAJ, reltol=1e-5, abstol=1e-7)
+    monkeypatch.delenv("LDEQ_MLP_NO_RESIDENT", raising=False)
+    # ONE forward solve, then both adjoint kernels on the SAME tape: two discrete adjoints of an identical step
+    # sequence must agree to Float32 rounding (two separate solves would only agree to the solver tolerance)
+    zz, pp, dd = (torch.from_numpy(a).to(DEV) for a in (z0, p, d))
+    tr, st, tape = ldeq.mlp_solve_raw(zz, pp, dims, t, ldeq.default_opts(**kw), want_tape=True)
+    na = st.naccept.cpu().numpy()
+    assert (st.retcode.cpu().numpy() == 0).all() and len(set(na.tolist())) > 2 and (na[0:32:2] != na[1:32:2]).any()
+    gz, gp = (a.cpu().numpy() for a in ldeq.mlp_bwd_raw(tape, dd))
+    monkeypatch.setenv("LDEQ_MLP_NO_RESIDENT", "1")
+    gz2, gp2 = (a.cpu().numpy() for a in ldeq.mlp_bwd_raw(tape, dd))
+    monkeypatch.delenv("LDEQ_MLP_NO_RESIDENT")
+    tape.free()
+    assert np.abs(gz - gz2).max() <= 2e-5 * np.abs(gz2).max()
+    assert np.abs(gp - gp2).max() <= 2e-5 * np.abs(gp2).max()
+    # failures: maxiters = 3 stops every trajectory -> NaN block, zero gradients
+    tr, gz, gp = _solve(ldeq, z0, p, dims, t, want_grad=d, maxiters=3, **kw)
+    assert np.isnan(tr).all() and (gz == 0).all() and (gp == 0).all()
+
+
 # ---- tcgen05 / TMEM path (LDEQ_MLP_MATH_BF16X3) ---------------------------------------------------------------
 @pytest.mark.parametrize("B", [256, 1000, 20000])
 def test_tensor_core_path_matches_oracle_and_exact_path(ldeq, B):
