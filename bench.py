@@ -393,52 +393,117 @@ def run_training(args):
         dist.destroy_process_group()
 
 
-def run_latentode(args):
-    """`--workload c2` (BASELINE.json configs[1]: LatentODE, small-MLP RHS 16-200-200-16, batch 256, T = 50) and
-    `--workload mlp` (the same network at batch 18 944 = 128 trajectories per SM: where batch x hidden is a genuine
-    dense contraction).  Forward solve, adaptive Tsit5, per-trajectory and global (reference) error norm, exact CUDA-core
-    path vs the tcgen05 path.  Unit: accepted RK steps per trajectory per second and trajectory-steps/s."""
-    import torch
+def _latentode_inputs(workload):
+    from oracle import mlp as om   # weights only (glorot init of nODE.jl:14-16)
 
-    import latentdiffeq_jl_b200 as ldeq
-    from oracle import mlp as om   # weights only (glorot init of nODE.jl:14-16); nothing of the oracle is timed here
-
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
-    B = 256 if args.workload == "c2" else 18944
+    B = 256 if workload == "c2" else 18944
     T, dims = 50, [16, 200, 200, 16]
     rng = np.random.Generator(np.random.PCG64(1))
     layers = [(om.glorot_uniform(rng, dims[i + 1], dims[i]), np.zeros(dims[i + 1], np.float32)) for i in range(3)]
-    p = torch.from_numpy(om.pack_params(layers).astype(np.float32)).to(dev)
-    z = torch.from_numpy((0.5 * rng.standard_normal((B, 16))).astype(np.float32)).to(dev)
-    t = 0.05 * np.arange(T)
+    p = om.pack_params(layers).astype(np.float32)
+    z = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
+    d = rng.standard_normal((T, B, 16)).astype(np.float32)
+    return B, T, dims, p, z, d, 0.05 * np.arange(T)
+
+
+def latentode_cpu_oracle(workload, reps=3, max_B=2048):
+    """The numpy restatement of the reference's LatentODE path (oracle/mlp.py: BLAS matmuls on the (D,B) state, the way
+    Flux Dense layers run on the CPU), forward solve with the batch-global norm + discrete adjoint, on the host cores.
+    Bounded sample: at most max_B trajectories of the workload."""
+    from oracle import mlp as om
+
+    B, T, dims, p, z, d, t = _latentode_inputs(workload)
+    Bs = min(B, max_B)
+    z, d = z[:Bs], d[:, :Bs]
+    om.solve(z, p, dims, t, norm_mode="global")  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        om.solve(z, p, dims, t, norm_mode="global")
+    fwd = (time.perf_counter() - t0) / reps
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        _, _, _, tape = om.solve(z, p, dims, t, norm_mode="global", record=True)
+        om.discrete_adjoint(p, dims, t, tape, d)
+    both = (time.perf_counter() - t0) / reps
+    return {"B": Bs, "fwd_ms": fwd * 1e3, "fwd_bwd_ms": both * 1e3, "traj_steps_per_s": Bs * (T - 1) / fwd,
+            "traj_steps_per_s_fwd_bwd": Bs * (T - 1) / both, "cores": os.cpu_count()}
+
+
+def run_latentode_reference(args):
+    """`--impl reference --workload c2|mlp`: the CPU oracle of the LatentODE path on the host cores (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    r = latentode_cpu_oracle(args.workload, reps=max(1, min(args.steps, 3)))
+    B, T = (256 if args.workload == "c2" else 18944), 50
+    line = {"impl": "reference", "metric": "latent trajectory-steps/sec (LatentODE forward solve)", "value": r["traj_steps_per_s"],
+            "unit": UNIT, "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)), "warmup": 1, "ms_per_step": r["fwd_ms"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{'C2' if args.workload == 'c2' else 'MLP sweep'}: LatentODE, MLP RHS 16-200-200-16, batch {B}, T = {T}, "
+                                   "adaptive Tsit5 abstol 1e-6 reltol 1e-3, forward solve", "trajectories_per_step": r["B"]},
+            "cpu_baseline": {"value": r["traj_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                             "sample": f"{r['B']} of {B} trajectories per step, numpy/BLAS restatement of the reference algorithm "
+                                       "(Julia unavailable in this image)", "fwd_bwd_ms": r["fwd_bwd_ms"]},
+            "e2e": {"value": r["traj_steps_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_latentode(args):
+    """`--workload c2` (BASELINE.json configs[1]: LatentODE, small-MLP RHS 16-200-200-16, batch 256, T = 50) and
+    `--workload mlp` (the same network at batch 18 944 = 128 trajectories per SM: where batch x hidden is a genuine
+    dense contraction).  Adaptive Tsit5, per-trajectory and global (reference) error norm, exact CUDA-core path vs the
+    tcgen05 path; forward solve and forward + adjoint.  Unit: trajectory-steps/s (and accepted RK steps per trajectory
+    per second)."""
+    import torch
+
+    import latentdiffeq_jl_b200 as ldeq
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    B, T, dims, p_np, z_np, d_np, t = _latentode_inputs(args.workload)
+    p, z, d = (torch.from_numpy(a).to(dev) for a in (p_np, z_np, d_np))
     K, W = args.steps, max(args.warmup, 3)
     peak_bf16 = 1634.1
     try:
         peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
     except Exception:
         pass
+    h = ldeq.handle(dev.index or 0)
     res = {}
+    launches = 0
     for name, kw in (("tcgen05_bf16x3_global", dict(norm_mode=0, mlp_math=1)), ("tcgen05_bf16x3_per_traj", dict(norm_mode=1, mlp_math=1)),
                      ("exact_fp32_global", dict(norm_mode=0)), ("exact_fp32_per_traj", dict(norm_mode=1))):
         o = ldeq.default_opts(**kw)
+
+        def fwd_bwd():
+            tr, st, tape = ldeq.mlp_solve_raw(z, p, dims, t, o, want_tape=True)
+            g = ldeq.mlp_bwd_raw(tape, d)
+            tape.free()
+            return st
         try:
             for _ in range(W):
                 tr, st, _ = ldeq.mlp_solve_raw(z, p, dims, t, o)
+                fwd_bwd()
         except ldeq.LdeqError as e:
             res[name] = {"unavailable": str(e)}
             continue
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        l0 = h.launch_count()
         e0.record()
         for _ in range(K):
             tr, st, _ = ldeq.mlp_solve_raw(z, p, dims, t, o)
         e1.record()
+        for _ in range(K):
+            fwd_bwd()
+        e2.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / K
+        launches += h.launch_count() - l0
+        ms, ms2 = e0.elapsed_time(e1) / K, e1.elapsed_time(e2) / K
         att = float((st.naccept + st.nreject).float().mean())
         rhs = B * (6 * att + 2)
-        res[name] = {"ms": ms, "traj_steps_per_s": B * (T - 1) / (ms * 1e-3), "rk_steps_per_traj_per_s": B * att / (ms * 1e-3),
+        res[name] = {"ms": ms, "fwd_bwd_ms": ms2, "traj_steps_per_s": B * (T - 1) / (ms * 1e-3),
+                     "traj_steps_per_s_fwd_bwd": B * (T - 1) / (ms2 * 1e-3), "rk_steps_per_traj_per_s": B * att / (ms * 1e-3),
                      "naccept_mean": float(st.naccept.float().mean()), "algorithmic_tflops": rhs * 92800 / (ms * 1e-3) / 1e12}
         if "tcgen05" in name:
             # tensor-pipe work actually issued: padded widths (208) and three bf16 passes per product
@@ -447,12 +512,21 @@ def run_latentode(args):
                                      "frac": issued / peak_bf16, "traffic": None,
                                      "note": "bf16 flops issued to tcgen05 (3 passes, padded widths) / measured cuBLAS bf16 peak"}
     best = max((v["traj_steps_per_s"], k) for k, v in res.items() if "ms" in v)
-    print(json.dumps({"metric": "latent trajectory-steps/sec (LatentODE forward solve)", "value": best[0], "unit": UNIT, "n_gpus": 1,
-                      "steps": K, "warmup": W, "ms_per_step": res[best[1]]["ms"], "higher_is_better": True, "scaling": "weak",
-                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                      "config": {"workload": f"{'C2' if args.workload == 'c2' else 'MLP sweep'}: LatentODE, MLP RHS 16-200-200-16, batch {B}, T = 50, "
-                                             "adaptive Tsit5 abstol 1e-6 reltol 1e-3, forward solve", "best": best[1]},
-                      "variants": res}))
+    line = {"metric": "latent trajectory-steps/sec (LatentODE forward solve)", "value": best[0], "unit": UNIT, "n_gpus": 1,
+            "steps": K, "warmup": W, "ms_per_step": res[best[1]]["ms"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{'C2' if args.workload == 'c2' else 'MLP sweep'}: LatentODE, MLP RHS 16-200-200-16, batch {B}, T = 50, "
+                                   "adaptive Tsit5 abstol 1e-6 reltol 1e-3, forward solve", "best": best[1]},
+            "gpu_launches": launches, "variants": res}
+    tc = [v["roofline"] for k, v in res.items() if "roofline" in v]
+    if tc:
+        line["roofline"] = max(tc, key=lambda r: r["frac"])
+    if not args.no_cpu:
+        r = latentode_cpu_oracle(args.workload)
+        line["cpu_baseline"] = {"value": r["traj_steps_per_s"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                "sample": f"{r['B']} of {B} trajectories, numpy/BLAS restatement of the reference algorithm, forward solve "
+                                          "with the batch-global norm", "fwd_ms": r["fwd_ms"], "fwd_bwd_ms": r["fwd_bwd_ms"]}
+    print(json.dumps(line))
 
 
 def main():
@@ -468,7 +542,7 @@ def main():
     args = ap.parse_args()
     if args.workload in ("c2", "mlp"):
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "the reference arm covers the GOKU workloads (c4/c3/c1)"}))
+            run_latentode_reference(args)
         else:
             run_latentode(args)
     elif args.workload == "c5":
