@@ -204,6 +204,20 @@ int ldeq_allreduce_adamw_step(ldeq_handle* h, float* params, float* const* peer_
                               double lr, double beta1, double beta2, double eps, float decay, int64_t step,
                               float grad_scale, ldeq_stream stream);
 
+/* ---- NCCL route for the same exchange (the flat fp32 parameter gradient is summed over the ranks once
+ * per training step, model_train.jl:195-201 run data-parallel; the ODE state itself never crosses GPUs).  For hosts that
+ * cannot map peer memory themselves (the Julia glue: one process per GPU, no torch).  libnccl.so.2 is loaded at run
+ * time (LDEQ_NCCL_LIB overrides the name); the library has no link-time NCCL dependency.
+ *   ldeq_comm_unique_id  rank 0 fills a 128-byte id (ncclGetUniqueId) that the host distributes to the other ranks;
+ *   ldeq_comm_init       collective over the nranks processes (ncclCommInitRank) on the handle's device;
+ *   ldeq_allreduce_grads in-place sum of n floats on `stream` (ncclAllReduce, ncclFloat32, ncclSum);
+ *   ldeq_comm_destroy    also called by ldeq_destroy. */
+#define LDEQ_COMM_ID_BYTES 128
+int ldeq_comm_unique_id(ldeq_handle* h, void* id_out);
+int ldeq_comm_init(ldeq_handle* h, const void* unique_id, int rank, int nranks);
+int ldeq_allreduce_grads(ldeq_handle* h, float* grads_flat, int64_t n, ldeq_stream stream);
+int ldeq_comm_destroy(ldeq_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -163,4 +163,24 @@ function diffeq_layer(decoder::Decoder{M}, l̂::Tuple{Matrix{Float32},Matrix{Flo
     return transform_after_diffeq(ẑ, decoder.diffeq)
 end
 
+
+# ---- data-parallel training: one Julia process per GPU, flat gradient summed with NCCL through the C ABI ---------------
+# (no reference counterpart: examples/pendulum_friction-less/model_train.jl:186-208 is a single-process loop)
+function comm_init!(h, rank::Integer, nranks::Integer, idfile::AbstractString)
+    id = Vector{UInt8}(undef, 128)
+    if rank == 0
+        check(h, ccall((:ldeq_comm_unique_id, libldeq), Cint, (Ptr{Cvoid}, Ptr{UInt8}), h, id))
+        write(idfile * ".tmp", id); mv(idfile * ".tmp", idfile; force = true)
+    else
+        while !isfile(idfile); sleep(0.05); end
+        id = read(idfile)
+    end
+    check(h, ccall((:ldeq_comm_init, libldeq), Cint, (Ptr{Cvoid}, Ptr{UInt8}, Cint, Cint), h, id, rank, nranks))
+end
+
+# g = the flat gradient of Flux.destructure(model) order, a CuVector{Float32}; summed in place over the ranks
+allreduce_grads!(h, g::CuVector{Float32}) =
+    check(h, ccall((:ldeq_allreduce_grads, libldeq), Cint, (Ptr{Cvoid}, CuPtr{Cfloat}, Int64, Ptr{Cvoid}),
+                   h, g, length(g), CUDA.stream().handle))
+
 end # module

@@ -27,7 +27,9 @@ SYMBOLS = [
     "ldeq_solve_fwd_host", "ldeq_solve_bwd_host",
     "ldeq_mlp_solve_fwd", "ldeq_mlp_solve_bwd", "ldeq_mlp_tape_free",
     "ldeq_sample", "ldeq_elbo_fwd_bwd", "ldeq_adamw_step", "ldeq_allreduce_adamw_step",
+    "ldeq_comm_unique_id", "ldeq_comm_init", "ldeq_allreduce_grads", "ldeq_comm_destroy",
 ]
+COMM_ID_BYTES = 128
 
 
 class Opts(C.Structure):
@@ -93,6 +95,10 @@ def load() -> C.CDLL:
     lib.ldeq_elbo_fwd_bwd.argtypes = [vp, vp, vp, vp, vp, vp, i32, flt, i32, i32, i32, flt, vp, vp, vp, vp, vp]
     lib.ldeq_adamw_step.argtypes = [vp, vp, vp, vp, vp, i64, dbl, dbl, dbl, dbl, flt, i64, flt, vp]
     lib.ldeq_allreduce_adamw_step.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, i64, dbl, dbl, dbl, dbl, flt, i64, flt, vp]
+    lib.ldeq_comm_unique_id.argtypes = [vp, vp]
+    lib.ldeq_comm_init.argtypes = [vp, vp, i32, i32]
+    lib.ldeq_allreduce_grads.argtypes = [vp, vp, i64, vp]
+    lib.ldeq_comm_destroy.argtypes = [vp]
     _lib = lib
     return lib
 
@@ -146,6 +152,29 @@ class Handle:
             self.check(self._lib.ldeq_rhs_from_source(self._h, src.encode(), int(z_dim), int(p_dim), C.byref(r)))
             self._rhs[key] = r
         return self._rhs[key]
+
+    # ---- NCCL route of the gradient all-reduce (ldeq_comm.cu) ----
+    def comm_unique_id(self) -> bytes:
+        """Rank 0: a fresh 128-byte NCCL id; distribute it to the other ranks (file, socket, MPI ...)."""
+        buf = C.create_string_buffer(COMM_ID_BYTES)
+        self.check(self._lib.ldeq_comm_unique_id(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        if len(unique_id) != COMM_ID_BYTES:
+            raise ValueError("unique_id must be the 128 bytes of comm_unique_id()")
+        self.check(self._lib.ldeq_comm_init(self._h, C.c_char_p(unique_id), int(rank), int(nranks)))
+
+    def allreduce_grads(self, flat_grad, stream=None):
+        """In-place sum of a flat Float32 CUDA tensor over the ranks of ``comm_init``."""
+        import torch
+        if flat_grad.dtype != torch.float32 or not flat_grad.is_cuda or not flat_grad.is_contiguous():
+            raise TypeError("allreduce_grads: a contiguous Float32 CUDA tensor is required")
+        st = stream if stream is not None else torch.cuda.current_stream(flat_grad.device).cuda_stream
+        self.check(self._lib.ldeq_allreduce_grads(self._h, C.c_void_p(flat_grad.data_ptr()), flat_grad.numel(), C.c_void_p(st)))
+
+    def comm_destroy(self):
+        self.check(self._lib.ldeq_comm_destroy(self._h))
 
     def close(self):
         if self._h:

@@ -268,6 +268,7 @@ int ldeq_create(ldeq_handle** out, int device) {
 
 void ldeq_destroy(ldeq_handle* h) {
     if (!h) return;
+    ldeq_comm_destroy(h);
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     if (h->d_tgrid) cudaFree(h->d_tgrid);

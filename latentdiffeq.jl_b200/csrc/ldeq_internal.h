@@ -34,6 +34,11 @@ struct ldeq_handle {
     struct Slot { int32_t* h_info; cudaEvent_t ev; };
     std::vector<Slot> free_slots;
     std::vector<int32_t*> pinned_blocks;
+    // NCCL communicator of the gradient all-reduce (ldeq_comm.cu; libnccl is dlopen'ed on first use)
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    void* nccl_fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int nccl_rank = 0, nccl_nranks = 0;
 };
 
 struct ldeq_rhs {
