@@ -245,13 +245,15 @@ def run_ours(args):
     hdz0 = torch.empty(B, 2, dtype=torch.float32).pin_memory()
     hdth = torch.empty(B, 1, dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        _, tape = ldeq.goku_solve_host(hz0, hth, t, rhs, opts, device=local, want_tape=True, out=htraj)
-        ldeq.goku_bwd_host(tape, hd, hdz0, hdth)
+    def e2e_step(bufs=None, handle=None):
+        z_, th_, d_, tr_, gz_, gth_ = bufs or (hz0, hth, hd, htraj, hdz0, hdth)
+        _, tape = ldeq.goku_solve_host(z_, th_, t, rhs, opts, device=local, want_tape=True, out=tr_, handle=handle)
+        ldeq.goku_bwd_host(tape, d_, gz_, gth_)
         tape.free()
-        return float(hdz0[0, 0])  # the step's result is read on the host
+        return float(gz_[0, 0])  # the step's result is read on the host
 
-    Ke = max(3, min(K, 10))
+    Ke = max(4, min(K, 10))
+    Ke += Ke % 2
     for _ in range(2):
         e2e_step()
     barrier()
@@ -259,11 +261,52 @@ def run_ours(args):
     for _ in range(Ke):
         e2e_step()
     barrier()
-    e2e_ms = (time.perf_counter() - w0) * 1e3 / Ke
+    e2e_ms_single = (time.perf_counter() - w0) * 1e3 / Ke
+
+    # The entry points return when their result is on the host, so one host thread keeps only one direction of the
+    # PCIe link busy at a time (1.69 GB down after the forward kernel, 1.69 GB up before the adjoint).  Independent
+    # batches are served by two host threads, each with its own handle, stream and pinned buffers: the download of
+    # one overlaps the upload of the other.  Same calls, same work per step; the steps are split between the threads.
+    import threading
+    h2 = ldeq.Handle(local)
+    bufs2 = tuple(torch.empty_like(b).pin_memory() for b in (hz0, hth, hd, htraj, hdz0, hdth))
+    for dst, src in zip(bufs2[:3], (hz0, hth, hd)):
+        dst.copy_(src)
+    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+
+    def worker(i, n, go):
+        # thread 1 starts half a step late, so that one thread downloads while the other uploads
+        if i:
+            go.wait()
+        with torch.cuda.stream(streams[i]):
+            for k in range(n):
+                z_, th_, d_, tr_, gz_, gth_ = bufs2 if i else (hz0, hth, hd, htraj, hdz0, hdth)
+                _, tape = ldeq.goku_solve_host(z_, th_, t, rhs, opts, device=local, want_tape=True, out=tr_, handle=h2 if i else None)
+                if not i and k == 0:
+                    go.set()
+                ldeq.goku_bwd_host(tape, d_, gz_, gth_)
+                tape.free()
+                float(gz_[0, 0])
+
+    def run_pair(n):
+        go = threading.Event()
+        th = [threading.Thread(target=worker, args=(i, n, go)) for i in range(2)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+    run_pair(1)
+    barrier()
+    w0 = time.perf_counter()
+    run_pair(Ke // 2)
+    barrier()
+    e2e_ms_dual = (time.perf_counter() - w0) * 1e3 / Ke
+    e2e_streams = 2 if e2e_ms_dual < e2e_ms_single else 1
+    e2e_ms = min(e2e_ms_dual, e2e_ms_single)
     if world > 1:
-        tt = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+        tt = torch.tensor([e2e_ms, e2e_ms_single], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+        e2e_ms, e2e_ms_single = float(tt[0].item()), float(tt[1].item())
     e2e_value = world * B * (T - 1) / (e2e_ms * 1e-3)
     h2d = (hz0.numel() + hth.numel() + hd.numel()) * 4
     d2h = (htraj.numel() + hdz0.numel() + hdth.numel()) * 4
@@ -285,7 +328,8 @@ def run_ours(args):
                        "l2": "inputs larger than L2 (1.68 GB cotangent + 1.68 GB trajectories per step vs 126 MB L2)"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "steps": Ke,
+                    "ms_per_step": e2e_ms, "steps": Ke, "host_threads": e2e_streams,
+                    "single_thread": {"value": world * B * (T - 1) / (e2e_ms_single * 1e-3), "ms_per_step": e2e_ms_single},
                     "path": "ldeq_solve_fwd_host + ldeq_solve_bwd_host, pinned host buffers"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "tsit5_fwd_kernel<PendulumRHS<float,0>,float,TAPE=1>",

@@ -159,10 +159,12 @@ def goku_solve(z0: torch.Tensor, theta: torch.Tensor, t, rhs=_cabi.RHS_PENDULUM,
 # ---- host-buffer entry points (what a CPU-resident Flux model passes, GOKU.jl:102-103,128) --------
 def goku_solve_host(z0: torch.Tensor, theta: torch.Tensor, t, rhs=_cabi.RHS_PENDULUM,
                     opts: _cabi.Opts | None = None, device: int = 0, want_tape: bool = False,
-                    out: torch.Tensor | None = None):
-    """``ldeq_solve_fwd_host``: host tensors in, host tensor out; copies are inside the call."""
+                    out: torch.Tensor | None = None, handle: _cabi.Handle | None = None):
+    """``ldeq_solve_fwd_host``: host tensors in, host tensor out; copies are inside the call (which returns when the
+    result is on the host).  ``handle``: a private ``Handle`` for a second host thread (one handle per host thread)."""
     assert not z0.is_cuda and not theta.is_cuda
-    h = _cabi.handle(device)
+    h = handle or _cabi.handle(device)
+    device = h.device
     opts = opts or _cabi.default_opts()
     z0 = z0.contiguous()
     theta = theta.to(z0.dtype).contiguous()
