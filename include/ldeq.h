@@ -84,6 +84,15 @@ enum ldeq_mlp_math {
     LDEQ_MLP_MATH_BF16X3 = 1   /* tcgen05 tensor cores, 3-term bf16 split of fp32 operands, fp32 accumulate */
 };
 
+/* The diffeq struct's `sensealg` field (pendulum.jl:11,58: ForwardDiffSensitivity()).
+ *   LDEQ_SENSE_DISCRETE_ADJOINT  reverse sweep over the taped accepted steps of the primal solve: the exact derivative of
+ *        the primal discretisation (step sizes frozen), one kernel, ~the cost of the forward solve.  Default.
+ *   LDEQ_SENSE_FORWARD_DUAL      the reference's algorithm itself (SciMLSensitivity `ForwardDiffSensitivity`): two
+ *        dual-number re-solves per trajectory (seeded on theta, then on u0) whose error norm includes the partials, so
+ *        each takes its own step sequence; built-in right-hand sides only; ~5x the cost of the adjoint.
+ * The two agree within the solver tolerance; they coincide in fixed-step mode. */
+typedef enum { LDEQ_SENSE_DISCRETE_ADJOINT = 0, LDEQ_SENSE_FORWARD_DUAL = 1 } ldeq_sensealg;
+
 /* The keyword arguments the diffeq struct's `kwargs` field forwards to `solve` (pendulum.jl:11,43;
  * GOKU.jl:108,121).  ldeq_opts_default fills OrdinaryDiffEq's defaults for Tsit5. */
 typedef struct ldeq_opts {
@@ -107,7 +116,7 @@ typedef struct ldeq_opts {
                             what earlier solves on this handle needed (a too-small tape heals itself) */
     int32_t norm_mode;   /* ldeq_norm_mode, MLP solve only */
     int32_t mlp_math;    /* ldeq_mlp_math, MLP solve only */
-    int32_t reserved;
+    int32_t sensealg;    /* ldeq_sensealg: how ldeq_solve_bwd differentiates a GOKU solve */
 } ldeq_opts;
 
 int ldeq_version(void);

@@ -33,7 +33,7 @@ Base.@kwdef mutable struct Opts
     tape_steps::Int32 = 0
     norm_mode::Int32 = 0
     mlp_math::Int32 = 0
-    reserved::Int32 = 0
+    sensealg::Int32 = 0   # 0 discrete adjoint of the primal steps, 1 the reference's dual-number re-solves (LDEQ_SENSE_FORWARD_DUAL)
 end
 
 # the `kwargs` field of the diffeq struct is splatted into `solve` by the reference (GOKU.jl:108,121)

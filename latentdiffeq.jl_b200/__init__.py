@@ -10,7 +10,7 @@ through the repo-root shim: ``import latentdiffeq_jl_b200 as ldeq``.
 from . import _cabi
 from ._cabi import (F32, F64, RHS_PENDULUM, RHS_PENDULUM_FRICTION, RET_SUCCESS, RET_MAXITERS, RET_DTLESSTHANMIN,
                     RET_UNSTABLE, NORM_GLOBAL, NORM_PER_TRAJ, MLP_MATH_FP32, MLP_MATH_BF16X3, LdeqError, default_opts,
-                    handle, Handle)
+                    handle, Handle, SENSE_DISCRETE_ADJOINT, SENSE_FORWARD_DUAL)
 from .solve import (goku_solve, goku_solve_raw, goku_bwd_raw, goku_solve_host, goku_bwd_host, mlp_solve, mlp_solve_raw,
                     mlp_bwd_raw, sample_raw, sample_reparam, elbo_raw, elbo_loss, adamw_step, allreduce_adamw_step)
 from .diffeqs import (Tsit5, ForwardDiffSensitivity, InterpolatingAdjoint, ODEProblem, CudaRHS, Pendulum, Pendulum_friction,

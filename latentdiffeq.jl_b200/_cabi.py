@@ -30,6 +30,7 @@ SYMBOLS = [
     "ldeq_comm_unique_id", "ldeq_comm_init", "ldeq_allreduce_grads", "ldeq_comm_destroy",
 ]
 COMM_ID_BYTES = 128
+SENSE_DISCRETE_ADJOINT, SENSE_FORWARD_DUAL = 0, 1
 
 
 class Opts(C.Structure):
@@ -40,7 +41,7 @@ class Opts(C.Structure):
         ("dt", C.c_double), ("dtmax", C.c_double), ("dtmin", C.c_double), ("maxiters", C.c_int64),
         ("gamma", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double), ("beta1", C.c_double),
         ("beta2", C.c_double), ("qoldinit", C.c_double), ("qsteady_min", C.c_double), ("qsteady_max", C.c_double),
-        ("tape_steps", C.c_int32), ("norm_mode", C.c_int32), ("mlp_math", C.c_int32), ("reserved", C.c_int32),
+        ("tape_steps", C.c_int32), ("norm_mode", C.c_int32), ("mlp_math", C.c_int32), ("sensealg", C.c_int32),
     ]
 
 

@@ -315,6 +315,12 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
     if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
     for (int k = 1; k < T; ++k)
         if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
+    if (opts->sensealg != LDEQ_SENSE_DISCRETE_ADJOINT && opts->sensealg != LDEQ_SENSE_FORWARD_DUAL)
+        return set_err(h, LDEQ_ERR_INVALID, "sensealg");
+    const bool fwd_dual = tape_out && opts->sensealg == LDEQ_SENSE_FORWARD_DUAL;
+    if (fwd_dual && rhs->kind < 0)
+        return set_err(h, LDEQ_ERR_UNSUPPORTED, "LDEQ_SENSE_FORWARD_DUAL is built for the built-in right-hand sides; user-defined ones "
+                                                "differentiate through the discrete adjoint");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
     if (B == 0) return LDEQ_OK;
@@ -331,7 +337,10 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
         tape->z_dim = ZD; tape->p_dim = PD; tape->kopts = ko;
         tape->grid_t0 = h->grid_t0; tape->grid_h = h->grid_h; tape->grid_uniform = h->grid_uniform;
         long long cap = opts->tape_steps;
-        if (cap <= 0) {
+        tape->sense = opts->sensealg;
+        if (fwd_dual) {
+            cap = 1;  // the dual re-solves need only u0 (record 0), theta, the grid and the options
+        } else if (cap <= 0) {
             if (opts->adaptive) {
                 cap = T > 64 ? T : 64;
                 if (cap < (long long)h->tape_hint + h->tape_hint / 4) cap = (long long)h->tape_hint + h->tape_hint / 4;
@@ -351,6 +360,7 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
         }
         cudaMemcpyAsync(tape->theta, theta, (size_t)B * PD * es, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(tape->tgrid, h->d_tgrid, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);
+        if (fwd_dual) cudaMemcpyAsync(tape->u, z0, (size_t)B * ZD * es, cudaMemcpyDeviceToDevice, s);
     }
     int32_t* d_ret = tape ? tape->retcode : retcode;
     int32_t* d_na = tape ? tape->naccept : naccept;
@@ -378,6 +388,12 @@ int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0
     if (!tape || !dtraj || !dz0 || !dtheta) return set_err(h, LDEQ_ERR_INVALID, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
+    if (tape->sense == LDEQ_SENSE_FORWARD_DUAL) {
+        const cudaError_t e2 = launch_fwdsens(tape, dtraj, dz0, dtheta, s);
+        h->launches += 2;
+        if (e2 != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwdsens_kernel launch", e2);
+        return LDEQ_OK;
+    }
     int rc = tape_heal(h, tape, s);
     if (rc) return rc;
     const bool fr = tape->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION;

@@ -67,6 +67,7 @@ struct ldeq_tape {
     ldeq::KOpts kopts;
     double grid_t0 = 0.0, grid_h = 0.0;
     int grid_uniform = 0;
+    int sense = 0;  // ldeq_sensealg of the solve that made this tape
 };
 
 namespace ldeq {
@@ -75,6 +76,8 @@ int set_err(ldeq_handle* h, int code, const char* what, cudaError_t ce = cudaSuc
 int upload_tgrid(ldeq_handle* h, const double* t_host, int T, cudaStream_t s);
 int ensure_scratch(ldeq_handle* h, int slot, size_t bytes);
 KOpts to_kopts(const ldeq_opts* o);
+// ldeq_fwdsens.cu: the reference's ForwardDiffSensitivity pullback (two dual-number re-solves per trajectory)
+cudaError_t launch_fwdsens(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s);
 
 #define LDEQ_CUDA(call)                                                    \
     do {                                                                   \

@@ -28,12 +28,17 @@ class Tsit5:
 class ForwardDiffSensitivity:
     """Sensitivity request of the reference's diffeq structs (pendulum.jl:11).
 
-    The CUDA path always differentiates with the discrete adjoint of the accepted steps, which in
-    fixed-step mode is the same derivative ForwardDiff computes and otherwise agrees with it to the
-    solver tolerance (DESIGN.md "Gradients")."""
+    ``ForwardDiffSensitivity()`` differentiates with the discrete adjoint of the accepted steps of the primal solve
+    (``LDEQ_SENSE_DISCRETE_ADJOINT``): in fixed-step mode the same derivative ForwardDiff computes, otherwise equal to it
+    within the solver tolerance, at about the cost of the forward solve.
+    ``ForwardDiffSensitivity(dual_solves=True)`` runs the reference's algorithm itself (``LDEQ_SENSE_FORWARD_DUAL``): two
+    dual-number re-solves per trajectory whose error norm includes the partials (built-in right-hand sides only)."""
+
+    def __init__(self, dual_solves: bool = False):
+        self.dual_solves = bool(dual_solves)
 
     def __repr__(self):
-        return "ForwardDiffSensitivity()"
+        return "ForwardDiffSensitivity(dual_solves=True)" if self.dual_solves else "ForwardDiffSensitivity()"
 
 
 class InterpolatingAdjoint:

@@ -269,9 +269,11 @@ def transform_after_diffeq(x, diffeq):
     return f(x) if f is not None else x
 
 
-def _opts_from_kwargs(kwargs: dict) -> _cabi.Opts:
+def _opts_from_kwargs(kwargs: dict, sensealg=None) -> _cabi.Opts:
     kw = dict(kwargs)
     kw.pop("saveat", None)
+    if getattr(sensealg, "dual_solves", False):
+        kw["sensealg"] = _cabi.SENSE_FORWARD_DUAL
     return _cabi.default_opts(**kw)
 
 
@@ -286,7 +288,7 @@ def diffeq_layer(decoder, l_hat, t, stats_out=None):
         f = diffeq.prob.f
         if isinstance(f, CudaRHS):
             f = f.resolve(_cabi.handle(z0_hat.device.index or 0))
-        z = goku_solve(z0_hat, th_hat, t, f, _opts_from_kwargs(diffeq.kwargs), stats_out)
+        z = goku_solve(z0_hat, th_hat, t, f, _opts_from_kwargs(diffeq.kwargs, getattr(diffeq, 'sensealg', None)), stats_out)
         return transform_after_diffeq(z, diffeq)
     z0 = l_hat
     if diffeq.augment_dim:

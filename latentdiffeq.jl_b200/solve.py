@@ -109,7 +109,11 @@ def goku_solve_raw(z0: torch.Tensor, theta: torch.Tensor, t, rhs, opts: _cabi.Op
         h.check(h._lib.ldeq_solve_fwd(h.ptr, rhs_ptr, _dtype_code(z0.dtype), _p(z0), _p(theta),
                                       tg.ctypes.data_as(C.c_void_p), B, T, C.byref(opts), _p(traj), _p(ret), _p(na),
                                       _p(nr), C.byref(tape) if want_tape else None, _stream()))
-    return traj, SolveStats(ret, na, nr), (_Tape(h, tape) if want_tape else None)
+    tp = None
+    if want_tape:
+        tp = _Tape(h, tape)
+        tp.p_dim = theta.shape[1]
+    return traj, SolveStats(ret, na, nr), tp
 
 
 def goku_bwd_raw(tape: _Tape, dtraj: torch.Tensor):

@@ -8,6 +8,8 @@ import torch
 from conftest import pendulum_inputs
 from oracle import goku as og
 
+DEV = "cuda:0"
+
 pytestmark = pytest.mark.gpu
 
 
@@ -121,6 +123,59 @@ def test_adjoint_tight_tolerance_matches_reference_semantics(ldeq):
     rz, rp = og.grad(0, z0, th, t, d, og.Opts(abstol=1e-10, reltol=1e-10), norm_partials=True)
     assert np.abs(gz - rz).max() <= 1e-4 * np.abs(rz).max()
     assert np.abs(gp - rp).max() <= 1e-4 * np.abs(rp).max()
+
+
+@pytest.mark.parametrize("rhs", [0, 1])
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_forward_dual_mode_is_the_reference_gradient(ldeq, rhs, dtype):
+    # sensealg = LDEQ_SENSE_FORWARD_DUAL: the reference's own algorithm (two dual-number re-solves per trajectory whose
+    # error norm includes the partials) restated literally -- against the oracle's ForwardDiff-semantics gradient at the
+    # DEFAULT tolerance (abstol 1e-6, reltol 1e-3), where the discrete adjoint only agrees to 2e-2.
+    B, T = 512, 50
+    z0, th = pendulum_inputs(B, dtype=dtype)
+    t = 0.05 * np.arange(T)
+    d = np.random.default_rng(334).standard_normal((T, B, 2)).astype(dtype)
+    gz, gp = _grads(ldeq, rhs, z0, th, t, d, sensealg=ldeq.SENSE_FORWARD_DUAL)
+    rz, rp = og.grad(rhs, z0, th, t, d, norm_partials=True)
+    ez = np.abs(gz - rz).max(1) / np.abs(rz).max()
+    ep = np.abs(gp - rp).max(1) / np.abs(rp).max()
+    if dtype == "float64":
+        # north star: gradients within 1e-4 relative -- every trajectory, by a wide margin
+        assert ez.max() <= 1e-9 and ep.max() <= 1e-9
+    else:
+        # Float32: sinf/cosf of CUDA and glibc differ in the last bit, which moves an accept/reject decision on a few
+        # trajectories (a different, equally valid step sequence); the bulk agrees to rounding
+        assert np.quantile(ez, 0.95) <= 2e-5 and np.quantile(ep, 0.95) <= 2e-5
+        assert ez.max() <= 2e-2 and ep.max() <= 2e-2
+    # the trajectories themselves are those of the default mode (the primal solve is the same kernel)
+    a, _, _ = ldeq.goku_solve_raw(torch.from_numpy(z0).to(DEV), torch.from_numpy(th).to(DEV), t, rhs)
+    b, _, _ = ldeq.goku_solve_raw(torch.from_numpy(z0).to(DEV), torch.from_numpy(th).to(DEV), t, rhs,
+                                  ldeq.default_opts(sensealg=ldeq.SENSE_FORWARD_DUAL))
+    assert torch.equal(a, b)
+
+
+def test_forward_dual_mode_fixed_step_failures_and_user_rhs(ldeq):
+    B, T = 100, 30
+    z0, th = pendulum_inputs(B)
+    t = 0.05 * np.arange(T)
+    d = np.random.default_rng(1).standard_normal((T, B, 2)).astype(np.float32)
+    # fixed step: both sensitivity algorithms are the same derivative
+    g1 = _grads(ldeq, 0, z0, th, t, d, adaptive=False, dt=0.05, sensealg=ldeq.SENSE_FORWARD_DUAL)
+    g0 = _grads(ldeq, 0, z0, th, t, d, adaptive=False, dt=0.05)
+    for a, b in zip(g1, g0):
+        assert np.abs(a - b).max() <= 5e-6 * np.abs(b).max()
+    # a trajectory that fails in the primal solve: zero gradient, the others untouched
+    th2 = th.copy()
+    th2[3, 0] = 1e-4
+    gz, gp = _grads(ldeq, 0, z0, th2, t, d, maxiters=200, sensealg=ldeq.SENSE_FORWARD_DUAL)
+    assert (gz[3] == 0).all() and (gp[3] == 0).all() and np.isfinite(gz).all() and np.abs(gz[4]).max() > 0
+    # user-defined right-hand sides differentiate through the discrete adjoint only
+    h = ldeq.handle(0)
+    r = h.rhs_from_source("template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t) "
+                          "{ du[0] = u[1]; du[1] = -p[0] * sin(u[0]); }", 2, 1)
+    z = torch.from_numpy(z0).to(DEV).requires_grad_(True)
+    with pytest.raises(ldeq.LdeqError):
+        ldeq.goku_solve(z, torch.from_numpy(th).to(DEV), t, r, ldeq.default_opts(sensealg=ldeq.SENSE_FORWARD_DUAL))
 
 
 def test_failed_trajectory_is_nan_block_with_zero_gradient(ldeq):
