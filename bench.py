@@ -118,12 +118,21 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_cores() -> int:
+    """All the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_oracle_throughput(B, T, rhs, steps=1, warmup=0, nthreads=0):
     """The reference arm / cpu_baseline: the CPU oracle (C++/OpenMP restatement of the reference algorithm:
     per-trajectory Tsit5 under EnsembleThreads, gradients as ForwardDiffSensitivity computes them = 1 primal
     + 2 dual solves per trajectory) timed on the host cores.  Returns (traj-steps/s, ms per step, cores)."""
     from oracle import goku as og
     og.build()
+    nthreads = nthreads or host_cores()
     z0, th = pendulum_inputs(B)
     t = 0.05 * np.arange(T)
     d = np.random.default_rng(334).standard_normal((T, B, 2)).astype(np.float32)
@@ -136,7 +145,7 @@ def cpu_oracle_throughput(B, T, rhs, steps=1, warmup=0, nthreads=0):
         og.grad(rhs, z0, th, t, d, norm_partials=True, nthreads=nthreads)
         times.append(time.perf_counter() - t0)
     dt = float(np.mean(times))
-    return B * (T - 1) / dt, dt * 1e3, (nthreads or og.num_threads())
+    return B * (T - 1) / dt, dt * 1e3, nthreads
 
 
 def run_reference(args):
@@ -459,6 +468,11 @@ def latentode_cpu_oracle(workload, reps=3, max_B=2048):
     B, T, dims, p, z, d, t = _latentode_inputs(workload)
     Bs = min(B, max_B)
     z, d = z[:Bs], d[:, :Bs]
+    try:  # numpy's BLAS reads OMP_NUM_THREADS (1 under torchrun) at import: give it the host cores
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=host_cores())
+    except Exception:
+        pass
     om.solve(z, p, dims, t, norm_mode="global")  # warm-up
     t0 = time.perf_counter()
     for _ in range(reps):
@@ -470,7 +484,7 @@ def latentode_cpu_oracle(workload, reps=3, max_B=2048):
         om.discrete_adjoint(p, dims, t, tape, d)
     both = (time.perf_counter() - t0) / reps
     return {"B": Bs, "fwd_ms": fwd * 1e3, "fwd_bwd_ms": both * 1e3, "traj_steps_per_s": Bs * (T - 1) / fwd,
-            "traj_steps_per_s_fwd_bwd": Bs * (T - 1) / both, "cores": os.cpu_count()}
+            "traj_steps_per_s_fwd_bwd": Bs * (T - 1) / both, "cores": host_cores()}
 
 
 def run_latentode_reference(args):

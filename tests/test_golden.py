@@ -56,6 +56,12 @@ def test_cuda_matches_goku_golden(ldeq):
     p.grad = None
     ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM).backward(torch.from_numpy(g["dtraj"]).to(dev))
     assert np.abs(z.grad.cpu().numpy() - g["dz0_adaptive_fwddiff"]).max() <= 2e-2 * np.abs(g["dz0_adaptive_fwddiff"]).max()
+    # ... and with the reference's own algorithm (dual-number re-solves): the north star's 1e-4
+    z.grad = None
+    p.grad = None
+    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM, ldeq.default_opts(sensealg=ldeq.SENSE_FORWARD_DUAL)).backward(
+        torch.from_numpy(g["dtraj"]).to(dev))
+    assert np.abs(z.grad.cpu().numpy() - g["dz0_adaptive_fwddiff"]).max() <= 1e-4 * np.abs(g["dz0_adaptive_fwddiff"]).max()
     g = _load("c3_goku_friction.npz")
     for dt, key, rtol in ((torch.float64, "traj_f64", 1e-5), (torch.float32, "traj_f32", 1e-3)):
         tr, stt, _ = ldeq.goku_solve_raw(torch.from_numpy(g["z0"]).to(dev, dt), torch.from_numpy(g["theta"]).to(dev, dt),
