@@ -74,12 +74,21 @@ KOpts to_kopts(const ldeq_opts* o) {
     return k;
 }
 
+// The forward kernel fills the tape's own copies (theta, grid, statistics) itself; a replay into a fresh tape (tape_heal)
+// reads theta / the grid FROM the tape, where they already are.
+template <class S>
+static TapeView<S> fwd_tape_view(const ldeq_tape* tape, const void* theta, const double* tg) {
+    return TapeView<S>{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap,
+                       theta == tape->theta ? nullptr : (S*)tape->theta, tg == tape->tgrid ? nullptr : tape->tgrid,
+                       tape->retcode, tape->naccept, tape->nreject};
+}
+
 template <class S, bool FRICTION, bool TAPE>
 static cudaError_t launch_fwd(const void* z0, const void* theta, const double* tg, int B, int T, const KOpts& ko,
                               void* traj, int32_t* ret, int32_t* na, int32_t* nr, const ldeq_tape* tape,
                               const GridInfo& gi, cudaStream_t s) {
-    TapeView<S> tv{nullptr, nullptr, nullptr, nullptr, 0};
-    if (TAPE) tv = TapeView<S>{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap};
+    TapeView<S> tv{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    if (TAPE) tv = fwd_tape_view<S>(tape, theta, tg);
     const int grid = (B + LDEQ_FWD_THREADS - 1) / LDEQ_FWD_THREADS;
     const size_t smem = Ring<S, 2>::bytes(LDEQ_FWD_THREADS) + (T <= LDEQ_TGRID_SMEM_MAX ? (size_t)T * sizeof(double) : 0);
     tsit5_fwd_kernel<PendulumRHS<S, FRICTION>, S, TAPE><<<grid, LDEQ_FWD_THREADS, smem, s>>>(
@@ -89,7 +98,7 @@ static cudaError_t launch_fwd(const void* z0, const void* theta, const double* t
 
 template <class S, bool FRICTION>
 static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
-    TapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap};
+    TapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int grid = (tape->B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
     const size_t smem =
         Ring<S, 2>::bytes(LDEQ_BWD_THREADS) + (tape->T <= LDEQ_TGRID_SMEM_MAX ? (size_t)tape->T * sizeof(double) : 0);
@@ -113,8 +122,8 @@ static size_t ring_smem(int z_dim, size_t es, int threads, int T) {
 static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg,
                                    int B, int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
                                    const ldeq_tape* tape, const GridInfo& gi, cudaStream_t s) {
-    TapeView<float> tv{nullptr, nullptr, nullptr, nullptr, 0};  // identical layout for float and double
-    if (tape) tv = TapeView<float>{tape->t, tape->dt, (float*)tape->u, tape->info, tape->cap};
+    TapeView<float> tv{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};  // identical layout for float and double
+    if (tape) tv = fwd_tape_view<float>(tape, theta, tg);
     KOpts kov = ko;
     GridInfo giv = gi;
     void* args[] = {&z0, &theta, &tg, &B, &T, &kov, &traj, &ret, &na, &nr, &tv, &giv};
@@ -124,7 +133,7 @@ static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z
     return cudaLaunchKernel(fn, dim3(grid), dim3(LDEQ_FWD_THREADS), args, ring_smem(rhs->z_dim, es, LDEQ_FWD_THREADS, T), s);
 }
 static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
-    TapeView<float> tv{tape->t, tape->dt, (float*)tape->u, tape->info, tape->cap};
+    TapeView<float> tv{tape->t, tape->dt, (float*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
     const void* theta = tape->theta;
     const double* tg = tape->tgrid;
     int B = tape->B, T = tape->T;
@@ -223,8 +232,8 @@ static int tape_heal(ldeq_handle* h, ldeq_tape* tape, cudaStream_t s) {
     cudaMemcpyAsync(tape->tgrid, old.tgrid, (size_t)tape->T * 8, cudaMemcpyDeviceToDevice, s);
     // step 0 of the old tape holds u0 for every trajectory (capacity is always >= 1)
     cudaError_t e = dispatch_fwd(tape->rhs, tape->dtype, old.u, tape->theta,
-                                 tape->tgrid, tape->B, tape->T, tape->kopts, nullptr, tape->retcode, tape->naccept,
-                                 tape->nreject, tape, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform}, s);
+                                 tape->tgrid, tape->B, tape->T, tape->kopts, nullptr, nullptr, nullptr,
+                                 nullptr, tape, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform}, s);
     h->launches += 1;
     cudaFreeAsync(old.base, s);
     if (e != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwd_kernel (tape replay) launch", e);
@@ -358,14 +367,10 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
             delete tape;
             return set_err(h, LDEQ_ERR_NOMEM, "tape host mirror");
         }
-        cudaMemcpyAsync(tape->theta, theta, (size_t)B * PD * es, cudaMemcpyDeviceToDevice, s);
-        cudaMemcpyAsync(tape->tgrid, h->d_tgrid, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);
+        // theta, the grid and the statistics reach the tape through the forward kernel itself (TapeView)
         if (fwd_dual) cudaMemcpyAsync(tape->u, z0, (size_t)B * ZD * es, cudaMemcpyDeviceToDevice, s);
     }
-    int32_t* d_ret = tape ? tape->retcode : retcode;
-    int32_t* d_na = tape ? tape->naccept : naccept;
-    int32_t* d_nr = tape ? tape->nreject : nreject;
-    cudaError_t e = dispatch_fwd(rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, d_ret, d_na, d_nr, tape,
+    cudaError_t e = dispatch_fwd(rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, retcode, naccept, nreject, tape,
                                  GridInfo{h->grid_t0, h->grid_h, h->grid_uniform}, s);
     h->launches += 1;
     if (e != cudaSuccess) {
@@ -373,9 +378,6 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
         return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwd_kernel launch", e);
     }
     if (tape) {
-        if (retcode) cudaMemcpyAsync(retcode, tape->retcode, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
-        if (naccept) cudaMemcpyAsync(naccept, tape->naccept, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
-        if (nreject) cudaMemcpyAsync(nreject, tape->nreject, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(tape->h_info, tape->info, 8, cudaMemcpyDeviceToHost, s);
         cudaEventRecord(tape->ready, s);
         *tape_out = tape;

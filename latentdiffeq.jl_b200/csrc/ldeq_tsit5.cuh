@@ -34,6 +34,13 @@ template <class S> struct TapeView {
     S* u;
     int* info;  // info[0]: trajectories that ran past `cap`; info[1]: largest accepted-step count
     int cap;
+    // the tape's own copies of what the reverse pass needs, written by the forward kernel itself (no extra copy
+    // launches around a solve: at small batches they cost as much as the kernel); null = skip
+    S* theta;        // (p,B)
+    double* tgrid;   // T
+    int* ret;        // B
+    int* na;         // B
+    int* nr;         // B
 };
 
 // ---- the seven stages --------------------------------------------------------------------------
@@ -285,6 +292,14 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
     load_vec<S, ZD>(z0 + (size_t)bb * ZD, u);
 #pragma unroll
     for (int i = 0; i < PD; ++i) p[i] = theta[(size_t)bb * PD + i];
+    if (TAPE) {
+        if (tape.theta && live) {
+#pragma unroll
+            for (int i = 0; i < PD; ++i) tape.theta[(size_t)b * PD + i] = p[i];
+        }
+        if (tape.tgrid && blockIdx.x == 0)
+            for (int kk = threadIdx.x; kk < T; kk += blockDim.x) tape.tgrid[kk] = tg_global[kk];
+    }
 
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
@@ -466,6 +481,9 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
     if (naccept) naccept[b] = na;
     if (nreject) nreject[b] = nr;
     if (TAPE) {
+        if (tape.ret) tape.ret[b] = ret;
+        if (tape.na) tape.na[b] = na;
+        if (tape.nr) tape.nr[b] = nr;
         // tape.info = {trajectories that ran past the capacity, largest accepted-step count}; one atomic per warp
         const unsigned am = __activemask();
         const int wmax = __reduce_max_sync(am, ret == RET_SUCCESS ? na : 0);
