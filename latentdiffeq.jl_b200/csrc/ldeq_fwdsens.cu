@@ -112,11 +112,11 @@ template <class S, int NP> __device__ __forceinline__ S fd_rms(const FD<S, NP>* 
 }
 
 // pendulum.jl:19-26 / :65-74 on duals (G, b, m are Float32 literals of the reference, rounded to S)
+// mgl = -G/L is a constant of the trajectory: evaluated once by the caller (same value as evaluating it per call)
 template <class S, int NP, bool FRICTION>
-__device__ __forceinline__ void fd_rhs(FD<S, NP>* du, const FD<S, NP>* u, FD<S, NP> L) {
-    const FD<S, NP> G = fd_make<S, NP>((S)10.0f);
+__device__ __forceinline__ void fd_rhs(FD<S, NP>* du, const FD<S, NP>* u, FD<S, NP> mgl) {
     du[0] = u[1];
-    const FD<S, NP> a = (-G / L) * fd_sin(u[0]);
+    const FD<S, NP> a = mgl * fd_sin(u[0]);
     if (FRICTION) {
         const S bm = (S)0.7f / (S)1.0f;
         du[1] = a - bm * u[1];
@@ -145,6 +145,7 @@ tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, cons
     }
     D L = fd_make<S, NP>(theta[b]);
     if (SEED_P) L.d[0] = (S)1;
+    L = (-fd_make<S, NP>((S)10.0f)) / L;  // from here on L holds -G/L (pendulum.jl:24, :72)
 
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
