@@ -89,7 +89,7 @@ enum ldeq_mlp_math {
  *        the primal discretisation (step sizes frozen), one kernel, ~the cost of the forward solve.  Default.
  *   LDEQ_SENSE_FORWARD_DUAL      the reference's algorithm itself (SciMLSensitivity `ForwardDiffSensitivity`): two
  *        dual-number re-solves per trajectory (seeded on theta, then on u0) whose error norm includes the partials, so
- *        each takes its own step sequence; built-in right-hand sides only; ~5x the cost of the adjoint.
+ *        each takes its own step sequence; ~7x the cost of the adjoint.
  * The two agree within the solver tolerance; they coincide in fixed-step mode. */
 typedef enum { LDEQ_SENSE_DISCRETE_ADJOINT = 0, LDEQ_SENSE_FORWARD_DUAL = 1 } ldeq_sensealg;
 

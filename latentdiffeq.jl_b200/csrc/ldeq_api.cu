@@ -147,6 +147,23 @@ static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, voi
     return cudaLaunchKernel(fn, dim3(grid), dim3(LDEQ_BWD_THREADS), args, ring_smem(tape->z_dim, es, LDEQ_BWD_THREADS, T), s);
 }
 
+// fn[6..9] = forward-dual pullback {theta-seeded f32, u0-seeded f32, theta-seeded f64, u0-seeded f64}
+static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
+    const void* z0 = tape->u;
+    const void* theta = tape->theta;
+    const double* tg = tape->tgrid;
+    int B = tape->B, T = tape->T, np = 1;
+    KOpts kov = tape->kopts;
+    const int32_t* ret = tape->retcode;
+    const int grid = (B + 127) / 128;
+    const int base = tape->dtype == LDEQ_F32 ? 6 : 8;
+    void* args_p[] = {&z0, &theta, &tg, &B, &T, &kov, &np, &dtraj, &ret, &dtheta};
+    cudaError_t e = cudaLaunchKernel(tape->rhs->fn[base], dim3(grid), dim3(128), args_p, 0, s);
+    if (e != cudaSuccess) return e;
+    void* args_u[] = {&z0, &theta, &tg, &B, &T, &kov, &np, &dtraj, &ret, &dz0};
+    return cudaLaunchKernel(tape->rhs->fn[base + 1], dim3(grid), dim3(128), args_u, 0, s);
+}
+
 static bool slot_get(ldeq_handle* h, ldeq_tape* tape) {
     if (h->free_slots.empty()) {
         const int n = 64;
@@ -327,9 +344,6 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
     if (opts->sensealg != LDEQ_SENSE_DISCRETE_ADJOINT && opts->sensealg != LDEQ_SENSE_FORWARD_DUAL)
         return set_err(h, LDEQ_ERR_INVALID, "sensealg");
     const bool fwd_dual = tape_out && opts->sensealg == LDEQ_SENSE_FORWARD_DUAL;
-    if (fwd_dual && rhs->kind < 0)
-        return set_err(h, LDEQ_ERR_UNSUPPORTED, "LDEQ_SENSE_FORWARD_DUAL is built for the built-in right-hand sides; user-defined ones "
-                                                "differentiate through the discrete adjoint");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
     if (B == 0) return LDEQ_OK;
@@ -391,7 +405,7 @@ int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
     if (tape->sense == LDEQ_SENSE_FORWARD_DUAL) {
-        const cudaError_t e2 = launch_fwdsens(tape, dtraj, dz0, dtheta, s);
+        const cudaError_t e2 = tape->rhs_kind < 0 ? launch_user_fwdsens(tape, dtraj, dz0, dtheta, s) : launch_fwdsens(tape, dtraj, dz0, dtheta, s);
         h->launches += 2;
         if (e2 != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwdsens_kernel launch", e2);
         return LDEQ_OK;

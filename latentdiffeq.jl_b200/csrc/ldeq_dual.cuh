@@ -12,6 +12,7 @@
 namespace ldeq {
 
 template <class S, int N> struct Dual {
+    typedef S value_type;
     S v;
     S d[N];
     __device__ __forceinline__ Dual() {}
@@ -41,8 +42,9 @@ LDEQ_DUAL_T Dual<S, N> operator*(const Dual<S, N>& a, const Dual<S, N>& b) {
     return r;
 }
 LDEQ_DUAL_T Dual<S, N> operator/(const Dual<S, N>& a, const Dual<S, N>& b) {
-    Dual<S, N> r; const S ib = (S)1 / b.v; r.v = a.v * ib;
-    _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) * ib;
+    // ForwardDiff's quotient rule with true divisions (the forward-dual pullback restates the reference literally)
+    Dual<S, N> r; r.v = a.v / b.v;
+    _Pragma("unroll") for (int i = 0; i < N; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v;
     return r;
 }
 // mixed with plain scalars (anything convertible to S)

@@ -45,7 +45,7 @@ struct ldeq_rhs {
     int kind = 0;  // ldeq_rhs_kind, or -1 for an NVRTC-compiled user RHS
     int z_dim = 2, p_dim = 1;
     void* module = nullptr;  // CUmodule of a user RHS
-    void* fn[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    void* fn[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 struct ldeq_tape {

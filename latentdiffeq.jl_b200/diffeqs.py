@@ -32,7 +32,7 @@ class ForwardDiffSensitivity:
     (``LDEQ_SENSE_DISCRETE_ADJOINT``): in fixed-step mode the same derivative ForwardDiff computes, otherwise equal to it
     within the solver tolerance, at about the cost of the forward solve.
     ``ForwardDiffSensitivity(dual_solves=True)`` runs the reference's algorithm itself (``LDEQ_SENSE_FORWARD_DUAL``): two
-    dual-number re-solves per trajectory whose error norm includes the partials (built-in right-hand sides only)."""
+    dual-number re-solves per trajectory whose error norm includes the partials."""
 
     def __init__(self, dual_solves: bool = False):
         self.dual_solves = bool(dual_solves)

@@ -192,6 +192,22 @@ def test_resident_adjoint_adaptive_ragged_steps_and_failures(ldeq, monkeypatch):
     assert np.isnan(tr).all() and (gz == 0).all() and (gp == 0).all()
 
 
+def test_resident_path_long_nonuniform_grid_and_single_trajectory(ldeq):
+    # more save points than the on-chip copy of the grid holds (falls back to the global grid), unevenly spaced, B = 1
+    dims, p, rng = _net(bias_scale=0.1)
+    T = 300
+    t = np.cumsum(np.r_[0.0, rng.uniform(0.002, 0.01, T - 1)])
+    for B in (1, 5):
+        z0 = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
+        d = rng.standard_normal((T, B, 16)).astype(np.float32)
+        tr, gz, gp = _solve(ldeq, z0, p, dims, t, want_grad=d, adaptive=False, dt=0.004)
+        otr, _, _, tape = om.solve(z0.astype(np.float64), p.astype(np.float64), dims, t, og.Opts(adaptive=False, dt=0.004), record=True)
+        oz, op = om.discrete_adjoint(p.astype(np.float64), dims, t, tape, d.astype(np.float64))
+        assert np.abs(tr - otr).max() <= 2e-5 * np.abs(otr).max()
+        assert np.abs(gz - oz).max() <= 2e-4 * np.abs(oz).max()
+        assert np.abs(gp - op).max() <= 2e-4 * np.abs(op).max()
+
+
 # ---- tcgen05 / TMEM path (LDEQ_MLP_MATH_BF16X3) ---------------------------------------------------------------
 @pytest.mark.parametrize("B", [256, 1000, 20000])
 def test_tensor_core_path_matches_oracle_and_exact_path(ldeq, B):
