@@ -25,7 +25,7 @@ template <bool FRICTION> struct PendulumDualRHS {
 };
 
 template <class S, int NP, bool FRICTION, bool SEED_P>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, int T,
                      KOpts o, int norm_partials, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                      S* __restrict__ dout) {
