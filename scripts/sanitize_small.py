@@ -20,10 +20,22 @@ if which in ("all", "goku"):
     rhs = h.rhs_from_source("template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t) { du[0] = u[1]; du[1] = -p[0]*sin(u[0]); du[2] = p[1]*u[0] - u[2]; }", 3, 2)
     z = torch.randn(37, 3, device=dev, requires_grad=True); p = (1 + torch.rand(37, 2, device=dev)).requires_grad_(True)
     tr = ldeq.goku_solve(z, p, 0.05 * np.arange(30), rhs); tr.backward(torch.ones_like(tr))
+    # forward-dual pullback: built-in (both dtypes, friction) and the user function
+    for dtype in ("float32", "float64"):
+        z0, th = pendulum_inputs(131, dtype=dtype)
+        for kind in (0, 1):
+            z = torch.from_numpy(z0).to(dev).requires_grad_(True); p = torch.from_numpy(th).to(dev).requires_grad_(True)
+            tr = ldeq.goku_solve(z, p, 0.05 * np.arange(23), kind, ldeq.default_opts(sensealg=1)); tr.backward(torch.ones_like(tr))
+    z = torch.randn(37, 3, device=dev, requires_grad=True); p = (1 + torch.rand(37, 2, device=dev)).requires_grad_(True)
+    tr = ldeq.goku_solve(z, p, 0.05 * np.arange(30), rhs, ldeq.default_opts(sensealg=1)); tr.backward(torch.ones_like(tr))
 if which in ("all", "mlp"):
     from oracle import mlp as om
     rng = np.random.Generator(np.random.PCG64(1)); dims = [16, 200, 200, 16]
     pp = torch.from_numpy(om.pack_params([(om.glorot_uniform(rng, dims[i + 1], dims[i]), np.zeros(dims[i + 1], np.float32)) for i in range(3)]).astype(np.float32)).to(dev)
+    for dims2 in ([6, 50, 30, 6], [8, 64, 64, 32, 8], [10, 10]):
+        q = (0.1 * torch.randn(om.n_params(dims2), device=dev)).requires_grad_(True)
+        z = (0.5 * torch.randn(7, dims2[0], device=dev)).requires_grad_(True)
+        tr = ldeq.mlp_solve(z, q, dims2, 0.05 * np.arange(9), ldeq.default_opts(norm_mode=1)); tr.backward(torch.ones_like(tr))
     for B in (3, 130):
         for kw in (dict(norm_mode=0), dict(norm_mode=1), dict(norm_mode=1, mlp_math=1), dict(norm_mode=0, mlp_math=1), dict(adaptive=False, dt=0.05, mlp_math=1)):
             z = (0.5 * torch.randn(B, 16, device=dev)).requires_grad_(True); q = pp.clone().requires_grad_(True)
