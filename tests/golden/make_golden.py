@@ -36,8 +36,11 @@ def main():
     tr64, _, na64, _ = og.solve(og.PENDULUM_FRICTION, z0, th, t)
     tr32, _, na32, _ = og.solve(og.PENDULUM_FRICTION, z0.astype(np.float32), th.astype(np.float32), t)
     gz, gp = og.grad(og.PENDULUM_FRICTION, z0, th, t, d, norm_partials=False)
+    # the reference's own semantics (ForwardDiffSensitivity: partials in the error norm), Float64, default tolerance
+    rz, rp = og.grad(og.PENDULUM_FRICTION, z0, th, t, d, norm_partials=True)
     np.savez_compressed(os.path.join(HERE, "c3_goku_friction.npz"), z0=z0, theta=th, t=t, dtraj=d, traj_f64=tr64,
-                        naccept_f64=na64, traj_f32=tr32, naccept_f32=na32, dz0_f64_frozen=gz, dtheta_f64_frozen=gp)
+                        naccept_f64=na64, traj_f32=tr32, naccept_f32=na32, dz0_f64_frozen=gz, dtheta_f64_frozen=gp,
+                        dz0_f64_fwddiff=rz, dtheta_f64_fwddiff=rp)
     # C2: LatentODE, D = 16, H = 200, first 8 of the B = 256 batch solved as a batch of 8 (global norm), seed 1
     rng = np.random.Generator(np.random.PCG64(1))
     dims = [16, 200, 200, 16]

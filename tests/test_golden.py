@@ -72,6 +72,14 @@ def test_cuda_matches_goku_golden(ldeq):
     ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM_FRICTION).backward(torch.from_numpy(g["dtraj"]).to(dev))
     assert np.abs(z.grad.cpu().numpy() - g["dz0_f64_frozen"]).max() <= 1e-4 * np.abs(g["dz0_f64_frozen"]).max()
     assert np.abs(p.grad.cpu().numpy() - g["dtheta_f64_frozen"]).max() <= 1e-4 * np.abs(g["dtheta_f64_frozen"]).max()
+    # Float64, default tolerance, the reference's own sensitivity algorithm (dual-number re-solves) against the frozen
+    # ForwardDiff-semantics gradient: every trajectory far inside the north star's 1e-4
+    z = torch.from_numpy(g["z0"]).to(dev).requires_grad_(True)
+    p = torch.from_numpy(g["theta"]).to(dev).requires_grad_(True)
+    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM_FRICTION, ldeq.default_opts(sensealg=ldeq.SENSE_FORWARD_DUAL)).backward(
+        torch.from_numpy(g["dtraj"]).to(dev))
+    assert np.abs(z.grad.cpu().numpy() - g["dz0_f64_fwddiff"]).max() <= 1e-8 * np.abs(g["dz0_f64_fwddiff"]).max()
+    assert np.abs(p.grad.cpu().numpy() - g["dtheta_f64_fwddiff"]).max() <= 1e-8 * np.abs(g["dtheta_f64_fwddiff"]).max()
 
 
 @pytest.mark.gpu
