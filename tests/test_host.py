@@ -50,6 +50,22 @@ def test_diffeq_struct_contract(ldeq):
     assert ldeq.Pendulum_friction().prob.f == ldeq.RHS_PENDULUM_FRICTION
 
 
+def test_sensealg_maps_to_the_solver_options(ldeq):
+    # the diffeq struct's sensealg field (pendulum.jl:11) selects how the reverse pass differentiates
+    from importlib import import_module
+    model = import_module(ldeq.__name__ + ".model") if hasattr(ldeq, "__path__") else ldeq.model
+    p = ldeq.Pendulum()
+    assert repr(p.sensealg) == "ForwardDiffSensitivity()" and not p.sensealg.dual_solves
+    o = model._opts_from_kwargs(p.kwargs, p.sensealg)
+    assert o.sensealg == ldeq.SENSE_DISCRETE_ADJOINT == 0
+    q = ldeq.Pendulum(sensalg=ldeq.ForwardDiffSensitivity(dual_solves=True), reltol=1e-5)
+    assert repr(q.sensealg) == "ForwardDiffSensitivity(dual_solves=True)"
+    o = model._opts_from_kwargs(q.kwargs, q.sensealg)
+    assert o.sensealg == ldeq.SENSE_FORWARD_DUAL == 1 and o.reltol == 1e-5
+    o = model._opts_from_kwargs({"saveat": [0.0, 1.0], "abstol": 1e-9}, None)      # saveat is the layer's own argument
+    assert o.sensealg == 0 and o.abstol == 1e-9
+
+
 def test_utils(ldeq):
     mu, lv = torch.randn(5, 3), torch.randn(5, 3)
     assert torch.allclose(ldeq.kl(mu, lv), (lv.exp() + mu ** 2 - lv - 1) / 2)
