@@ -377,7 +377,7 @@ def run_ours(args):
                          "peak_source": peak_src, "launch_ms": fwd_ms, "algorithmic_bytes_per_launch": alg_fwd,
                          "traffic": profile_traffic("tsit5_fwd_kernel_tape"),
                          "note": "per-trajectory work is ~37 k issued instructions for 1.6 kB of output: the kernel is "
-                                 "instruction-issue bound (ncu: 73% issue-active), not HBM bound"},
+                                 "instruction-issue bound (ncu: 79% issue-active), not HBM bound"},
             "roofline_bwd": {"bound": "hbm", "kernel": "tsit5_bwd_kernel<PendulumRHS<float,0>,float>",
                              "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
                              "launch_ms": bwd_ms, "algorithmic_bytes_per_launch": alg_bwd,
