@@ -146,7 +146,29 @@ function mlp_fwd(diffeq, ẑ₀::CuMatrix{T}, t; tape::Bool) where {T}
     check(h, rc)
     return ẑ, Tape(tp[], true)
 end
-# (rrule for the LatentODE method: ldeq_mlp_solve_bwd -> (dẑ₀, dparams_flat), `re`-structured into a dudt tangent)
+
+# reverse pass of the LatentODE method (replaces DiffEqFlux's InterpolatingAdjoint pullback, LatentODE.jl:70-72 under Zygote):
+# ldeq_mlp_solve_bwd -> (dẑ₀ (D,B), dparams_flat in Flux.destructure order), the latter restructured into a tangent of `dudt`
+function ChainRulesCore.rrule(::typeof(diffeq_layer), decoder::Decoder{LatentODE}, ẑ₀::CuMatrix{T}, t) where {T}
+    diffeq = decoder.diffeq
+    ẑ, tape = mlp_fwd(diffeq, ẑ₀, t; tape = true)
+    p, re = Flux.destructure(diffeq.dudt)
+    function pullback(Δ)
+        h = handle()
+        Δc = CuArray{T}(unthunk(Δ))                       # (D+aug, B, T), same layout as ẑ
+        du0 = CUDA.zeros(T, size(ẑ, 1), size(ẑ, 2))
+        dp = CUDA.zeros(T, length(p))
+        check(h, ccall((:ldeq_mlp_solve_bwd, libldeq), Cint,
+                       (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                       h, tape.ptr, Δc, du0, dp, CUDA.stream().handle))
+        ccall((:ldeq_mlp_tape_free, libldeq), Cvoid, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), h, tape.ptr, CUDA.stream().handle)
+        dẑ₀ = diffeq.augment_dim == 0 ? du0 : du0[1:size(ẑ₀, 1), :]   # the zero-padded rows carry no input gradient
+        ddudt = re(Array(dp))                              # a Chain whose arrays are the gradients (structural tangent)
+        ddecoder = Tangent{typeof(decoder)}(; diffeq = Tangent{typeof(diffeq)}(; dudt = ddudt))
+        return NoTangent(), ddecoder, dẑ₀, NoTangent()
+    end
+    return transform_after_diffeq(ẑ, diffeq), pullback
+end
 
 # ---- the host-array methods of the reference (GOKU.jl:102-103: `cpu(...)`) can use the *_host entry points ------
 function diffeq_layer(decoder::Decoder{M}, l̂::Tuple{Matrix{Float32},Matrix{Float32}}, t) where {M<:GOKU}
