@@ -313,19 +313,26 @@ def run_ours(args):
         dst.copy_(src)
     streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
 
+    errors = []
+
     def worker(i, n, go):
         # thread 1 starts half a step late, so that one thread downloads while the other uploads
-        if i:
-            go.wait()
-        with torch.cuda.stream(streams[i]):
-            for k in range(n):
-                z_, th_, d_, tr_, gz_, gth_ = bufs2 if i else (hz0, hth, hd, htraj, hdz0, hdth)
-                _, tape = ldeq.goku_solve_host(z_, th_, t, rhs, opts, device=local, want_tape=True, out=tr_, handle=h2 if i else None)
-                if not i and k == 0:
-                    go.set()
-                ldeq.goku_bwd_host(tape, d_, gz_, gth_)
-                tape.free()
-                float(gz_[0, 0])
+        try:
+            if i:
+                go.wait(120)
+            with torch.cuda.stream(streams[i]):
+                for k in range(n):
+                    z_, th_, d_, tr_, gz_, gth_ = bufs2 if i else (hz0, hth, hd, htraj, hdz0, hdth)
+                    _, tape = ldeq.goku_solve_host(z_, th_, t, rhs, opts, device=local, want_tape=True, out=tr_, handle=h2 if i else None)
+                    if not i and k == 0:
+                        go.set()
+                    ldeq.goku_bwd_host(tape, d_, gz_, gth_)
+                    tape.free()
+                    float(gz_[0, 0])
+        except BaseException as e:  # noqa: BLE001 -- re-raised on the main thread
+            errors.append(e)
+        finally:
+            go.set()
 
     def run_pair(n):
         go = threading.Event()
@@ -334,6 +341,8 @@ def run_ours(args):
             x.start()
         for x in th:
             x.join()
+        if errors:
+            raise errors[0]
     run_pair(1)
     barrier()
     w0 = time.perf_counter()
