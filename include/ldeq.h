@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define LDEQ_VERSION 100
+#define LDEQ_VERSION 200
 
 typedef struct ldeq_handle ldeq_handle;
 typedef struct ldeq_rhs ldeq_rhs;
@@ -53,7 +53,9 @@ enum ldeq_status {
     LDEQ_ERR_CUDA = -2,        /* CUDA runtime error; text in ldeq_last_error */
     LDEQ_ERR_UNSUPPORTED = -3, /* combination not built (e.g. z_dim of a compiled RHS too large) */
     LDEQ_ERR_NOMEM = -4,
-    LDEQ_ERR_COMPILE = -5      /* NVRTC could not compile a user RHS; log in ldeq_last_error */
+    LDEQ_ERR_COMPILE = -5,     /* NVRTC could not compile a user RHS; log in ldeq_last_error */
+    LDEQ_ERR_TAPE_OVERFLOW = -6 /* ldeq_mlp_solve_bwd: the solve took more accepted steps than the tape holds; the
+                                   message names the count -- repeat the forward solve with opts.tape_steps >= it */
 };
 
 enum ldeq_dtype { LDEQ_F32 = 0, LDEQ_F64 = 1 };
@@ -85,13 +87,19 @@ enum ldeq_mlp_math {
 };
 
 /* The diffeq struct's `sensealg` field (pendulum.jl:11,58: ForwardDiffSensitivity()).
- *   LDEQ_SENSE_DISCRETE_ADJOINT  reverse sweep over the taped accepted steps of the primal solve: the exact derivative of
- *        the primal discretisation (step sizes frozen), one kernel, ~the cost of the forward solve.  Default.
  *   LDEQ_SENSE_FORWARD_DUAL      the reference's algorithm itself (SciMLSensitivity `ForwardDiffSensitivity`): two
  *        dual-number re-solves per trajectory (seeded on theta, then on u0) whose error norm includes the partials, so
- *        each takes its own step sequence; ~7x the cost of the adjoint.
- * The two agree within the solver tolerance; they coincide in fixed-step mode. */
+ *        each takes its own step sequence.  DEFAULT (ldeq_opts_default): it is what the reference's structs request,
+ *        and the only mode whose gradients equal the reference's to 1e-4 at the default tolerances.
+ *   LDEQ_SENSE_DISCRETE_ADJOINT  reverse sweep over the taped accepted steps of the primal solve: the exact derivative of
+ *        the primal discretisation (step sizes frozen), one kernel, ~the cost of the forward solve, ~3x cheaper than
+ *        the dual solves.  An explicit opt-in (Python: `sensealg = DiscreteAdjoint()`): it agrees with the reference's
+ *        gradient only within the solver tolerance (2e-2 at reltol 1e-3), exactly in fixed-step mode. */
 typedef enum { LDEQ_SENSE_DISCRETE_ADJOINT = 0, LDEQ_SENSE_FORWARD_DUAL = 1 } ldeq_sensealg;
+
+/* The diffeq struct's `solver` field (pendulum.jl:11,58: Tsit5()).  Anything else is refused with
+ * LDEQ_ERR_UNSUPPORTED rather than silently replaced. */
+typedef enum { LDEQ_SOLVER_TSIT5 = 0 } ldeq_solver;
 
 /* The keyword arguments the diffeq struct's `kwargs` field forwards to `solve` (pendulum.jl:11,43;
  * GOKU.jl:108,121).  ldeq_opts_default fills OrdinaryDiffEq's defaults for Tsit5. */
@@ -116,7 +124,9 @@ typedef struct ldeq_opts {
                             what earlier solves on this handle needed (a too-small tape heals itself) */
     int32_t norm_mode;   /* ldeq_norm_mode, MLP solve only */
     int32_t mlp_math;    /* ldeq_mlp_math, MLP solve only */
-    int32_t sensealg;    /* ldeq_sensealg: how ldeq_solve_bwd differentiates a GOKU solve */
+    int32_t sensealg;    /* ldeq_sensealg: how ldeq_solve_bwd differentiates a GOKU solve (default FORWARD_DUAL) */
+    int32_t solver;      /* ldeq_solver (default TSIT5) */
+    int32_t reserved_;   /* keeps the struct a multiple of 8 bytes */
 } ldeq_opts;
 
 int ldeq_version(void);
@@ -147,7 +157,7 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
                    const double* t_host, int B, int T, const ldeq_opts* opts, void* traj_out,
                    int32_t* retcode, int32_t* naccept, int32_t* nreject, ldeq_tape** tape_out,
                    ldeq_stream stream);
-/* Discrete adjoint of the recorded steps: dtraj (z,B,T) -> dz0 (z,B), dtheta (p,B). */
+/* Pullback dtraj (z,B,T) -> dz0 (z,B), dtheta (p,B) by the tape's sensealg (dual re-solves or discrete adjoint). */
 int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta,
                    ldeq_stream stream);
 /* Trajectories whose accepted steps exceeded the tape capacity.  ldeq_solve_bwd heals such a tape by
@@ -157,14 +167,25 @@ int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0
 int ldeq_tape_overflow(ldeq_handle* h, ldeq_tape* tape, int32_t* count_host, ldeq_stream stream);
 void ldeq_tape_free(ldeq_handle* h, ldeq_tape* tape, ldeq_stream stream);
 
-/* Same calls with HOST buffers (what a CPU-resident Flux model passes, GOKU.jl:102-103,128): the
- * library stages through its own device scratch; copies are inside the call; returns after sync. */
+/* Same calls with HOST buffers (what a CPU-resident Flux model passes, GOKU.jl:102-103,128): the library stages
+ * through its own device scratch; copies are inside the call; returns after sync.  The batch is cut into column
+ * slabs (trajectories are independent): transfers of one slab run on the library's copy streams under the kernels
+ * of the next, so one caller thread keeps the PCIe link and the SMs busy together.  Pinned host buffers make the
+ * copies asynchronous; pageable ones work (the runtime stages them). */
 int ldeq_solve_fwd_host(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0_host,
                         const void* theta_host, const double* t_host, int B, int T, const ldeq_opts* opts,
                         void* traj_out_host, int32_t* retcode_host, int32_t* naccept_host,
                         int32_t* nreject_host, ldeq_tape** tape_out, ldeq_stream stream);
 int ldeq_solve_bwd_host(ldeq_handle* h, ldeq_tape* tape, const void* dtraj_host, void* dz0_host,
                         void* dtheta_host, ldeq_stream stream);
+/* Forward solve and pullback of a KNOWN cotangent in one call (replaying a stored batch, gradient checks, the
+ * throughput benchmark): the cotangent slabs go up while the trajectory slabs come down -- both directions of the
+ * link at once, from a single caller thread.  No tape is returned. */
+int ldeq_solve_fwd_bwd_host(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0_host,
+                            const void* theta_host, const double* t_host, int B, int T, const ldeq_opts* opts,
+                            const void* dtraj_host, void* traj_out_host, void* dz0_host, void* dtheta_host,
+                            int32_t* retcode_host, int32_t* naccept_host, int32_t* nreject_host,
+                            ldeq_stream stream);
 
 /* ---- LatentODE path: one solve on the (D,B) matrix state with an MLP right-hand side ------------ */
 /* params_flat is Flux.destructure order: per layer vec(W) with W (out,in) column-major, then b.
@@ -226,6 +247,14 @@ int ldeq_comm_unique_id(ldeq_handle* h, void* id_out);
 int ldeq_comm_init(ldeq_handle* h, const void* unique_id, int rank, int nranks);
 int ldeq_allreduce_grads(ldeq_handle* h, float* grads_flat, int64_t n, ldeq_stream stream);
 int ldeq_comm_destroy(ldeq_handle* h);
+
+/* ---- diagnostics: the Float32 sine / cosine the integrator kernels evaluate, on device arrays of n arguments.
+ * which = 0: the 13/19-instruction pair of the primal / adjoint kernels (csrc/ldeq_common.cuh);
+ * which = 1: Base.sin / Base.cos(::Float32) as Julia computes them, used by the forward-dual pullback
+ *            (csrc/ldeq_julia_trig.cuh; bit-equal to the oracle's restatement);
+ * which = 2: the sine of the forward kernel alone (cos_out is zeroed). */
+int ldeq_debug_trig(ldeq_handle* h, int which, const float* x, float* sin_out, float* cos_out, int64_t n,
+                    ldeq_stream stream);
 
 #ifdef __cplusplus
 }

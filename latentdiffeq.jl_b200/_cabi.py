@@ -17,14 +17,15 @@ RHS_PENDULUM, RHS_PENDULUM_FRICTION = 0, 1
 RET_SUCCESS, RET_MAXITERS, RET_DTLESSTHANMIN, RET_UNSTABLE = 0, 1, 2, 3
 NORM_GLOBAL, NORM_PER_TRAJ = 0, 1
 MLP_MATH_FP32, MLP_MATH_BF16X3 = 0, 1
-OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_COMPILE = 0, -1, -2, -3, -4, -5
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_COMPILE, ERR_TAPE_OVERFLOW = 0, -1, -2, -3, -4, -5, -6
+SOLVER_TSIT5 = 0
 
 # every symbol include/ldeq.h declares (tests check the library exports exactly these)
 SYMBOLS = [
     "ldeq_version", "ldeq_opts_default", "ldeq_create", "ldeq_destroy", "ldeq_last_error", "ldeq_launch_count",
     "ldeq_rhs_builtin", "ldeq_rhs_from_source", "ldeq_rhs_dims", "ldeq_rhs_free",
     "ldeq_solve_fwd", "ldeq_solve_bwd", "ldeq_tape_overflow", "ldeq_tape_free",
-    "ldeq_solve_fwd_host", "ldeq_solve_bwd_host",
+    "ldeq_solve_fwd_host", "ldeq_solve_bwd_host", "ldeq_solve_fwd_bwd_host", "ldeq_debug_trig",
     "ldeq_mlp_solve_fwd", "ldeq_mlp_solve_bwd", "ldeq_mlp_tape_free",
     "ldeq_sample", "ldeq_elbo_fwd_bwd", "ldeq_adamw_step", "ldeq_allreduce_adamw_step",
     "ldeq_comm_unique_id", "ldeq_comm_init", "ldeq_allreduce_grads", "ldeq_comm_destroy",
@@ -42,6 +43,7 @@ class Opts(C.Structure):
         ("gamma", C.c_double), ("qmin", C.c_double), ("qmax", C.c_double), ("beta1", C.c_double),
         ("beta2", C.c_double), ("qoldinit", C.c_double), ("qsteady_min", C.c_double), ("qsteady_max", C.c_double),
         ("tape_steps", C.c_int32), ("norm_mode", C.c_int32), ("mlp_math", C.c_int32), ("sensealg", C.c_int32),
+        ("solver", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 
@@ -88,6 +90,8 @@ def load() -> C.CDLL:
     lib.ldeq_tape_free.restype = None
     lib.ldeq_solve_fwd_host.argtypes = [vp, vp, i32, vp, vp, vp, i32, i32, C.POINTER(Opts), vp, vp, vp, vp, pvp, vp]
     lib.ldeq_solve_bwd_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ldeq_solve_fwd_bwd_host.argtypes = [vp, vp, i32, vp, vp, vp, i32, i32, C.POINTER(Opts), vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ldeq_debug_trig.argtypes = [vp, i32, vp, vp, vp, i64, vp]
     lib.ldeq_mlp_solve_fwd.argtypes = [vp, i32, vp, vp, vp, i32, vp, i32, i32, C.POINTER(Opts), vp, vp, vp, vp, pvp, vp]
     lib.ldeq_mlp_solve_bwd.argtypes = [vp, vp, vp, vp, vp, vp]
     lib.ldeq_mlp_tape_free.argtypes = [vp, vp, vp]

@@ -9,6 +9,7 @@
 #include "ldeq_internal.h"
 #include "ldeq_rhs.cuh"
 #include "ldeq_tsit5.cuh"
+#include "ldeq_julia_trig.cuh"
 
 namespace ldeq {
 
@@ -78,7 +79,7 @@ KOpts to_kopts(const ldeq_opts* o) {
 // reads theta / the grid FROM the tape, where they already are.
 template <class S>
 static TapeView<S> fwd_tape_view(const ldeq_tape* tape, const void* theta, const double* tg) {
-    return TapeView<S>{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap,
+    return TapeView<S>{tape->t, (S*)tape->u, tape->info, tape->cap,
                        theta == tape->theta ? nullptr : (S*)tape->theta, tg == tape->tgrid ? nullptr : tape->tgrid,
                        tape->retcode, tape->naccept, tape->nreject};
 }
@@ -87,7 +88,7 @@ template <class S, bool FRICTION, bool TAPE>
 static cudaError_t launch_fwd(const void* z0, const void* theta, const double* tg, int B, int T, const KOpts& ko,
                               void* traj, int32_t* ret, int32_t* na, int32_t* nr, const ldeq_tape* tape,
                               const GridInfo& gi, cudaStream_t s) {
-    TapeView<S> tv{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+    TapeView<S> tv{nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
     if (TAPE) tv = fwd_tape_view<S>(tape, theta, tg);
     const int grid = (B + LDEQ_FWD_THREADS - 1) / LDEQ_FWD_THREADS;
     const size_t smem = Ring<S, 2>::bytes(LDEQ_FWD_THREADS) + (T <= LDEQ_TGRID_SMEM_MAX ? (size_t)T * sizeof(double) : 0);
@@ -97,14 +98,14 @@ static cudaError_t launch_fwd(const void* z0, const void* theta, const double* t
 }
 
 template <class S, bool FRICTION>
-static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
-    TapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
+static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
+    TapeView<S> tv{tape->t, (S*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
     const int grid = (tape->B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
     const size_t smem =
         Ring<S, 2>::bytes(LDEQ_BWD_THREADS) + (tape->T <= LDEQ_TGRID_SMEM_MAX ? (size_t)tape->T * sizeof(double) : 0);
     tsit5_bwd_kernel<PendulumRHS<S, FRICTION>, S><<<grid, LDEQ_BWD_THREADS, smem, s>>>(
         (const S*)tape->theta, tape->tgrid, tape->B, tape->T, (const S*)dtraj, tv, tape->retcode, tape->naccept,
-        (S*)dz0, (S*)dtheta, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform});
+        (S*)dz0, (S*)dtheta, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld});
     return cudaGetLastError();
 }
 
@@ -122,7 +123,7 @@ static size_t ring_smem(int z_dim, size_t es, int threads, int T) {
 static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg,
                                    int B, int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
                                    const ldeq_tape* tape, const GridInfo& gi, cudaStream_t s) {
-    TapeView<float> tv{nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};  // identical layout for float and double
+    TapeView<float> tv{nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};  // identical layout for float and double
     if (tape) tv = fwd_tape_view<float>(tape, theta, tg);
     KOpts kov = ko;
     GridInfo giv = gi;
@@ -132,14 +133,14 @@ static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z
     void* fn = rhs->fn[(dtype == LDEQ_F32 ? 0 : 2) + (tape ? 1 : 0)];
     return cudaLaunchKernel(fn, dim3(grid), dim3(LDEQ_FWD_THREADS), args, ring_smem(rhs->z_dim, es, LDEQ_FWD_THREADS, T), s);
 }
-static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
-    TapeView<float> tv{tape->t, tape->dt, (float*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
+static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
+    TapeView<float> tv{tape->t, (float*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
     const void* theta = tape->theta;
     const double* tg = tape->tgrid;
     int B = tape->B, T = tape->T;
     const int32_t* ret = tape->retcode;
     const int32_t* na = tape->naccept;
-    GridInfo giv{tape->grid_t0, tape->grid_h, tape->grid_uniform};
+    GridInfo giv{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld};
     void* args[] = {&theta, &tg, &B, &T, &dtraj, &tv, &ret, &na, &dz0, &dtheta, &giv};
     const int grid = (B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
     const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
@@ -148,7 +149,7 @@ static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, voi
 }
 
 // fn[6..9] = forward-dual pullback {theta-seeded f32, u0-seeded f32, theta-seeded f64, u0-seeded f64}
-static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
+static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     const void* z0 = tape->u;
     const void* theta = tape->theta;
     const double* tg = tape->tgrid;
@@ -157,10 +158,10 @@ static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj,
     const int32_t* ret = tape->retcode;
     const int grid = (B + 127) / 128;
     const int base = tape->dtype == LDEQ_F32 ? 6 : 8;
-    void* args_p[] = {&z0, &theta, &tg, &B, &T, &kov, &np, &dtraj, &ret, &dtheta};
+    void* args_p[] = {&z0, &theta, &tg, &B, &ld, &T, &kov, &np, &dtraj, &ret, &dtheta};
     cudaError_t e = cudaLaunchKernel(tape->rhs->fn[base], dim3(grid), dim3(128), args_p, 0, s);
     if (e != cudaSuccess) return e;
-    void* args_u[] = {&z0, &theta, &tg, &B, &T, &kov, &np, &dtraj, &ret, &dz0};
+    void* args_u[] = {&z0, &theta, &tg, &B, &ld, &T, &kov, &np, &dtraj, &ret, &dz0};
     return cudaLaunchKernel(tape->rhs->fn[base + 1], dim3(grid), dim3(128), args_u, 0, s);
 }
 
@@ -197,7 +198,6 @@ static int tape_alloc(ldeq_handle* h, ldeq_tape* tape, int cap, cudaStream_t s) 
     const size_t nB = (size_t)tape->B, c = (size_t)cap, ZD = tape->z_dim, PD = tape->p_dim;
     size_t off = 0;
     const size_t o_t = off;   off += align_up(c * nB * 8);
-    const size_t o_dt = off;  off += align_up(c * nB * 8);
     const size_t o_u = off;   off += align_up(c * nB * ZD * es);
     const size_t o_th = off;  off += align_up(nB * PD * es);
     const size_t o_tg = off;  off += align_up((size_t)tape->T * 8);
@@ -210,7 +210,7 @@ static int tape_alloc(ldeq_handle* h, ldeq_tape* tape, int cap, cudaStream_t s) 
     if (e != cudaSuccess) return set_err(h, LDEQ_ERR_NOMEM, "cudaMallocAsync(tape)", e);
     char* bp = (char*)base;
     tape->base = base; tape->cap = cap;
-    tape->t = (double*)(bp + o_t); tape->dt = (double*)(bp + o_dt); tape->u = bp + o_u;
+    tape->t = (double*)(bp + o_t); tape->u = bp + o_u;
     tape->theta = bp + o_th; tape->tgrid = (double*)(bp + o_tg); tape->retcode = (int32_t*)(bp + o_ret);
     tape->naccept = (int32_t*)(bp + o_na); tape->nreject = (int32_t*)(bp + o_nr);
     tape->info = (int32_t*)(bp + o_info);
@@ -250,7 +250,7 @@ static int tape_heal(ldeq_handle* h, ldeq_tape* tape, cudaStream_t s) {
     // step 0 of the old tape holds u0 for every trajectory (capacity is always >= 1)
     cudaError_t e = dispatch_fwd(tape->rhs, tape->dtype, old.u, tape->theta,
                                  tape->tgrid, tape->B, tape->T, tape->kopts, nullptr, nullptr, nullptr,
-                                 nullptr, tape, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform}, s);
+                                 nullptr, tape, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform, tape->B}, s);
     h->launches += 1;
     cudaFreeAsync(old.base, s);
     if (e != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwd_kernel (tape replay) launch", e);
@@ -271,6 +271,8 @@ void ldeq_opts_default(ldeq_opts* o) {
     o->dtmin = 0.0; o->maxiters = 1000000; o->gamma = 0.9; o->qmin = 0.2; o->qmax = 10.0; o->beta1 = 7.0 / 50.0;
     o->beta2 = 2.0 / 25.0; o->qoldinit = 1e-4; o->qsteady_min = 1.0; o->qsteady_max = 1.0; o->tape_steps = 0;
     o->norm_mode = LDEQ_NORM_GLOBAL; o->mlp_math = LDEQ_MLP_MATH_FP32;
+    o->sensealg = LDEQ_SENSE_FORWARD_DUAL;  // what the reference's diffeq structs ask for (pendulum.jl:11,58)
+    o->solver = LDEQ_SOLVER_TSIT5;
 }
 
 int ldeq_create(ldeq_handle** out, int device) {
@@ -302,6 +304,12 @@ void ldeq_destroy(ldeq_handle* h) {
         if (h->scratch[i]) cudaFree(h->scratch[i]);
     if (h->d_partials) cudaFree(h->d_partials);
     if (h->d_counter) cudaFree(h->d_counter);
+    if (h->up) {
+        cudaStreamDestroy(h->up);
+        cudaStreamDestroy(h->down);
+        for (int i = 0; i < LDEQ_MAX_SLABS; ++i) { cudaEventDestroy(h->ev_fwd[i]); cudaEventDestroy(h->ev_up[i]); }
+        cudaEventDestroy(h->ev_join);
+    }
     for (auto& sl : h->free_slots) cudaEventDestroy(sl.ev);
     for (auto* blk : h->pinned_blocks) cudaFreeHost(blk);
     delete h;
@@ -329,32 +337,23 @@ int ldeq_rhs_dims(const ldeq_rhs* rhs, int* z_dim, int* p_dim) {
     return LDEQ_OK;
 }
 
-int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta,
-                   const double* t_host, int B, int T, const ldeq_opts* opts, void* traj_out, int32_t* retcode,
-                   int32_t* naccept, int32_t* nreject, ldeq_tape** tape_out, ldeq_stream stream) {
-    if (!h) return LDEQ_ERR_INVALID;
-    if (tape_out) *tape_out = nullptr;
-    if (!rhs || !z0 || !theta || !t_host || !opts) return set_err(h, LDEQ_ERR_INVALID, "null argument");
-    if (!traj_out && !tape_out && !naccept) return set_err(h, LDEQ_ERR_INVALID, "nothing to compute: traj_out, tape_out and naccept are all null");
-    if (B < 0 || T < 1) return set_err(h, LDEQ_ERR_INVALID, "B must be >= 0 and T >= 1");
-    if (dtype != LDEQ_F32 && dtype != LDEQ_F64) return set_err(h, LDEQ_ERR_INVALID, "dtype");
-    if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
-    for (int k = 1; k < T; ++k)
-        if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
-    if (opts->sensealg != LDEQ_SENSE_DISCRETE_ADJOINT && opts->sensealg != LDEQ_SENSE_FORWARD_DUAL)
-        return set_err(h, LDEQ_ERR_INVALID, "sensealg");
-    const bool fwd_dual = tape_out && opts->sensealg == LDEQ_SENSE_FORWARD_DUAL;
-    cudaStream_t s = (cudaStream_t)stream;
-    LDEQ_CUDA(cudaSetDevice(h->device));
-    if (B == 0) return LDEQ_OK;
-    int rc = upload_tgrid(h, t_host, T, s);
-    if (rc) return rc;
-    KOpts ko = to_kopts(opts);
-    const size_t es = dtype == LDEQ_F32 ? 4 : 8;
-    const int ZD = rhs->z_dim, PD = rhs->p_dim;
+}  // extern "C"
 
+namespace ldeq {
+
+// ---- one column slab of a solve -----------------------------------------------------------------------
+// All pointers are already offset to the slab's first trajectory; `ld` is the row stride of traj (trajectories of
+// the whole batch).  The grid has been uploaded (upload_tgrid) by the caller.
+static int solve_fwd_slab(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* t_host,
+                          int B, int ld, int T, const ldeq_opts* opts, void* traj_out, int32_t* retcode, int32_t* naccept,
+                          int32_t* nreject, ldeq_tape** tape_out, cudaStream_t s) {
+    KOpts ko = to_kopts(opts);
+    const int ZD = rhs->z_dim, PD = rhs->p_dim;
+    const bool fwd_dual = tape_out && opts->sensealg == LDEQ_SENSE_FORWARD_DUAL;
     ldeq_tape* tape = nullptr;
+    int rc;
     if (tape_out) {
+        *tape_out = nullptr;
         tape = new ldeq_tape();
         tape->dtype = dtype; tape->rhs_kind = rhs->kind; tape->rhs = rhs; tape->B = B; tape->T = T;
         tape->z_dim = ZD; tape->p_dim = PD; tape->kopts = ko;
@@ -381,11 +380,10 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
             delete tape;
             return set_err(h, LDEQ_ERR_NOMEM, "tape host mirror");
         }
-        // theta, the grid and the statistics reach the tape through the forward kernel itself (TapeView)
-        if (fwd_dual) cudaMemcpyAsync(tape->u, z0, (size_t)B * ZD * es, cudaMemcpyDeviceToDevice, s);
+        // theta, the grid, the statistics and u0 (record 0) reach the tape through the forward kernel itself (TapeView)
     }
     cudaError_t e = dispatch_fwd(rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, retcode, naccept, nreject, tape,
-                                 GridInfo{h->grid_t0, h->grid_h, h->grid_uniform}, s);
+                                 GridInfo{h->grid_t0, h->grid_h, h->grid_uniform, ld}, s);
     h->launches += 1;
     if (e != cudaSuccess) {
         if (tape) { cudaFreeAsync(tape->base, s); cudaEventRecord(tape->ready, s); slot_put(h, tape); delete tape; }
@@ -399,13 +397,11 @@ int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z
     return LDEQ_OK;
 }
 
-int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, ldeq_stream stream) {
-    if (!h) return LDEQ_ERR_INVALID;
-    if (!tape || !dtraj || !dz0 || !dtheta) return set_err(h, LDEQ_ERR_INVALID, "null argument");
-    cudaStream_t s = (cudaStream_t)stream;
-    LDEQ_CUDA(cudaSetDevice(h->device));
+// reverse pass of one slab (a single-part tape); dtraj / dz0 / dtheta already offset, ld = row stride of dtraj
+static int solve_bwd_slab(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     if (tape->sense == LDEQ_SENSE_FORWARD_DUAL) {
-        const cudaError_t e2 = tape->rhs_kind < 0 ? launch_user_fwdsens(tape, dtraj, dz0, dtheta, s) : launch_fwdsens(tape, dtraj, dz0, dtheta, s);
+        const cudaError_t e2 = tape->rhs_kind < 0 ? launch_user_fwdsens(tape, dtraj, ld, dz0, dtheta, s)
+                                                  : launch_fwdsens(tape, dtraj, ld, dz0, dtheta, s);
         h->launches += 2;
         if (e2 != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwdsens_kernel launch", e2);
         return LDEQ_OK;
@@ -415,26 +411,146 @@ int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0
     const bool fr = tape->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION;
     cudaError_t e;
     if (tape->rhs_kind < 0)
-        e = launch_user_bwd(tape, dtraj, dz0, dtheta, s);
+        e = launch_user_bwd(tape, dtraj, ld, dz0, dtheta, s);
     else if (tape->dtype == LDEQ_F32)
-        e = fr ? launch_bwd<float, true>(tape, dtraj, dz0, dtheta, s) : launch_bwd<float, false>(tape, dtraj, dz0, dtheta, s);
+        e = fr ? launch_bwd<float, true>(tape, dtraj, ld, dz0, dtheta, s) : launch_bwd<float, false>(tape, dtraj, ld, dz0, dtheta, s);
     else
-        e = fr ? launch_bwd<double, true>(tape, dtraj, dz0, dtheta, s) : launch_bwd<double, false>(tape, dtraj, dz0, dtheta, s);
+        e = fr ? launch_bwd<double, true>(tape, dtraj, ld, dz0, dtheta, s) : launch_bwd<double, false>(tape, dtraj, ld, dz0, dtheta, s);
     h->launches += 1;
     if (e != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_bwd_kernel launch", e);
     return LDEQ_OK;
 }
 
+static int check_solve_args(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* t_host,
+                            int B, int T, const ldeq_opts* opts) {
+    if (!rhs || !z0 || !theta || !t_host || !opts) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    if (B < 0 || T < 1) return set_err(h, LDEQ_ERR_INVALID, "B must be >= 0 and T >= 1");
+    if (dtype != LDEQ_F32 && dtype != LDEQ_F64) return set_err(h, LDEQ_ERR_INVALID, "dtype");
+    if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
+    for (int k = 1; k < T; ++k)
+        if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
+    if (opts->sensealg != LDEQ_SENSE_DISCRETE_ADJOINT && opts->sensealg != LDEQ_SENSE_FORWARD_DUAL)
+        return set_err(h, LDEQ_ERR_INVALID, "sensealg");
+    if (opts->solver != LDEQ_SOLVER_TSIT5)
+        return set_err(h, LDEQ_ERR_UNSUPPORTED, "solver: only LDEQ_SOLVER_TSIT5 is built (the reference's examples use Tsit5(), pendulum.jl:11,58)");
+    return LDEQ_OK;
+}
+
+static void free_parts(ldeq_handle* h, ldeq_tape* tape, cudaStream_t s) {
+    for (ldeq_tape* p : tape->parts) {
+        if (p->base) cudaFreeAsync(p->base, s);
+        slot_put(h, p);
+        delete p;
+    }
+    tape->parts.clear();
+}
+
+// ---- host-buffer pipeline ---------------------------------------------------------------------------------
+// Trajectories are independent, so a host-resident batch is cut into column slabs: the download of slab i's
+// trajectories (copy stream "down") runs under the kernel of slab i+1 (the caller's stream), and the upload of slab
+// i+1's cotangent (copy stream "up") under the reverse pass of slab i.  B200 has separate copy engines per direction:
+// in the combined call the PCIe link is busy in both directions at once.
+static int host_streams(ldeq_handle* h) {
+    if (h->up) return LDEQ_OK;
+    LDEQ_CUDA(cudaStreamCreateWithFlags(&h->up, cudaStreamNonBlocking));
+    LDEQ_CUDA(cudaStreamCreateWithFlags(&h->down, cudaStreamNonBlocking));
+    for (int i = 0; i < LDEQ_MAX_SLABS; ++i) {
+        LDEQ_CUDA(cudaEventCreateWithFlags(&h->ev_fwd[i], cudaEventDisableTiming));
+        LDEQ_CUDA(cudaEventCreateWithFlags(&h->ev_up[i], cudaEventDisableTiming));
+    }
+    LDEQ_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    return LDEQ_OK;
+}
+static int slab_count(int B) {
+    // slabs of at least 32 Ki trajectories (a slab must still fill the GPU: 148 SMs x 640 resident threads), at most 8
+    int n = B / 32768;
+    return n < 1 ? 1 : n > LDEQ_MAX_SLABS ? LDEQ_MAX_SLABS : n;
+}
+static void slab_bounds(int B, int n, int i, int* b0, int* nb) {
+    // multiples of 128 trajectories (CTA size), remainder to the last slab
+    int per = ((B / n) + 127) / 128 * 128;
+    *b0 = i * per < B ? i * per : B;
+    int e = (i == n - 1) ? B : ((i + 1) * per < B ? (i + 1) * per : B);
+    *nb = e - *b0;
+}
+
+struct HostBufs {
+    char *z0, *th, *traj, *dtraj, *dz0, *dth;
+    int32_t *ret, *na, *nr;
+};
+static int host_bufs(ldeq_handle* h, size_t nz, size_t np, size_t nt, int B, bool fwd, bool bwd, HostBufs* hb) {
+    int rc;
+    if ((rc = ensure_scratch(h, 0, 2 * align_up(nz) + 2 * align_up(np) + 3 * align_up((size_t)B * 4)))) return rc;
+    char* in = (char*)h->scratch[0];
+    hb->z0 = in; in += align_up(nz);
+    hb->th = in; in += align_up(np);
+    hb->dz0 = in; in += align_up(nz);
+    hb->dth = in; in += align_up(np);
+    hb->ret = (int32_t*)in; in += align_up((size_t)B * 4);
+    hb->na = (int32_t*)in; in += align_up((size_t)B * 4);
+    hb->nr = (int32_t*)in;
+    hb->traj = hb->dtraj = nullptr;
+    if (fwd) { if ((rc = ensure_scratch(h, 1, nt))) return rc; hb->traj = (char*)h->scratch[1]; }
+    if (bwd) { if ((rc = ensure_scratch(h, 2, nt))) return rc; hb->dtraj = (char*)h->scratch[2]; }
+    return LDEQ_OK;
+}
+
+}  // namespace ldeq
+
+using namespace ldeq;
+
+extern "C" {
+
+int ldeq_solve_fwd(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta,
+                   const double* t_host, int B, int T, const ldeq_opts* opts, void* traj_out, int32_t* retcode,
+                   int32_t* naccept, int32_t* nreject, ldeq_tape** tape_out, ldeq_stream stream) {
+    if (!h) return LDEQ_ERR_INVALID;
+    if (tape_out) *tape_out = nullptr;
+    int rc = check_solve_args(h, rhs, dtype, z0, theta, t_host, B, T, opts);
+    if (rc) return rc;
+    if (!traj_out && !tape_out && !naccept) return set_err(h, LDEQ_ERR_INVALID, "nothing to compute: traj_out, tape_out and naccept are all null");
+    cudaStream_t s = (cudaStream_t)stream;
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    if (B == 0) return LDEQ_OK;
+    if ((rc = upload_tgrid(h, t_host, T, s))) return rc;
+    return solve_fwd_slab(h, rhs, dtype, z0, theta, t_host, B, B, T, opts, traj_out, retcode, naccept, nreject, tape_out, s);
+}
+
+int ldeq_solve_bwd(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, ldeq_stream stream) {
+    if (!h) return LDEQ_ERR_INVALID;
+    if (!tape || !dtraj || !dz0 || !dtheta) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    if (tape->parts.empty()) return solve_bwd_slab(h, tape, dtraj, tape->B, dz0, dtheta, s);
+    // a tape recorded slab by slab (ldeq_solve_fwd_host): same column slabs of the device arrays
+    const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
+    for (size_t i = 0; i < tape->parts.size(); ++i) {
+        ldeq_tape* p = tape->parts[i];
+        const size_t b0 = (size_t)tape->part_b0[i];
+        int rc = solve_bwd_slab(h, p, (const char*)dtraj + b0 * tape->z_dim * es, tape->B, (char*)dz0 + b0 * tape->z_dim * es,
+                                (char*)dtheta + b0 * tape->p_dim * es, s);
+        if (rc) return rc;
+    }
+    return LDEQ_OK;
+}
+
 int ldeq_tape_overflow(ldeq_handle* h, ldeq_tape* tape, int32_t* count_host, ldeq_stream) {
     if (!h || !tape || !count_host) return LDEQ_ERR_INVALID;
-    LDEQ_CUDA(cudaEventSynchronize(tape->ready));
-    *count_host = tape->checked && tape->h_info[0] > 0 && tape->cap >= tape->h_info[1] ? 0 : tape->h_info[0];
+    *count_host = 0;
+    auto one = [&](ldeq_tape* t) -> int {
+        LDEQ_CUDA(cudaEventSynchronize(t->ready));
+        *count_host += t->checked && t->h_info[0] > 0 && t->cap >= t->h_info[1] ? 0 : t->h_info[0];
+        return LDEQ_OK;
+    };
+    if (tape->parts.empty()) return one(tape);
+    for (ldeq_tape* p : tape->parts) { int rc = one(p); if (rc) return rc; }
     return LDEQ_OK;
 }
 
 void ldeq_tape_free(ldeq_handle* h, ldeq_tape* tape, ldeq_stream stream) {
     if (!tape) return;
     if (h) cudaSetDevice(h->device);
+    free_parts(h, tape, (cudaStream_t)stream);
     if (tape->base) cudaFreeAsync(tape->base, (cudaStream_t)stream);
     slot_put(h, tape);
     delete tape;
@@ -445,30 +561,49 @@ int ldeq_solve_fwd_host(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const vo
                         int32_t* retcode_host, int32_t* naccept_host, int32_t* nreject_host, ldeq_tape** tape_out,
                         ldeq_stream stream) {
     if (!h) return LDEQ_ERR_INVALID;
-    if (!rhs || !z0_host || !theta_host || !traj_out_host) return set_err(h, LDEQ_ERR_INVALID, "null argument");
-    if (B <= 0 || T < 1) return set_err(h, LDEQ_ERR_INVALID, "B must be > 0 and T >= 1");
+    if (tape_out) *tape_out = nullptr;
+    int rc = check_solve_args(h, rhs, dtype, z0_host, theta_host, t_host, B, T, opts);
+    if (rc) return rc;
+    if (!traj_out_host) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    if (B <= 0) return set_err(h, LDEQ_ERR_INVALID, "B must be > 0");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
-    const size_t es = dtype == LDEQ_F32 ? 4 : 8;
-    const size_t nz = (size_t)B * rhs->z_dim * es, np = (size_t)B * rhs->p_dim * es, nt = nz * (size_t)T;
-    int rc;
-    if ((rc = ensure_scratch(h, 0, align_up(nz) + align_up(np) + 3 * align_up((size_t)B * 4)))) return rc;
-    if ((rc = ensure_scratch(h, 1, nt))) return rc;
-    char* in = (char*)h->scratch[0];
-    void* d_z0 = in;
-    void* d_th = in + align_up(nz);
-    int32_t* d_ret = (int32_t*)(in + align_up(nz) + align_up(np));
-    int32_t* d_na = (int32_t*)((char*)d_ret + align_up((size_t)B * 4));
-    int32_t* d_nr = (int32_t*)((char*)d_na + align_up((size_t)B * 4));
-    LDEQ_CUDA(cudaMemcpyAsync(d_z0, z0_host, nz, cudaMemcpyHostToDevice, s));
-    LDEQ_CUDA(cudaMemcpyAsync(d_th, theta_host, np, cudaMemcpyHostToDevice, s));
-    rc = ldeq_solve_fwd(h, rhs, dtype, d_z0, d_th, t_host, B, T, opts, h->scratch[1], d_ret, d_na, d_nr, tape_out, s);
-    if (rc) return rc;
-    LDEQ_CUDA(cudaMemcpyAsync(traj_out_host, h->scratch[1], nt, cudaMemcpyDeviceToHost, s));
-    if (retcode_host) LDEQ_CUDA(cudaMemcpyAsync(retcode_host, d_ret, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (naccept_host) LDEQ_CUDA(cudaMemcpyAsync(naccept_host, d_na, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (nreject_host) LDEQ_CUDA(cudaMemcpyAsync(nreject_host, d_nr, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if ((rc = host_streams(h))) return rc;
+    const size_t es = dtype == LDEQ_F32 ? 4 : 8, zb = (size_t)rhs->z_dim * es, pb = (size_t)rhs->p_dim * es;
+    const size_t nz = (size_t)B * zb, np = (size_t)B * pb, nt = nz * (size_t)T;
+    HostBufs hb;
+    if ((rc = host_bufs(h, nz, np, nt, B, true, false, &hb))) return rc;
+    if ((rc = upload_tgrid(h, t_host, T, s))) return rc;
+    LDEQ_CUDA(cudaMemcpyAsync(hb.z0, z0_host, nz, cudaMemcpyHostToDevice, s));
+    LDEQ_CUDA(cudaMemcpyAsync(hb.th, theta_host, np, cudaMemcpyHostToDevice, s));
+    ldeq_tape* parent = nullptr;
+    if (tape_out) {
+        parent = new ldeq_tape();
+        parent->dtype = dtype; parent->rhs_kind = rhs->kind; parent->rhs = rhs; parent->B = B; parent->T = T;
+        parent->z_dim = rhs->z_dim; parent->p_dim = rhs->p_dim; parent->sense = opts->sensealg;
+    }
+    const int ns = slab_count(B);
+    for (int i = 0; i < ns; ++i) {
+        int b0, nb;
+        slab_bounds(B, ns, i, &b0, &nb);
+        if (nb <= 0) continue;
+        ldeq_tape* part = nullptr;
+        rc = solve_fwd_slab(h, rhs, dtype, hb.z0 + b0 * zb, hb.th + b0 * pb, t_host, nb, B, T, opts, hb.traj + b0 * zb, hb.ret + b0,
+                            hb.na + b0, hb.nr + b0, parent ? &part : nullptr, s);
+        if (rc) { if (parent) { free_parts(h, parent, s); delete parent; } return rc; }
+        if (parent) { parent->parts.push_back(part); parent->part_b0.push_back(b0); }
+        // this slab's columns of every row: a strided (2-D) download behind the kernel that produced them
+        LDEQ_CUDA(cudaEventRecord(h->ev_fwd[i], s));
+        LDEQ_CUDA(cudaStreamWaitEvent(h->down, h->ev_fwd[i], 0));
+        LDEQ_CUDA(cudaMemcpy2DAsync((char*)traj_out_host + b0 * zb, (size_t)B * zb, hb.traj + b0 * zb, (size_t)B * zb, (size_t)nb * zb,
+                                    (size_t)T, cudaMemcpyDeviceToHost, h->down));
+    }
+    if (retcode_host) LDEQ_CUDA(cudaMemcpyAsync(retcode_host, hb.ret, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (naccept_host) LDEQ_CUDA(cudaMemcpyAsync(naccept_host, hb.na, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (nreject_host) LDEQ_CUDA(cudaMemcpyAsync(nreject_host, hb.nr, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
     LDEQ_CUDA(cudaStreamSynchronize(s));
+    LDEQ_CUDA(cudaStreamSynchronize(h->down));
+    if (tape_out) *tape_out = parent;
     return LDEQ_OK;
 }
 
@@ -478,20 +613,113 @@ int ldeq_solve_bwd_host(ldeq_handle* h, ldeq_tape* tape, const void* dtraj_host,
     if (!tape || !dtraj_host || !dz0_host || !dtheta_host) return set_err(h, LDEQ_ERR_INVALID, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
-    const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
-    const size_t nz = (size_t)tape->B * tape->z_dim * es, np = (size_t)tape->B * tape->p_dim * es,
-                 nt = nz * (size_t)tape->T;
     int rc;
-    if ((rc = ensure_scratch(h, 2, nt))) return rc;
-    if ((rc = ensure_scratch(h, 3, align_up(nz) + align_up(np)))) return rc;
-    void* d_dz0 = h->scratch[3];
-    void* d_dth = (char*)h->scratch[3] + align_up(nz);
-    LDEQ_CUDA(cudaMemcpyAsync(h->scratch[2], dtraj_host, nt, cudaMemcpyHostToDevice, s));
-    rc = ldeq_solve_bwd(h, tape, h->scratch[2], d_dz0, d_dth, s);
-    if (rc) return rc;
-    LDEQ_CUDA(cudaMemcpyAsync(dz0_host, d_dz0, nz, cudaMemcpyDeviceToHost, s));
-    LDEQ_CUDA(cudaMemcpyAsync(dtheta_host, d_dth, np, cudaMemcpyDeviceToHost, s));
+    if ((rc = host_streams(h))) return rc;
+    const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8, zb = (size_t)tape->z_dim * es, pb = (size_t)tape->p_dim * es;
+    const int B = tape->B, T = tape->T;
+    const size_t nz = (size_t)B * zb, np = (size_t)B * pb, nt = nz * (size_t)T;
+    HostBufs hb;
+    if ((rc = host_bufs(h, nz, np, nt, B, false, true, &hb))) return rc;
+    // every part's cotangent slab goes up on the copy stream; its reverse pass follows on the caller's stream
+    const size_t nparts = tape->parts.empty() ? 1 : tape->parts.size();
+    LDEQ_CUDA(cudaEventRecord(h->ev_join, s));   // uploads must not overtake earlier work of the caller on this scratch
+    LDEQ_CUDA(cudaStreamWaitEvent(h->up, h->ev_join, 0));
+    for (size_t i = 0; i < nparts; ++i) {
+        ldeq_tape* p = tape->parts.empty() ? tape : tape->parts[i];
+        const size_t b0 = tape->parts.empty() ? 0 : (size_t)tape->part_b0[i];
+        LDEQ_CUDA(cudaMemcpy2DAsync(hb.dtraj + b0 * zb, (size_t)B * zb, (const char*)dtraj_host + b0 * zb, (size_t)B * zb,
+                                    (size_t)p->B * zb, (size_t)T, cudaMemcpyHostToDevice, h->up));
+        LDEQ_CUDA(cudaEventRecord(h->ev_up[i % LDEQ_MAX_SLABS], h->up));
+        LDEQ_CUDA(cudaStreamWaitEvent(s, h->ev_up[i % LDEQ_MAX_SLABS], 0));
+        rc = solve_bwd_slab(h, p, hb.dtraj + b0 * zb, B, hb.dz0 + b0 * zb, hb.dth + b0 * pb, s);
+        if (rc) return rc;
+    }
+    LDEQ_CUDA(cudaMemcpyAsync(dz0_host, hb.dz0, nz, cudaMemcpyDeviceToHost, s));
+    LDEQ_CUDA(cudaMemcpyAsync(dtheta_host, hb.dth, np, cudaMemcpyDeviceToHost, s));
     LDEQ_CUDA(cudaStreamSynchronize(s));
+    return LDEQ_OK;
+}
+
+int ldeq_solve_fwd_bwd_host(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const void* z0_host, const void* theta_host,
+                            const double* t_host, int B, int T, const ldeq_opts* opts, const void* dtraj_host,
+                            void* traj_out_host, void* dz0_host, void* dtheta_host, int32_t* retcode_host,
+                            int32_t* naccept_host, int32_t* nreject_host, ldeq_stream stream) {
+    if (!h) return LDEQ_ERR_INVALID;
+    int rc = check_solve_args(h, rhs, dtype, z0_host, theta_host, t_host, B, T, opts);
+    if (rc) return rc;
+    if (!dtraj_host || !traj_out_host || !dz0_host || !dtheta_host) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    if (B <= 0) return set_err(h, LDEQ_ERR_INVALID, "B must be > 0");
+    cudaStream_t s = (cudaStream_t)stream;
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    if ((rc = host_streams(h))) return rc;
+    const size_t es = dtype == LDEQ_F32 ? 4 : 8, zb = (size_t)rhs->z_dim * es, pb = (size_t)rhs->p_dim * es;
+    const size_t nz = (size_t)B * zb, np = (size_t)B * pb, nt = nz * (size_t)T;
+    HostBufs hb;
+    if ((rc = host_bufs(h, nz, np, nt, B, true, true, &hb))) return rc;
+    if ((rc = upload_tgrid(h, t_host, T, s))) return rc;
+    LDEQ_CUDA(cudaMemcpyAsync(hb.z0, z0_host, nz, cudaMemcpyHostToDevice, s));
+    LDEQ_CUDA(cudaMemcpyAsync(hb.th, theta_host, np, cudaMemcpyHostToDevice, s));
+    LDEQ_CUDA(cudaEventRecord(h->ev_join, s));
+    LDEQ_CUDA(cudaStreamWaitEvent(h->up, h->ev_join, 0));
+    const int ns = slab_count(B);
+    // the whole cotangent streams up slab by slab while the forward slabs stream down
+    for (int i = 0; i < ns; ++i) {
+        int b0, nb;
+        slab_bounds(B, ns, i, &b0, &nb);
+        if (nb <= 0) continue;
+        LDEQ_CUDA(cudaMemcpy2DAsync(hb.dtraj + b0 * zb, (size_t)B * zb, (const char*)dtraj_host + b0 * zb, (size_t)B * zb,
+                                    (size_t)nb * zb, (size_t)T, cudaMemcpyHostToDevice, h->up));
+        LDEQ_CUDA(cudaEventRecord(h->ev_up[i], h->up));
+    }
+    for (int i = 0; i < ns; ++i) {
+        int b0, nb;
+        slab_bounds(B, ns, i, &b0, &nb);
+        if (nb <= 0) continue;
+        ldeq_tape* part = nullptr;
+        rc = solve_fwd_slab(h, rhs, dtype, hb.z0 + b0 * zb, hb.th + b0 * pb, t_host, nb, B, T, opts, hb.traj + b0 * zb, hb.ret + b0,
+                            hb.na + b0, hb.nr + b0, &part, s);
+        if (rc) return rc;
+        LDEQ_CUDA(cudaEventRecord(h->ev_fwd[i], s));
+        LDEQ_CUDA(cudaStreamWaitEvent(h->down, h->ev_fwd[i], 0));
+        LDEQ_CUDA(cudaMemcpy2DAsync((char*)traj_out_host + b0 * zb, (size_t)B * zb, hb.traj + b0 * zb, (size_t)B * zb, (size_t)nb * zb,
+                                    (size_t)T, cudaMemcpyDeviceToHost, h->down));
+        LDEQ_CUDA(cudaStreamWaitEvent(s, h->ev_up[i], 0));
+        rc = solve_bwd_slab(h, part, hb.dtraj + b0 * zb, B, hb.dz0 + b0 * zb, hb.dth + b0 * pb, s);
+        cudaFreeAsync(part->base, s);
+        slot_put(h, part);
+        delete part;
+        if (rc) return rc;
+    }
+    LDEQ_CUDA(cudaMemcpyAsync(dz0_host, hb.dz0, nz, cudaMemcpyDeviceToHost, s));
+    LDEQ_CUDA(cudaMemcpyAsync(dtheta_host, hb.dth, np, cudaMemcpyDeviceToHost, s));
+    if (retcode_host) LDEQ_CUDA(cudaMemcpyAsync(retcode_host, hb.ret, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (naccept_host) LDEQ_CUDA(cudaMemcpyAsync(naccept_host, hb.na, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    if (nreject_host) LDEQ_CUDA(cudaMemcpyAsync(nreject_host, hb.nr, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+    LDEQ_CUDA(cudaStreamSynchronize(s));
+    LDEQ_CUDA(cudaStreamSynchronize(h->down));
+    return LDEQ_OK;
+}
+
+// ---- diagnostics ------------------------------------------------------------------------------------------
+__global__ void debug_trig_kernel(int which, const float* __restrict__ x, float* __restrict__ sn, float* __restrict__ cs, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float a, b;
+    if (which == 0) fast_sincosf(x[i], &a, &b);
+    else if (which == 1) jl_sincosf(x[i], &a, &b);
+    else { a = fast_sinf(x[i]); b = 0.0f; }
+    sn[i] = a;
+    cs[i] = b;
+}
+
+int ldeq_debug_trig(ldeq_handle* h, int which, const float* x, float* sin_out, float* cos_out, int64_t n, ldeq_stream stream) {
+    if (!h) return LDEQ_ERR_INVALID;
+    if (!x || !sin_out || !cos_out || n < 0 || which < 0 || which > 2) return set_err(h, LDEQ_ERR_INVALID, "bad argument");
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    if (n == 0) return LDEQ_OK;
+    debug_trig_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(which, x, sin_out, cos_out, n);
+    h->launches += 1;
+    LDEQ_CUDA(cudaGetLastError());
     return LDEQ_OK;
 }
 

@@ -161,6 +161,65 @@ template <class S> __device__ __forceinline__ bool s_finite(S a);
 template <> __device__ __forceinline__ bool s_finite<float>(float a) { return isfinite(a); }
 template <> __device__ __forceinline__ bool s_finite<double>(double a) { return isfinite(a); }
 
+// ---- Float32 sine / cosine of the pendulum right-hand sides ------------------------------------------
+// sinf / sincosf of libdevice cost ~25 / ~40 instructions (quadrant selection, a Payne-Hanek slow path behind a branch);
+// the integrator kernels are instruction-issue bound and evaluate 6-7 of them per step.  These versions reduce by
+// multiples of pi with a three-term Cody-Waite split (k pi_hi exact in the FMA), then ONE odd minimax polynomial of
+// degree 9 on [-pi/2, pi/2] (approximation error 6e-9 relative) and, for the cosine, an even one of degree 10
+// (2.4e-10 absolute): 13 / 19 instructions.  Measured against Float64 (tests/test_goku_gpu.py::test_fast_sincos_accuracy):
+// sine <= 1.8 ulp everywhere on |x| <= 1e4 (mean 0.33 ulp, 99.1 % of the arguments within 1 ulp), cosine <= 2e-7 absolute.
+// Arguments beyond 1e4 (never reached by a pendulum angle in radians, but legal) take libdevice's sinf / sincosf.
+#define LDEQ_SINCOS_FAST_MAX 1.0e4f
+__device__ __forceinline__ float fast_sin_reduce(float x, unsigned& sign) {
+    const float kf = fmaf(x, 0.318309886183790672f, 12582912.0f);  // 1.5 * 2^23: the integer lands in the low mantissa bits
+    sign = __float_as_uint(kf) << 31;
+    const float k = kf - 12582912.0f;
+    float r = fmaf(k, -3.14159274101257324f, x);
+    r = fmaf(k, 8.74227765734758577e-08f, r);
+    return fmaf(k, 3.43024902734575342e-15f, r);
+}
+__device__ __forceinline__ float fast_sin_poly(float r, float r2) {
+    float p = fmaf(r2, 2.6057520614159343e-06f, -1.9809590781843947e-04f);
+    p = fmaf(r2, p, 8.3330660931473012e-03f);
+    p = fmaf(r2, p, -1.6666659545045038e-01f);
+    return fmaf(r * r2, p, r);
+}
+__device__ __forceinline__ float fast_cos_poly(float r2) {
+    float q = fmaf(r2, -2.6076832445861094e-07f, 2.4761871604948579e-05f);
+    q = fmaf(r2, q, -1.3888403241539062e-03f);
+    q = fmaf(r2, q, 4.1666640709316493e-02f);
+    q = fmaf(r2, q, -4.9999999549160074e-01f);
+    return fmaf(r2, q, 1.0f);
+}
+// out of line: six or seven inlined copies of libdevice's slow path would triple the kernels' code size
+static __device__ __noinline__ float slow_sinf(float x) { return sinf(x); }
+static __device__ __noinline__ void slow_sincosf(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ float fast_sinf(float x) {
+    if (!(fabsf(x) <= LDEQ_SINCOS_FAST_MAX)) return slow_sinf(x);
+    unsigned sg;
+    const float r = fast_sin_reduce(x, sg);
+    return __uint_as_float(__float_as_uint(fast_sin_poly(r, r * r)) ^ sg);
+}
+__device__ __forceinline__ void fast_sincosf(float x, float* s, float* c) {
+    if (!(fabsf(x) <= LDEQ_SINCOS_FAST_MAX)) { slow_sincosf(x, s, c); return; }
+    unsigned sg;
+    const float r = fast_sin_reduce(x, sg);
+    const float r2 = r * r;
+    *s = __uint_as_float(__float_as_uint(fast_sin_poly(r, r2)) ^ sg);
+    *c = __uint_as_float(__float_as_uint(fast_cos_poly(r2)) ^ sg);
+}
+template <class S> __device__ __forceinline__ S s_sin_fast(S x);
+template <> __device__ __forceinline__ float s_sin_fast<float>(float x) { return fast_sinf(x); }
+template <> __device__ __forceinline__ double s_sin_fast<double>(double x) { return sin(x); }
+template <class S> __device__ __forceinline__ void s_sincos_fast(S x, S* s, S* c);
+template <> __device__ __forceinline__ void s_sincos_fast<float>(float x, float* s, float* c) { fast_sincosf(x, s, c); }
+template <> __device__ __forceinline__ void s_sincos_fast<double>(double x, double* s, double* c) { sincos(x, s, c); }
+// quotient for the scaled error estimate: MUFU.RCP + one multiply in Float32 (2 ulp; the estimate itself carries the
+// cancellation noise of sum_j btilde_j k_j, ~1e-3 relative), IEEE in Float64
+template <class S> __device__ __forceinline__ S s_div_fast(S a, S b);
+template <> __device__ __forceinline__ float s_div_fast<float>(float a, float b) { return __fdividef(a, b); }
+template <> __device__ __forceinline__ double s_div_fast<double>(double a, double b) { return a / b; }
+
 // vector load/store of one trajectory's ZD-vector (coalesced 8/16-byte accesses for ZD = 2)
 template <class S, int ZD> __device__ __forceinline__ void load_vec(const S* __restrict__ p, S* v) {
 #pragma unroll
@@ -184,5 +243,53 @@ template <> __device__ __forceinline__ void store_vec<float, 2>(float* __restric
 template <> __device__ __forceinline__ void store_vec<double, 2>(double* __restrict__ p, const double* v) {
     *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
 }
+
+// ---- ZD-vector arithmetic with a scalar coefficient -------------------------------------------------
+// Every stage combination, dense-output coefficient, error estimate and adjoint update of the integrators is
+// "scalar x ZD-vector (+ ZD-vector)".  For the two-dimensional Float32 state of the GOKU pendulums that is exactly one
+// packed fma.rn.f32x2 (FFMA2 in SASS, sm_100): half the issue slots of two FFMAs, and the scalar rides along as an
+// immediate / 32-bit register broadcast.  NVRTC (user right-hand sides) takes the generic loops.
+template <class S, int N> struct VecOps {
+    // out = a * x
+    __device__ __forceinline__ static void scale(S* out, S a, const S* x) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = a * x[i];
+    }
+    // y += a * x
+    __device__ __forceinline__ static void axpy(S* y, S a, const S* x) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] = s_fma<S>(a, x[i], y[i]);
+    }
+    // out = a * x + y
+    __device__ __forceinline__ static void fma(S* out, S a, const S* x, const S* y) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) out[i] = s_fma<S>(a, x[i], y[i]);
+    }
+    // y += x
+    __device__ __forceinline__ static void add(S* y, const S* x) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) y[i] += x[i];
+    }
+};
+#if !defined(__CUDACC_RTC__) && !defined(LDEQ_NO_F32X2)
+template <> struct VecOps<float, 2> {
+    __device__ __forceinline__ static void scale(float* out, float a, const float* x) {
+        const float2 r = __fmul2_rn(make_float2(a, a), make_float2(x[0], x[1]));
+        out[0] = r.x; out[1] = r.y;
+    }
+    __device__ __forceinline__ static void axpy(float* y, float a, const float* x) {
+        const float2 r = __ffma2_rn(make_float2(a, a), make_float2(x[0], x[1]), make_float2(y[0], y[1]));
+        y[0] = r.x; y[1] = r.y;
+    }
+    __device__ __forceinline__ static void fma(float* out, float a, const float* x, const float* y) {
+        const float2 r = __ffma2_rn(make_float2(a, a), make_float2(x[0], x[1]), make_float2(y[0], y[1]));
+        out[0] = r.x; out[1] = r.y;
+    }
+    __device__ __forceinline__ static void add(float* y, const float* x) {
+        const float2 r = __fadd2_rn(make_float2(y[0], y[1]), make_float2(x[0], x[1]));
+        y[0] = r.x; y[1] = r.y;
+    }
+};
+#endif
 
 }  // namespace ldeq

@@ -8,6 +8,7 @@
 #pragma once
 
 #include "ldeq_common.cuh"
+#include "ldeq_julia_trig.cuh"
 
 namespace ldeq {
 
@@ -78,9 +79,11 @@ LDEQ_DUAL_T Dual<S, N> dual_chain(const Dual<S, N>& a, S f, S fp) {
 }  // namespace ldeq
 
 // elementary functions, found by argument-dependent lookup from user code written as sin(x), exp(x), ...
+// sin / cos of a Float32 dual follow Julia's Base.sin / Base.cos bit for bit (ldeq_julia_trig.cuh): the forward-dual
+// pullback restates the reference's dual-number solves literally
 namespace ldeq {
-template <class S, int N> __device__ __forceinline__ Dual<S, N> sin(const Dual<S, N>& a) { S s, c; s_sincos<S>(a.v, &s, &c); return dual_chain(a, s, c); }
-template <class S, int N> __device__ __forceinline__ Dual<S, N> cos(const Dual<S, N>& a) { S s, c; s_sincos<S>(a.v, &s, &c); return dual_chain(a, c, -s); }
+template <class S, int N> __device__ __forceinline__ Dual<S, N> sin(const Dual<S, N>& a) { S s, c; s_sincos_julia<S>(a.v, &s, &c); return dual_chain(a, s, c); }
+template <class S, int N> __device__ __forceinline__ Dual<S, N> cos(const Dual<S, N>& a) { S s, c; s_sincos_julia<S>(a.v, &s, &c); return dual_chain(a, c, -s); }
 template <class S, int N> __device__ __forceinline__ Dual<S, N> tan(const Dual<S, N>& a) { const S t = ::tan(a.v); return dual_chain(a, t, (S)1 + t * t); }
 template <class S, int N> __device__ __forceinline__ Dual<S, N> exp(const Dual<S, N>& a) { const S e = ::exp(a.v); return dual_chain(a, e, e); }
 template <class S, int N> __device__ __forceinline__ Dual<S, N> log(const Dual<S, N>& a) { return dual_chain(a, (S)::log(a.v), (S)1 / a.v); }

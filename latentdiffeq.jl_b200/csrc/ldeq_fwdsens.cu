@@ -26,27 +26,27 @@ template <bool FRICTION> struct PendulumDualRHS {
 
 template <class S, int NP, bool FRICTION, bool SEED_P>
 __global__ void __launch_bounds__(128, 4)
-tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, int T,
+tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, int ld, int T,
                      KOpts o, int norm_partials, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                      S* __restrict__ dout) {
-    tsit5_fwdsens_body<PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, T, o, norm_partials, dtraj, primal_ret, dout);
+    tsit5_fwdsens_body<PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, ld, T, o, norm_partials, dtraj, primal_ret, dout);
 }
 
 template <class S, bool FR>
-static cudaError_t launch_fwdsens_t(const ldeq_tape* tp, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
+static cudaError_t launch_fwdsens_t(const ldeq_tape* tp, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     const int B = tp->B, grid = (B + 127) / 128;
-    tsit5_fwdsens_kernel<S, 1, FR, true><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, tp->T, tp->kopts, 1,
+    tsit5_fwdsens_kernel<S, 1, FR, true><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, ld, tp->T, tp->kopts, 1,
                                                              (const S*)dtraj, tp->retcode, (S*)dtheta);
-    tsit5_fwdsens_kernel<S, 2, FR, false><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, tp->T, tp->kopts, 1,
+    tsit5_fwdsens_kernel<S, 2, FR, false><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, ld, tp->T, tp->kopts, 1,
                                                               (const S*)dtraj, tp->retcode, (S*)dz0);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fwdsens(const ldeq_tape* tp, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s) {
+cudaError_t launch_fwdsens(const ldeq_tape* tp, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     const bool fr = tp->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION;
     if (tp->dtype == LDEQ_F32)
-        return fr ? launch_fwdsens_t<float, true>(tp, dtraj, dz0, dtheta, s) : launch_fwdsens_t<float, false>(tp, dtraj, dz0, dtheta, s);
-    return fr ? launch_fwdsens_t<double, true>(tp, dtraj, dz0, dtheta, s) : launch_fwdsens_t<double, false>(tp, dtraj, dz0, dtheta, s);
+        return fr ? launch_fwdsens_t<float, true>(tp, dtraj, ld, dz0, dtheta, s) : launch_fwdsens_t<float, false>(tp, dtraj, ld, dz0, dtheta, s);
+    return fr ? launch_fwdsens_t<double, true>(tp, dtraj, ld, dz0, dtheta, s) : launch_fwdsens_t<double, false>(tp, dtraj, ld, dz0, dtheta, s);
 }
 
 }  // namespace ldeq

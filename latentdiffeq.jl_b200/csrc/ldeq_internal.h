@@ -10,6 +10,8 @@
 #include "../../include/ldeq.h"
 #include "ldeq_common.cuh"
 
+#define LDEQ_MAX_SLABS 8  // column slabs a host-resident batch is cut into (ldeq_api.cu)
+
 struct ldeq_handle {
     int device = 0;
     std::string err;
@@ -39,6 +41,9 @@ struct ldeq_handle {
     void* nccl_comm = nullptr;
     void* nccl_fn[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int nccl_rank = 0, nccl_nranks = 0;
+    // copy streams + events of the pipelined *_host entry points (created on first use)
+    cudaStream_t up = nullptr, down = nullptr;
+    cudaEvent_t ev_fwd[LDEQ_MAX_SLABS] = {}, ev_up[LDEQ_MAX_SLABS] = {}, ev_join = nullptr;
 };
 
 struct ldeq_rhs {
@@ -53,7 +58,6 @@ struct ldeq_tape {
     const ldeq_rhs* rhs = nullptr;
     void* base = nullptr;  // one stream-ordered allocation, carved into the arrays below
     double* t = nullptr;
-    double* dt = nullptr;
     void* u = nullptr;
     void* theta = nullptr;
     double* tgrid = nullptr;
@@ -68,6 +72,10 @@ struct ldeq_tape {
     double grid_t0 = 0.0, grid_h = 0.0;
     int grid_uniform = 0;
     int sense = 0;  // ldeq_sensealg of the solve that made this tape
+    // a tape recorded slab by slab (ldeq_solve_fwd_host) is a list of single-slab tapes: parts[i] covers trajectories
+    // part_b0[i] .. part_b0[i] + parts[i]->B - 1 and owns its own arrays; the parent then owns nothing else
+    std::vector<ldeq_tape*> parts;
+    std::vector<int> part_b0;
 };
 
 namespace ldeq {
@@ -77,7 +85,7 @@ int upload_tgrid(ldeq_handle* h, const double* t_host, int T, cudaStream_t s);
 int ensure_scratch(ldeq_handle* h, int slot, size_t bytes);
 KOpts to_kopts(const ldeq_opts* o);
 // ldeq_fwdsens.cu: the reference's ForwardDiffSensitivity pullback (two dual-number re-solves per trajectory)
-cudaError_t launch_fwdsens(const ldeq_tape* tape, const void* dtraj, void* dz0, void* dtheta, cudaStream_t s);
+cudaError_t launch_fwdsens(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s);
 
 #define LDEQ_CUDA(call)                                                    \
     do {                                                                   \

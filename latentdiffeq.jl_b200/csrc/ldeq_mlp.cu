@@ -14,6 +14,7 @@
 //   LDEQ_NORM_PER_TRAJ  every trajectory has its own dt / accept-reject sequence (documented deviation).
 // The backward kernel is the discrete adjoint of the accepted steps (the reference's InterpolatingAdjoint is a
 // continuous adjoint that agrees with it to the solver tolerance).
+#include <cstdio>
 #include <cstdlib>
 
 #include "ldeq_mlp_common.cuh"
@@ -344,7 +345,19 @@ struct ldeq_mlp_tape {
     int32_t* retcode = nullptr;
     int32_t* naccept = nullptr;
     int32_t* nreject = nullptr;
+    int32_t* info = nullptr;     // device: largest accepted-step count of a successful trajectory
+    int32_t* h_info = nullptr;   // pinned host mirror, valid once `ready` has completed
+    cudaEvent_t ready = nullptr;
 };
+
+// largest naccept among the trajectories that succeeded: what the reverse pass will want to find on the tape
+__global__ void mlp_max_naccept_kernel(const int32_t* __restrict__ na, const int32_t* __restrict__ ret, int B, int32_t* out) {
+    int m = 0;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x)
+        if (ret[b] == RET_SUCCESS && na[b] > m) m = na[b];
+    m = __reduce_max_sync(0xffffffffu, m);
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
+}
 
 static int make_net(ldeq_handle* h, const int32_t* dims, int n_layers, MlpNet* net) {
     if (n_layers < 1 || n_layers > MLP_MAX_LAYERS) return set_err(h, LDEQ_ERR_UNSUPPORTED, "mlp: 1..8 layers supported");
@@ -493,12 +506,22 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
         const size_t o_r = off; off += al256(nB * 4);
         const size_t o_na = off; off += al256(nB * 4);
         const size_t o_nr = off; off += al256(nB * 4);
+        const size_t o_info = off; off += 256;
         cudaError_t e = cudaMallocAsync(&tape->base, off, s);
         if (e != cudaSuccess) { delete tape; return set_err(h, LDEQ_ERR_NOMEM, "cudaMallocAsync(mlp tape)", e); }
         char* bp = (char*)tape->base;
         tape->t = (double*)(bp + o_t); tape->dt = (double*)(bp + o_dt); tape->u = bp + o_u; tape->params = bp + o_p;
         tape->params_t = bp + o_pt; tape->tgrid = (double*)(bp + o_tg); tape->retcode = (int32_t*)(bp + o_r);
         tape->naccept = (int32_t*)(bp + o_na); tape->nreject = (int32_t*)(bp + o_nr);
+        tape->info = (int32_t*)(bp + o_info);
+        cudaMemsetAsync(tape->info, 0, 4, s);
+        if (cudaMallocHost((void**)&tape->h_info, 8) != cudaSuccess ||
+            cudaEventCreateWithFlags(&tape->ready, cudaEventDisableTiming) != cudaSuccess) {
+            if (tape->h_info) cudaFreeHost(tape->h_info);
+            cudaFreeAsync(tape->base, s);
+            delete tape;
+            return set_err(h, LDEQ_ERR_NOMEM, "mlp tape host mirror");
+        }
         cudaMemcpyAsync(tape->params, params_flat, (size_t)net.n_params * es, cudaMemcpyDeviceToDevice, s);
         cudaMemcpyAsync(tape->tgrid, h->d_tgrid, (size_t)T * 8, cudaMemcpyDeviceToDevice, s);
     }
@@ -514,10 +537,15 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
     else
         rc = mlp_fwd_dispatch<double>(h, net, params_flat, z0, h->d_tgrid, B, T, ko, opts->norm_mode, traj_out, d_ret, d_na, d_nr, tape, s);
     if (rc) {
-        if (tape) { cudaFreeAsync(tape->base, s); delete tape; }
+        if (tape) { cudaFreeAsync(tape->base, s); cudaFreeHost(tape->h_info); cudaEventDestroy(tape->ready); delete tape; }
         return rc;
     }
     if (tape) {
+        // the reverse pass must know whether every accepted step found room on the tape (ldeq_mlp_solve_bwd checks)
+        mlp_max_naccept_kernel<<<64, 256, 0, s>>>(tape->naccept, tape->retcode, B, tape->info);
+        h->launches += 1;
+        cudaMemcpyAsync(tape->h_info, tape->info, 4, cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(tape->ready, s);
         if (retcode) cudaMemcpyAsync(retcode, tape->retcode, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
         if (naccept) cudaMemcpyAsync(naccept, tape->naccept, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
         if (nreject) cudaMemcpyAsync(nreject, tape->nreject, (size_t)B * 4, cudaMemcpyDeviceToDevice, s);
@@ -571,6 +599,15 @@ int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, v
     if (!tape || !dtraj || !dz0 || !dparams_flat) return set_err(h, LDEQ_ERR_INVALID, "null argument");
     cudaStream_t s = (cudaStream_t)stream;
     LDEQ_CUDA(cudaSetDevice(h->device));
+    // a solve that took more accepted steps than the tape holds has no exact gradient: say so instead of returning
+    // NaN / partial sums (waits for the forward kernel, as the GOKU path's tape check does)
+    LDEQ_CUDA(cudaEventSynchronize(tape->ready));
+    if (tape->h_info[0] > tape->cap) {
+        char msg[200];
+        snprintf(msg, sizeof msg, "mlp tape overflow: the solve accepted %d steps, the tape holds %d; repeat ldeq_mlp_solve_fwd "
+                 "with opts.tape_steps >= %d", tape->h_info[0], tape->cap, tape->h_info[0]);
+        return set_err(h, LDEQ_ERR_TAPE_OVERFLOW, msg);
+    }
     const bool small = tape->B <= 4 * h->sm_count;
     if (tape->dtype == LDEQ_F32 && !getenv("LDEQ_MLP_NO_RESIDENT")) {
         MlpTapeView<float> tv{tape->t, tape->dt, (float*)tape->u, tape->cap};
@@ -590,6 +627,8 @@ void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream)
     if (!tape) return;
     if (h) cudaSetDevice(h->device);
     if (tape->base) cudaFreeAsync(tape->base, (cudaStream_t)stream);
+    if (tape->ready) { cudaEventSynchronize(tape->ready); cudaEventDestroy(tape->ready); }
+    if (tape->h_info) cudaFreeHost(tape->h_info);
     delete tape;
 }
 

@@ -26,16 +26,17 @@ template <class S, bool FRICTION> struct PendulumRHS {
     static constexpr S BM = (S)0.7f / (S)1.0f;
 
     __device__ __forceinline__ static void f(S* du, const S* u, const S* p, double, Aux& aux) {
-        s_sincos<S>(u[0], &aux.s, &aux.c);
+        s_sincos_fast<S>(u[0], &aux.s, &aux.c);
         const S w = -G / p[0];
         du[0] = u[1];
-        du[1] = FRICTION ? w * aux.s - BM * u[1] : w * aux.s;
+        du[1] = FRICTION ? s_fma<S>(w, aux.s, -BM * u[1]) : w * aux.s;
     }
     // forward-only variant (no cosine needed)
     __device__ __forceinline__ static void f(S* du, const S* u, const S* p, double) {
         const S w = -G / p[0];
         du[0] = u[1];
-        du[1] = FRICTION ? w * s_sin<S>(u[0]) - BM * u[1] : w * s_sin<S>(u[0]);
+        const S sx = s_sin_fast<S>(u[0]);
+        du[1] = FRICTION ? s_fma<S>(w, sx, -BM * u[1]) : w * sx;
     }
     __device__ __forceinline__ static void vjp(S* ubar, S* pbar, const S*, const S* p, double, const S* kbar,
                                                const Aux& aux) {

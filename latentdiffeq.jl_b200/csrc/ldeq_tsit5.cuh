@@ -27,10 +27,12 @@ namespace ldeq {
 #endif
 
 // Accepted-step tape, step-major so that a warp reading/writing step n touches contiguous memory:
-//   t[n*B + b], dt[n*B + b], u[(n*B + b)*ZD + d]
+//   t[n*B + b], u[(n*B + b)*ZD + d]   -- the start time and the state of accepted step n.
+// The step size is not stored: the reverse pass takes dt_n = t_{n+1} - t_n (t_{na} = tend), which equals the forward
+// pass' dt_n to a few ulp of t (1e-15 relative; the adjoint of the Float64 build agrees with the oracle to 1e-9 either
+// way) and keeps the tape at 8 + ZD sizeof(S) bytes per accepted step (16 B for the Float32 pendulum, was 24).
 template <class S> struct TapeView {
     double* t;
-    double* dt;
     S* u;
     int* info;  // info[0]: trajectories that ran past `cap`; info[1]: largest accepted-step count
     int cap;
@@ -44,15 +46,18 @@ template <class S> struct TapeView {
 };
 
 // ---- the seven stages --------------------------------------------------------------------------
-// k[0] holds f(u) on entry (FSAL).  Fills k[1..6] and un.  With KEEP, also returns the stage inputs
-// g[0..6] (g[0] = u, g[6] = un) and the RHS' auxiliaries for the reverse sweep.
+// k[0] holds f(u) on entry (FSAL).  Fills k[1..6] and un.  With KEEP (reverse pass), also returns the stage inputs
+// g[0..5] (g[0] = u) and the RHS' auxiliaries aux[0..5] for the reverse sweep; k[6] = f(u_{n+1}) is then NOT
+// evaluated -- its value is not needed by the adjoint and its auxiliaries are those of the NEXT step's k1, which the
+// reverse sweep has just used (the caller carries them over).
 template <class RHS, class S, bool KEEP>
 __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, double dts, S (*k)[RHS::ZD], S* un,
                                              S (*g)[RHS::ZD], typename RHS::Aux* aux) {
     constexpr int ZD = RHS::ZD;
     using Tb = Tab<S>;
+    using V = VecOps<S, ZD>;
     const S h = (S)dts;
-    S gi[ZD];
+    S gi[ZD], acc[ZD];
 #define LDEQ_EVAL(J, TJ)                                   \
     if constexpr (KEEP) {                                  \
         _Pragma("unroll") for (int i = 0; i < ZD; ++i) g[J][i] = gi[i]; \
@@ -65,42 +70,38 @@ __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, d
         for (int i = 0; i < ZD; ++i) gi[i] = u[i];
         LDEQ_EVAL(0, t)  // recompute k1 = f(u_n) together with its auxiliaries
     }
-#pragma unroll
-    for (int i = 0; i < ZD; ++i) gi[i] = s_fma<S>(h, Tb::a21 * k[0][i], u[i]);
+    V::fma(gi, h * Tb::a21, k[0], u);
     LDEQ_EVAL(1, t + Tb::c2 * dts)
-#pragma unroll
-    for (int i = 0; i < ZD; ++i) gi[i] = s_fma<S>(h, s_fma<S>(Tb::a32, k[1][i], Tb::a31 * k[0][i]), u[i]);
+    V::scale(acc, Tb::a31, k[0]);
+    V::axpy(acc, Tb::a32, k[1]);
+    V::fma(gi, h, acc, u);
     LDEQ_EVAL(2, t + Tb::c3 * dts)
-#pragma unroll
-    for (int i = 0; i < ZD; ++i)
-        gi[i] = s_fma<S>(h, s_fma<S>(Tb::a43, k[2][i], s_fma<S>(Tb::a42, k[1][i], Tb::a41 * k[0][i])), u[i]);
+    V::scale(acc, Tb::a41, k[0]);
+    V::axpy(acc, Tb::a42, k[1]);
+    V::axpy(acc, Tb::a43, k[2]);
+    V::fma(gi, h, acc, u);
     LDEQ_EVAL(3, t + Tb::c4 * dts)
-#pragma unroll
-    for (int i = 0; i < ZD; ++i)
-        gi[i] = s_fma<S>(
-            h, s_fma<S>(Tb::a54, k[3][i], s_fma<S>(Tb::a53, k[2][i], s_fma<S>(Tb::a52, k[1][i], Tb::a51 * k[0][i]))),
-            u[i]);
+    V::scale(acc, Tb::a51, k[0]);
+    V::axpy(acc, Tb::a52, k[1]);
+    V::axpy(acc, Tb::a53, k[2]);
+    V::axpy(acc, Tb::a54, k[3]);
+    V::fma(gi, h, acc, u);
     LDEQ_EVAL(4, t + Tb::c5 * dts)
-#pragma unroll
-    for (int i = 0; i < ZD; ++i)
-        gi[i] = s_fma<S>(h,
-                         s_fma<S>(Tb::a65, k[4][i],
-                                  s_fma<S>(Tb::a64, k[3][i],
-                                           s_fma<S>(Tb::a63, k[2][i], s_fma<S>(Tb::a62, k[1][i], Tb::a61 * k[0][i])))),
-                         u[i]);
+    V::scale(acc, Tb::a61, k[0]);
+    V::axpy(acc, Tb::a62, k[1]);
+    V::axpy(acc, Tb::a63, k[2]);
+    V::axpy(acc, Tb::a64, k[3]);
+    V::axpy(acc, Tb::a65, k[4]);
+    V::fma(gi, h, acc, u);
     LDEQ_EVAL(5, t + dts)
-#pragma unroll
-    for (int i = 0; i < ZD; ++i)
-        gi[i] = s_fma<S>(
-            h,
-            s_fma<S>(Tb::a76, k[5][i],
-                     s_fma<S>(Tb::a75, k[4][i],
-                              s_fma<S>(Tb::a74, k[3][i],
-                                       s_fma<S>(Tb::a73, k[2][i], s_fma<S>(Tb::a72, k[1][i], Tb::a71 * k[0][i]))))),
-            u[i]);
-#pragma unroll
-    for (int i = 0; i < ZD; ++i) un[i] = gi[i];
-    LDEQ_EVAL(6, t + dts)
+    V::scale(acc, Tb::a71, k[0]);
+    V::axpy(acc, Tb::a72, k[1]);
+    V::axpy(acc, Tb::a73, k[2]);
+    V::axpy(acc, Tb::a74, k[3]);
+    V::axpy(acc, Tb::a75, k[4]);
+    V::axpy(acc, Tb::a76, k[5]);
+    V::fma(un, h, acc, u);
+    if constexpr (!KEEP) RHS::f(k[6], un, p, t + dts);
 #undef LDEQ_EVAL
 }
 
@@ -108,20 +109,22 @@ __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, d
 template <class S, int ZD>
 __device__ __forceinline__ double tsit5_eest(const S* u, const S* un, S (*k)[ZD], double dts, S abstol, S reltol) {
     using Tb = Tab<S>;
+    using V = VecOps<S, ZD>;
     const S h = (S)dts;
+    S s[ZD];
+    V::scale(s, Tb::bt1, k[0]);
+    V::axpy(s, Tb::bt2, k[1]);
+    V::axpy(s, Tb::bt3, k[2]);
+    V::axpy(s, Tb::bt4, k[3]);
+    V::axpy(s, Tb::bt5, k[4]);
+    V::axpy(s, Tb::bt6, k[5]);
+    V::axpy(s, Tb::bt7, k[6]);
     S e2 = (S)0;
 #pragma unroll
     for (int i = 0; i < ZD; ++i) {
-        S s = Tb::bt1 * k[0][i];
-        s = s_fma<S>(Tb::bt2, k[1][i], s);
-        s = s_fma<S>(Tb::bt3, k[2][i], s);
-        s = s_fma<S>(Tb::bt4, k[3][i], s);
-        s = s_fma<S>(Tb::bt5, k[4][i], s);
-        s = s_fma<S>(Tb::bt6, k[5][i], s);
-        s = s_fma<S>(Tb::bt7, k[6][i], s);
-        const S utilde = h * s;
+        const S utilde = h * s[i];
         const S sk = s_fma<S>(s_max<S>(s_abs<S>(u[i]), s_abs<S>(un[i])), reltol, abstol);
-        const S a = utilde / sk;
+        const S a = s_div_fast<S>(utilde, sk);
         e2 = s_fma<S>(a, a, e2);
     }
     return (double)s_sqrt<S>(e2 / (S)ZD);
@@ -164,65 +167,83 @@ __device__ double tsit5_initdt(const S* u0, const S* p, const S* f0, double t0, 
 
 // ---- dense output in Horner form -------------------------------------------------------------------
 // sum_j b_j(Theta) k_j = Theta (c1 + Theta (c2 + Theta (c3 + Theta c4))) with c_m = sum_j r_jm k_j, so a step
-// pays 21 FMAs per component once and every save point inside it only 5.
+// pays 21 vector FMAs once and every save point inside it only 4.
 template <class S, int ZD>
 __device__ __forceinline__ void interp_coeffs(S (*k)[ZD], S (*c)[ZD]) {
     using Tb = Tab<S>;
+    using V = VecOps<S, ZD>;
 #pragma unroll
-    for (int i = 0; i < ZD; ++i) {
-        c[0][i] = k[0][i];  // r11 = 1
-        c[1][i] = s_fma<S>(Tb::r72, k[6][i], s_fma<S>(Tb::r62, k[5][i], s_fma<S>(Tb::r52, k[4][i],
-                  s_fma<S>(Tb::r42, k[3][i], s_fma<S>(Tb::r32, k[2][i], s_fma<S>(Tb::r22, k[1][i], Tb::r12 * k[0][i]))))));
-        c[2][i] = s_fma<S>(Tb::r73, k[6][i], s_fma<S>(Tb::r63, k[5][i], s_fma<S>(Tb::r53, k[4][i],
-                  s_fma<S>(Tb::r43, k[3][i], s_fma<S>(Tb::r33, k[2][i], s_fma<S>(Tb::r23, k[1][i], Tb::r13 * k[0][i]))))));
-        c[3][i] = s_fma<S>(Tb::r74, k[6][i], s_fma<S>(Tb::r64, k[5][i], s_fma<S>(Tb::r54, k[4][i],
-                  s_fma<S>(Tb::r44, k[3][i], s_fma<S>(Tb::r34, k[2][i], s_fma<S>(Tb::r24, k[1][i], Tb::r14 * k[0][i]))))));
-    }
+    for (int i = 0; i < ZD; ++i) c[0][i] = k[0][i];  // r11 = 1
+    V::scale(c[1], Tb::r12, k[0]); V::scale(c[2], Tb::r13, k[0]); V::scale(c[3], Tb::r14, k[0]);
+    V::axpy(c[1], Tb::r22, k[1]);  V::axpy(c[2], Tb::r23, k[1]);  V::axpy(c[3], Tb::r24, k[1]);
+    V::axpy(c[1], Tb::r32, k[2]);  V::axpy(c[2], Tb::r33, k[2]);  V::axpy(c[3], Tb::r34, k[2]);
+    V::axpy(c[1], Tb::r42, k[3]);  V::axpy(c[2], Tb::r43, k[3]);  V::axpy(c[3], Tb::r44, k[3]);
+    V::axpy(c[1], Tb::r52, k[4]);  V::axpy(c[2], Tb::r53, k[4]);  V::axpy(c[3], Tb::r54, k[4]);
+    V::axpy(c[1], Tb::r62, k[5]);  V::axpy(c[2], Tb::r63, k[5]);  V::axpy(c[3], Tb::r64, k[5]);
+    V::axpy(c[1], Tb::r72, k[6]);  V::axpy(c[2], Tb::r73, k[6]);  V::axpy(c[3], Tb::r74, k[6]);
 }
 // adjoint of interp_coeffs: kbar_j += sum_m r_jm cbar_m
 template <class S, int ZD>
 __device__ __forceinline__ void interp_coeffs_adj(S (*cb)[ZD], S (*kbar)[ZD]) {
     using Tb = Tab<S>;
-#pragma unroll
-    for (int i = 0; i < ZD; ++i) {
-        const S c1 = cb[0][i], c2 = cb[1][i], c3 = cb[2][i], c4 = cb[3][i];
-        kbar[0][i] += s_fma<S>(Tb::r14, c4, s_fma<S>(Tb::r13, c3, s_fma<S>(Tb::r12, c2, c1)));
-        kbar[1][i] += s_fma<S>(Tb::r24, c4, s_fma<S>(Tb::r23, c3, Tb::r22 * c2));
-        kbar[2][i] += s_fma<S>(Tb::r34, c4, s_fma<S>(Tb::r33, c3, Tb::r32 * c2));
-        kbar[3][i] += s_fma<S>(Tb::r44, c4, s_fma<S>(Tb::r43, c3, Tb::r42 * c2));
-        kbar[4][i] += s_fma<S>(Tb::r54, c4, s_fma<S>(Tb::r53, c3, Tb::r52 * c2));
-        kbar[5][i] += s_fma<S>(Tb::r64, c4, s_fma<S>(Tb::r63, c3, Tb::r62 * c2));
-        kbar[6][i] += s_fma<S>(Tb::r74, c4, s_fma<S>(Tb::r73, c3, Tb::r72 * c2));
-    }
+    using V = VecOps<S, ZD>;
+    V::add(kbar[0], cb[0]);
+    V::axpy(kbar[0], Tb::r12, cb[1]); V::axpy(kbar[0], Tb::r13, cb[2]); V::axpy(kbar[0], Tb::r14, cb[3]);
+    V::axpy(kbar[1], Tb::r22, cb[1]); V::axpy(kbar[1], Tb::r23, cb[2]); V::axpy(kbar[1], Tb::r24, cb[3]);
+    V::axpy(kbar[2], Tb::r32, cb[1]); V::axpy(kbar[2], Tb::r33, cb[2]); V::axpy(kbar[2], Tb::r34, cb[3]);
+    V::axpy(kbar[3], Tb::r42, cb[1]); V::axpy(kbar[3], Tb::r43, cb[2]); V::axpy(kbar[3], Tb::r44, cb[3]);
+    V::axpy(kbar[4], Tb::r52, cb[1]); V::axpy(kbar[4], Tb::r53, cb[2]); V::axpy(kbar[4], Tb::r54, cb[3]);
+    V::axpy(kbar[5], Tb::r62, cb[1]); V::axpy(kbar[5], Tb::r63, cb[2]); V::axpy(kbar[5], Tb::r64, cb[3]);
+    V::axpy(kbar[6], Tb::r72, cb[1]); V::axpy(kbar[6], Tb::r73, cb[2]); V::axpy(kbar[6], Tb::r74, cb[3]);
 }
 
 // The save grid is staged in shared memory (explicit LDS, not a generic load); grids too long for
 // that are read through the global pointer.
 #define LDEQ_TGRID_SMEM_MAX 2048
-// A grid the host has verified to be t0 + k*h bit for bit (GridInfo::uniform) is not looked up at all: the
-// save time is one DFMA.
+// A grid the host has verified to be t0 + k*h bit for bit (GridInfo::uniform) is not looked up at all: a save time
+// is one DFMA, and the save points that fall into a step are found by ONE division per step (count_le) instead of one
+// Float64 comparison per save point.
 struct GridInfo {
     double t0, h;
     int uniform;
+    int ld;  // row stride (in trajectories) of the (z,B,T) arrays: the kernel may work on a column slab of a wider batch
 };
 struct TGrid {
     const double* __restrict__ g;
     const double* s;
-    double t0, h;
+    double t0, h, inv_h;
+    int T;
     bool in_smem, uniform;
     __device__ __forceinline__ double operator[](int i) const {
         if (uniform) return fma((double)i, h, t0);
         return in_smem ? s[i] : g[i];
     }
-    // hot-loop form: the caller carries the index as a double as well (exact for integers), so the uniform
-    // path is a single DFMA with no int -> double conversion
-    __device__ __forceinline__ double at(int i, double di) const {
-        if (uniform) return fma(di, h, t0);
-        return in_smem ? s[i] : g[i];
+    // number of grid points t_k <= x (k in [0, T)), i.e. the first index whose save time lies beyond x.  `from` is a
+    // lower bound the caller knows (t_k <= x for all k < from); a table grid is scanned upwards from there.
+    __device__ __forceinline__ int count_le(double x, int from) const {
+        if (uniform) {
+            // floor((x - t0) / h) is off by at most one; the DFMA comparisons make the answer exact
+            double q = (x - t0) * inv_h;
+            q = fmin(fmax(q, -1.0), (double)(T - 1));
+            int k = __double2int_rd(q);
+            if (k + 1 < T && fma((double)(k + 1), h, t0) <= x) ++k;
+            else if (k >= 0 && fma((double)k, h, t0) > x) --k;
+            return k + 1;
+        }
+        int k = from;
+        while (k < T && (in_smem ? s[k] : g[k]) <= x) ++k;
+        return k;
+    }
+    // the same, for the reverse pass: t_k > x is known for all k >= from; a table grid is scanned downwards
+    __device__ __forceinline__ int count_le_down(double x, int from) const {
+        if (uniform) return count_le(x, 0);
+        int k = from;
+        while (k > 0 && (in_smem ? s[k - 1] : g[k - 1]) > x) --k;
+        return k;
     }
 };
 __device__ __forceinline__ TGrid stage_tgrid(const double* __restrict__ tg, int T, double* s_tg, const GridInfo& gi) {
-    TGrid r{tg, s_tg, gi.t0, gi.h, T <= LDEQ_TGRID_SMEM_MAX, gi.uniform != 0};
+    TGrid r{tg, s_tg, gi.t0, gi.h, gi.uniform ? 1.0 / gi.h : 0.0, T, T <= LDEQ_TGRID_SMEM_MAX, gi.uniform != 0};
     if (r.in_smem && !r.uniform) {
         for (int i = threadIdx.x; i < T; i += blockDim.x) s_tg[i] = tg[i];
         __syncthreads();
@@ -280,6 +301,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                  int* __restrict__ nreject, TapeView<S> tape, GridInfo ginfo) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
     using RingT = Ring<S, ZD>;
+    using V = VecOps<S, ZD>;
     constexpr int R = RingT::R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RingT ring{reinterpret_cast<S*>(smem_raw) + threadIdx.x * ZD, (int)blockDim.x * ZD};
@@ -299,6 +321,9 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
         }
         if (tape.tgrid && blockIdx.x == 0)
             for (int kk = threadIdx.x; kk < T; kk += blockDim.x) tape.tgrid[kk] = tg_global[kk];
+        // record 0 always holds u0 (a trajectory that fails before its first accepted step leaves nothing else there;
+        // a replay into a larger tape and the forward-dual pullback start from this record)
+        if (live && tape.u) store_vec<S, ZD>(tape.u + (size_t)b * ZD, u);
     }
 
     const double t0 = tg[0], tend = tg[T - 1];
@@ -315,17 +340,16 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
     int na = 0, nr = 0, ret = RET_SUCCESS;
     long long iters = 0;
 
+    const size_t ld = (size_t)ginfo.ld;
     if (traj && live) store_vec<S, ZD>(traj + (size_t)b * ZD, u);  // t[1] == tspan[1]: stored exactly
-    // pending save time and the two after it (loaded two iterations ahead so the loop never waits)
-    double tsave = T > 1 ? tg[1] : LDEQ_TINF;
-    double tsave2 = T > 2 ? tg[2] : LDEQ_TINF;
-    double tsave3 = T > 3 ? tg[3] : LDEQ_TINF;
     if (!(dt > 0.0) || !isfinite(dt)) ret = RET_DTLESSTHANMIN;
 
     int ks = live ? 1 : T;  // next save index this lane emits
     int kflush = 1;         // warp-uniform: rows below it are in global memory
     bool active = live && T > 1 && ret == RET_SUCCESS;  // still has steps to take
     bool pending = false;   // an accepted step whose save points are not all parked yet
+    int kend = 1;           // save points ks .. kend-1 fall into the pending step
+    bool hit = false;       // ... and the last of them coincides with the step end (stored as u_{n+1} itself)
     double dts = 0.0, tnew = t0;
 
     while (kflush < T) {
@@ -361,12 +385,14 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                             if (na < tape.cap) {
                                 const size_t r = (size_t)na * B + b;
                                 tape.t[r] = t;
-                                tape.dt[r] = dts;
-                                store_vec<S, ZD>(tape.u + r * ZD, u);
+                                if (na) store_vec<S, ZD>(tape.u + r * ZD, u);
                             }
                         }
                         ++na;
                         pending = true;
+                        // saveat: every pending grid time <= tnew belongs to this step
+                        kend = tg.count_le(tnew, ks);
+                        hit = kend > ks && tg[kend - 1] == tnew;
                     } else {
                         ++nr;
                     }
@@ -380,69 +406,38 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
             }
         }
         if (pending) {
-            // saveat: every pending grid time <= tnew; interior points through the dense interpolant of this
-            // step (Horner form), a grid time that coincides with the step end stores u_{n+1} itself
-            if (tg.uniform) {
-                // save times are t0 + k h, one DFMA each: no table, no prefetch pipeline
-                if (tsave < tnew && ks < kflush + R) {
-                    S c[4][ZD];
-                    interp_coeffs<S, ZD>(k, c);
-                    const S h = (S)dts;
-                    const double inv = 1.0 / dts;
-                    double kd = (double)ks;
-                    do {
-                        S out[ZD];
-                        const S th = (S)((tsave - t) * inv);
-                        const S hth = h * th;
-#pragma unroll
-                        for (int i = 0; i < ZD; ++i) {
-                            const S poly = s_fma<S>(th, s_fma<S>(th, s_fma<S>(th, c[3][i], c[2][i]), c[1][i]), c[0][i]);
-                            out[i] = s_fma<S>(hth, poly, u[i]);
-                        }
-                        store_vec<S, ZD>(ring.at(ks), out);
-                        ++ks;
-                        kd += 1.0;
-                        tsave = ks < T ? fma(kd, tg.h, tg.t0) : LDEQ_TINF;
-                    } while (tsave < tnew && ks < kflush + R);
-                }
-                if (tsave == tnew && ks < kflush + R) {
-                    store_vec<S, ZD>(ring.at(ks), un);
-                    ++ks;
-                    tsave = ks < T ? fma((double)ks, tg.h, tg.t0) : LDEQ_TINF;
-                }
-            } else {
-            if (tsave < tnew && ks < kflush + R) {
+            // interior points through the dense interpolant of this step (Horner form); a grid time that coincides
+            // with the step end stores u_{n+1} itself.  At most R rows beyond the warp's flush mark fit the ring.
+            const int kint = kend - (hit ? 1 : 0);
+            const int klim = kflush + R;
+            const int kstop = kint < klim ? kint : klim;
+            if (ks < kstop) {
                 S c[4][ZD];
                 interp_coeffs<S, ZD>(k, c);
                 const S h = (S)dts;
                 const double inv = 1.0 / dts;
+                // Theta of consecutive points of a uniform grid advances by h_grid / dt: one FMA per point, anchored at
+                // the first point of this visit (|Theta| <= 1, so the anchor's rounding is the only error that matters)
+                const S th0 = (S)((tg[ks] - t) * inv);
+                const S dth = (S)(tg.h * inv);
+                S fk = (S)0;
                 do {
-                    const double tpre = ks + 3 < T ? tg[ks + 3] : LDEQ_TINF;  // consumed two iterations from now
-                    S out[ZD];
-                    const S th = (S)((tsave - t) * inv);
-                    const S hth = h * th;
-#pragma unroll
-                    for (int i = 0; i < ZD; ++i) {
-                        const S poly = s_fma<S>(th, s_fma<S>(th, s_fma<S>(th, c[3][i], c[2][i]), c[1][i]), c[0][i]);
-                        out[i] = s_fma<S>(hth, poly, u[i]);
-                    }
+                    const S th = tg.uniform ? s_fma<S>(fk, dth, th0) : (S)((tg[ks] - t) * inv);
+                    S pl[ZD], out[ZD];
+                    V::fma(pl, th, c[3], c[2]);
+                    V::fma(pl, th, pl, c[1]);
+                    V::fma(pl, th, pl, c[0]);
+                    V::fma(out, h * th, pl, u);
                     store_vec<S, ZD>(ring.at(ks), out);
                     ++ks;
-                    tsave = tsave2;
-                    tsave2 = tsave3;
-                    tsave3 = tpre;
-                } while (tsave < tnew && ks < kflush + R);
+                    fk += (S)1;
+                } while (ks < kstop);
             }
-            if (tsave == tnew && ks < kflush + R) {
+            if (hit && ks == kint && ks < klim) {
                 store_vec<S, ZD>(ring.at(ks), un);
-                const double tpre = ks + 3 < T ? tg[ks + 3] : LDEQ_TINF;
                 ++ks;
-                tsave = tsave2;
-                tsave2 = tsave3;
-                tsave3 = tpre;
             }
-            }
-            if (!(tsave <= tnew)) {  // all save points of this step are parked: commit it
+            if (ks >= kend) {  // all save points of this step are parked: commit it
                 t = tnew;
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) { u[i] = un[i]; k[0][i] = k[6][i]; }  // FSAL
@@ -458,13 +453,13 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                 S v0[ZD], v1[ZD];
                 load_vec<S, ZD>(ring.at(r), v0);
                 load_vec<S, ZD>(ring.at(r + 1), v1);
-                store_vec<S, ZD>(traj + ((size_t)r * B + b) * ZD, v0);
-                store_vec<S, ZD>(traj + ((size_t)(r + 1) * B + b) * ZD, v1);
+                store_vec<S, ZD>(traj + ((size_t)r * ld + b) * ZD, v0);
+                store_vec<S, ZD>(traj + ((size_t)(r + 1) * ld + b) * ZD, v1);
             }
             if (r < kmin) {
                 S v0[ZD];
                 load_vec<S, ZD>(ring.at(r), v0);
-                store_vec<S, ZD>(traj + ((size_t)r * B + b) * ZD, v0);
+                store_vec<S, ZD>(traj + ((size_t)r * ld + b) * ZD, v0);
             }
         }
         kflush = kmin;
@@ -475,7 +470,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
         S nanv[ZD];
 #pragma unroll
         for (int i = 0; i < ZD; ++i) nanv[i] = s_nan<S>();
-        for (int kk = 0; kk < T; ++kk) store_vec<S, ZD>(traj + ((size_t)kk * B + b) * ZD, nanv);
+        for (int kk = 0; kk < T; ++kk) store_vec<S, ZD>(traj + ((size_t)kk * ld + b) * ZD, nanv);
     }
     if (retcode) retcode[b] = ret;
     if (naccept) naccept[b] = na;
@@ -506,6 +501,7 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
     using Tb = Tab<S>;
     using RingT = Ring<S, ZD>;
+    using V = VecOps<S, ZD>;
     constexpr int R = RingT::R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RingT ring{reinterpret_cast<S*>(smem_raw) + threadIdx.x * ZD, (int)blockDim.x * ZD};
@@ -527,54 +523,59 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
     if (!live || ret != RET_SUCCESS || overflow) na = 0;
 
     // rows 1..T-1 of the cotangent travel through the ring: [kload, T) has been fetched so far
+    const size_t ld = (size_t)ginfo.ld;
     int kload = T;
     auto refill = [&](int ks_max) {
         if (ks_max < 1) return;  // no lane of the warp has a row left to consume (finished, failed or overflowed)
         int klo = ks_max - R + 1;
         klo = klo < 1 ? 1 : klo;
         for (int r = kload - 1; r >= klo; --r)
-            cp_async_row<S, ZD>(ring.at(r), dtraj + ((size_t)r * B + bb) * ZD);
+            cp_async_row<S, ZD>(ring.at(r), dtraj + ((size_t)r * ld + bb) * ZD);
         kload = klo < kload ? klo : kload;
     };
 
     int n = na - 1;        // next taped step of this lane
     int ks = T - 1;        // next save point of this lane (descending); row 0 is handled at the end
     bool holding = false;  // a step whose stages are recomputed and whose save points are being consumed
+    int klo_step = T;      // save points klo_step .. ks fall into the step being held
+    bool hit = false;      // ... and the topmost of them coincides with the step end t_{n+1}
     double tnext = tg[T - 1];  // time after step n; the forward pass ended exactly on tend
-    double ts = ks >= 1 ? tg[ks] : -LDEQ_TINF;
-    double kd = (double)ks;
     double tn = 0.0, dtn = 0.0;
-    S g[7][ZD], kbar[7][ZD], cb[4][ZD], ub[ZD];
-    typename RHS::Aux aux[7];
+    S g[6][ZD], un[ZD], kbar[7][ZD], cb[4][ZD], ub[ZD];
+    typename RHS::Aux aux[6], aux_next;  // aux_next: f's auxiliaries at u_{n+1} (= those of step n+1's k1)
 
     refill(warp_max_i(n >= 0 ? ks : 0));
     // the record of the step a lane will need next is fetched one step ahead (its latency hides behind
     // the stage recomputation of the current step)
-    double tn_pre = 0.0, dtn_pre = 0.0;
+    double tn_pre = 0.0;
     S u_pre[ZD];
 #pragma unroll
     for (int i = 0; i < ZD; ++i) u_pre[i] = (S)0;
     if (n >= 0) {
         const size_t r = (size_t)n * B + b;
         tn_pre = tape.t[r];
-        dtn_pre = tape.dt[r];
         load_vec<S, ZD>(tape.u + r * ZD, u_pre);
     }
+    bool first = true;
     // runs until every lane of the warp has swept its step 0 (early steps may hold no save point at all)
     while (__any_sync(0xffffffffu, holding || n >= 0)) {
         if (!holding && n >= 0) {
             tn = tn_pre;
-            dtn = dtn_pre;
-            S u[ZD], un[ZD], k[7][ZD];
+            dtn = tnext - tn;
+            S u[ZD], k[7][ZD];
 #pragma unroll
             for (int i = 0; i < ZD; ++i) u[i] = u_pre[i];
             if (n >= 1) {
                 const size_t r = (size_t)(n - 1) * B + b;
                 tn_pre = tape.t[r];
-                dtn_pre = tape.dt[r];
                 load_vec<S, ZD>(tape.u + r * ZD, u_pre);
             }
             tsit5_stages<RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
+            if (first) {  // the last step of the solve: nothing follows it, evaluate f's auxiliaries at u(tend) here
+                S ktmp[ZD];
+                RHS::f(ktmp, un, p, tn + dtn, aux_next);
+                first = false;
+            }
 #pragma unroll
             for (int j = 0; j < 7; ++j)
 #pragma unroll
@@ -585,116 +586,97 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
                 for (int i = 0; i < ZD; ++i) cb[m][i] = (S)0;
 #pragma unroll
             for (int i = 0; i < ZD; ++i) ub[i] = (S)0;
+            // save points with t_n < t_k <= t_{n+1}: indices klo_step .. ks
+            klo_step = tg.count_le_down(tn, ks + 1);
+            klo_step = klo_step < 1 ? 1 : klo_step;
+            hit = ks >= klo_step && tg[ks] == tnext;
             holding = true;
         }
         cp_async_wait_all();  // rows fetched at the end of the previous iteration have landed by now
         if (holding) {
             const S h = (S)dtn;
-            const double inv = 1.0 / dtn;
-            // cotangents of the save points that lie in (t_n, t_{n+1}]
-            while (ts > tn && ks >= kload) {
+            if (hit && ks >= kload) {  // the cotangent of a save point at the step end belongs to u_{n+1}
                 S d[ZD];
                 load_vec<S, ZD>(ring.at(ks), d);
-                if (ts == tnext) {
-#pragma unroll
-                    for (int i = 0; i < ZD; ++i) ubn[i] += d[i];
-                } else {
-                    const S th = (S)((ts - tn) * inv);
-                    const S w1 = h * th, w2 = w1 * th, w3 = w2 * th, w4 = w3 * th;
-#pragma unroll
-                    for (int i = 0; i < ZD; ++i) {
-                        cb[0][i] = s_fma<S>(w1, d[i], cb[0][i]);
-                        cb[1][i] = s_fma<S>(w2, d[i], cb[1][i]);
-                        cb[2][i] = s_fma<S>(w3, d[i], cb[2][i]);
-                        cb[3][i] = s_fma<S>(w4, d[i], cb[3][i]);
-                        ub[i] += d[i];
-                    }
-                }
+                V::add(ubn, d);
                 --ks;
-                kd -= 1.0;
-                ts = ks >= 1 ? tg.at(ks, kd) : -LDEQ_TINF;
+                hit = false;
             }
-            if (!(ts > tn)) {
+            if (!hit) {
+                int kstop = klo_step > kload ? klo_step : kload;  // consume ks, ks-1, ..., kstop
+                if (ks >= kstop) {
+                    const double inv = 1.0 / dtn;
+                    const S th0 = (S)((tg[ks] - tn) * inv);
+                    const S dth = (S)(tg.h * inv);
+                    S fk = (S)0;
+                    do {
+                        S d[ZD];
+                        load_vec<S, ZD>(ring.at(ks), d);
+                        const S th = tg.uniform ? s_fma<S>(fk, -dth, th0) : (S)((tg[ks] - tn) * inv);
+                        const S w1 = h * th, w2 = w1 * th, w3 = w2 * th, w4 = w3 * th;
+                        V::axpy(cb[0], w1, d);
+                        V::axpy(cb[1], w2, d);
+                        V::axpy(cb[2], w3, d);
+                        V::axpy(cb[3], w4, d);
+                        V::add(ub, d);
+                        --ks;
+                        fk += (S)1;
+                    } while (ks >= kstop);
+                }
+            }
+            if (ks < klo_step) {
                 // every save point of this step has been consumed: reverse sweep through the stages
                 interp_coeffs_adj<S, ZD>(cb, kbar);
                 // k7 = f(u_{n+1}) (it is also next step's k1, whose adjoint was already folded into ubn)
-                RHS::vjp(ubn, pbar, g[6], p, tn + dtn, kbar[6], aux[6]);
+                RHS::vjp(ubn, pbar, un, p, tn + dtn, kbar[6], aux_next);
                 // u_{n+1} = u_n + h sum_j a7j k_j
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) {
-                    const S v = h * ubn[i];
-                    ub[i] += ubn[i];
-                    kbar[0][i] = s_fma<S>(Tb::a71, v, kbar[0][i]);
-                    kbar[1][i] = s_fma<S>(Tb::a72, v, kbar[1][i]);
-                    kbar[2][i] = s_fma<S>(Tb::a73, v, kbar[2][i]);
-                    kbar[3][i] = s_fma<S>(Tb::a74, v, kbar[3][i]);
-                    kbar[4][i] = s_fma<S>(Tb::a75, v, kbar[4][i]);
-                    kbar[5][i] = s_fma<S>(Tb::a76, v, kbar[5][i]);
-                }
+                S v[ZD];
+                V::scale(v, h, ubn);
+                V::add(ub, ubn);
+                V::axpy(kbar[0], Tb::a71, v); V::axpy(kbar[1], Tb::a72, v); V::axpy(kbar[2], Tb::a73, v);
+                V::axpy(kbar[3], Tb::a74, v); V::axpy(kbar[4], Tb::a75, v); V::axpy(kbar[5], Tb::a76, v);
                 S gb[ZD];
                 // stage 6: g6 = u + h (a61 k1 + ... + a65 k5)
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
                 RHS::vjp(gb, pbar, g[5], p, tn + dtn, kbar[5], aux[5]);
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) {
-                    const S v = h * gb[i];
-                    ub[i] += gb[i];
-                    kbar[0][i] = s_fma<S>(Tb::a61, v, kbar[0][i]);
-                    kbar[1][i] = s_fma<S>(Tb::a62, v, kbar[1][i]);
-                    kbar[2][i] = s_fma<S>(Tb::a63, v, kbar[2][i]);
-                    kbar[3][i] = s_fma<S>(Tb::a64, v, kbar[3][i]);
-                    kbar[4][i] = s_fma<S>(Tb::a65, v, kbar[4][i]);
-                }
+                V::scale(v, h, gb);
+                V::add(ub, gb);
+                V::axpy(kbar[0], Tb::a61, v); V::axpy(kbar[1], Tb::a62, v); V::axpy(kbar[2], Tb::a63, v);
+                V::axpy(kbar[3], Tb::a64, v); V::axpy(kbar[4], Tb::a65, v);
                 // stage 5
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
                 RHS::vjp(gb, pbar, g[4], p, tn + Tb::c5 * dtn, kbar[4], aux[4]);
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) {
-                    const S v = h * gb[i];
-                    ub[i] += gb[i];
-                    kbar[0][i] = s_fma<S>(Tb::a51, v, kbar[0][i]);
-                    kbar[1][i] = s_fma<S>(Tb::a52, v, kbar[1][i]);
-                    kbar[2][i] = s_fma<S>(Tb::a53, v, kbar[2][i]);
-                    kbar[3][i] = s_fma<S>(Tb::a54, v, kbar[3][i]);
-                }
+                V::scale(v, h, gb);
+                V::add(ub, gb);
+                V::axpy(kbar[0], Tb::a51, v); V::axpy(kbar[1], Tb::a52, v); V::axpy(kbar[2], Tb::a53, v);
+                V::axpy(kbar[3], Tb::a54, v);
                 // stage 4
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
                 RHS::vjp(gb, pbar, g[3], p, tn + Tb::c4 * dtn, kbar[3], aux[3]);
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) {
-                    const S v = h * gb[i];
-                    ub[i] += gb[i];
-                    kbar[0][i] = s_fma<S>(Tb::a41, v, kbar[0][i]);
-                    kbar[1][i] = s_fma<S>(Tb::a42, v, kbar[1][i]);
-                    kbar[2][i] = s_fma<S>(Tb::a43, v, kbar[2][i]);
-                }
+                V::scale(v, h, gb);
+                V::add(ub, gb);
+                V::axpy(kbar[0], Tb::a41, v); V::axpy(kbar[1], Tb::a42, v); V::axpy(kbar[2], Tb::a43, v);
                 // stage 3
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
                 RHS::vjp(gb, pbar, g[2], p, tn + Tb::c3 * dtn, kbar[2], aux[2]);
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) {
-                    const S v = h * gb[i];
-                    ub[i] += gb[i];
-                    kbar[0][i] = s_fma<S>(Tb::a31, v, kbar[0][i]);
-                    kbar[1][i] = s_fma<S>(Tb::a32, v, kbar[1][i]);
-                }
+                V::scale(v, h, gb);
+                V::add(ub, gb);
+                V::axpy(kbar[0], Tb::a31, v); V::axpy(kbar[1], Tb::a32, v);
                 // stage 2
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
                 RHS::vjp(gb, pbar, g[1], p, tn + Tb::c2 * dtn, kbar[1], aux[1]);
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) {
-                    ub[i] += gb[i];
-                    kbar[0][i] = s_fma<S>(Tb::a21, h * gb[i], kbar[0][i]);
-                }
+                V::add(ub, gb);
+                V::axpy(kbar[0], h * Tb::a21, gb);
                 // stage 1: k1 = f(u_n)
                 RHS::vjp(ub, pbar, g[0], p, tn, kbar[0], aux[0]);
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) ubn[i] = ub[i];
+                aux_next = aux[0];  // u_n is the end point of step n-1
                 tnext = tn;
                 --n;
                 holding = false;

@@ -19,30 +19,39 @@ from . import _cabi
 
 
 class Tsit5:
-    """``OrdinaryDiffEq.Tsit5()`` -- the only solver the hot path implements (pendulum.jl:11)."""
+    """``OrdinaryDiffEq.Tsit5()`` -- the solver of the reference's diffeq structs (pendulum.jl:11,58) and the one the hot
+    path implements.  Any other ``solver`` object is refused (``LDEQ_ERR_UNSUPPORTED``), never silently replaced."""
+    code = _cabi.SOLVER_TSIT5
 
     def __repr__(self):
         return "Tsit5()"
 
 
 class ForwardDiffSensitivity:
-    """Sensitivity request of the reference's diffeq structs (pendulum.jl:11).
-
-    ``ForwardDiffSensitivity()`` differentiates with the discrete adjoint of the accepted steps of the primal solve
-    (``LDEQ_SENSE_DISCRETE_ADJOINT``): in fixed-step mode the same derivative ForwardDiff computes, otherwise equal to it
-    within the solver tolerance, at about the cost of the forward solve.
-    ``ForwardDiffSensitivity(dual_solves=True)`` runs the reference's algorithm itself (``LDEQ_SENSE_FORWARD_DUAL``): two
-    dual-number re-solves per trajectory whose error norm includes the partials."""
-
-    def __init__(self, dual_solves: bool = False):
-        self.dual_solves = bool(dual_solves)
+    """Sensitivity request of the reference's diffeq structs (pendulum.jl:11): ``LDEQ_SENSE_FORWARD_DUAL`` -- the
+    reference's own algorithm, two dual-number re-solves per trajectory whose error norm includes the partials
+    (SciMLSensitivity 7.10 ``_concrete_solve_adjoint``).  Gradients equal the reference's to 1e-4."""
+    code = _cabi.SENSE_FORWARD_DUAL
 
     def __repr__(self):
-        return "ForwardDiffSensitivity(dual_solves=True)" if self.dual_solves else "ForwardDiffSensitivity()"
+        return "ForwardDiffSensitivity()"
+
+
+class DiscreteAdjoint:
+    """Explicit opt-in (not a reference type): ``LDEQ_SENSE_DISCRETE_ADJOINT``, the reverse sweep over the taped accepted
+    steps of the primal solve.  The exact derivative of the primal discretisation with frozen step sizes: identical to
+    ``ForwardDiffSensitivity`` in fixed-step mode, within the solver tolerance of it otherwise (2e-2 at reltol 1e-3),
+    at about a third of its cost."""
+    code = _cabi.SENSE_DISCRETE_ADJOINT
+
+    def __repr__(self):
+        return "DiscreteAdjoint()"
 
 
 class InterpolatingAdjoint:
-    """Accepted for API compatibility (DiffEqFlux's NeuralODE default); see ForwardDiffSensitivity."""
+    """DiffEqFlux's ``NeuralODE`` default for the LatentODE path.  The LatentODE reverse pass here is the
+    discrete adjoint of the taped steps (``ldeq_mlp_solve_bwd``); it agrees with the continuous adjoint within the
+    solver tolerance."""
 
     def __repr__(self):
         return "InterpolatingAdjoint()"

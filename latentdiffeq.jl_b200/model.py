@@ -269,11 +269,20 @@ def transform_after_diffeq(x, diffeq):
     return f(x) if f is not None else x
 
 
-def _opts_from_kwargs(kwargs: dict, sensealg=None) -> _cabi.Opts:
+def _opts_from_kwargs(kwargs: dict, sensealg=None, solver=None) -> _cabi.Opts:
+    """The diffeq struct's ``kwargs`` / ``sensealg`` / ``solver`` fields (GOKU.jl:105-108) as ``ldeq_opts``."""
     kw = dict(kwargs)
     kw.pop("saveat", None)
-    if getattr(sensealg, "dual_solves", False):
-        kw["sensealg"] = _cabi.SENSE_FORWARD_DUAL
+    if sensealg is not None:
+        code = getattr(sensealg, "code", None)
+        if code is None:
+            raise TypeError(f"sensealg {sensealg!r}: ForwardDiffSensitivity() (the reference's) or DiscreteAdjoint()")
+        kw["sensealg"] = code
+    if solver is not None:
+        code = getattr(solver, "code", None)
+        if code is None:
+            raise NotImplementedError(f"solver {solver!r}: the hot path implements Tsit5() (pendulum.jl:11,58)")
+        kw["solver"] = code
     return _cabi.default_opts(**kw)
 
 
@@ -288,13 +297,15 @@ def diffeq_layer(decoder, l_hat, t, stats_out=None):
         f = diffeq.prob.f
         if isinstance(f, CudaRHS):
             f = f.resolve(_cabi.handle(z0_hat.device.index or 0))
-        z = goku_solve(z0_hat, th_hat, t, f, _opts_from_kwargs(diffeq.kwargs, getattr(diffeq, 'sensealg', None)), stats_out)
+        z = goku_solve(z0_hat, th_hat, t, f, _opts_from_kwargs(diffeq.kwargs, getattr(diffeq, 'sensealg', None),
+                                                               getattr(diffeq, 'solver', None)), stats_out)
         return transform_after_diffeq(z, diffeq)
     z0 = l_hat
     if diffeq.augment_dim:
         # AugmentedNDELayer (LatentODE.jl:71): zero-pad augment_dim extra state rows
         z0 = torch.cat([z0, z0.new_zeros(z0.shape[0], diffeq.augment_dim)], dim=1)
-    z = mlp_solve(z0, diffeq.flat_params(), diffeq.dims, t, _opts_from_kwargs(diffeq.kwargs), stats_out)
+    z = mlp_solve(z0, diffeq.flat_params(), diffeq.dims, t, _opts_from_kwargs(diffeq.kwargs, None, getattr(diffeq, 'solver', None)),
+                  stats_out)
     return transform_after_diffeq(z, diffeq)
 
 

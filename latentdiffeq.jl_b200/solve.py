@@ -40,6 +40,12 @@ def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def _aligned16(x: torch.Tensor) -> torch.Tensor:
+    """A contiguous view may start anywhere inside its storage (``time_loader`` slices); the vectorised kernels want
+    16-byte aligned bases."""
+    return x if x.data_ptr() % 16 == 0 else x.clone(memory_format=torch.contiguous_format)
+
+
 def _p(x: torch.Tensor | None) -> C.c_void_p:
     return C.c_void_p(0 if x is None else x.data_ptr())
 
@@ -51,6 +57,10 @@ class _Tape:
         self.h, self.ptr, self.mlp = h, ptr, mlp
 
     def overflow(self) -> int:
+        if self.mlp:
+            raise TypeError("overflow() is a GOKU-tape query; an MLP tape reports overflow from mlp_bwd_raw (LdeqError -6)")
+        if not self.ptr:
+            raise RuntimeError("tape already freed")
         n = C.c_int32(0)
         self.h.check(self.h._lib.ldeq_tape_overflow(self.h.ptr, self.ptr, C.byref(n), _stream()))
         return int(n.value)
@@ -117,8 +127,11 @@ def goku_solve_raw(z0: torch.Tensor, theta: torch.Tensor, t, rhs, opts: _cabi.Op
 
 
 def goku_bwd_raw(tape: _Tape, dtraj: torch.Tensor):
-    """One call of ``ldeq_solve_bwd``: discrete adjoint of the taped steps."""
+    """One call of ``ldeq_solve_bwd``: the pullback by the tape's sensealg (dual re-solves or discrete adjoint)."""
     h = tape.h
+    if not tape.ptr:
+        raise RuntimeError("the tape of this solve was already consumed and freed (backward twice? the tape is released "
+                           "after the first pullback; re-run the forward solve)")
     dtraj = dtraj.contiguous()
     T, B, Z = dtraj.shape
     dz0 = torch.empty((B, Z), dtype=dtraj.dtype, device=dtraj.device)
@@ -145,6 +158,8 @@ class _GokuSolve(torch.autograd.Function):
     def backward(ctx, dtraj):
         tape = ctx.tape
         if tape is None:
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                raise RuntimeError("goku_solve: backward called twice; the tape is released after the first pullback")
             return None, None, None, None, None, None
         dz0, dth = goku_bwd_raw(tape, dtraj)
         tape.free()
@@ -155,8 +170,8 @@ class _GokuSolve(torch.autograd.Function):
 def goku_solve(z0: torch.Tensor, theta: torch.Tensor, t, rhs=_cabi.RHS_PENDULUM, opts: _cabi.Opts | None = None,
                stats_out: list | None = None) -> torch.Tensor:
     """Differentiable batched solve: the body of ``diffeq_layer(::Decoder{<:GOKU}, (z0, theta), t)``
-    (reference ``src/models/GOKU.jl:98-130``).  Gradients flow to ``z0`` and ``theta`` through the
-    discrete adjoint of the accepted steps."""
+    (reference ``src/models/GOKU.jl:98-130``).  Gradients flow to ``z0`` and ``theta`` by ``opts.sensealg``: the
+    reference's dual-number re-solves (default) or the discrete adjoint of the accepted steps."""
     return _GokuSolve.apply(z0, theta, _tgrid(t), rhs, opts, stats_out)
 
 
@@ -204,6 +219,45 @@ def goku_bwd_host(tape: _Tape, dtraj: torch.Tensor, dz0: torch.Tensor | None = N
     with torch.cuda.device(h.device):
         h.check(h._lib.ldeq_solve_bwd_host(h.ptr, tape.ptr, _p(dtraj), _p(dz0), _p(dtheta), _stream()))
     return dz0, dtheta
+
+
+def goku_fwd_bwd_host(z0: torch.Tensor, theta: torch.Tensor, t, dtraj: torch.Tensor, rhs=_cabi.RHS_PENDULUM,
+                      opts: _cabi.Opts | None = None, device: int = 0, out: torch.Tensor | None = None,
+                      dz0: torch.Tensor | None = None, dtheta: torch.Tensor | None = None, handle: _cabi.Handle | None = None):
+    """``ldeq_solve_fwd_bwd_host``: forward solve and pullback of a known cotangent, host tensors in and out, one call;
+    the cotangent slabs go up while the trajectory slabs come down."""
+    assert not z0.is_cuda and not theta.is_cuda and not dtraj.is_cuda
+    h = handle or _cabi.handle(device)
+    opts = opts or _cabi.default_opts()
+    z0 = z0.contiguous()
+    theta = theta.to(z0.dtype).contiguous()
+    dtraj = dtraj.to(z0.dtype).contiguous()
+    tg = _tgrid(t)
+    B, Z = z0.shape
+    T = tg.shape[0]
+    assert tuple(dtraj.shape) == (T, B, Z)
+    rhs_ptr = h.rhs_builtin(rhs) if isinstance(rhs, int) else rhs
+    if out is None:
+        out = torch.empty((T, B, Z), dtype=z0.dtype, pin_memory=True)
+    if dz0 is None:
+        dz0 = torch.empty((B, Z), dtype=z0.dtype, pin_memory=True)
+    if dtheta is None:
+        dtheta = torch.empty((B, theta.shape[1]), dtype=z0.dtype, pin_memory=True)
+    with torch.cuda.device(h.device):
+        h.check(h._lib.ldeq_solve_fwd_bwd_host(h.ptr, rhs_ptr, _dtype_code(z0.dtype), _p(z0), _p(theta),
+                                               tg.ctypes.data_as(C.c_void_p), B, T, C.byref(opts), _p(dtraj), _p(out), _p(dz0),
+                                               _p(dtheta), None, None, None, _stream()))
+    return out, dz0, dtheta
+
+
+def debug_trig(x: torch.Tensor, which: int = 0):
+    """``ldeq_debug_trig``: the kernels' Float32 sine / cosine on a CUDA tensor (0 fast pair, 1 Julia's, 2 fast sine)."""
+    h = _cabi.handle(x.device.index or 0)
+    x = x.contiguous().float()
+    s, c = torch.empty_like(x), torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        h.check(h._lib.ldeq_debug_trig(h.ptr, int(which), _p(x), _p(s), _p(c), x.numel(), _stream()))
+    return s, c
 
 
 # ---- LatentODE path: one solve on the (D,B) matrix state with an MLP right-hand side ---------------
@@ -267,6 +321,8 @@ class _MlpSolve(torch.autograd.Function):
     def backward(ctx, dtraj):
         tape = ctx.tape
         if tape is None:
+            if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+                raise RuntimeError("mlp_solve: backward called twice; the tape is released after the first pullback")
             return None, None, None, None, None, None
         dz0, dp = mlp_bwd_raw(tape, dtraj)
         tape.free()
@@ -316,8 +372,8 @@ def elbo_raw(x: torch.Tensor, xhat: torch.Tensor, mus, logvars, beta: float, wan
     """``ldeq_elbo_fwd_bwd``: ``x, xhat`` are ``[T, B, P]``; ``mus/logvars`` lists of ``[B, d_h]`` heads.
     Returns ``(loss3 = [total, reconstruction, kl], dxhat, dmus, dlogvars)``."""
     h = _cabi.handle(x.device.index or 0)
-    x = x.contiguous().float()
-    xhat = xhat.contiguous().float()
+    x = _aligned16(x.contiguous().float())
+    xhat = _aligned16(xhat.contiguous().float())
     T, B, P = x.shape
     mus = [m.contiguous().float() for m in mus]
     logvars = [l.contiguous().float() for l in logvars]

@@ -163,3 +163,12 @@ def steps(rhs: int, z0, theta, t, opts: Opts | None = None, cap: int = 100000):
     n = lib().oracle_goku_steps_f64(ctypes.c_int(rhs), _ptr(z0), _ptr(theta), _ptr(t), ctypes.c_int(t.shape[0]),
                                     ctypes.byref(co), _ptr(ts), _ptr(dts), ctypes.c_int(cap))
     return ts[:n].copy(), dts[:n].copy()
+
+
+def jl_sincosf(x: np.ndarray):
+    """``Base.sin`` / ``Base.cos`` of Float32 arguments as Julia 1.8 computes them (the restatement in
+    ``ldeq_oracle.cpp``; every Float32 sine / cosine of the oracle goes through it)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    s, c = np.empty_like(x), np.empty_like(x)
+    lib().oracle_jl_sincosf(_ptr(x), _ptr(s), _ptr(c), ctypes.c_int(x.size))
+    return s, c

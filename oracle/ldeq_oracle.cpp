@@ -144,10 +144,80 @@ template <class S, int NP> inline Dual<S, NP> operator/(Dual<S, NP> a, Dual<S, N
     for (int i = 0; i < NP; ++i) r.d[i] = (a.d[i] - r.v * b.d[i]) / b.v;
     return r;
 }
+// ---------------------------------------------------------------------------------------------
+// Base.sin / Base.cos for Float32 (Julia 1.8 base/special/trig.jl + rem_pio2.jl, themselves a port of
+// FreeBSD msun k_sinf.c / k_cosf.c / e_rem_pio2f.c) [3P, restated from the published algorithm]: the
+// argument is widened to Float64, reduced by multiples of pi/2 (exact subtraction of the Float64 constant
+// for |x| <= 9pi/4, a two-term Cody-Waite reduction beyond), the msun polynomial kernels are evaluated in
+// Float64 WITHOUT fused multiply-adds (Julia does not contract) and the result is rounded to Float32 once.
+// The kernels' published error bounds (|sin - s| < 2^-37.5, |cos - c| < 2^-34.1 on [-pi/4, pi/4]) are
+// checked in tests/test_oracle_pins.py.  glibc's sinf differs from this in the last bit for ~1.3 % of the
+// arguments -- enough to move accept/reject decisions of a Float32 adaptive solve -- so the oracle follows
+// Julia here, and so does the forward-dual pullback of the product (csrc/ldeq_julia_trig.cuh), bit for bit.
+// ---------------------------------------------------------------------------------------------
+inline double jl_sin_kernel(double x) {
+    const double S1 = -0x15555554cbac77.0p-55, S2 = 0x111110896efbb2.0p-59, S3 = -0x1a00f9e2cae774.0p-65,
+                 S4 = 0x16cd878c3b46a7.0p-71;
+    const double z = x * x, w = z * z, r = S3 + z * S4, s = z * x;
+    return (x + s * (S1 + z * S2)) + s * w * r;
+}
+inline double jl_cos_kernel(double x) {
+    const double C0 = -0x1ffffffd0c5e81.0p-54, C1 = 0x155553e1053a42.0p-57, C2 = -0x16c087e80f1e27.0p-62,
+                 C3 = 0x199342e0ee5069.0p-68;
+    const double z = x * x, w = z * z, r = C2 + z * C3;
+    return ((1.0 + z * C0) + w * C1) + (w * z) * r;
+}
+// rem_pio2_kernel(x::Float32): quadrant n (mod 4 is all that is used) and the reduced argument
+inline int jl_rem_pio2f(float x, double* y) {
+    const double PI = 3.141592653589793, pio2_1 = 1.57079631090164184570e+00, pio2_1t = 1.58932547735281966916e-08,
+                 inv_pio2 = 6.36619772367581382433e-01;
+    const double xd = (double)x, ax = std::fabs(xd);
+    if (ax <= PI * 5 / 4) {
+        if (ax <= PI * 3 / 4) { *y = x > 0 ? xd - PI / 2 : xd + PI / 2; return x > 0 ? 1 : -1; }
+        *y = x > 0 ? xd - PI : xd + PI;
+        return x > 0 ? 2 : -2;
+    }
+    if (ax <= PI * 9 / 4) {
+        if (ax <= PI * 7 / 4) { *y = x > 0 ? xd - PI * 3 / 2 : xd + PI * 3 / 2; return x > 0 ? 3 : -3; }
+        *y = x > 0 ? xd - PI * 4 / 2 : xd + PI * 4 / 2;
+        return x > 0 ? 4 : -4;
+    }
+    const double fn = std::nearbyint(xd * inv_pio2);
+    const double r = xd - fn * pio2_1, w = fn * pio2_1t;
+    *y = r - w;
+    return (int)(long long)fn;
+}
+inline float jl_sinf(float x) {
+    const float ax = std::fabs(x);
+    if (ax < 0.7853982f) {  // Float32(pi)/4
+        if (ax < 0.00034526698f) return x;  // sqrt(eps(Float32))
+        return (float)jl_sin_kernel((double)x);
+    }
+    if (!(ax < 8.4e8f)) return (float)std::sin((double)x);  // Float32(pi)/2 * 2^28 and beyond (incl. NaN/Inf): Payne-Hanek in Julia
+    double y;
+    const int n = jl_rem_pio2f(x, &y) & 3;
+    return n == 0 ? (float)jl_sin_kernel(y) : n == 1 ? (float)jl_cos_kernel(y) : n == 2 ? -(float)jl_sin_kernel(y) : -(float)jl_cos_kernel(y);
+}
+inline float jl_cosf(float x) {
+    const float ax = std::fabs(x);
+    if (ax < 0.7853982f) {
+        if (ax < 0.00024414062f) return 1.0f;  // sqrt(eps(Float32)/2)
+        return (float)jl_cos_kernel((double)x);
+    }
+    if (!(ax < 8.4e8f)) return (float)std::cos((double)x);
+    double y;
+    const int n = jl_rem_pio2f(x, &y) & 3;
+    return n == 0 ? (float)jl_cos_kernel(y) : n == 1 ? -(float)jl_sin_kernel(y) : n == 2 ? -(float)jl_cos_kernel(y) : (float)jl_sin_kernel(y);
+}
+inline float sin_s(float x) { return jl_sinf(x); }
+inline float cos_s(float x) { return jl_cosf(x); }
+inline double sin_s(double x) { return std::sin(x); }
+inline double cos_s(double x) { return std::cos(x); }
+
 template <class S, int NP> inline Dual<S, NP> dsin(Dual<S, NP> a) {
     Dual<S, NP> r;
-    S c = std::cos(a.v);
-    r.v = std::sin(a.v);
+    S c = cos_s(a.v);
+    r.v = sin_s(a.v);
     for (int i = 0; i < NP; ++i) r.d[i] = c * a.d[i];
     return r;
 }
@@ -604,6 +674,11 @@ int oracle_goku_steps_f64(int rhs, const double* z0, const double* theta, const 
 }
 
 double oracle_fastpow(double x, double y) { return fastpow(x, y); }
+
+// Base.sin / Base.cos(::Float32) restatement, for the pins in tests/test_oracle_pins.py and the GPU bit-equality test
+void oracle_jl_sincosf(const float* x, float* s, float* c, int n) {
+    for (int i = 0; i < n; ++i) { s[i] = jl_sinf(x[i]); c[i] = jl_cosf(x[i]); }
+}
 
 int oracle_num_threads(void) {
 #ifdef _OPENMP

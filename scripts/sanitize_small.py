@@ -12,14 +12,14 @@ if which in ("all", "goku"):
         for B, T in ((129, 23), (5, 2), (70, 200)):
             z0, th = pendulum_inputs(B, dtype=dtype)
             t = np.cumsum(np.r_[0.0, np.linspace(0.01, 0.09, T - 1)]) if B == 129 else 0.05 * np.arange(T)
-            for kw in (dict(), dict(adaptive=False, dt=0.07), dict(tape_steps=2)):
+            for kw in (dict(sensealg=0), dict(sensealg=0, adaptive=False, dt=0.07), dict(sensealg=0, tape_steps=2), dict()):
                 z = torch.from_numpy(z0).to(dev).requires_grad_(True); p = torch.from_numpy(th).to(dev).requires_grad_(True)
                 tr = ldeq.goku_solve(z, p, t, 1, ldeq.default_opts(**kw))
                 tr.backward(torch.ones_like(tr))
     h = ldeq.handle(0)
     rhs = h.rhs_from_source("template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t) { du[0] = u[1]; du[1] = -p[0]*sin(u[0]); du[2] = p[1]*u[0] - u[2]; }", 3, 2)
     z = torch.randn(37, 3, device=dev, requires_grad=True); p = (1 + torch.rand(37, 2, device=dev)).requires_grad_(True)
-    tr = ldeq.goku_solve(z, p, 0.05 * np.arange(30), rhs); tr.backward(torch.ones_like(tr))
+    tr = ldeq.goku_solve(z, p, 0.05 * np.arange(30), rhs, ldeq.default_opts(sensealg=0)); tr.backward(torch.ones_like(tr))
     # forward-dual pullback: built-in (both dtypes, friction) and the user function
     for dtype in ("float32", "float64"):
         z0, th = pendulum_inputs(131, dtype=dtype)
@@ -28,6 +28,17 @@ if which in ("all", "goku"):
             tr = ldeq.goku_solve(z, p, 0.05 * np.arange(23), kind, ldeq.default_opts(sensealg=1)); tr.backward(torch.ones_like(tr))
     z = torch.randn(37, 3, device=dev, requires_grad=True); p = (1 + torch.rand(37, 2, device=dev)).requires_grad_(True)
     tr = ldeq.goku_solve(z, p, 0.05 * np.arange(30), rhs, ldeq.default_opts(sensealg=1)); tr.backward(torch.ones_like(tr))
+    # host-buffer entry points, several column slabs, both pullbacks, and the trig diagnostics
+    z0, th = pendulum_inputs(70001)
+    tt = 0.05 * np.arange(9)
+    dd = torch.randn(9, 70001, 2)
+    for sense in (0, 1):
+        o = ldeq.default_opts(sensealg=sense)
+        out, tape = ldeq.goku_solve_host(torch.from_numpy(z0), torch.from_numpy(th), tt, 0, o, want_tape=True)
+        ldeq.goku_bwd_host(tape, dd)
+        ldeq.goku_fwd_bwd_host(torch.from_numpy(z0), torch.from_numpy(th), tt, dd, 0, o)
+    for w in (0, 1, 2):
+        ldeq.debug_trig(torch.linspace(-20, 20, 1001, device=dev), w)
 if which in ("all", "mlp"):
     from oracle import mlp as om
     rng = np.random.Generator(np.random.PCG64(1)); dims = [16, 200, 200, 16]

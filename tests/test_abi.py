@@ -37,7 +37,9 @@ def test_opts_layout_and_defaults(ldeq):
     assert (o.gamma, o.qmin, o.qmax, o.qoldinit, o.qsteady_min, o.qsteady_max) == (0.9, 0.2, 10.0, 1e-4, 1.0, 1.0)
     assert abs(o.beta1 - 7 / 50) < 1e-16 and abs(o.beta2 - 2 / 25) < 1e-16 and o.maxiters == 1000000
     assert o.dt == 0.0 and o.dtmax == 0.0 and o.dtmin == 0.0 and o.tape_steps == 0 and o.norm_mode == 0 and o.mlp_math == 0
-    assert ctypes.sizeof(o) == 136
+    assert ctypes.sizeof(o) == 144
+    # what the reference's diffeq structs request (pendulum.jl:11): ForwardDiffSensitivity(), Tsit5()
+    assert o.sensealg == ldeq.SENSE_FORWARD_DUAL == 1 and o.solver == 0
     o2 = ldeq.default_opts(adaptive=False, dt=0.05, abstol=1e-8)
     assert (o2.adaptive, o2.dt, o2.abstol) == (0, 0.05, 1e-8)
     with pytest.raises(TypeError):
@@ -46,7 +48,7 @@ def test_opts_layout_and_defaults(ldeq):
 
 def test_version_and_clean_failure_without_a_device(ldeq):
     lib = ldeq._cabi.load()
-    assert lib.ldeq_version() == 100
+    assert lib.ldeq_version() == 200
     import torch
     if not torch.cuda.is_available():
         # the product path must fail loudly, not fall back to the CPU

@@ -70,7 +70,10 @@ def test_c4_shape_forward_vs_oracle(ldeq):
 
 
 def _grads(ldeq, rhs, z0, th, t, d, **kw):
+    """Gradients through ``goku_solve``.  The tests of the adjoint KERNEL ask for it explicitly (the library default is
+    the reference's forward-dual algorithm); tests of the forward-dual mode pass ``sensealg=SENSE_FORWARD_DUAL``."""
     dev = torch.device("cuda:0")
+    kw.setdefault("sensealg", ldeq.SENSE_DISCRETE_ADJOINT)
     opts = ldeq.default_opts(**kw)
     z = torch.from_numpy(z0).to(dev).requires_grad_(True)
     p = torch.from_numpy(th).to(dev).requires_grad_(True)
@@ -143,15 +146,25 @@ def test_forward_dual_mode_is_the_reference_gradient(ldeq, rhs, dtype):
         # north star: gradients within 1e-4 relative -- every trajectory, by a wide margin
         assert ez.max() <= 1e-9 and ep.max() <= 1e-9
     else:
-        # Float32: sinf/cosf of CUDA and glibc differ in the last bit, which moves an accept/reject decision on a few
-        # trajectories (a different, equally valid step sequence); the bulk agrees to rounding
-        assert np.quantile(ez, 0.95) <= 2e-5 and np.quantile(ep, 0.95) <= 2e-5
+        # Float32: kernel and oracle share Julia's sin/cos arithmetic bit for bit and the Float64-promoted stage
+        # updates; what is left (exp2f / pow of the controller, fused vs unfused products inside the dual quotient)
+        # moves an accept/reject decision on well under 1 % of the trajectories: q99 within the north star's 1e-4
+        print("fp32 forward-dual: q99", np.quantile(ez, 0.99), np.quantile(ep, 0.99), "max", ez.max(), ep.max(),
+              "frac > 1e-4", (ez > 1e-4).mean(), (ep > 1e-4).mean())
+        assert np.quantile(ez, 0.99) <= 1e-4 and np.quantile(ep, 0.99) <= 1e-4
         assert ez.max() <= 2e-2 and ep.max() <= 2e-2
-    # the trajectories themselves are those of the default mode (the primal solve is the same kernel)
-    a, _, _ = ldeq.goku_solve_raw(torch.from_numpy(z0).to(DEV), torch.from_numpy(th).to(DEV), t, rhs)
+    # the trajectories do not depend on the sensitivity mode (the primal solve is the same kernel), and the library
+    # default IS this mode (what the reference's diffeq structs request, pendulum.jl:11)
+    a, _, _ = ldeq.goku_solve_raw(torch.from_numpy(z0).to(DEV), torch.from_numpy(th).to(DEV), t, rhs,
+                                  ldeq.default_opts(sensealg=ldeq.SENSE_DISCRETE_ADJOINT))
     b, _, _ = ldeq.goku_solve_raw(torch.from_numpy(z0).to(DEV), torch.from_numpy(th).to(DEV), t, rhs,
                                   ldeq.default_opts(sensealg=ldeq.SENSE_FORWARD_DUAL))
     assert torch.equal(a, b)
+    assert ldeq.default_opts().sensealg == ldeq.SENSE_FORWARD_DUAL
+    z = torch.from_numpy(z0).to(DEV).requires_grad_(True)
+    p = torch.from_numpy(th).to(DEV).requires_grad_(True)
+    ldeq.goku_solve(z, p, t, rhs).backward(torch.from_numpy(d).to(DEV))
+    assert np.array_equal(z.grad.cpu().numpy(), gz) and np.array_equal(p.grad.cpu().numpy(), gp)
 
 
 def test_forward_dual_mode_fixed_step_and_failures(ldeq):
@@ -218,8 +231,9 @@ def test_failed_trajectory_is_nan_block_with_zero_gradient(ldeq):
     ok = np.arange(B) != 3
     assert np.isfinite(tr[:, ok, :]).all()
     d = np.ones((T, B, 2), dtype=np.float32)
-    gz, gp = _grads(ldeq, 0, z0, th, t, d, maxiters=50)
-    assert (gz[3] == 0).all() and (gp[3] == 0).all() and np.isfinite(gz).all()
+    for sense in (ldeq.SENSE_DISCRETE_ADJOINT, ldeq.SENSE_FORWARD_DUAL):
+        gz, gp = _grads(ldeq, 0, z0, th, t, d, maxiters=50, sensealg=sense)
+        assert (gz[3] == 0).all() and (gp[3] == 0).all() and np.isfinite(gz).all()
 
 
 def test_edge_shapes(ldeq):
@@ -238,13 +252,49 @@ def test_host_entry_points_match_device(ldeq):
     z0, th = pendulum_inputs(B)
     t = 0.05 * np.arange(T)
     d = np.random.default_rng(5).standard_normal((T, B, 2)).astype(np.float32)
-    out, tape = ldeq.goku_solve_host(torch.from_numpy(z0).pin_memory(), torch.from_numpy(th).pin_memory(), t, 0,
-                                     want_tape=True)
-    dz0, dth = ldeq.goku_bwd_host(tape, torch.from_numpy(d).pin_memory())
     tr, *_ = _run(ldeq, 0, z0, th, t)
-    gz, gp = _grads(ldeq, 0, z0, th, t, d)
-    assert np.array_equal(out.numpy(), tr)
-    assert np.array_equal(dz0.numpy(), gz) and np.array_equal(dth.numpy(), gp)
+    for sense in (ldeq.SENSE_DISCRETE_ADJOINT, ldeq.SENSE_FORWARD_DUAL):
+        o = ldeq.default_opts(sensealg=sense)
+        out, tape = ldeq.goku_solve_host(torch.from_numpy(z0).pin_memory(), torch.from_numpy(th).pin_memory(), t, 0, o,
+                                         want_tape=True)
+        dz0, dth = ldeq.goku_bwd_host(tape, torch.from_numpy(d).pin_memory())
+        gz, gp = _grads(ldeq, 0, z0, th, t, d, sensealg=sense)
+        assert np.array_equal(out.numpy(), tr)
+        assert np.array_equal(dz0.numpy(), gz) and np.array_equal(dth.numpy(), gp)
+        # the combined call (cotangent up while trajectories come down): same numbers
+        out2, dz2, dth2 = ldeq.goku_fwd_bwd_host(torch.from_numpy(z0).pin_memory(), torch.from_numpy(th).pin_memory(), t,
+                                                 torch.from_numpy(d).pin_memory(), 0, o)
+        assert np.array_equal(out2.numpy(), tr) and np.array_equal(dz2.numpy(), gz) and np.array_equal(dth2.numpy(), gp)
+
+
+def test_host_entry_points_slabbed_batch(ldeq):
+    # a batch large enough to be cut into several column slabs (ragged: not a multiple of the slab or CTA size), pageable
+    # AND pinned host buffers, a failing trajectory in the second slab: identical to the one-launch device path
+    B, T = 100_003, 20
+    z0, th = pendulum_inputs(B)
+    th[70_001, 0] = 1e-4
+    t = 0.05 * np.arange(T)
+    d = np.random.default_rng(5).standard_normal((T, B, 2)).astype(np.float32)
+    for sense in (ldeq.SENSE_DISCRETE_ADJOINT, ldeq.SENSE_FORWARD_DUAL):
+        o = ldeq.default_opts(sensealg=sense, maxiters=300)
+        dev = torch.device(DEV)
+        zt, tt = torch.from_numpy(z0).to(dev).requires_grad_(True), torch.from_numpy(th).to(dev).requires_grad_(True)
+        tr = ldeq.goku_solve(zt, tt, t, 0, o)
+        tr.backward(torch.from_numpy(d).to(dev))
+        for pin in (True, False):
+            f = (lambda a: torch.from_numpy(a).pin_memory()) if pin else torch.from_numpy
+            out, tape = ldeq.goku_solve_host(f(z0), f(th), t, 0, o, want_tape=True, out=None if pin else torch.empty(T, B, 2))
+            dz0, dth = ldeq.goku_bwd_host(tape, f(d), None if pin else torch.empty(B, 2), None if pin else torch.empty(B, 1))
+            assert np.array_equal(out.numpy(), tr.detach().cpu().numpy(), equal_nan=True)
+            assert np.isnan(out.numpy()[:, 70_001]).all() and (dz0.numpy()[70_001] == 0).all()
+            assert np.array_equal(dz0.numpy(), zt.grad.cpu().numpy()) and np.array_equal(dth.numpy(), tt.grad.cpu().numpy())
+            out2, dz2, dth2 = ldeq.goku_fwd_bwd_host(f(z0), f(th), t, f(d), 0, o)
+            assert np.array_equal(out2.numpy(), out.numpy(), equal_nan=True)
+            assert np.array_equal(dz2.numpy(), dz0.numpy()) and np.array_equal(dth2.numpy(), dth.numpy())
+        # a slabbed tape also serves the device-pointer pullback
+        out, tape = ldeq.goku_solve_host(torch.from_numpy(z0), torch.from_numpy(th), t, 0, o, want_tape=True)
+        g = ldeq.goku_bwd_raw(tape, torch.from_numpy(d).to(dev))
+        assert np.array_equal(g[0].cpu().numpy(), zt.grad.cpu().numpy())
 
 
 def test_small_tape_heals_itself(ldeq):
@@ -289,3 +339,86 @@ def test_adjoint_every_trajectory_adaptive_fp64(ldeq):
     oz, op = og.grad(0, z0, th, t, d, og.Opts(controller_pow=1), norm_partials=False)
     assert np.abs(gz - oz).max() <= 1e-5 * np.abs(oz).max()
     assert np.abs(gp - op).max() <= 1e-5 * np.abs(op).max()
+
+
+def test_fast_sincos_accuracy(ldeq):
+    # the 13 / 19-instruction sine / cosine of the primal and adjoint kernels against Float64, in ulps of the result
+    rng = np.random.default_rng(0)
+    for lo, hi in [(-1.6, 1.6), (-3.2, 3.2), (-30.0, 30.0), (-1e4, 1e4)]:
+        x = rng.uniform(lo, hi, 1 << 22).astype(np.float32)
+        s, c = ldeq.debug_trig(torch.from_numpy(x).to(DEV), 0)
+        s2, _ = ldeq.debug_trig(torch.from_numpy(x).to(DEV), 2)
+        assert torch.equal(s, s2)
+        s, c = s.cpu().numpy().astype(np.float64), c.cpu().numpy().astype(np.float64)
+        rs, rc = np.sin(x.astype(np.float64)), np.cos(x.astype(np.float64))
+        ulp = np.spacing(np.abs(rs).astype(np.float32)).astype(np.float64)
+        es = np.abs(s - rs) / ulp
+        print(f"[{lo}, {hi}] sine: max {es.max():.2f} ulp, mean {es.mean():.3f}, within 1 ulp {np.mean(es <= 1):.4f}; "
+              f"cosine max abs err {np.abs(c - rc).max():.2e}")
+        assert es.max() <= 2.0 and np.mean(es <= 1.0) >= 0.985 and es.mean() <= 0.4
+        assert np.abs(c - rc).max() <= 2.5e-7
+    # beyond the fast range: libdevice's own sinf / sincosf (checked fallback), still accurate
+    x = np.array([1.0e4 + 1, -2.5e5, 3.0e7, 1e30], np.float32)
+    s, c = ldeq.debug_trig(torch.from_numpy(x).to(DEV), 0)
+    assert np.allclose(s.cpu().numpy(), np.sin(x.astype(np.float64)), atol=2e-7)
+    assert np.allclose(c.cpu().numpy(), np.cos(x.astype(np.float64)), atol=2e-7)
+    x = np.array([np.nan, np.inf], np.float32)
+    s, _ = ldeq.debug_trig(torch.from_numpy(x).to(DEV), 0)
+    assert torch.isnan(s).all()
+
+
+def test_julia_trig_is_bit_equal_to_the_oracle(ldeq):
+    # Base.sin / Base.cos(::Float32) restated twice (oracle/ldeq_oracle.cpp, csrc/ldeq_julia_trig.cuh): same bits
+    rng = np.random.default_rng(1)
+    x = np.concatenate([rng.uniform(-1.0, 1.0, 1 << 21), rng.uniform(-8.0, 8.0, 1 << 21), rng.uniform(-1e3, 1e3, 1 << 18),
+                        rng.uniform(-1e-3, 1e-3, 1 << 16), np.array([0.0, -0.0, 0.78539816, 0.7853982, 2.3561945, 3.9269908,
+                                                                     5.497787, 7.0685835, 1e6, -3e8])]).astype(np.float32)
+    s, c = ldeq.debug_trig(torch.from_numpy(x).to(DEV), 1)
+    os_, oc = og.jl_sincosf(x)
+    assert np.array_equal(s.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+    assert np.array_equal(c.cpu().numpy().view(np.uint32), oc.view(np.uint32))
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_c4_full_size_sampled_parity(ldeq, dtype):
+    # BASELINE.json configs[3] at its benchmarked size: 2^20 trajectories x 200 save points on the GPU; trajectories are
+    # independent, so a random sample of them is checked against the oracle run on exactly those columns
+    B, T, NS = 1 << 20, 200, 4096
+    z0, th = pendulum_inputs(B, dtype=dtype)
+    t = 0.05 * np.arange(T)
+    dev = torch.device(DEV)
+    dsc = torch.Generator(device=dev)
+    dsc.manual_seed(334)
+    d = torch.randn(T, B, 2, device=dev, generator=dsc, dtype=getattr(torch, dtype))
+    z = torch.from_numpy(z0).to(dev).requires_grad_(True)
+    p = torch.from_numpy(th).to(dev).requires_grad_(True)
+    stats = []
+    traj = ldeq.goku_solve(z, p, t, 0, None, stats)        # library default: the reference's forward-dual gradient
+    traj.backward(d)
+    assert int((stats[0].retcode != 0).sum()) == 0
+    idx = np.sort(np.random.default_rng(9).choice(B, NS, replace=False))
+    ti = torch.from_numpy(idx).to(dev)
+    tr = traj.detach()[:, ti].cpu().numpy()
+    dd = d[:, ti].cpu().numpy()
+    gz, gp = z.grad[ti].cpu().numpy(), p.grad[ti].cpu().numpy()
+    na = stats[0].naccept[ti].cpu().numpy()
+    otr, oret, ona, _ = og.solve(0, z0[idx], th[idx], t)
+    rz, rp = og.grad(0, z0[idx], th[idx], t, dd, norm_partials=True)
+    assert np.abs(tr - otr).max() <= (1e-3 if dtype == "float32" else 1e-5) * np.abs(otr).max()
+    ez = np.abs(gz - rz).max(1) / np.abs(rz).max()
+    ep = np.abs(gp - rp).max(1) / np.abs(rp).max()
+    print(dtype, "traj max rel", np.abs(tr - otr).max() / np.abs(otr).max(), "naccept equal", (na == ona).mean(),
+          "grad q99", np.quantile(ez, 0.99), np.quantile(ep, 0.99), "max", ez.max(), ep.max())
+    if dtype == "float64":
+        assert ez.max() <= 1e-4 and ep.max() <= 1e-4 and (na == ona).mean() > 0.99
+    else:
+        assert np.quantile(ez, 0.99) <= 1e-4 and np.quantile(ep, 0.99) <= 1e-4
+    # the explicit opt-in, same batch: the discrete adjoint agrees with it within the solver tolerance
+    z2 = torch.from_numpy(z0).to(dev).requires_grad_(True)
+    p2 = torch.from_numpy(th).to(dev).requires_grad_(True)
+    ldeq.goku_solve(z2, p2, t, 0, ldeq.default_opts(sensealg=ldeq.SENSE_DISCRETE_ADJOINT)).backward(d)
+    az, ap = z2.grad[ti].cpu().numpy(), p2.grad[ti].cpu().numpy()
+    oz, op = og.grad(0, z0[idx], th[idx], t, dd, norm_partials=False)
+    e2 = np.abs(az - oz).max(1) / np.abs(oz).max()
+    assert np.quantile(e2, 0.9) <= (2e-4 if dtype == "float32" else 1e-9)
+    assert np.abs(az - rz).max() <= 5e-2 * np.abs(rz).max() and np.abs(ap - rp).max() <= 5e-2 * np.abs(rp).max()

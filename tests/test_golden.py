@@ -51,17 +51,18 @@ def test_cuda_matches_goku_golden(ldeq):
     assert np.abs(p.grad.cpu().numpy() - g["dtheta_fixed"]).max() <= 1e-4 * np.abs(g["dtheta_fixed"]).max()
     tr, stt, _ = ldeq.goku_solve_raw(z.detach(), p.detach(), g["t"], ldeq.RHS_PENDULUM)
     assert np.abs(tr.cpu().numpy() - g["traj_adaptive"]).max() <= 1e-3 * np.abs(g["traj_adaptive"]).max()
-    # adaptive gradients vs the reference's ForwardDiff semantics: agreement at the solver tolerance
+    # adaptive gradients, explicit discrete adjoint vs the reference's ForwardDiff semantics: the solver tolerance
+    z.grad = None
+    p.grad = None
+    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM, ldeq.default_opts(sensealg=ldeq.SENSE_DISCRETE_ADJOINT)).backward(
+        torch.from_numpy(g["dtraj"]).to(dev))
+    assert np.abs(z.grad.cpu().numpy() - g["dz0_adaptive_fwddiff"]).max() <= 2e-2 * np.abs(g["dz0_adaptive_fwddiff"]).max()
+    # ... and the library default = the reference's own algorithm (dual-number re-solves): the north star's 1e-4
     z.grad = None
     p.grad = None
     ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM).backward(torch.from_numpy(g["dtraj"]).to(dev))
-    assert np.abs(z.grad.cpu().numpy() - g["dz0_adaptive_fwddiff"]).max() <= 2e-2 * np.abs(g["dz0_adaptive_fwddiff"]).max()
-    # ... and with the reference's own algorithm (dual-number re-solves): the north star's 1e-4
-    z.grad = None
-    p.grad = None
-    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM, ldeq.default_opts(sensealg=ldeq.SENSE_FORWARD_DUAL)).backward(
-        torch.from_numpy(g["dtraj"]).to(dev))
     assert np.abs(z.grad.cpu().numpy() - g["dz0_adaptive_fwddiff"]).max() <= 1e-4 * np.abs(g["dz0_adaptive_fwddiff"]).max()
+    assert np.abs(p.grad.cpu().numpy() - g["dtheta_adaptive_fwddiff"]).max() <= 1e-4 * np.abs(g["dtheta_adaptive_fwddiff"]).max()
     g = _load("c3_goku_friction.npz")
     for dt, key, rtol in ((torch.float64, "traj_f64", 1e-5), (torch.float32, "traj_f32", 1e-3)):
         tr, stt, _ = ldeq.goku_solve_raw(torch.from_numpy(g["z0"]).to(dev, dt), torch.from_numpy(g["theta"]).to(dev, dt),
@@ -69,7 +70,8 @@ def test_cuda_matches_goku_golden(ldeq):
         assert np.abs(tr.cpu().numpy() - g[key]).max() <= rtol * np.abs(g[key]).max()
     z = torch.from_numpy(g["z0"]).to(dev).requires_grad_(True)
     p = torch.from_numpy(g["theta"]).to(dev).requires_grad_(True)
-    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM_FRICTION).backward(torch.from_numpy(g["dtraj"]).to(dev))
+    ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM_FRICTION, ldeq.default_opts(sensealg=ldeq.SENSE_DISCRETE_ADJOINT)).backward(
+        torch.from_numpy(g["dtraj"]).to(dev))
     assert np.abs(z.grad.cpu().numpy() - g["dz0_f64_frozen"]).max() <= 1e-4 * np.abs(g["dz0_f64_frozen"]).max()
     assert np.abs(p.grad.cpu().numpy() - g["dtheta_f64_frozen"]).max() <= 1e-4 * np.abs(g["dtheta_f64_frozen"]).max()
     # Float64, default tolerance, the reference's own sensitivity algorithm (dual-number re-solves) against the frozen

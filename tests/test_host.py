@@ -1,6 +1,10 @@
 """CPU tier: host-side mirror of the reference API (layers, model container, utilities, data-parallel helpers)."""
 import numpy as np
+import os
+
 import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 import torch
 
 
@@ -50,20 +54,49 @@ def test_diffeq_struct_contract(ldeq):
     assert ldeq.Pendulum_friction().prob.f == ldeq.RHS_PENDULUM_FRICTION
 
 
-def test_sensealg_maps_to_the_solver_options(ldeq):
-    # the diffeq struct's sensealg field (pendulum.jl:11) selects how the reverse pass differentiates
+def test_sensealg_and_solver_map_to_the_solver_options(ldeq):
+    # the diffeq struct's sensealg / solver fields (pendulum.jl:11) are read, not ignored
     from importlib import import_module
     model = import_module(ldeq.__name__ + ".model") if hasattr(ldeq, "__path__") else ldeq.model
     p = ldeq.Pendulum()
-    assert repr(p.sensealg) == "ForwardDiffSensitivity()" and not p.sensealg.dual_solves
-    o = model._opts_from_kwargs(p.kwargs, p.sensealg)
-    assert o.sensealg == ldeq.SENSE_DISCRETE_ADJOINT == 0
-    q = ldeq.Pendulum(sensalg=ldeq.ForwardDiffSensitivity(dual_solves=True), reltol=1e-5)
-    assert repr(q.sensealg) == "ForwardDiffSensitivity(dual_solves=True)"
-    o = model._opts_from_kwargs(q.kwargs, q.sensealg)
-    assert o.sensealg == ldeq.SENSE_FORWARD_DUAL == 1 and o.reltol == 1e-5
+    assert repr(p.sensealg) == "ForwardDiffSensitivity()" and repr(p.solver) == "Tsit5()"
+    o = model._opts_from_kwargs(p.kwargs, p.sensealg, p.solver)
+    assert o.sensealg == ldeq.SENSE_FORWARD_DUAL == 1 and o.solver == 0      # the reference's own algorithm by default
+    q = ldeq.Pendulum(sensalg=ldeq.DiscreteAdjoint(), reltol=1e-5)            # the cheaper discrete adjoint: explicit opt-in
+    assert repr(q.sensealg) == "DiscreteAdjoint()"
+    o = model._opts_from_kwargs(q.kwargs, q.sensealg, q.solver)
+    assert o.sensealg == ldeq.SENSE_DISCRETE_ADJOINT == 0 and o.reltol == 1e-5
     o = model._opts_from_kwargs({"saveat": [0.0, 1.0], "abstol": 1e-9}, None)      # saveat is the layer's own argument
-    assert o.sensealg == 0 and o.abstol == 1e-9
+    assert o.sensealg == ldeq.SENSE_FORWARD_DUAL and o.abstol == 1e-9
+    with pytest.raises(TypeError):
+        model._opts_from_kwargs({}, object())
+    with pytest.raises(NotImplementedError):
+        model._opts_from_kwargs({}, None, "Rodas5()")
+
+
+def test_user_rhs_translation_unit_compiles_with_nvrtc():
+    """The text ldeq_rhs_from_source hands to NVRTC (the integrator headers embedded in the library + a user function +
+    the kernel entry points) compiles for sm_100a; NVRTC needs no GPU."""
+    import re
+    nvrtc = pytest.importorskip("cuda.bindings.nvrtc")
+    csrc = os.path.join(ROOT, "latentdiffeq.jl_b200", "csrc")
+
+    def strip(fn):
+        txt = open(os.path.join(csrc, fn)).read()
+        txt = re.sub(r'^\s*#pragma once\s*$', '', txt, flags=re.M)
+        return re.sub(r'^\s*#include "ldeq_[a-z0-9_]+\.cuh"\s*$', '', txt, flags=re.M)
+    wrapper = re.search(r'kWrapper = R"LDEQ\((.*?)\)LDEQ";', open(os.path.join(csrc, "ldeq_user_rhs.cu")).read(), re.S).group(1)
+    user = ("template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t) { du[0] = u[1]; "
+            "du[1] = -p[0] * sin(u[0]) - S(0.1) * u[1]; du[2] = p[1] * u[0] - u[2] + exp(-t); }")
+    src = ("#define LDEQ_USER_ZD 3\n#define LDEQ_USER_PD 2\n" + "".join(strip(f) for f in (
+        "ldeq_common.cuh", "ldeq_tsit5.cuh", "ldeq_julia_trig.cuh", "ldeq_dual.cuh", "ldeq_fwdsens.cuh")) + "\n" + user + "\n" + wrapper)
+    err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"u.cu", 0, [], [])
+    opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-default-device", b"--fmad=true", b"-DLDEQ_NVRTC=1"]
+    err, = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
+    _, n = nvrtc.nvrtcGetProgramLogSize(prog)
+    log = b" " * n
+    nvrtc.nvrtcGetProgramLog(prog, log)
+    assert int(err) == 0, log.decode()[:2000]
 
 
 def test_utils(ldeq):

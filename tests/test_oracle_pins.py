@@ -281,3 +281,51 @@ def test_reference_continuous_adjoint_converges_to_the_discrete_adjoint():
     assert gaps[0][0] > gaps[1][0] > gaps[2][0] and gaps[0][1] > gaps[1][1] > gaps[2][1]
     assert gaps[0][0] < 5e-2 and gaps[0][1] < 2e-1          # default tolerance: O(reltol^(1/3)) apart
     assert gaps[2][0] < 1e-3 and gaps[2][1] < 5e-3
+
+
+def test_julia_float32_trig_restatement():
+    """Base.sin / Base.cos(::Float32) as restated in the oracle (msun kernels in Float64, rounded once): the published
+    bounds of the kernels hold (|sin - s| < 2^-37.5, |cos - c| < 2^-34.1 on [-pi/4, pi/4] before the final rounding),
+    the Float32 results are within 0.51 ulp of the truth on the pendulum's range and across the quadrant boundaries of
+    rem_pio2_kernel, and they differ from glibc's sinf in about 1 % of the arguments -- which is why the oracle does
+    not simply call sinf."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-np.pi / 4, np.pi / 4, 400000), rng.uniform(-10, 10, 400000), rng.uniform(-1e3, 1e3, 100000),
+                        rng.uniform(-3e-4, 3e-4, 1000)]).astype(np.float32)
+    s, c = og.jl_sincosf(x)
+    xd = x.astype(np.float64)
+    for got, ref in ((s, np.sin(xd)), (c, np.cos(xd))):
+        ulp = np.spacing(np.abs(ref).astype(np.float32)).astype(np.float64)
+        e = np.abs(got.astype(np.float64) - ref) / ulp
+        assert e.max() <= 0.51, e.max()
+    # kernel bounds, evaluated in Float64 exactly as the oracle does
+    S = [float.fromhex(h) for h in ("-0x15555554cbac77.0p-55", "0x111110896efbb2.0p-59", "-0x1a00f9e2cae774.0p-65", "0x16cd878c3b46a7.0p-71")]
+    C = [float.fromhex(h) for h in ("-0x1ffffffd0c5e81.0p-54", "0x155553e1053a42.0p-57", "-0x16c087e80f1e27.0p-62", "0x199342e0ee5069.0p-68")]
+    y = np.linspace(-np.pi / 4, np.pi / 4, 200001)
+    z = y * y
+    w = z * z
+    sk = (y + (z * y) * (S[0] + z * S[1])) + (z * y) * w * (S[2] + z * S[3])
+    ck = ((1 + z * C[0]) + w * C[1]) + (w * z) * (C[2] + z * C[3])
+    assert np.abs(sk - np.sin(y)).max() < 2.0 ** -37.5 and np.abs(ck - np.cos(y)).max() < 2.0 ** -34.0
+    # the first 50000 arguments lie in [-pi/4, pi/4]: the Float32 result is the rounded kernel value
+    assert np.array_equal(s[:50000], sk_f32(x[:50000], S))
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    libm.sinf.restype = ctypes.c_float
+    libm.sinf.argtypes = [ctypes.c_float]
+    sub = x[400000:420000]
+    g = np.array([libm.sinf(float(v)) for v in sub], np.float32)
+    frac = float((g != s[400000:420000]).mean())
+    assert 0.001 < frac < 0.05, frac
+
+
+def sk_f32(x, S):
+    xd = x.astype(np.float64)
+    z = xd * xd
+    w = z * z
+    r = S[2] + z * S[3]
+    s = z * xd
+    out = ((xd + s * (S[0] + z * S[1])) + s * w * r).astype(np.float32)
+    tiny = np.abs(x) < np.float32(0.00034526698)
+    out[tiny] = x[tiny]
+    return out

@@ -31,6 +31,7 @@ def _solve(ldeq, rhs, z0, th, t, d=None, **kw):
     z = torch.from_numpy(z0).to(DEV).requires_grad_(d is not None)
     p = torch.from_numpy(th).to(DEV).requires_grad_(d is not None)
     st = []
+    kw.setdefault("sensealg", ldeq.SENSE_DISCRETE_ADJOINT)   # these tests exercise the adjoint kernels of a user RHS
     tr = ldeq.goku_solve(z, p, t, rhs, ldeq.default_opts(**kw), st)
     if d is None:
         return tr.detach().cpu().numpy(), st[0]
