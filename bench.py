@@ -30,16 +30,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "latent trajectory-steps/sec (forward + adjoint)"
+METRIC = "latent trajectory-steps/sec (forward solve + gradient, the reference's ForwardDiffSensitivity semantics)"
 UNIT = "traj-steps/s"
 WORKLOADS = {
     # name: (B per GPU, T, rhs kind, description)
-    "c4": (1 << 20, 200, 0, "C4 sweep: 2^20 pendulum trajectories x 200 save points (t = 0:0.05:9.95), forward + adjoint, "
+    "c4": (1 << 20, 200, 0, "C4 sweep: 2^20 pendulum trajectories x 200 save points (t = 0:0.05:9.95), forward solve + gradient, "
                             "adaptive Tsit5 abstol 1e-6 reltol 1e-3, fp32 state / fp64 time"),
-    "c3": (1024, 50, 1, "C3: pendulum with friction, B = 1024, T = 50, forward + adjoint"),
-    "c1": (64, 50, 0, "C1: friction-less pendulum tutorial shape, B = 64, T = 50, forward + adjoint"),
+    "c3": (1024, 50, 1, "C3: pendulum with friction, B = 1024, T = 50, forward solve + gradient"),
+    "c1": (64, 50, 0, "C1: friction-less pendulum tutorial shape, B = 64, T = 50, forward solve + gradient"),
 }
-CPU_SAMPLE_B = 1 << 18  # bounded CPU sample of the c4 workload (same T, same distribution)
+SENSE_DESC = ("ForwardDiffSensitivity (pendulum.jl:11): 1 primal + 2 dual-number solves per trajectory, partials in the error "
+              "norm -- the library default (LDEQ_SENSE_FORWARD_DUAL) and what the reference arm computes")
+CPU_BUDGET_S = 150.0   # wall-clock bound of the CPU arm's timed steps
+TRAIN_GB, TRAIN_T = 65536, 50   # C5: global batch, frames per sequence
+
+
+def workload_config(name, B, T):
+    """The `config` object: identical on the GPU arm and the reference arm (same workload, same sizes, same gradient)."""
+    return {"workload": WORKLOADS[name][3], "trajectories_per_gpu": B, "save_points": T, "gradient": SENSE_DESC,
+            "sharding": f"independent trajectories, {B} per GPU, no data-path collective (GOKU.jl:111: prob_func indexes column i)",
+            "l2": "inputs larger than L2 (1.68 GB cotangent + 1.68 GB trajectories per step vs 126 MB L2)" if B * T * 8 > (1 << 28)
+                  else "working set smaller than L2: an L2-sized buffer is rewritten between timed steps"}
 
 
 def pendulum_inputs(B, seed=333):
@@ -61,7 +72,7 @@ def measured_peak():
 
 
 def profile_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/)."""
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         return json.load(open(p)).get(kernel)
@@ -126,10 +137,11 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_oracle_throughput(B, T, rhs, steps=1, warmup=0, nthreads=0):
+def cpu_oracle_throughput(B, T, rhs, steps=1, warmup=0, nthreads=0, budget_s=CPU_BUDGET_S):
     """The reference arm / cpu_baseline: the CPU oracle (C++/OpenMP restatement of the reference algorithm:
     per-trajectory Tsit5 under EnsembleThreads, gradients as ForwardDiffSensitivity computes them = 1 primal
-    + 2 dual solves per trajectory) timed on the host cores.  Returns (traj-steps/s, ms per step, cores)."""
+    + 2 dual solves per trajectory) timed on the host cores.  Stops early when the wall-clock budget is spent.
+    Returns (traj-steps/s, ms per step, cores, steps done)."""
     from oracle import goku as og
     og.build()
     nthreads = nthreads or host_cores()
@@ -138,38 +150,106 @@ def cpu_oracle_throughput(B, T, rhs, steps=1, warmup=0, nthreads=0):
     d = np.random.default_rng(334).standard_normal((T, B, 2)).astype(np.float32)
     for _ in range(warmup):
         og.solve(rhs, z0[:4096], th[:4096], t, nthreads=nthreads)
+        og.grad(rhs, z0[:4096], th[:4096], t, d[:, :4096], norm_partials=True, nthreads=nthreads)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
         og.solve(rhs, z0, th, t, nthreads=nthreads)
         og.grad(rhs, z0, th, t, d, norm_partials=True, nthreads=nthreads)
         times.append(time.perf_counter() - t0)
+        if sum(times) + times[-1] > budget_s:
+            break
     dt = float(np.mean(times))
-    return B * (T - 1) / dt, dt * 1e3, nthreads
+    return B * (T - 1) / dt, dt * 1e3, nthreads, len(times)
+
+
+def cpu_training_hot_path(Bs=4096, T=TRAIN_T, reps=2):
+    """The hot-path part of one C5 training step on the host cores, the way the reference runs it: solve + ForwardDiff
+    pullback (oracle, OpenMP), ELBO reduction with its gradient and one ADAMW update (numpy restatements, oracle/loss.py)
+    on a bounded sample of `Bs` sequences.  The encoder / decoder layers are NOT included (out of the hot path)."""
+    from oracle import goku as og
+    from oracle import loss as ol
+    z0, th = pendulum_inputs(Bs, seed=1)
+    t = 0.05 * np.arange(T)
+    rng = np.random.default_rng(0)
+    x = rng.random((T, Bs, 784), dtype=np.float32)
+    xh = rng.random((T, Bs, 784), dtype=np.float32)
+    mus = [rng.standard_normal((Bs, 16)).astype(np.float32) for _ in range(2)]
+    lvs = [0.1 * rng.standard_normal((Bs, 16)).astype(np.float32) for _ in range(2)]
+    n = 503387
+    prm, g, m, v = (rng.standard_normal(n).astype(np.float32) for _ in range(4))
+    d = rng.standard_normal((T, Bs, 2)).astype(np.float32)
+    nth = host_cores()
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        og.solve(0, z0, th, t, nthreads=nth)
+        og.grad(0, z0, th, t, d, norm_partials=True, nthreads=nth)
+        ol.elbo(x, xh, mus, lvs, 0.5)
+        ol.elbo_grad(x, xh, mus, lvs, 0.5)
+        ol.adamw_step(prm, g, np.abs(m), np.abs(v), 1)
+        ts.append(time.perf_counter() - t0)
+    dt = min(ts)
+    return {"value": Bs / dt, "unit": "samples/s", "ms_per_step": dt * 1e3, "cores": nth, "kind": "port",
+            "sample": f"{Bs} of {TRAIN_GB} sequences x {T} frames",
+            "scope": "hot-path part of a training step only (latent solve + ForwardDiff pullback + ELBO + its gradient + ADAMW); "
+                     "the dense / recurrent encoder-decoder layers are not included, so this is an upper bound for the reference"}
 
 
 def run_reference(args):
-    """`--impl reference`: rank 0 only; each step is a bounded sample of the workload on the host cores."""
+    """`--impl reference`: rank 0 only; the reference's algorithm (CPU oracle, Julia is unavailable) on the host cores, on the
+    same workload, sizes and gradient semantics as the GPU arm; the number of timed steps is bounded by a wall-clock budget."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     B, T, rhs, desc = WORKLOADS[args.workload]
-    Bs = min(B, CPU_SAMPLE_B)
-    steps = max(1, min(args.steps, 5))
-    val, ms, cores = cpu_oracle_throughput(Bs, T, rhs, steps=steps, warmup=1)
-    sample = f"{Bs} of {B} trajectories per step (same T={T}, same input distribution), forward + ForwardDiff-style gradient"
+    val, ms, cores, done = cpu_oracle_throughput(B, T, rhs, steps=max(1, args.steps), warmup=1)
+    sample = (f"all {B} trajectories of one GPU's share per step, {done} timed steps of the {args.steps} requested "
+              f"(wall-clock budget {CPU_BUDGET_S:.0f} s), {cores} host threads")
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": done,
         "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "trajectories_per_step": Bs, "save_points": T},
+        "config": workload_config(args.workload, B, T),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "CPU restatement of the reference algorithm (Julia unavailable in this image); "
                                  "optimistic stand-in for Julia+Zygote (no per-trajectory allocation or AD overhead)"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if args.workload == "c4" and not args.no_training:
+        try:
+            line["training"] = cpu_training_hot_path()
+        except Exception as e:  # noqa: BLE001
+            line["training"] = {"unavailable": repr(e)}
     print(json.dumps(line))
+
+
+def _bind_numa(local):
+    """Run this rank (and first-touch its pinned staging buffers) on the NUMA node its GPU hangs off, when the box exposes
+    more than one; returns a short description for the record."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local).pci_bus_id
+        dom = torch.cuda.get_device_properties(local).pci_domain_id
+        dev = torch.cuda.get_device_properties(local).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        want = set()
+        for part in cpus.split(","):
+            lo, _, hi = part.partition("-")
+            want.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = want & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"bound to numa node {node} ({len(use)} cpus)"
+        return f"numa node {node} (no rebinding needed)"
+    except Exception as e:  # noqa: BLE001
+        return f"numa binding skipped: {type(e).__name__}"
 
 
 def run_ours(args):
@@ -185,6 +265,7 @@ def run_ours(args):
         raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_numa(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T, rhs, desc = WORKLOADS[args.workload]
@@ -197,85 +278,69 @@ def run_ours(args):
     gen = torch.Generator(device=dev)
     gen.manual_seed(334 + rank)
     dtraj = torch.randn(T, B, 2, device=dev, generator=gen)
-    opts = ldeq.default_opts()
     h = ldeq.handle(local)
-
-    def step(ev=None):
-        if ev:
-            ev[0].record()
-        traj, _, tape = ldeq.goku_solve_raw(z0, th, t, rhs, opts, want_tape=True, want_stats=False)
-        tape.p_dim = 1
-        if ev:
-            ev[1].record()
-        g = ldeq.goku_bwd_raw(tape, dtraj)
-        if ev:
-            ev[2].record()
-        tape.free()
-        return traj, g
+    small = B * T * 8 <= (1 << 28)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if small else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(W):
-        step()
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    launches0 = h.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(K):
-        step(evs[i])
-    e1.record()
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    launches = h.launch_count() - launches0
-    clocks = sampler.stop() if sampler else None
-    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
-    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
-    if world > 1:
-        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        total_ms = float(tt.item())
-    ms_per_step = total_ms / K
-    value = world * B * (T - 1) / (ms_per_step * 1e-3)
-
-    # the same step with the reference's OWN sensitivity algorithm (two dual-number re-solves per trajectory,
-    # LDEQ_SENSE_FORWARD_DUAL) instead of the discrete adjoint: the parity mode, reported next to the headline
-    ref_sem = None
-    if rhs in (ldeq.RHS_PENDULUM, ldeq.RHS_PENDULUM_FRICTION):
-        import copy
-        opts_fd = copy.copy(opts)
-        opts_fd.sensealg = ldeq.SENSE_FORWARD_DUAL
-
-        def step_fd():
-            _, _, tape = ldeq.goku_solve_raw(z0, th, t, rhs, opts_fd, want_tape=True, want_stats=False)
-            ldeq.goku_bwd_raw(tape, dtraj)
-            tape.free()
-        Kf = max(2, min(K, 5))
-        for _ in range(2):
-            step_fd()
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        for _ in range(Kf):
-            step_fd()
-        f1.record()
-        barrier()
-        fd_ms = f0.elapsed_time(f1) / Kf
+    def allmax(x):
         if world > 1:
-            tt = torch.tensor([fd_ms], device=dev, dtype=torch.float64)
+            tt = torch.tensor([x], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            fd_ms = float(tt.item())
-        ref_sem = {"sensealg": "LDEQ_SENSE_FORWARD_DUAL (ForwardDiffSensitivity restated: dual-number re-solves, partials in the "
-                               "error norm)", "ms_per_step": fd_ms, "value": world * B * (T - 1) / (fd_ms * 1e-3), "unit": UNIT, "steps": Kf}
+            return float(tt.item())
+        return float(x)
 
-    # ---- end to end through the host-buffer C-ABI entry points (pinned host memory) -------------------
+    def device_leg(opts, K, W, sample_clocks=False):
+        """K timed steps of (forward solve recording what the pullback needs, pullback); CUDA events around every kernel
+        group, the total between two barriers."""
+        def step(ev=None):
+            if flush is not None:
+                flush.fill_(1)
+            if ev:
+                ev[0].record()
+            traj, _, tape = ldeq.goku_solve_raw(z0, th, t, rhs, opts, want_tape=True, want_stats=False)
+            tape.p_dim = 1
+            if ev:
+                ev[1].record()
+            g = ldeq.goku_bwd_raw(tape, dtraj)
+            if ev:
+                ev[2].record()
+            tape.free()
+            return traj, g
+        for _ in range(W):
+            step()
+        barrier()
+        sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
+        if sampler:
+            sampler.start()
+        l0 = h.launch_count()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        barrier()
+        for i in range(K):
+            step(evs[i])
+        barrier()
+        launches = h.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in evs]))
+        bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in evs]))
+        # the step = the two kernel groups (the L2 flush of a small workload sits outside the event pairs)
+        total_ms = allmax(float(np.sum([e[0].elapsed_time(e[2]) for e in evs])))
+        return {"ms_per_step": total_ms / K, "fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "launches": int(launches), "clocks": clocks}
+
+    # headline: the library default = the reference's own gradient (dual-number re-solves)
+    opts_fd = ldeq.default_opts()
+    assert opts_fd.sensealg == ldeq.SENSE_FORWARD_DUAL
+    fd = device_leg(opts_fd, K, W, sample_clocks=True)
+    value = world * B * (T - 1) / (fd["ms_per_step"] * 1e-3)
+    # the explicit opt-in: discrete adjoint of the taped accepted steps
+    opts_da = ldeq.default_opts(sensealg=ldeq.SENSE_DISCRETE_ADJOINT)
+    da = device_leg(opts_da, K, W)
+
+    # ---- end to end through the host-buffer C-ABI entry points, ONE caller thread, pinned host memory -----------------
     hz0 = torch.from_numpy(z0n).pin_memory()
     hth = torch.from_numpy(thn).pin_memory()
     hd = torch.empty(T, B, 2, dtype=torch.float32).pin_memory()
@@ -284,121 +349,97 @@ def run_ours(args):
     hdz0 = torch.empty(B, 2, dtype=torch.float32).pin_memory()
     hdth = torch.empty(B, 1, dtype=torch.float32).pin_memory()
 
-    def e2e_step(bufs=None, handle=None):
-        z_, th_, d_, tr_, gz_, gth_ = bufs or (hz0, hth, hd, htraj, hdz0, hdth)
-        _, tape = ldeq.goku_solve_host(z_, th_, t, rhs, opts, device=local, want_tape=True, out=tr_, handle=handle)
-        ldeq.goku_bwd_host(tape, d_, gz_, gth_)
-        tape.free()
-        return float(gz_[0, 0])  # the step's result is read on the host
+    def e2e_leg(opts, combined, Ke):
+        def one():
+            if combined:   # ldeq_solve_fwd_bwd_host: cotangent slabs up while trajectory slabs come down
+                ldeq.goku_fwd_bwd_host(hz0, hth, t, hd, rhs, opts, device=local, out=htraj, dz0=hdz0, dtheta=hdth)
+            else:          # ldeq_solve_fwd_host, then ldeq_solve_bwd_host (what a training step calls)
+                _, tape = ldeq.goku_solve_host(hz0, hth, t, rhs, opts, device=local, want_tape=True, out=htraj)
+                ldeq.goku_bwd_host(tape, hd, hdz0, hdth)
+                tape.free()
+            return float(hdz0[0, 0]) + float(htraj[-1, 0, 0])  # the step's results are read on the host
+        for _ in range(2):
+            one()
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(Ke):
+            one()
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - w0) * 1e3 / Ke
+        barrier()
+        return allmax(ms)
 
     Ke = max(4, min(K, 10))
-    Ke += Ke % 2
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_step()
-    barrier()
-    e2e_ms_single = (time.perf_counter() - w0) * 1e3 / Ke
-
-    # The entry points return when their result is on the host, so one host thread keeps only one direction of the
-    # PCIe link busy at a time (1.69 GB down after the forward kernel, 1.69 GB up before the adjoint).  Independent
-    # batches are served by two host threads, each with its own handle, stream and pinned buffers: the download of
-    # one overlaps the upload of the other.  Same calls, same work per step; the steps are split between the threads.
-    import threading
-    h2 = ldeq.Handle(local)
-    bufs2 = tuple(torch.empty_like(b).pin_memory() for b in (hz0, hth, hd, htraj, hdz0, hdth))
-    for dst, src in zip(bufs2[:3], (hz0, hth, hd)):
-        dst.copy_(src)
-    streams = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-
-    errors = []
-
-    def worker(i, n, go):
-        # thread 1 starts half a step late, so that one thread downloads while the other uploads
-        try:
-            if i:
-                go.wait(120)
-            with torch.cuda.stream(streams[i]):
-                for k in range(n):
-                    z_, th_, d_, tr_, gz_, gth_ = bufs2 if i else (hz0, hth, hd, htraj, hdz0, hdth)
-                    _, tape = ldeq.goku_solve_host(z_, th_, t, rhs, opts, device=local, want_tape=True, out=tr_, handle=h2 if i else None)
-                    if not i and k == 0:
-                        go.set()
-                    ldeq.goku_bwd_host(tape, d_, gz_, gth_)
-                    tape.free()
-                    float(gz_[0, 0])
-        except BaseException as e:  # noqa: BLE001 -- re-raised on the main thread
-            errors.append(e)
-        finally:
-            go.set()
-
-    def run_pair(n):
-        go = threading.Event()
-        th = [threading.Thread(target=worker, args=(i, n, go)) for i in range(2)]
-        for x in th:
-            x.start()
-        for x in th:
-            x.join()
-        if errors:
-            raise errors[0]
-    run_pair(1)
-    barrier()
-    w0 = time.perf_counter()
-    run_pair(Ke // 2)
-    barrier()
-    e2e_ms_dual = (time.perf_counter() - w0) * 1e3 / Ke
-    e2e_streams = 2 if e2e_ms_dual < e2e_ms_single else 1
-    e2e_ms = min(e2e_ms_dual, e2e_ms_single)
-    if world > 1:
-        tt = torch.tensor([e2e_ms, e2e_ms_single], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms, e2e_ms_single = float(tt[0].item()), float(tt[1].item())
-    e2e_value = world * B * (T - 1) / (e2e_ms * 1e-3)
+    e2e_comb = e2e_leg(opts_fd, True, Ke)
+    e2e_sep = e2e_leg(opts_fd, False, Ke)
+    e2e_da_comb = e2e_leg(opts_da, True, Ke)
     h2d = (hz0.numel() + hth.numel() + hd.numel()) * 4
     d2h = (htraj.numel() + hdz0.numel() + hdth.numel()) * 4
 
+    line = None
     if rank == 0:
         peak, peak_src = measured_peak()
-        # algorithmic bytes: forward reads (z+p) s and writes T z s per trajectory; the adjoint
-        # reads the cotangent T z s and writes (z+p) s.  Tape traffic is implementation overhead, not counted.
+        # algorithmic bytes: forward reads (z+p) s and writes T z s per trajectory; a pullback reads the
+        # cotangent T z s (+ z0, theta) and writes its gradient.  Tape traffic is implementation overhead, not counted.
         alg_fwd = B * (12 + 8 * T)
-        alg_bwd = B * (8 * T + 12)
-        fwd_gbs = alg_fwd / (fwd_ms * 1e-3) / 1e9
-        bwd_gbs = alg_bwd / (bwd_ms * 1e-3) / 1e9
+        alg_bwd = B * (8 * T + 12 + 12)
+        alg_fd = 2 * B * (8 * T + 12) + B * 12     # two dual solves, each streams the cotangent once
+        fwd_gbs = alg_fwd / (fd["fwd_ms"] * 1e-3) / 1e9
+        fdp_gbs = alg_fd / (fd["bwd_ms"] * 1e-3) / 1e9
+        bwd_gbs = alg_bwd / (da["bwd_ms"] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": fd["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "trajectories_per_gpu": B, "save_points": T,
-                       "sharding": f"independent trajectories, {B} per GPU, no data-path collective",
-                       "l2": "inputs larger than L2 (1.68 GB cotangent + 1.68 GB trajectories per step vs 126 MB L2)"},
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms, "steps": Ke, "host_threads": e2e_streams,
-                    "single_thread": {"value": world * B * (T - 1) / (e2e_ms_single * 1e-3), "ms_per_step": e2e_ms_single},
-                    "path": "ldeq_solve_fwd_host + ldeq_solve_bwd_host, pinned host buffers"},
-            "gpu_launches": int(launches),
-            "reference_semantics_gradient": ref_sem,
-            "roofline": {"bound": "hbm", "kernel": "tsit5_fwd_kernel<PendulumRHS<float,0>,float,TAPE=1>",
-                         "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak,
-                         "peak_source": peak_src, "launch_ms": fwd_ms, "algorithmic_bytes_per_launch": alg_fwd,
-                         "traffic": profile_traffic("tsit5_fwd_kernel_tape"),
-                         "note": "per-trajectory work is ~37 k issued instructions for 1.6 kB of output: the kernel is "
-                                 "instruction-issue bound (ncu: 79% issue-active), not HBM bound"},
-            "roofline_bwd": {"bound": "hbm", "kernel": "tsit5_bwd_kernel<PendulumRHS<float,0>,float>",
-                             "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
-                             "launch_ms": bwd_ms, "algorithmic_bytes_per_launch": alg_bwd,
-                             "traffic": profile_traffic("tsit5_bwd_kernel")},
+            "config": workload_config(args.workload, B, T),
+            "clocks": fd["clocks"],
+            "e2e": {"value": world * B * (T - 1) / (e2e_comb * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_comb, "steps": Ke, "host_threads": 1, "numa": numa,
+                    "path": "ldeq_solve_fwd_bwd_host (one call, one caller thread, pinned host buffers; batch cut into column slabs, "
+                            "cotangent upload / trajectory download / kernels overlapped on the library's own streams)",
+                    "separate_calls": {"value": world * B * (T - 1) / (e2e_sep * 1e-3), "ms_per_step": e2e_sep,
+                                       "path": "ldeq_solve_fwd_host then ldeq_solve_bwd_host (the pair a training step calls: the "
+                                               "cotangent exists only after the forward result is back on the host)"}},
+            "gpu_launches": fd["launches"],
+            "roofline": {"bound": "hbm", "limiter": "instruction issue",
+                         "kernel": "tsit5_fwdsens_kernel (theta-seeded NP=1 + u0-seeded NP=2 launches of one pullback)",
+                         "achieved": fdp_gbs, "peak": peak, "unit": "GB/s", "frac": fdp_gbs / peak,
+                         "peak_source": peak_src, "launch_ms": fd["bwd_ms"], "algorithmic_bytes_per_launch": alg_fd,
+                         "traffic": profile_traffic("tsit5_fwdsens_kernels"),
+                         "note": "the dominant kernels of the headline step; the dual solves restate the reference's arithmetic "
+                                 "literally (Float64-promoted stage updates, Julia's Float32 sin/cos in Float64): ~1e5 issued "
+                                 "instructions per trajectory for 1.6 kB of cotangent -- instruction-issue bound, not HBM bound; "
+                                 "see issue_model"},
+            "kernels": {
+                "tsit5_fwd_kernel<PendulumRHS<float,0>,float,TAPE=1>": {
+                    "bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak, "launch_ms": fd["fwd_ms"],
+                    "algorithmic_bytes_per_launch": alg_fwd, "traffic": profile_traffic("tsit5_fwd_kernel_tape")},
+                "tsit5_bwd_kernel<PendulumRHS<float,0>,float>": {
+                    "bound": "hbm", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "launch_ms": da["bwd_ms"],
+                    "algorithmic_bytes_per_launch": alg_bwd, "traffic": profile_traffic("tsit5_bwd_kernel")}},
+            "issue_model": profile_traffic("issue_model"),
+            "discrete_adjoint": {
+                "sensealg": "LDEQ_SENSE_DISCRETE_ADJOINT (explicit opt-in: exact derivative of the primal discretisation; equals the "
+                            "reference's gradient only within the solver tolerance)",
+                "value": world * B * (T - 1) / (da["ms_per_step"] * 1e-3), "unit": UNIT, "ms_per_step": da["ms_per_step"],
+                "fwd_ms": da["fwd_ms"], "bwd_ms": da["bwd_ms"], "gpu_launches": da["launches"],
+                "e2e": {"value": world * B * (T - 1) / (e2e_da_comb * 1e-3), "ms_per_step": e2e_da_comb}},
         }
         if world == 1 and not args.no_cpu:
-            Bs = min(B, CPU_SAMPLE_B)
-            val, ms, cores = cpu_oracle_throughput(Bs, T, rhs, steps=1, warmup=1)
+            Bs = min(B, 1 << 18)
+            val, ms, cores, _ = cpu_oracle_throughput(Bs, T, rhs, steps=1, warmup=1)
             line["cpu_baseline"] = {
                 "value": val, "unit": UNIT, "cores": cores, "kind": "port",
                 "sample": f"{Bs} of {B} trajectories (same T={T}), forward + ForwardDiff-style gradient "
                           f"(1 primal + 2 dual solves per trajectory), {ms:.0f} ms"}
+    # ---- C5: GOKU-net data-parallel training step around the hot path (samples/s; gradient all-reduce measured) --------
+    if args.workload == "c4" and not args.no_training:
+        del dtraj, hd, htraj, flush
+        torch.cuda.empty_cache()
+        tr = training_record(ldeq, dev, world, rank, local, steps=max(3, min(K, 8)), warmup=3)
+        if rank == 0:
+            line["training"] = tr
+    if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -411,16 +452,115 @@ def synthetic_frames(theta_angle, device):
     T, B = theta_angle.shape
     ys, xs = torch.meshgrid(torch.arange(28, device=device, dtype=torch.float32),
                             torch.arange(28, device=device, dtype=torch.float32), indexing="ij")
-    cx = 13.5 + 9.5 * torch.cos(torch.pi / 2 + theta_angle)
-    cy = 5.0 + 9.5 * torch.sin(torch.pi / 2 + theta_angle)
-    d2 = (xs.reshape(1, 1, -1) - cx.unsqueeze(-1)) ** 2 + (ys.reshape(1, 1, -1) - cy.unsqueeze(-1)) ** 2
-    return torch.exp(-d2 / (2 * 1.5 ** 2))
+    out = torch.empty(T, B, 784, device=device)
+    for lo in range(0, B, 8192):   # in slices: the (T, B, 784) intermediates of one expression would need 4x the output
+        a = theta_angle[:, lo:lo + 8192]
+        cx = 13.5 + 9.5 * torch.cos(torch.pi / 2 + a)
+        cy = 5.0 + 9.5 * torch.sin(torch.pi / 2 + a)
+        d2 = (xs.reshape(1, 1, -1) - cx.unsqueeze(-1)) ** 2 + (ys.reshape(1, 1, -1) - cy.unsqueeze(-1)) ** 2
+        out[:, lo:lo + 8192] = torch.exp(-d2 / (2 * 1.5 ** 2))
+    return out
+
+
+def training_record(ldeq, dev, world, rank, local, steps, warmup, GB=TRAIN_GB, T=TRAIN_T):
+    """BASELINE.json configs[4] / metric M2: GOKU-net data-parallel training, default architecture (GOKU.jl:199-274, 503 387
+    parameters), global batch 65 536 pendulum sequences of 50 frames cut into contiguous slices (strong scaling), loss =
+    mean over the GLOBAL batch, ONE gradient all-reduce of the flat fp32 bucket per step, identical AdamW on every rank
+    (model_train.jl:186-208 run data-parallel).  Both exchange routes are timed: NCCL all-reduce + AdamW kernel, and the
+    all-reduce fused with AdamW over NVLink peer memory.  Before timing, the two routes take one step from identical
+    weights on identical data and must agree (the multi-rank parity self-test); a mismatch fails the run."""
+    import torch
+    import torch.distributed as dist
+
+    lo, hi = ldeq.shard_bounds(GB, rank, world)
+    Bl = hi - lo
+    t = 0.05 * np.arange(T)
+    z0n, thn = pendulum_inputs(GB, seed=1)
+    with torch.no_grad():   # synthetic data: true pendulum angles from the hot path itself, rasterised on the device
+        ang, _, _ = ldeq.goku_solve_raw(torch.from_numpy(z0n[lo:hi]).to(dev), torch.from_numpy(thn[lo:hi]).to(dev), t, 0)
+        x = synthetic_frames(ang[..., 0], dev)
+    h = ldeq.handle(local)
+
+    def make(symmetric):
+        torch.manual_seed(333)   # same initial weights on every rank and for every route
+        mt = ldeq.GOKU_basic()
+        enc, dec = ldeq.default_layers(mt, 784, ldeq.Pendulum(), device=dev)
+        model = ldeq.LatentDiffEqModel(mt, enc, dec)
+        flat = ldeq.FlatParams(model, symmetric=symmetric)
+        return model, flat, ldeq.ADAMW(flat, 1e-3, (0.9, 0.999), 1e-3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world > 1:
+            tt = torch.tensor(v, device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return [float(a) for a in tt]
+        return [float(a) for a in v]
+
+    routes = [("nccl", False)] + ([("fused", True)] if world > 1 else [])
+    built = {name: make(sym) for name, sym in routes}
+    rec = {"metric": "GOKU-net training samples/sec", "unit": "samples/s", "scaling": "strong", "global_batch": GB, "per_gpu_batch": Bl,
+           "frames_per_sequence": T, "params": int(built["nccl"][1].n), "gradient": "library default (ForwardDiffSensitivity dual solves)",
+           "layers": "encoder / decoder dense and recurrent layers: stock PyTorch fp32 + cuDNN RNN/LSTM (outside the hot path); solve, "
+                     "pullback, sample, ELBO, all-reduce + AdamW: libldeq.so"}
+    # ---- multi-rank parity self-test: fused peer-memory route vs NCCL route, one step from identical state ----
+    if world > 1:
+        torch.manual_seed(1234)
+        ldeq.train_step(*built["nccl"], x, t, beta=0.5, variational=False, global_batch=GB)
+        ldeq.train_step(*built["fused"], x, t, beta=0.5, variational=False, global_batch=GB)
+        a, b = built["nccl"][1].flat[:built["nccl"][1].n], built["fused"][1].flat[:built["fused"][1].n]
+        err = float((a - b).abs().max() / a.abs().max())
+        # replicas must also be identical ACROSS ranks after the step
+        chk = torch.stack([a.double().sum(), b.double().sum()])
+        lo_, hi_ = chk.clone(), chk.clone()
+        dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+        spread = float((hi_ - lo_).abs().max())
+        errs = allmax([err, spread])
+        rec["selftest"] = {"fused_vs_nccl_max_rel_param_diff_after_one_step": errs[0], "replica_checksum_spread_across_ranks": errs[1],
+                           "ranks": world, "pass": bool(errs[0] <= 1e-5 and errs[1] == 0.0)}
+        if not rec["selftest"]["pass"]:
+            raise RuntimeError(f"multi-rank parity self-test failed: {rec['selftest']}")
+    for name, _ in routes:
+        model, flat, opt = built[name]
+        tm = {}
+        for _ in range(warmup):
+            ldeq.train_step(model, flat, opt, x, t, beta=0.5, variational=True, global_batch=GB)
+        barrier()
+        l0 = h.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        segs = []
+        e0.record()
+        for _ in range(steps):
+            tm = {}
+            loss = ldeq.train_step(model, flat, opt, x, t, beta=0.5, variational=True, global_batch=GB, timers=tm)
+            segs.append(tm)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        def seg(a, b):
+            return float(np.mean([s[a].elapsed_time(s[b]) for s in segs]))
+        fwd, bwd, xch = seg("start", "loss"), seg("loss", "backward"), seg("backward", "update")
+        ms, fwd, bwd, xch = allmax([ms, fwd, bwd, xch])
+        rec[name] = {"value": GB / (ms * 1e-3), "ms_per_step": ms, "steps": steps,
+                     "forward_ms": fwd, "backward_ms": bwd, "allreduce_adamw_us": xch * 1e3,
+                     "libldeq_launches_per_step": (h.launch_count() - l0) / steps, "loss": float(loss),
+                     "exchange": ("local AdamW kernel (one GPU: no exchange)" if world == 1 else
+                                  "ncclAllReduce of the 2.0 MB flat fp32 bucket + AdamW kernel" if name == "nccl" else
+                                  "ONE kernel: all-reduce over NVLink peer memory fused with AdamW (+ 2 symmetric-memory barriers)")}
+    best = max((rec[n]["value"], n) for n, _ in routes)
+    rec["value"], rec["route"] = best
+    del built, x
+    torch.cuda.empty_cache()
+    return rec
 
 
 def run_training(args):
-    """`--workload c5`: GOKU-net data-parallel training (BASELINE.json configs[4]): default GOKU architecture
-    (GOKU.jl:199-274), global batch 65 536 pendulum sequences of 50 frames split over the ranks (strong scaling), one
-    flat-bucket NCCL gradient all-reduce + fused AdamW per step.  Metric: training samples/s."""
+    """`--workload c5`: only the training record (see training_record)."""
     import torch
     import torch.distributed as dist
 
@@ -433,55 +573,14 @@ def run_training(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    GB, T = args.global_batch, 50
-    lo, hi = ldeq.shard_bounds(GB, rank, world)
-    B = hi - lo
-    K, W = args.steps, max(args.warmup, 3)
-    torch.manual_seed(333)                                   # same initial weights on every rank
-    mt = ldeq.GOKU_basic()
-    enc, dec = ldeq.default_layers(mt, 784, ldeq.Pendulum(), device=dev)
-    model = ldeq.LatentDiffEqModel(mt, enc, dec)
-    flat = ldeq.FlatParams(model, symmetric=(world > 1 and not args.nccl_allreduce))
-    opt = ldeq.ADAMW(flat, 1e-3, (0.9, 0.999), 1e-3)
-    # synthetic data: true pendulum angles from the hot path itself, rasterised on the device
-    z0n, thn = pendulum_inputs(GB, seed=1)
-    t = 0.05 * np.arange(T)
-    with torch.no_grad():
-        ang, _, _ = ldeq.goku_solve_raw(torch.from_numpy(z0n[lo:hi]).to(dev), torch.from_numpy(thn[lo:hi]).to(dev), t, 0)
-        x = synthetic_frames(ang[..., 0], dev)
-    h = ldeq.handle(local)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(W):
-        ldeq.train_step(model, flat, opt, x, t, beta=0.5, variational=True, global_batch=GB)
-    barrier()
-    l0 = h.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        loss = ldeq.train_step(model, flat, opt, x, t, beta=0.5, variational=True, global_batch=GB)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1) / K
-    if world > 1:
-        tt = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms = float(tt.item())
+    rec = training_record(ldeq, dev, world, rank, local, steps=args.steps, warmup=max(args.warmup, 3), GB=args.global_batch)
     if rank == 0:
         print(json.dumps({
-            "metric": "GOKU-net training samples/sec", "value": GB / (ms * 1e-3), "unit": "samples/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C5: GOKU-net pendulum data-parallel training, default architecture (503 387 params), "
-                                   f"global batch {GB} x 50 frames of 28x28, {B} per GPU, encoder/decoder layers stock PyTorch fp32, "
-                                   "solve + sample + ELBO + AdamW in libldeq.so; gradient: " +
-                                   ("all-reduce fused with AdamW over NVLink peer memory (one kernel)" if flat.symm is not None
-                                    else "one NCCL all-reduce of the 2.0 MB flat bucket + AdamW kernel" if world > 1 else "local")},
-            "gpu_launches": int(h.launch_count() - l0), "loss": float(loss)}))
+            "metric": rec["metric"], "value": rec["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": rec[rec["route"]]["ms_per_step"], "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C5: GOKU-net pendulum data-parallel training, default architecture", "global_batch": args.global_batch},
+            "gpu_launches": int(rec[rec["route"]]["libldeq_launches_per_step"] * args.steps), "training": rec}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -636,7 +735,7 @@ def main():
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS) + ["c5", "c2", "mlp"])
     ap.add_argument("--global-batch", type=int, default=65536, help="c5 only")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--nccl-allreduce", action="store_true", help="c5: NCCL all-reduce + AdamW instead of the fused peer-memory kernel")
+    ap.add_argument("--no-training", action="store_true", help="skip the C5 training sub-record of the default run")
     args = ap.parse_args()
     if args.workload in ("c2", "mlp"):
         if args.impl == "reference":
@@ -645,8 +744,15 @@ def main():
             run_latentode(args)
     elif args.workload == "c5":
         if args.impl == "reference":
-            print(json.dumps({"impl": "reference", "unavailable": "C5 is a training-loop workload: the reference arm "
-                              "(CPU oracle) covers the hot path only (c4/c3/c1)"}))
+            if int(os.environ.get("RANK", "0")) == 0:
+                r = cpu_training_hot_path()
+                print(json.dumps({"impl": "reference", "metric": "GOKU-net training samples/sec", "value": r["value"], "unit": "samples/s",
+                                  "n_gpus": args.gpus, "steps": 2, "warmup": 0, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                                  "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                                  "config": {"workload": "C5: GOKU-net pendulum data-parallel training, default architecture",
+                                             "global_batch": args.global_batch},
+                                  "cpu_baseline": r, "e2e": {"value": r["value"], "unit": "samples/s", "h2d_bytes_per_step": 0,
+                                                             "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
         else:
             run_training(args)
     elif args.impl == "reference":

@@ -94,37 +94,54 @@ __device__ __forceinline__ float ctrl_powf(double x, float y, int exact) {
 // (bit-identical to evaluating fastpow(qold, beta2) then, one logarithm per step instead of two).
 struct PiState {
     float qold_pow;  // fastpow(qold, beta2)
+    // loop invariants, converted to Float32 once per trajectory (they were re-derived from the Float64 options on every
+    // step: 10 F2F + 2 MUFU per step on the quarter-rate XU pipe)
+    float inv_gamma, qlo, qhi, beta1, beta2, qsteady_min, qsteady_max, qoldinit, lg_qoldinit, q22_init;
+    int exact_pow;
 };
-__device__ __forceinline__ PiState pi_init(const KOpts& o) { return PiState{ctrl_powf(o.qoldinit, (float)o.beta2, o.controller_pow)}; }
+__device__ __forceinline__ PiState pi_init(const KOpts& o) {
+    PiState st;
+    st.inv_gamma = (float)(1.0 / o.gamma);
+    st.qlo = (float)(1.0 / o.qmax);
+    st.qhi = (float)(1.0 / o.qmin);
+    st.beta1 = (float)o.beta1;
+    st.beta2 = (float)o.beta2;
+    st.qsteady_min = (float)o.qsteady_min;
+    st.qsteady_max = (float)o.qsteady_max;
+    st.qoldinit = (float)o.qoldinit;
+    st.lg_qoldinit = fastlog2_dev(st.qoldinit);
+    st.exact_pow = o.controller_pow;
+    st.q22_init = ctrl_powf(o.qoldinit, (float)o.beta2, o.controller_pow);
+    st.qold_pow = st.q22_init;
+    return st;
+}
 __device__ __forceinline__ bool pi_controller(const KOpts& o, double EEst, double dts, double dtmax, PiState& st,
                                               double& dt_next) {
     float q, q11 = 1.0f, q22_next = st.qold_pow;
-    const float inv_gamma = (float)(1.0 / o.gamma), qlo = (float)(1.0 / o.qmax), qhi = (float)(1.0 / o.qmin);
     if (EEst == 0.0) {
-        q = qlo;
-        q22_next = ctrl_powf(o.qoldinit, (float)o.beta2, o.controller_pow);
+        q = st.qlo;
+        q22_next = st.q22_init;
     } else {
-        if (o.controller_pow) {
+        if (st.exact_pow) {
             q11 = (float)pow(EEst, o.beta1);
             q22_next = (float)pow(fmax(EEst, o.qoldinit), o.beta2);
         } else {
             const float ef = fabsf((float)EEst);
             const float lg = fastlog2_dev(ef);
-            q11 = exp2f(__fmul_rn((float)o.beta1, lg));
+            q11 = exp2f(__fmul_rn(st.beta1, lg));
             // fastpow(max(EEst, qoldinit), beta2): the Float32 demotion commutes with max
-            const float qf = (float)o.qoldinit;
-            q22_next = exp2f(__fmul_rn((float)o.beta2, ef >= qf ? lg : fastlog2_dev(qf)));
+            q22_next = exp2f(__fmul_rn(st.beta2, ef >= st.qoldinit ? lg : st.lg_qoldinit));
         }
         q = __fdiv_rn(q11, st.qold_pow);
-        q = fmaxf(qlo, fminf(qhi, q * inv_gamma));
+        q = fmaxf(st.qlo, fminf(st.qhi, q * st.inv_gamma));
     }
     const bool accept = EEst <= 1.0;
     if (accept) {
-        if ((float)o.qsteady_min <= q && q <= (float)o.qsteady_max) q = 1.0f;
+        if (st.qsteady_min <= q && q <= st.qsteady_max) q = 1.0f;
         st.qold_pow = q22_next;
         dt_next = fmin(dtmax, dts * (double)__frcp_rn(q));
     } else {
-        dt_next = dts * (double)__frcp_rn(fminf(qhi, q11 * inv_gamma));
+        dt_next = dts * (double)__frcp_rn(fminf(st.qhi, q11 * st.inv_gamma));
     }
     return accept;
 }
@@ -194,6 +211,21 @@ __device__ __forceinline__ float fast_cos_poly(float r2) {
 // out of line: six or seven inlined copies of libdevice's slow path would triple the kernels' code size
 static __device__ __noinline__ float slow_sinf(float x) { return sinf(x); }
 static __device__ __noinline__ void slow_sincosf(float x, float* s, float* c) { sincosf(x, s, c); }
+// The integrators call the unchecked forms: the range test is made ONCE per step on the step's end points (a step whose
+// u_n or u_{n+1} leaves the fast range is redone with libdevice's functions, see tsit5_stages' SAFE flag); the reduction
+// itself stays valid far beyond the tested range (the magic-number rounding up to |x| < 2^22 pi).
+__device__ __forceinline__ float fast_sinf_unchecked(float x) {
+    unsigned sg;
+    const float r = fast_sin_reduce(x, sg);
+    return __uint_as_float(__float_as_uint(fast_sin_poly(r, r * r)) ^ sg);
+}
+__device__ __forceinline__ void fast_sincosf_unchecked(float x, float* s, float* c) {
+    unsigned sg;
+    const float r = fast_sin_reduce(x, sg);
+    const float r2 = r * r;
+    *s = __uint_as_float(__float_as_uint(fast_sin_poly(r, r2)) ^ sg);
+    *c = __uint_as_float(__float_as_uint(fast_cos_poly(r2)) ^ sg);
+}
 __device__ __forceinline__ float fast_sinf(float x) {
     if (!(fabsf(x) <= LDEQ_SINCOS_FAST_MAX)) return slow_sinf(x);
     unsigned sg;
@@ -214,6 +246,12 @@ template <> __device__ __forceinline__ double s_sin_fast<double>(double x) { ret
 template <class S> __device__ __forceinline__ void s_sincos_fast(S x, S* s, S* c);
 template <> __device__ __forceinline__ void s_sincos_fast<float>(float x, float* s, float* c) { fast_sincosf(x, s, c); }
 template <> __device__ __forceinline__ void s_sincos_fast<double>(double x, double* s, double* c) { sincos(x, s, c); }
+template <class S> __device__ __forceinline__ S s_sin_unchecked(S x);
+template <> __device__ __forceinline__ float s_sin_unchecked<float>(float x) { return fast_sinf_unchecked(x); }
+template <> __device__ __forceinline__ double s_sin_unchecked<double>(double x) { return sin(x); }
+template <class S> __device__ __forceinline__ void s_sincos_unchecked(S x, S* s, S* c);
+template <> __device__ __forceinline__ void s_sincos_unchecked<float>(float x, float* s, float* c) { fast_sincosf_unchecked(x, s, c); }
+template <> __device__ __forceinline__ void s_sincos_unchecked<double>(double x, double* s, double* c) { sincos(x, s, c); }
 // quotient for the scaled error estimate: MUFU.RCP + one multiply in Float32 (2 ulp; the estimate itself carries the
 // cancellation noise of sum_j btilde_j k_j, ~1e-3 relative), IEEE in Float64
 template <class S> __device__ __forceinline__ S s_div_fast(S a, S b);

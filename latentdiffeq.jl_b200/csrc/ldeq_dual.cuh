@@ -114,7 +114,10 @@ template <class S, int ZD_, int PD_> struct UserRHS {
     static constexpr int ZD = ZD_;
     static constexpr int PD = PD_;
     struct Aux {};
+    __device__ __forceinline__ static bool fast_ok(const S*) { return true; }  // no reduced-range fast path to guard
+    template <bool SAFE = true>
     __device__ __forceinline__ static void f(S* du, const S* u, const S* p, double t) { ::ldeq_user_rhs<S>(du, u, p, (S)t); }
+    template <bool SAFE = true>
     __device__ __forceinline__ static void f(S* du, const S* u, const S* p, double t, Aux&) { ::ldeq_user_rhs<S>(du, u, p, (S)t); }
     // ubar += (df/du)^T kbar, pbar += (df/dp)^T kbar through one forward-mode evaluation with ZD+PD directions
     __device__ __forceinline__ static void vjp(S* ubar, S* pbar, const S* u, const S* p, double t, const S* kbar,

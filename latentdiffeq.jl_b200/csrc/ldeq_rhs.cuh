@@ -25,17 +25,29 @@ template <class S, bool FRICTION> struct PendulumRHS {
     static constexpr S G = (S)10.0f;
     static constexpr S BM = (S)0.7f / (S)1.0f;
 
+    // SAFE = false: the 13/19-instruction sine / cosine without their range test (the integrator tests the step's end
+    // points once, fast_ok, and redoes the step with SAFE = true -- libdevice -- if one of them is out of range)
+    template <bool SAFE> __device__ __forceinline__ static void sc(S x, S* s, S* c) {
+        if constexpr (SAFE) s_sincos_fast<S>(x, s, c); else s_sincos_unchecked<S>(x, s, c);
+    }
+    template <bool SAFE> __device__ __forceinline__ static S sn(S x) {
+        if constexpr (SAFE) return s_sin_fast<S>(x); else return s_sin_unchecked<S>(x);
+    }
+    __device__ __forceinline__ static bool fast_ok(const S* u) { return sizeof(S) == 8 || s_abs<S>(u[0]) <= (S)LDEQ_SINCOS_FAST_MAX; }
+
+    template <bool SAFE = true>
     __device__ __forceinline__ static void f(S* du, const S* u, const S* p, double, Aux& aux) {
-        s_sincos_fast<S>(u[0], &aux.s, &aux.c);
+        sc<SAFE>(u[0], &aux.s, &aux.c);
         const S w = -G / p[0];
         du[0] = u[1];
         du[1] = FRICTION ? s_fma<S>(w, aux.s, -BM * u[1]) : w * aux.s;
     }
     // forward-only variant (no cosine needed)
+    template <bool SAFE = true>
     __device__ __forceinline__ static void f(S* du, const S* u, const S* p, double) {
         const S w = -G / p[0];
         du[0] = u[1];
-        const S sx = s_sin_fast<S>(u[0]);
+        const S sx = sn<SAFE>(u[0]);
         du[1] = FRICTION ? s_fma<S>(w, sx, -BM * u[1]) : w * sx;
     }
     __device__ __forceinline__ static void vjp(S* ubar, S* pbar, const S*, const S* p, double, const S* kbar,

@@ -50,7 +50,7 @@ template <class S> struct TapeView {
 // g[0..5] (g[0] = u) and the RHS' auxiliaries aux[0..5] for the reverse sweep; k[6] = f(u_{n+1}) is then NOT
 // evaluated -- its value is not needed by the adjoint and its auxiliaries are those of the NEXT step's k1, which the
 // reverse sweep has just used (the caller carries them over).
-template <class RHS, class S, bool KEEP>
+template <class RHS, class S, bool KEEP, bool SAFE>
 __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, double dts, S (*k)[RHS::ZD], S* un,
                                              S (*g)[RHS::ZD], typename RHS::Aux* aux) {
     constexpr int ZD = RHS::ZD;
@@ -61,9 +61,9 @@ __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, d
 #define LDEQ_EVAL(J, TJ)                                   \
     if constexpr (KEEP) {                                  \
         _Pragma("unroll") for (int i = 0; i < ZD; ++i) g[J][i] = gi[i]; \
-        RHS::f(k[J], gi, p, (TJ), aux[J]);                 \
+        RHS::template f<SAFE>(k[J], gi, p, (TJ), aux[J]);  \
     } else {                                               \
-        RHS::f(k[J], gi, p, (TJ));                         \
+        RHS::template f<SAFE>(k[J], gi, p, (TJ));          \
     }
     if constexpr (KEEP) {
 #pragma unroll
@@ -101,8 +101,15 @@ __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, d
     V::axpy(acc, Tb::a75, k[4]);
     V::axpy(acc, Tb::a76, k[5]);
     V::fma(un, h, acc, u);
-    if constexpr (!KEEP) RHS::f(k[6], un, p, t + dts);
+    if constexpr (!KEEP) RHS::template f<SAFE>(k[6], un, p, t + dts);
 #undef LDEQ_EVAL
+}
+
+// out of line: the redo of a step whose end points left the fast sine's range (keeps the hot loop's code small)
+template <class RHS, class S, bool KEEP>
+__device__ __forceinline__ void tsit5_stages_safe(const S* u, const S* p, double t, double dts, S (*k)[RHS::ZD], S* un,
+                                               S (*g)[RHS::ZD], typename RHS::Aux* aux) {
+    tsit5_stages<RHS, S, KEEP, true>(u, p, t, dts, k, un, g, aux);
 }
 
 // scaled RMS error estimate
@@ -338,7 +345,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
     double dt = (o.adaptive && !(o.dt > 0.0)) ? tsit5_initdt<RHS, S>(u, p, k[0], t0, dtmax, dtmin, o) : o.dt;
     PiState pist = pi_init(o);
     int na = 0, nr = 0, ret = RET_SUCCESS;
-    long long iters = 0;
+    int iters_left = (int)(o.maxiters < 0x7fffffffLL ? o.maxiters : 0x7fffffffLL);
 
     const size_t ld = (size_t)ginfo.ld;
     if (traj && live) store_vec<S, ZD>(traj + (size_t)b * ZD, u);  // t[1] == tspan[1]: stored exactly
@@ -354,17 +361,19 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
 
     while (kflush < T) {
         if (active && !pending) {
-            if (iters >= o.maxiters) {
+            if (iters_left <= 0) {
                 ret = RET_MAXITERS;
                 active = false;
             } else {
-                ++iters;
+                --iters_left;
                 // tstop handling: never step past tend; snap onto it within 100 ulp
                 dts = fmin(dt, tend - t);
                 tnew = t + dts;
                 if (fabs(tnew - tend) < (fabs(t) > abs_tend ? 100.0 * ulp_of(fabs(t)) : snap_end)) tnew = tend;
 
-                tsit5_stages<RHS, S, false>(u, p, t, dts, k, un, nullptr, nullptr);
+                tsit5_stages<RHS, S, false, false>(u, p, t, dts, k, un, nullptr, nullptr);
+                if (!(RHS::fast_ok(u) && RHS::fast_ok(un)))  // an end point outside the fast sine's range: libdevice (never for a pendulum)
+                    tsit5_stages_safe<RHS, S, false>(u, p, t, dts, k, un, nullptr, nullptr);
 
                 bool finite = true;
 #pragma unroll
@@ -482,7 +491,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
         // tape.info = {trajectories that ran past the capacity, largest accepted-step count}; one atomic per warp
         const unsigned am = __activemask();
         const int wmax = __reduce_max_sync(am, ret == RET_SUCCESS ? na : 0);
-        const int wover = __reduce_add_sync(am, na > tape.cap ? 1 : 0);
+        const int wover = __reduce_add_sync(am, (ret == RET_SUCCESS && na > tape.cap) ? 1 : 0);
         if ((threadIdx.x & 31) == (__ffs(am) - 1)) {
             if (wover) atomicAdd(tape.info, wover);
             atomicMax(tape.info + 1, wmax);
@@ -519,7 +528,7 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
     const int ret = retcode[bb];
 #pragma unroll
     for (int i = 0; i < PD; ++i) p[i] = theta[(size_t)bb * PD + i];
-    const bool overflow = na > tape.cap;
+    const bool overflow = ret == RET_SUCCESS && na > tape.cap;  // a failed solve has a zero gradient whatever it recorded
     if (!live || ret != RET_SUCCESS || overflow) na = 0;
 
     // rows 1..T-1 of the cotangent travel through the ring: [kload, T) has been fetched so far
@@ -570,7 +579,8 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
                 tn_pre = tape.t[r];
                 load_vec<S, ZD>(tape.u + r * ZD, u_pre);
             }
-            tsit5_stages<RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
+            tsit5_stages<RHS, S, true, false>(u, p, tn, dtn, k, un, g, aux);
+            if (!(RHS::fast_ok(u) && RHS::fast_ok(un))) tsit5_stages_safe<RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
             if (first) {  // the last step of the solve: nothing follows it, evaluate f's auxiliaries at u(tend) here
                 S ktmp[ZD];
                 RHS::f(ktmp, un, p, tn + dtn, aux_next);
