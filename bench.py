@@ -1,17 +1,19 @@
 #!/usr/bin/env python
 """bench.py -- the measurement contract.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c1|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c4|c1|c3|c2|mlp|c5]
 
-Workload (``config.workload``): BASELINE.json configs[3], the C4 sweep at its largest size -- 2^20
-independent pendulum trajectories x 200 save points, forward + adjoint, Float32 state / Float64 time --
-per GPU (weak scaling: every rank integrates its own slice, no data-path collective).  A "step" is
-one pass of the hot path over that batch: ``ldeq_solve_fwd`` (recording the tape) followed by
-``ldeq_solve_bwd``.  ``value`` = trajectory-steps/s (B*(T-1) saved grid intervals per solve) with the
-inputs resident in HBM; ``e2e`` = the same through the host-buffer C-ABI entry points
-(``ldeq_solve_fwd_host`` / ``ldeq_solve_bwd_host``) with pinned host buffers, copies inside the
-timed region.  ``--impl reference`` times the CPU oracle (the reference is pure Julia, which this
-image does not have: the oracle port is the reference arm) on the host cores.
+Default workload (``config.workload``): BASELINE.json configs[3], the C4 sweep at its largest size -- 2^20 independent
+pendulum trajectories x 200 save points, Float32 state / Float64 time -- per GPU (weak scaling: every rank integrates its
+own slice, no data-path collective).  A "step" is one pass of the hot path over that batch: the forward solve
+(``ldeq_solve_fwd``) followed by the pullback of a cotangent (``ldeq_solve_bwd``) in the library's DEFAULT sensitivity
+mode, which is the reference's own: ``ForwardDiffSensitivity`` = two dual-number re-solves per trajectory
+(pendulum.jl:11).  ``value`` = trajectory-steps/s (B*(T-1) saved grid intervals per solve) with the inputs resident in
+HBM; ``e2e`` = the same through ``ldeq_solve_fwd_bwd_host`` from ONE caller thread with pinned host buffers, copies
+inside the timed region.  The cheaper discrete adjoint (explicit opt-in) is reported under ``discrete_adjoint``; a C5
+data-parallel training step (samples/s, gradient all-reduce measured, fused-vs-NCCL parity self-test) under
+``training``.  ``--impl reference`` times the CPU oracle (the reference is pure Julia, which this image does not have:
+the oracle port is the reference arm) on the host cores, same workload, same sizes, same gradient semantics.
 
 One JSON line on stdout (rank 0).
 """
@@ -177,7 +179,8 @@ def cpu_training_hot_path(Bs=4096, T=TRAIN_T, reps=2):
     mus = [rng.standard_normal((Bs, 16)).astype(np.float32) for _ in range(2)]
     lvs = [0.1 * rng.standard_normal((Bs, 16)).astype(np.float32) for _ in range(2)]
     n = 503387
-    prm, g, m, v = (rng.standard_normal(n).astype(np.float32) for _ in range(4))
+    prm, g = (rng.standard_normal(n).astype(np.float32) for _ in range(2))
+    opt = ol.ADAMW(1e-3, (0.9, 0.999), np.float32(0.001))
     d = rng.standard_normal((T, Bs, 2)).astype(np.float32)
     nth = host_cores()
     ts = []
@@ -185,9 +188,9 @@ def cpu_training_hot_path(Bs=4096, T=TRAIN_T, reps=2):
         t0 = time.perf_counter()
         og.solve(0, z0, th, t, nthreads=nth)
         og.grad(0, z0, th, t, d, norm_partials=True, nthreads=nth)
-        ol.elbo(x, xh, mus, lvs, 0.5)
-        ol.elbo_grad(x, xh, mus, lvs, 0.5)
-        ol.adamw_step(prm, g, np.abs(m), np.abs(v), 1)
+        ol.loss_batch(x, xh, mus, lvs, 0.5)
+        ol.loss_batch_grads(x, xh, mus, lvs, 0.5)
+        opt.update("flat", prm, g)
         ts.append(time.perf_counter() - t0)
     dt = min(ts)
     return {"value": Bs / dt, "unit": "samples/s", "ms_per_step": dt * 1e3, "cores": nth, "kind": "port",
@@ -586,13 +589,16 @@ def run_training(args):
 
 
 def _latentode_inputs(workload):
-    from oracle import mlp as om   # weights only (glorot init of nODE.jl:14-16)
-
+    """Flux-default weights of nODE.jl:14-16 (glorot_uniform, zero bias) packed in Flux.destructure order."""
     B = 256 if workload == "c2" else 18944
     T, dims = 50, [16, 200, 200, 16]
     rng = np.random.Generator(np.random.PCG64(1))
-    layers = [(om.glorot_uniform(rng, dims[i + 1], dims[i]), np.zeros(dims[i + 1], np.float32)) for i in range(3)]
-    p = om.pack_params(layers).astype(np.float32)
+    parts = []
+    for i in range(3):
+        lim = np.sqrt(6.0 / (dims[i] + dims[i + 1]))
+        W = rng.uniform(-lim, lim, (dims[i + 1], dims[i])).astype(np.float32)
+        parts += [W.T.reshape(-1), np.zeros(dims[i + 1], np.float32)]
+    p = np.concatenate(parts).astype(np.float32)
     z = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
     d = rng.standard_normal((T, B, 16)).astype(np.float32)
     return B, T, dims, p, z, d, 0.05 * np.arange(T)

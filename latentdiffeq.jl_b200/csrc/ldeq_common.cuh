@@ -286,8 +286,11 @@ template <> __device__ __forceinline__ void store_vec<double, 2>(double* __restr
 // Every stage combination, dense-output coefficient, error estimate and adjoint update of the integrators is
 // "scalar x ZD-vector (+ ZD-vector)".  For the two-dimensional Float32 state of the GOKU pendulums that is exactly one
 // packed fma.rn.f32x2 (FFMA2 in SASS, sm_100): half the issue slots of two FFMAs, and the scalar rides along as an
-// immediate / 32-bit register broadcast.  NVRTC (user right-hand sides) takes the generic loops.
-template <class S, int N> struct VecOps {
+// immediate / 32-bit register broadcast.  Measured at 2^20 x 200 (same box, A/B builds): the adjoint kernel gains 8 %
+// (1.185 -> 1.097 ms: its reverse sweep is 21 + 21 vector updates per step with no scalar work in between), the forward
+// kernel LOSES 3 % (1.240 -> 1.281 ms: pairing the operands costs register moves around the scalar sine chains), so the
+// kernels choose per call site (PACK).  NVRTC (user right-hand sides) takes the generic loops.
+template <class S, int N, bool PACK = true> struct VecOps {
     // out = a * x
     __device__ __forceinline__ static void scale(S* out, S a, const S* x) {
 #pragma unroll
@@ -310,7 +313,7 @@ template <class S, int N> struct VecOps {
     }
 };
 #if !defined(__CUDACC_RTC__) && !defined(LDEQ_NO_F32X2)
-template <> struct VecOps<float, 2> {
+template <> struct VecOps<float, 2, true> {
     __device__ __forceinline__ static void scale(float* out, float a, const float* x) {
         const float2 r = __fmul2_rn(make_float2(a, a), make_float2(x[0], x[1]));
         out[0] = r.x; out[1] = r.y;

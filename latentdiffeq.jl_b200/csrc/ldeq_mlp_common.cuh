@@ -521,7 +521,8 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
                         const double e2 = GLOBAL ? part / ((double)D * (double)B) : ts->esum[b] / (double)D;
                         const double EEst = (double)s_sqrt<S>((S)e2);
                         if (EEst != EEst) finite = false;
-                        PiState pst{(float)ts->qold[b]};
+                        PiState pst = pi_init(o);  // loop invariants; the controller memory lives in shared memory per row
+                        pst.qold_pow = (float)ts->qold[b];
                         accept = pi_controller(o, EEst, ts->dts[b], dtmax, pst, dt_next);
                         ts->qold[b] = (double)pst.qold_pow;
                     }

@@ -50,12 +50,12 @@ template <class S> struct TapeView {
 // g[0..5] (g[0] = u) and the RHS' auxiliaries aux[0..5] for the reverse sweep; k[6] = f(u_{n+1}) is then NOT
 // evaluated -- its value is not needed by the adjoint and its auxiliaries are those of the NEXT step's k1, which the
 // reverse sweep has just used (the caller carries them over).
-template <class RHS, class S, bool KEEP, bool SAFE>
+template <class RHS, class S, bool KEEP, bool SAFE, bool PACK = KEEP>
 __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, double dts, S (*k)[RHS::ZD], S* un,
                                              S (*g)[RHS::ZD], typename RHS::Aux* aux) {
     constexpr int ZD = RHS::ZD;
     using Tb = Tab<S>;
-    using V = VecOps<S, ZD>;
+    using V = VecOps<S, ZD, PACK>;
     const S h = (S)dts;
     S gi[ZD], acc[ZD];
 #define LDEQ_EVAL(J, TJ)                                   \
@@ -116,7 +116,7 @@ __device__ __forceinline__ void tsit5_stages_safe(const S* u, const S* p, double
 template <class S, int ZD>
 __device__ __forceinline__ double tsit5_eest(const S* u, const S* un, S (*k)[ZD], double dts, S abstol, S reltol) {
     using Tb = Tab<S>;
-    using V = VecOps<S, ZD>;
+    using V = VecOps<S, ZD, false>;
     const S h = (S)dts;
     S s[ZD];
     V::scale(s, Tb::bt1, k[0]);
@@ -178,7 +178,7 @@ __device__ double tsit5_initdt(const S* u0, const S* p, const S* f0, double t0, 
 template <class S, int ZD>
 __device__ __forceinline__ void interp_coeffs(S (*k)[ZD], S (*c)[ZD]) {
     using Tb = Tab<S>;
-    using V = VecOps<S, ZD>;
+    using V = VecOps<S, ZD, false>;
 #pragma unroll
     for (int i = 0; i < ZD; ++i) c[0][i] = k[0][i];  // r11 = 1
     V::scale(c[1], Tb::r12, k[0]); V::scale(c[2], Tb::r13, k[0]); V::scale(c[3], Tb::r14, k[0]);
@@ -308,7 +308,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                  int* __restrict__ nreject, TapeView<S> tape, GridInfo ginfo) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
     using RingT = Ring<S, ZD>;
-    using V = VecOps<S, ZD>;
+    using V = VecOps<S, ZD, false>;  // forward kernel: scalar FFMAs (see VecOps)
     constexpr int R = RingT::R;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RingT ring{reinterpret_cast<S*>(smem_raw) + threadIdx.x * ZD, (int)blockDim.x * ZD};

@@ -18,11 +18,9 @@ def loss_batch(model, x, t, beta, variational):
     """model_train.jl:225-238.  ``x`` is ``[T, B, P]``."""
     X_hat, mu, logvar = model(x, t, variational)
     x_hat, z_hat, l_hat = X_hat
-    if x.is_cuda:
-        return elbo_loss(x, x_hat, mu, logvar, beta)
-    from .utils import vector_kl
-    rec = ((x - x_hat) ** 2).mean(dim=(0, 1)).sum()
-    return rec + beta * vector_kl(mu, logvar)
+    if not x.is_cuda:
+        raise RuntimeError("loss_batch runs in libldeq.so on a CUDA device (no CPU fallback)")
+    return elbo_loss(x, x_hat, mu, logvar, beta)
 
 
 def shard_bounds(n: int, rank: int, world: int):
@@ -114,20 +112,30 @@ def allreduce_grads(flat: FlatParams):
         dist.all_reduce(flat.grad, op=dist.ReduceOp.SUM)
 
 
-def train_step(model, flat: FlatParams, opt: ADAMW, x_local, t, beta, variational=True, global_batch=None):
+def train_step(model, flat: FlatParams, opt: ADAMW, x_local, t, beta, variational=True, global_batch=None, timers=None):
     """One data-parallel training step on this rank's slice ``x_local`` ``[T, B_local, P]``.
 
     The loss is a mean over the GLOBAL batch: the local loss is scaled by ``B_local / B_global`` before the
-    backward pass, gradients are summed across ranks, and every rank applies the same AdamW update."""
+    backward pass, gradients are summed across ranks, and every rank applies the same AdamW update.
+    ``timers`` (a dict) receives CUDA events at the phase boundaries: start, loss, backward, update."""
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     B_local = x_local.shape[1]
     B_global = global_batch or B_local * world
+    def mark(name):
+        if timers is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            timers[name] = ev
+    mark("start")
     flat.zero_grad()
     loss = loss_batch(model, x_local, t, beta, variational)
+    mark("loss")
     (loss * (B_local / B_global)).backward()
+    mark("backward")
     if flat.symm is not None:
         opt.fused_allreduce_step()
     else:
         allreduce_grads(flat)
         opt.step()
+    mark("update")
     return loss.detach()
