@@ -33,8 +33,22 @@ Base.@kwdef mutable struct Opts
     tape_steps::Int32 = 0
     norm_mode::Int32 = 0
     mlp_math::Int32 = 0
-    sensealg::Int32 = 0   # 0 discrete adjoint of the primal steps, 1 the reference's dual-number re-solves (LDEQ_SENSE_FORWARD_DUAL)
+    sensealg::Int32 = 1   # 1 = LDEQ_SENSE_FORWARD_DUAL, the reference's dual-number re-solves (default); 0 = discrete adjoint
+    solver::Int32 = 0     # 0 = LDEQ_SOLVER_TSIT5
+    reserved_::Int32 = 0
 end
+
+# explicit opt-in sensealg of this glue (not a SciMLSensitivity type): the discrete adjoint of the taped accepted steps
+struct DiscreteAdjoint end
+
+# the diffeq struct's `sensealg` and `solver` fields (pendulum.jl:11,58; read at GOKU.jl:106-107) -> ldeq_opts codes.
+# Anything libldeq does not implement is an error, never silently replaced.
+function sensealg_code(s)
+    s isa DiscreteAdjoint && return Int32(0)
+    nameof(typeof(s)) === :ForwardDiffSensitivity && return Int32(1)   # SciMLSensitivity / DiffEqSensitivity, whichever is loaded
+    error("sensealg $(typeof(s)) not supported by libldeq: use ForwardDiffSensitivity() (the reference's) or LatentDiffEqB200.DiscreteAdjoint()")
+end
+solver_code(s) = nameof(typeof(s)) === :Tsit5 ? Int32(0) : error("solver $(typeof(s)) not supported by libldeq: the hot path implements Tsit5()")
 
 # the `kwargs` field of the diffeq struct is splatted into `solve` by the reference (GOKU.jl:108,121)
 function Opts(kwargs::Union{NamedTuple,Base.Pairs,Dict})
@@ -44,6 +58,14 @@ function Opts(kwargs::Union{NamedTuple,Base.Pairs,Dict})
         hasproperty(o, k) || error("solver option $k is not supported by libldeq")
         setproperty!(o, k, convert(fieldtype(Opts, k), v))
     end
+    return o
+end
+
+# everything the reference reads from a GOKU diffeq struct (GOKU.jl:105-108): kwargs, sensealg, solver
+function Opts(diffeq)
+    o = Opts(diffeq.kwargs)
+    hasproperty(diffeq, :sensealg) && (o.sensealg = sensealg_code(diffeq.sensealg))
+    hasproperty(diffeq, :solver) && (o.solver = solver_code(diffeq.solver))
     return o
 end
 
@@ -63,14 +85,43 @@ end
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float64}) = Cint(1)
 
-# which built-in right-hand side a diffeq struct stands for; user structs add a method (or use ldeq_rhs_from_source)
-rhs_kind(diffeq) = error("define LatentDiffEqB200.rhs_kind(::$(typeof(diffeq))) (0 = Pendulum, 1 = Pendulum_friction)")
+# Right-hand side of a diffeq struct.  Built-ins: define `rhs_kind(::MyPendulum) = 0` (Pendulum) or `1` (Pendulum_friction).
+# Any other `f!`: define `rhs_source(::MyDiffEq)` returning CUDA C for
+#     template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t)
+# (compiled once per handle by NVRTC through ldeq_rhs_from_source; z_dim / p_dim come from `prob.u0` / `prob.p`,
+# exactly what GOKU.jl:207-208 reads).
+rhs_kind(diffeq) = nothing
+rhs_source(diffeq) = nothing
 
+# one ldeq_rhs per (handle, diffeq type): created on first use, released by `release!` (or process exit)
+const RHS_CACHE = Dict{Tuple{Ptr{Cvoid},DataType},Ptr{Cvoid}}()
 function rhs_object(h, diffeq)
-    r = Ref{Ptr{Cvoid}}(C_NULL)
-    check(h, ccall((:ldeq_rhs_builtin, libldeq), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}), h, rhs_kind(diffeq), r))
-    r[]
+    get!(RHS_CACHE, (h, typeof(diffeq))) do
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        if rhs_kind(diffeq) !== nothing
+            check(h, ccall((:ldeq_rhs_builtin, libldeq), Cint, (Ptr{Cvoid}, Cint, Ptr{Ptr{Cvoid}}), h, rhs_kind(diffeq), r))
+        elseif rhs_source(diffeq) !== nothing
+            check(h, ccall((:ldeq_rhs_from_source, libldeq), Cint, (Ptr{Cvoid}, Cstring, Cint, Cint, Ptr{Ptr{Cvoid}}),
+                           h, rhs_source(diffeq), length(diffeq.prob.u0), length(diffeq.prob.p), r))
+        else
+            error("define LatentDiffEqB200.rhs_kind(::$(typeof(diffeq))) or LatentDiffEqB200.rhs_source(::$(typeof(diffeq)))")
+        end
+        r[]
+    end
 end
+
+# free every cached right-hand side and handle (call before unloading the library / at the end of a script)
+function release!()
+    for ((h, _), r) in RHS_CACHE
+        ccall((:ldeq_rhs_free, libldeq), Cvoid, (Ptr{Cvoid}, Ptr{Cvoid}), h, r)
+    end
+    empty!(RHS_CACHE)
+    for (_, h) in HANDLES
+        ccall((:ldeq_destroy, libldeq), Cvoid, (Ptr{Cvoid},), h)
+    end
+    empty!(HANDLES)
+end
+atexit(release!)
 
 mutable struct Tape
     ptr::Ptr{Cvoid}
@@ -83,7 +134,7 @@ function solve_fwd(diffeq, ẑ₀::CuMatrix{T}, θ̂::CuMatrix{T}, t; tape::Bool
     z, B = size(ẑ₀)
     tt = collect(Float64, t)                           # the reference's t is a Float64 range
     ẑ = CUDA.zeros(T, z, B, length(tt))                # (z, B, T): what permutedims(.,[1,3,2]) yields, GOKU.jl:125
-    opts = Ref(Opts(diffeq.kwargs))
+    opts = Ref(Opts(diffeq))                           # kwargs + sensealg + solver
     tp = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:ldeq_solve_fwd, libldeq), Cint,
                (Ptr{Cvoid}, Ptr{Cvoid}, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Ref{Opts}, CuPtr{Cvoid},
@@ -136,7 +187,7 @@ function mlp_fwd(diffeq, ẑ₀::CuMatrix{T}, t; tape::Bool) where {T}
     dims = mlp_dims(diffeq.dudt)
     tt = collect(Float64, t)
     ẑ = CUDA.zeros(T, D, B, length(tt))
-    opts = Ref(Opts(diffeq.kwargs))
+    opts = Ref(Opts(diffeq))                          # kwargs + solver (a NODE struct has no sensealg field, nODE.jl:3-12)
     tp = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:ldeq_mlp_solve_fwd, libldeq), Cint,
                (Ptr{Cvoid}, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Int32}, Cint, Ptr{Cdouble}, Cint, Cint, Ref{Opts}, CuPtr{Cvoid},
@@ -170,20 +221,78 @@ function ChainRulesCore.rrule(::typeof(diffeq_layer), decoder::Decoder{LatentODE
     return transform_after_diffeq(ẑ, diffeq), pullback
 end
 
-# ---- the host-array methods of the reference (GOKU.jl:102-103: `cpu(...)`) can use the *_host entry points ------
-function diffeq_layer(decoder::Decoder{M}, l̂::Tuple{Matrix{Float32},Matrix{Float32}}, t) where {M<:GOKU}
+# ---- the host-array path the reference actually takes (GOKU.jl:102-103: `cpu(...)`, then `solve` on the CPU) ---------
+# Forward: ldeq_solve_fwd_host; pullback: ldeq_solve_bwd_host (host cotangent in, host gradients out).  The library cuts
+# the batch into column slabs and overlaps the copies with the kernels on its own streams.
+function solve_fwd_host(diffeq, ẑ₀::Matrix{T}, θ̂::Matrix{T}, t; tape::Bool) where {T<:Union{Float32,Float64}}
     h = handle()
-    ẑ₀, θ̂ = l̂
     z, B = size(ẑ₀)
     tt = collect(Float64, t)
-    ẑ = Array{Float32}(undef, z, B, length(tt))
+    ẑ = Array{T}(undef, z, B, length(tt))
+    tp = Ref{Ptr{Cvoid}}(C_NULL)
     check(h, ccall((:ldeq_solve_fwd_host, libldeq), Cint,
                    (Ptr{Cvoid}, Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}, Cint, Cint, Ref{Opts}, Ptr{Cvoid},
                     Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
-                   h, rhs_object(h, decoder.diffeq), Cint(0), ẑ₀, θ̂, tt, B, length(tt), Ref(Opts(decoder.diffeq.kwargs)), ẑ,
-                   C_NULL, C_NULL, C_NULL, C_NULL, CUDA.stream().handle))
+                   h, rhs_object(h, diffeq), dtype_code(T), ẑ₀, θ̂, tt, B, length(tt), Ref(Opts(diffeq)), ẑ,
+                   C_NULL, C_NULL, C_NULL, tape ? tp : C_NULL, CUDA.stream().handle))
+    return ẑ, Tape(tp[], false)
+end
+
+function diffeq_layer(decoder::Decoder{M}, l̂::Tuple{Matrix{T},Matrix{T}}, t) where {M<:GOKU,T<:Union{Float32,Float64}}
+    ẑ, _ = solve_fwd_host(decoder.diffeq, l̂[1], l̂[2], t; tape = false)
     return transform_after_diffeq(ẑ, decoder.diffeq)
 end
+
+function ChainRulesCore.rrule(::typeof(diffeq_layer), decoder::Decoder{M}, l̂::Tuple{Matrix{T},Matrix{T}}, t) where {M<:GOKU,T<:Union{Float32,Float64}}
+    ẑ₀, θ̂ = l̂
+    ẑ, tape = solve_fwd_host(decoder.diffeq, ẑ₀, θ̂, t; tape = true)
+    function pullback(Δ)
+        h = handle()
+        Δh = convert(Array{T,3}, unthunk(Δ))
+        dẑ₀, dθ̂ = similar(ẑ₀), similar(θ̂)
+        check(h, ccall((:ldeq_solve_bwd_host, libldeq), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                       h, tape.ptr, Δh, dẑ₀, dθ̂, CUDA.stream().handle))
+        ccall((:ldeq_tape_free, libldeq), Cvoid, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), h, tape.ptr, CUDA.stream().handle)
+        return NoTangent(), NoTangent(), Tangent{typeof(l̂)}(dẑ₀, dθ̂), NoTangent()
+    end
+    return transform_after_diffeq(ẑ, decoder.diffeq), pullback
+end
+
+# ---- the steps either side of the solve that libldeq also provides (GOKU.jl:155-173, model_train.jl:225-238, :138) ------
+# z̃ = μ + ε ⊙ exp(logσ²/2) with ε drawn on the device (the reference draws it on the host and uploads it, GOKU.jl:169-170)
+function sample_device(μ::CuMatrix{Float32}, logσ²::CuMatrix{Float32}; seed::Integer = rand(UInt64), offset::Integer = 0)
+    h = handle()
+    z̃, ε = similar(μ), similar(μ)
+    check(h, ccall((:ldeq_sample, libldeq), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, Int64, UInt64, UInt64, Ptr{Cvoid}),
+                   h, μ, logσ², z̃, ε, length(μ), seed, offset, CUDA.stream().handle))
+    return z̃, ε
+end
+
+# loss_batch's reduction + its gradient in one pass: x, x̂ (P,B,T); μs / logσ²s tuples of (d,B) heads
+function elbo_fwd_bwd(x::CuArray{Float32,3}, x̂::CuArray{Float32,3}, μs::Tuple, logσ²s::Tuple, β::Real; grad_scale::Real = 1)
+    h = handle()
+    P, B, T = size(x)
+    nh = length(μs)
+    loss = CUDA.zeros(Float32, 3)
+    dx̂ = similar(x̂)
+    dμs, dlvs = map(similar, μs), map(similar, logσ²s)
+    ptrs(xs) = Ptr{Cvoid}[reinterpret(Ptr{Cvoid}, pointer(a)) for a in xs]
+    check(h, ccall((:ldeq_elbo_fwd_bwd, libldeq), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cfloat}, CuPtr{Cfloat}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Cint, Cfloat, Cint, Cint, Cint,
+                    Cfloat, CuPtr{Cfloat}, CuPtr{Cfloat}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
+                   h, x, x̂, ptrs(μs), ptrs(logσ²s), Int32[size(m, 1) for m in μs], nh, β, B, T, P, grad_scale, loss, dx̂,
+                   ptrs(dμs), ptrs(dlvs), CUDA.stream().handle))
+    return loss, dx̂, dμs, dlvs
+end
+
+# Flux ADAMW(η, (β₁, β₂), decay) on the flat parameter vector of Flux.destructure(model); `step` is 1-based
+adamw_step!(p::CuVector{Float32}, g::CuVector{Float32}, m::CuVector{Float32}, v::CuVector{Float32}, step::Integer;
+            η = 1e-3, β = (0.9, 0.999), ϵ = 1e-8, decay = 1f-3, grad_scale = 1f0) =
+    check(handle(), ccall((:ldeq_adamw_step, libldeq), Cint,
+                          (Ptr{Cvoid}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, Int64, Cdouble, Cdouble, Cdouble, Cdouble,
+                           Cfloat, Int64, Cfloat, Ptr{Cvoid}),
+                          handle(), p, g, m, v, length(p), η, β[1], β[2], ϵ, decay, step, grad_scale, CUDA.stream().handle))
 
 
 # ---- data-parallel training: one Julia process per GPU, flat gradient summed with NCCL through the C ABI ---------------

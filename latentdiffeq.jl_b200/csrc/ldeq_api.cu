@@ -154,14 +154,15 @@ static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj,
     const void* theta = tape->theta;
     const double* tg = tape->tgrid;
     int B = tape->B, T = tape->T, np = 1;
+    GridInfo gi{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld};
     KOpts kov = tape->kopts;
     const int32_t* ret = tape->retcode;
     const int grid = (B + 127) / 128;
     const int base = tape->dtype == LDEQ_F32 ? 6 : 8;
-    void* args_p[] = {&z0, &theta, &tg, &B, &ld, &T, &kov, &np, &dtraj, &ret, &dtheta};
+    void* args_p[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &dtraj, &ret, &dtheta};
     cudaError_t e = cudaLaunchKernel(tape->rhs->fn[base], dim3(grid), dim3(128), args_p, 0, s);
     if (e != cudaSuccess) return e;
-    void* args_u[] = {&z0, &theta, &tg, &B, &ld, &T, &kov, &np, &dtraj, &ret, &dz0};
+    void* args_u[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &dtraj, &ret, &dz0};
     return cudaLaunchKernel(tape->rhs->fn[base + 1], dim3(grid), dim3(128), args_u, 0, s);
 }
 

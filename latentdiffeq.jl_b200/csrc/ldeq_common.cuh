@@ -65,6 +65,14 @@ struct KOpts {
     int controller_pow;
 };
 
+// the save grid as the kernels see it: t0 + k h when the host has verified that bit for bit (uniform), and the row
+// stride of the (z,B,T) arrays (a kernel may work on a column slab of a wider batch)
+struct GridInfo {
+    double t0, h;
+    int uniform;
+    int ld;  // row stride (in trajectories) of the (z,B,T) arrays: the kernel may work on a column slab of a wider batch
+};
+
 enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTLESSTHANMIN = 2, RET_UNSTABLE = 3 };
 
 // ---- DiffEqBase.fastpow: Float32 rational log2 on the significand, Float32 exp2 ------------------

@@ -26,18 +26,19 @@ template <bool FRICTION> struct PendulumDualRHS {
 
 template <class S, int NP, bool FRICTION, bool SEED_P>
 __global__ void __launch_bounds__(128, 4)
-tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, int ld, int T,
+tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
                      KOpts o, int norm_partials, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                      S* __restrict__ dout) {
-    tsit5_fwdsens_body<PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, ld, T, o, norm_partials, dtraj, primal_ret, dout);
+    tsit5_fwdsens_body<PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, gi, T, o, norm_partials, dtraj, primal_ret, dout);
 }
 
 template <class S, bool FR>
 static cudaError_t launch_fwdsens_t(const ldeq_tape* tp, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     const int B = tp->B, grid = (B + 127) / 128;
-    tsit5_fwdsens_kernel<S, 1, FR, true><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, ld, tp->T, tp->kopts, 1,
+    const GridInfo gi{tp->grid_t0, tp->grid_h, tp->grid_uniform, ld};
+    tsit5_fwdsens_kernel<S, 1, FR, true><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, gi, tp->T, tp->kopts, 1,
                                                              (const S*)dtraj, tp->retcode, (S*)dtheta);
-    tsit5_fwdsens_kernel<S, 2, FR, false><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, ld, tp->T, tp->kopts, 1,
+    tsit5_fwdsens_kernel<S, 2, FR, false><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, gi, tp->T, tp->kopts, 1,
                                                               (const S*)dtraj, tp->retcode, (S*)dz0);
     return cudaGetLastError();
 }

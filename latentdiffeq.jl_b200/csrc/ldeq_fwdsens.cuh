@@ -68,7 +68,7 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 // SEED_P: partials seeded on theta (NP = PD) -> dout = dtheta (p,B);  else on u0 (NP = ZD) -> dout = dz0 (z,B)
 template <class RHS, class S, int NP, bool SEED_P>
 __device__ __forceinline__ void
-tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, int ld, int T,
+tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
                    KOpts o, int norm_partials, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                    S* __restrict__ dout) {
     constexpr int Z = RHS::ZD, PD = RHS::PD;
@@ -77,6 +77,9 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
     using Td = Tab<double>;
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const int ld = gi.ld;
+    // save times of a verified-uniform grid are one DFMA (bit-identical to the table, ldeq_api.cu::upload_tgrid), not a load
+    auto tgrid = [&](int k) -> double { return gi.uniform ? fma((double)k, gi.h, gi.t0) : tg[k]; };
     const bool wp = norm_partials != 0;
     D u[Z], k[7][Z], unew[Z], tmp[Z], sum, L[PD];
     for (int i = 0; i < Z; ++i) {
@@ -209,8 +212,8 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
             for (int i = 0; i < Z; ++i) wsum[i] = w1[i] = w2[i] = w3[i] = w4[i] = (S)0;
             bool interior = false;
             const double inv = 1.0 / dts;
-            while (ks < T && tg[ks] <= tnew) {
-                const double tsv = tg[ks];
+            double tsv = ks < T ? tgrid(ks) : 0.0;
+            while (ks < T && tsv <= tnew) {
                 S dv[Z];
 #pragma unroll
                 for (int i = 0; i < Z; ++i) dv[i] = dtraj[((size_t)ks * ld + b) * Z + i];
@@ -233,6 +236,7 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
                     interior = true;
                 }
                 ++ks;
+                tsv = ks < T ? tgrid(ks) : 0.0;
             }
             if (interior) {
 #pragma unroll

@@ -210,11 +210,6 @@ __device__ __forceinline__ void interp_coeffs_adj(S (*cb)[ZD], S (*kbar)[ZD]) {
 // A grid the host has verified to be t0 + k*h bit for bit (GridInfo::uniform) is not looked up at all: a save time
 // is one DFMA, and the save points that fall into a step are found by ONE division per step (count_le) instead of one
 // Float64 comparison per save point.
-struct GridInfo {
-    double t0, h;
-    int uniform;
-    int ld;  // row stride (in trajectories) of the (z,B,T) arrays: the kernel may work on a column slab of a wider batch
-};
 struct TGrid {
     const double* __restrict__ g;
     const double* s;

@@ -67,3 +67,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "libldeq_oracle" not in txt, f
+
+
+def test_c_program_compiles_against_the_header_alone():
+    """tests/cabi_smoke.c includes only include/ldeq.h + the CUDA runtime header; it must compile and link here (no GPU
+    needed for that) -- the executable stand-in for the Julia `ccall` sequence."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_entry", os.path.join(ROOT, "__graft_entry__.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    exe = m.build_cabi_smoke()
+    assert os.path.exists(exe)
+    src = open(os.path.join(ROOT, "tests", "cabi_smoke.c")).read()
+    assert "#include <Python.h>" not in src and "#include <torch" not in src
+
+
+@pytest.mark.gpu
+def test_c_program_drives_the_abi():
+    import subprocess
+    exe = os.path.join(ROOT, "tests", "cabi_smoke")
+    if not os.path.exists(exe):
+        pytest.skip("tests/cabi_smoke not built (run __graft_entry__.build())")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "cabi_smoke ok" in r.stdout, r.stdout + r.stderr
