@@ -733,6 +733,16 @@ def run_latentode(args):
 
 
 def main():
+    # the contract is ONE JSON line on stdout: libraries that print there (NCCL's version banner, warnings) are sent to
+    # stderr for the whole run, and the JSON line goes to the real stdout
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    _orig_print = print
+
+    def emit(*a, **k):
+        sys.stdout.flush()
+        os.write(real_stdout, (" ".join(str(x) for x in a) + "\n").encode())
+    globals()["print"] = emit
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -8,6 +8,7 @@ model / layer / diffeq-struct API above that ABI.  The directory name contains a
 through the repo-root shim: ``import latentdiffeq_jl_b200 as ldeq``.
 """
 from . import _cabi
+from . import bson_io
 from ._cabi import (F32, F64, RHS_PENDULUM, RHS_PENDULUM_FRICTION, RET_SUCCESS, RET_MAXITERS, RET_DTLESSTHANMIN,
                     RET_UNSTABLE, NORM_GLOBAL, NORM_PER_TRAJ, MLP_MATH_FP32, MLP_MATH_BF16X3, LdeqError, default_opts,
                     handle, Handle, SENSE_DISCRETE_ADJOINT, SENSE_FORWARD_DUAL)
