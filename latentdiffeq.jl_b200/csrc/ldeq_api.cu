@@ -540,6 +540,7 @@ int ldeq_tape_overflow(ldeq_handle* h, ldeq_tape* tape, int32_t* count_host, lde
     *count_host = 0;
     auto one = [&](ldeq_tape* t) -> int {
         LDEQ_CUDA(cudaEventSynchronize(t->ready));
+        if (t->sense == LDEQ_SENSE_FORWARD_DUAL) return LDEQ_OK;  // the dual re-solves keep no step records: nothing can overflow
         *count_host += t->checked && t->h_info[0] > 0 && t->cap >= t->h_info[1] ? 0 : t->h_info[0];
         return LDEQ_OK;
     };
