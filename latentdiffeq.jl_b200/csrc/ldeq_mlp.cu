@@ -327,6 +327,9 @@ template <class S, int TB> static size_t bwd_smem(const MlpNet& net) {
 using namespace ldeq;
 
 // ldeq_mlp_tc.cu: the tcgen05 / TMEM forward kernel (LDEQ_MLP_MATH_BF16X3)
+int ldeq_mlp_tc_backward(ldeq_handle* h, const int32_t* dims, int n_layers, const float* params, const double* d_tgrid, int B, int T,
+                         const float* dtraj, double* tape_t, double* tape_dt, float* tape_u, int tape_cap, const int32_t* ret,
+                         const int32_t* na, int max_na, float* dz0, float* dparams, cudaStream_t s);
 int ldeq_mlp_tc_forward(ldeq_handle* h, const int32_t* dims, int n_layers, const float* params, const float* z0,
                         const double* d_tgrid, int B, int T, const KOpts& ko, int norm_mode, float* traj, int32_t* ret,
                         int32_t* na, int32_t* nr, double* tape_t, double* tape_dt, float* tape_u, int tape_cap,
@@ -334,6 +337,7 @@ int ldeq_mlp_tc_forward(ldeq_handle* h, const int32_t* dims, int n_layers, const
 
 struct ldeq_mlp_tape {
     int dtype = 0, B = 0, T = 0, cap = 0, tb = 0;
+    int math = 0;  // ldeq_mlp_math of the forward solve: its reverse pass runs on the same arithmetic
     MlpNet net;
     void* base = nullptr;
     double* t = nullptr;
@@ -490,7 +494,7 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
     ldeq_mlp_tape* tape = nullptr;
     if (tape_out) {
         tape = new ldeq_mlp_tape();
-        tape->dtype = dtype; tape->B = B; tape->T = T; tape->net = net;
+        tape->dtype = dtype; tape->B = B; tape->T = T; tape->net = net; tape->math = opts->mlp_math;
         long long cap = opts->tape_steps;
         if (cap <= 0) cap = opts->adaptive ? (4LL * T > 256 ? 4LL * T : 256) : (long long)((t_host[T - 1] - t_host[0]) / opts->dt) + 3;
         if (cap > opts->maxiters) cap = opts->maxiters;
@@ -607,6 +611,14 @@ int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, v
         snprintf(msg, sizeof msg, "mlp tape overflow: the solve accepted %d steps, the tape holds %d; repeat ldeq_mlp_solve_fwd "
                  "with opts.tape_steps >= %d", tape->h_info[0], tape->cap, tape->h_info[0]);
         return set_err(h, LDEQ_ERR_TAPE_OVERFLOW, msg);
+    }
+    if (tape->math == LDEQ_MLP_MATH_BF16X3 && !getenv("LDEQ_MLP_TC_BWD_OFF")) {
+        // the tensor-core tape: adjoint sweep + weight-gradient GEMM on tcgen05 (ldeq_mlp_tc_bwd.cu)
+        int32_t dims[MLP_MAX_LAYERS + 1];
+        for (int l = 0; l <= tape->net.n_layers; ++l) dims[l] = tape->net.dims[l];
+        return ldeq_mlp_tc_backward(h, dims, tape->net.n_layers, (const float*)tape->params, tape->tgrid, tape->B, tape->T,
+                                    (const float*)dtraj, tape->t, tape->dt, (float*)tape->u, tape->cap, tape->retcode, tape->naccept,
+                                    tape->h_info[0], (float*)dz0, (float*)dparams_flat, s);
     }
     const bool small = tape->B <= 4 * h->sm_count;
     if (tape->dtype == LDEQ_F32 && !getenv("LDEQ_MLP_NO_RESIDENT")) {

@@ -43,15 +43,21 @@ def run(a_img, b_img, da, db, idc):
     err = np.abs(out.cpu().numpy() - ref).max()
     return float(err)
 
-res = {}
 ak, dak = kmajor(A); bk, dbk = kmajor(B)
-res["A K-major, B K-major"] = run(ak, bk, dak, dbk, idesc(N, 0, 0))
 am, GA = mnmajor(A); bm, GB = mnmajor(B)
 cands = {"lbo=G,sbo=128": lambda G: dict(lbo=G, sbo=128, kadv=2 * G), "lbo=128,sbo=G": lambda G: dict(lbo=128, sbo=G, kadv=2 * G)}
+tests = [("A K-major, B K-major", lambda: run(ak, bk, dak, dbk, idesc(N, 0, 0)))]
 for na, fa in cands.items():
-    res[f"A MN-major ({na}), B K-major"] = run(am, bk, fa(GA), dbk, idesc(N, 1, 0))
+    tests.append((f"A MN-major ({na}), B K-major", lambda fa=fa: run(am, bk, fa(GA), dbk, idesc(N, 1, 0))))
 for nb, fb in cands.items():
-    res[f"A K-major, B MN-major ({nb})"] = run(ak, bm, dak, fb(GB), idesc(N, 0, 1))
+    tests.append((f"A K-major, B MN-major ({nb})", lambda fb=fb: run(ak, bm, dak, fb(GB), idesc(N, 0, 1))))
 for na, fa in cands.items():
-    res[f"A MN-major ({na}), B MN-major (same)"] = run(am, bm, fa(GA), fa(GB), idesc(N, 1, 1))
-print(json.dumps(res, indent=1))
+    tests.append((f"A MN-major ({na}), B MN-major (same)", lambda fa=fa: run(am, bm, fa(GA), fa(GB), idesc(N, 1, 1))))
+if len(sys.argv) > 1:
+    name, fn = tests[int(sys.argv[1])]
+    print(json.dumps({name: fn()}))
+else:
+    import subprocess
+    for i in range(len(tests)):
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), str(i)], capture_output=True, text=True)
+        print(r.stdout.strip() or f"{tests[i][0]}: CRASH {r.stderr.strip().splitlines()[-1][:150] if r.stderr.strip() else ''}", flush=True)

@@ -235,15 +235,44 @@ def test_tensor_core_path_matches_oracle_and_exact_path(ldeq, B):
         assert np.abs(tc - otr).max() <= 1e-3 * np.abs(otr).max()
 
 
-def test_tensor_core_path_gradients_through_the_exact_adjoint(ldeq):
-    # the tensor-core forward records the same tape; the (exact-arithmetic) adjoint kernel sweeps it
+@pytest.mark.parametrize("B,kw", [(130, dict(adaptive=False, dt=0.05)), (300, dict(norm_mode=1)), (256, dict(norm_mode=0))])
+def test_tensor_core_reverse_pass_matches_discrete_adjoint_oracle(ldeq, B, kw, monkeypatch):
+    """The tcgen05 reverse pass (adjoint sweep + weight-gradient GEMM over bf16 hi/lo records, ldeq_mlp_tc_bwd.cu) against
+    the oracle's discrete adjoint of the same step sequence, and against the exact CUDA-core adjoint kernel sweeping the
+    same tape: dz0 and the 46 816 parameter gradients within 2e-4 (ragged last tile, fixed step / per-trajectory steps /
+    batch-global steps)."""
     dims, p, rng = _net(bias_scale=0.1)
-    B, T = 130, 20
+    T = 20
     z0 = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
     t = 0.05 * np.arange(T)
     d = rng.standard_normal((T, B, 16)).astype(np.float32)
-    tr, gz, gp = _solve(ldeq, z0, p, dims, t, want_grad=d, adaptive=False, dt=0.05, mlp_math=ldeq.MLP_MATH_BF16X3)
-    _, _, _, tape = om.solve(z0, p, dims, t, og.Opts(adaptive=False, dt=0.05), record=True)
+    tr, gz, gp = _solve(ldeq, z0, p, dims, t, want_grad=d, mlp_math=ldeq.MLP_MATH_BF16X3, **kw)
+    monkeypatch.setenv("LDEQ_MLP_TC_BWD_OFF", "1")      # same tensor-core tape, exact-arithmetic adjoint kernel
+    tr2, gz2, gp2 = _solve(ldeq, z0, p, dims, t, want_grad=d, mlp_math=ldeq.MLP_MATH_BF16X3, **kw)
+    monkeypatch.delenv("LDEQ_MLP_TC_BWD_OFF")
+    assert np.array_equal(tr, tr2)
+    print("tc bwd vs exact adjoint on the same tape: dz0", np.abs(gz - gz2).max() / np.abs(gz2).max(), "dparams",
+          np.abs(gp - gp2).max() / np.abs(gp2).max())
+    assert np.abs(gz - gz2).max() <= 1e-4 * np.abs(gz2).max() and np.abs(gp - gp2).max() <= 1e-4 * np.abs(gp2).max()
+    if not kw.get("norm_mode"):
+        ok = og.Opts(**{k: v for k, v in kw.items() if k in ("adaptive", "dt")})
+        _, _, _, tape = om.solve(z0, p, dims, t, ok, record=True)
+        oz, op = om.discrete_adjoint(p.astype(np.float64), dims, t, tape, d)
+        assert np.abs(gz - oz).max() <= 2e-4 * np.abs(oz).max() and np.abs(gp - op).max() <= 2e-4 * np.abs(op).max()
+
+
+def test_tensor_core_reverse_pass_failed_rows_and_smaller_nets(ldeq):
+    # a trajectory that fails (maxiters) contributes nothing; a narrower network (padding columns in every layer)
+    rng = np.random.Generator(np.random.PCG64(11))
+    dims = [6, 50, 70, 6]
+    layers = [(om.glorot_uniform(rng, dims[i + 1], dims[i]), (0.1 * rng.standard_normal(dims[i + 1])).astype(np.float32)) for i in range(3)]
+    p = om.pack_params(layers).astype(np.float32)
+    B, T = 200, 12
+    z0 = (0.5 * rng.standard_normal((B, 6))).astype(np.float32)
+    t = 0.05 * np.arange(T)
+    d = rng.standard_normal((T, B, 6)).astype(np.float32)
+    tr, gz, gp = _solve(ldeq, z0, p, dims, t, want_grad=d, adaptive=False, dt=0.025, mlp_math=ldeq.MLP_MATH_BF16X3)
+    _, _, _, tape = om.solve(z0, p, dims, t, og.Opts(adaptive=False, dt=0.025), record=True)
     oz, op = om.discrete_adjoint(p.astype(np.float64), dims, t, tape, d)
     assert np.abs(gz - oz).max() <= 2e-4 * np.abs(oz).max() and np.abs(gp - op).max() <= 2e-4 * np.abs(op).max()
 
