@@ -13,7 +13,7 @@
 //      What the parameter gradient needs -- per (tile, step, stage) the operands g, h1, h2, kbar, dz1, dz2 -- leaves the
 //      SM as bf16 hi/lo records, 16-byte chunks written straight into the MN-major canonical layout.
 //  mlp_tc_wgrad_kernel a split-K GEMM over those records:  dW2 += dz2^T h1,  dW1 += dz1^T [g 1],  dW3^T += h2^T kbar  with the
-//      record tiles bulk-copied (TMA) into a two-stage shared-memory ring as BOTH operands (MN-major A and B), fp32
+//      record slices (16 rows, one bulk TMA copy each) streamed through a four-stage shared-memory ring as BOTH operands (MN-major A and B), fp32
 //      accumulators for all three products resident in TMEM (416 + 64 + 32 = 512 columns), bf16x3 products.  The bias
 //      gradients are the constant-1 column of h1 / h2 / [g 1] (ldeq_mlp_tc.cuh: the padded bias entry is 1).
 //  mlp_tc_wgrad_reduce_kernel sums the per-CTA partials into Flux.destructure order.
@@ -22,21 +22,27 @@
 namespace ldeq {
 
 // ---- record geometry ------------------------------------------------------------------------------------------------
-// One block = the operands of one (tile, step, stage): 128 rows (the reduction dimension of the weight gradient).
-// A part of F features is stored as [16 row groups][F/8 chunks][8 rows] x 16 bytes: element (feature f, row r) at
-//   (r/8) * (F/8)*128 + (f/8)*128 + (r%8)*16 + (f%8)*2   -- the MN-major no-swizzle canonical layout (LBO = (F/8)*128, SBO = 128).
+// One block = the operands of one (tile, step, stage): 128 rows (the reduction dimension of the weight gradient), stored as
+// 8 SLICES of 16 rows; a slice is one pipeline stage of the weight-gradient kernel and is contiguous in memory, so that a
+// stage is ONE bulk copy.  Inside a slice every operand ("part") of F features holds its two 8-row groups as
+//   [2 row groups][F/8 chunks][8 rows] x 16 bytes: element (feature f, row r) at ((r/8)%2) * (F/8)*128 + (f/8)*128 + (r%8)*16 + (f%8)*2
+// -- the MN-major no-swizzle canonical layout (LBO = (F/8)*128 between row groups, SBO = 128 between feature chunks).
 struct TcRec {
     int nch1, nch2;                     // 16-byte chunks per row of an n1- / n2-wide part
-    unsigned p1, p2, pg, pd;            // bytes of one part: n1-wide, n2-wide, [g 1] (32 features), kbar (16 features)
-    unsigned o_h1h, o_h1l, o_z1h, o_z1l, o_h2h, o_h2l, o_z2h, o_z2l, o_gh, o_gl, o_dh, o_dl;
-    unsigned block_bytes;
+    // byte offsets of the parts inside a slice (A operands whose second M-tile reads past their own part come first)
+    unsigned o_z2h, o_z2l, o_z1h, o_z1l, o_h2h, o_h2l, o_h1h, o_h1l, o_gh, o_gl, o_dh, o_dl;
+    unsigned slice_bytes, block_bytes;
     int nsteps;                         // step slots per tile (largest accepted-step count of the batch)
 };
 #define TC_G_FEATS 32
 #define TC_D_FEATS 16
+#define TC_SLICE_ROWS 16
 
-__device__ __forceinline__ void st_chunk(unsigned char* part, int nch, int row, int chunk, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    *reinterpret_cast<uint4*>(part + ((size_t)(row >> 3) * nch + chunk) * 128 + (row & 7) * 16) = make_uint4(a, b, c, d);
+// 16 bytes (8 features) of `row` into chunk `chunk` of the part at offset `part_off` of its slice
+__device__ __forceinline__ void st_chunk(unsigned char* blk, const TcRec& rec, unsigned part_off, int nch, int row, int chunk, uint32_t a,
+                                         uint32_t b, uint32_t c, uint32_t d) {
+    *reinterpret_cast<uint4*>(blk + (size_t)(row >> 4) * rec.slice_bytes + part_off + ((size_t)((row >> 3) & 1) * nch + chunk) * 128 +
+                              (row & 7) * 16) = make_uint4(a, b, c, d);
 }
 __device__ __forceinline__ void tc_st4(uint32_t taddr, const uint32_t* r) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
@@ -54,7 +60,7 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float* v) {
 // forward epilogue of a hidden layer + record + relu mask: acc -> h = relu(acc + bias) -> bf16 hi/lo in place, the same
 // 16-byte chunks to the record, bit (c - c_lo + i) of `mask` = [h > 0]
 __device__ __forceinline__ void adj_epilogue_fwd(uint32_t region, const float* __restrict__ bias, int c_lo, int c_hi, int row,
-                                                 unsigned char* rec_hi, unsigned char* rec_lo, int nch, bool rec, uint32_t* mask) {
+                                                 unsigned char* blk, const TcRec& rec, unsigned o_hi, unsigned o_lo, int nch, uint32_t* mask) {
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += 16) {
         float v[16];
@@ -71,17 +77,15 @@ __device__ __forceinline__ void adj_epilogue_fwd(uint32_t region, const float* _
         split_pack16(v, hi, lo);
         tc_st8(region + c, hi);
         tc_st8(region + c + 8, lo);
-        if (rec) {
-            st_chunk(rec_hi, nch, row, c >> 3, hi[0], hi[1], hi[2], hi[3]);
-            st_chunk(rec_hi, nch, row, (c >> 3) + 1, hi[4], hi[5], hi[6], hi[7]);
-            st_chunk(rec_lo, nch, row, c >> 3, lo[0], lo[1], lo[2], lo[3]);
-            st_chunk(rec_lo, nch, row, (c >> 3) + 1, lo[4], lo[5], lo[6], lo[7]);
-        }
+        st_chunk(blk, rec, o_hi, nch, row, c >> 3, hi[0], hi[1], hi[2], hi[3]);
+        st_chunk(blk, rec, o_hi, nch, row, (c >> 3) + 1, hi[4], hi[5], hi[6], hi[7]);
+        st_chunk(blk, rec, o_lo, nch, row, c >> 3, lo[0], lo[1], lo[2], lo[3]);
+        st_chunk(blk, rec, o_lo, nch, row, (c >> 3) + 1, lo[4], lo[5], lo[6], lo[7]);
     }
 }
 // reverse epilogue: acc -> dz = acc .* mask -> bf16 hi/lo in place + record
-__device__ __forceinline__ void adj_epilogue_bwd(uint32_t region, int c_lo, int c_hi, int row, unsigned char* rec_hi,
-                                                 unsigned char* rec_lo, int nch, bool rec, const uint32_t* mask) {
+__device__ __forceinline__ void adj_epilogue_bwd(uint32_t region, int c_lo, int c_hi, int row, unsigned char* blk, const TcRec& rec,
+                                                 unsigned o_hi, unsigned o_lo, int nch, const uint32_t* mask) {
 #pragma unroll 1
     for (int c = c_lo; c < c_hi; c += 16) {
         float v[16];
@@ -94,12 +98,10 @@ __device__ __forceinline__ void adj_epilogue_bwd(uint32_t region, int c_lo, int 
         split_pack16(v, hi, lo);
         tc_st8(region + c, hi);
         tc_st8(region + c + 8, lo);
-        if (rec) {
-            st_chunk(rec_hi, nch, row, c >> 3, hi[0], hi[1], hi[2], hi[3]);
-            st_chunk(rec_hi, nch, row, (c >> 3) + 1, hi[4], hi[5], hi[6], hi[7]);
-            st_chunk(rec_lo, nch, row, c >> 3, lo[0], lo[1], lo[2], lo[3]);
-            st_chunk(rec_lo, nch, row, (c >> 3) + 1, lo[4], lo[5], lo[6], lo[7]);
-        }
+        st_chunk(blk, rec, o_hi, nch, row, c >> 3, hi[0], hi[1], hi[2], hi[3]);
+        st_chunk(blk, rec, o_hi, nch, row, (c >> 3) + 1, hi[4], hi[5], hi[6], hi[7]);
+        st_chunk(blk, rec, o_lo, nch, row, c >> 3, lo[0], lo[1], lo[2], lo[3]);
+        st_chunk(blk, rec, o_lo, nch, row, (c >> 3) + 1, lo[4], lo[5], lo[6], lo[7]);
     }
 }
 
@@ -251,16 +253,14 @@ mlp_tc_adj_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                     tc_st8(R1 + 8, lo);
                     tc_wait_st();
                     if (hf == 0) {  // [g 1]: 16 state features, the constant 1, zero padding
-                        unsigned char* gh = blk + rec.o_gh;
-                        unsigned char* gl = blk + rec.o_gl;
-                        st_chunk(gh, TC_G_FEATS / 8, row, 0, hi[0], hi[1], hi[2], hi[3]);
-                        st_chunk(gh, TC_G_FEATS / 8, row, 1, hi[4], hi[5], hi[6], hi[7]);
-                        st_chunk(gh, TC_G_FEATS / 8, row, 2, 0x00003F80u, 0u, 0u, 0u);  // bf16(1.0) in feature 16
-                        st_chunk(gh, TC_G_FEATS / 8, row, 3, 0u, 0u, 0u, 0u);
-                        st_chunk(gl, TC_G_FEATS / 8, row, 0, lo[0], lo[1], lo[2], lo[3]);
-                        st_chunk(gl, TC_G_FEATS / 8, row, 1, lo[4], lo[5], lo[6], lo[7]);
-                        st_chunk(gl, TC_G_FEATS / 8, row, 2, 0u, 0u, 0u, 0u);
-                        st_chunk(gl, TC_G_FEATS / 8, row, 3, 0u, 0u, 0u, 0u);
+                        st_chunk(blk, rec, rec.o_gh, TC_G_FEATS / 8, row, 0, hi[0], hi[1], hi[2], hi[3]);
+                        st_chunk(blk, rec, rec.o_gh, TC_G_FEATS / 8, row, 1, hi[4], hi[5], hi[6], hi[7]);
+                        st_chunk(blk, rec, rec.o_gh, TC_G_FEATS / 8, row, 2, 0x00003F80u, 0u, 0u, 0u);  // bf16(1.0) in feature 16
+                        st_chunk(blk, rec, rec.o_gh, TC_G_FEATS / 8, row, 3, 0u, 0u, 0u, 0u);
+                        st_chunk(blk, rec, rec.o_gl, TC_G_FEATS / 8, row, 0, lo[0], lo[1], lo[2], lo[3]);
+                        st_chunk(blk, rec, rec.o_gl, TC_G_FEATS / 8, row, 1, lo[4], lo[5], lo[6], lo[7]);
+                        st_chunk(blk, rec, rec.o_gl, TC_G_FEATS / 8, row, 2, 0u, 0u, 0u, 0u);
+                        st_chunk(blk, rec, rec.o_gl, TC_G_FEATS / 8, row, 3, 0u, 0u, 0u, 0u);
                     }
                 }
                 tc_fence_before();
@@ -276,7 +276,7 @@ mlp_tc_adj_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 mbar_wait(&mbar[hf], par_half);
                 par_half ^= 1;
                 tc_fence_after();
-                adj_epilogue_fwd(R0, bias1, c1_lo, c1_hi, row, blk + rec.o_h1h, blk + rec.o_h1l, rec.nch1, true, m1[st]);
+                adj_epilogue_fwd(R0, bias1, c1_lo, c1_hi, row, blk, rec, rec.o_h1h, rec.o_h1l, rec.nch1, m1[st]);
                 tc_wait_st();
                 tc_fence_before();
                 __syncthreads();
@@ -291,7 +291,7 @@ mlp_tc_adj_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 mbar_wait(&mbar[hf], par_half);
                 par_half ^= 1;
                 tc_fence_after();
-                adj_epilogue_fwd(R1, bias2, c2_lo, c2_hi, row, blk + rec.o_h2h, blk + rec.o_h2l, rec.nch2, true, m2[st]);
+                adj_epilogue_fwd(R1, bias2, c2_lo, c2_hi, row, blk, rec, rec.o_h2h, rec.o_h2l, rec.nch2, m2[st]);
                 tc_wait_st();
                 tc_fence_before();
                 __syncthreads();
@@ -332,8 +332,8 @@ mlp_tc_adj_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                     tc_st4(R1 + hf * 4, hi);
                     tc_st4(R1 + 8 + hf * 4, lo);
                     tc_wait_st();
-                    st_chunk(blk + rec.o_dh, TC_D_FEATS / 8, row, hf, hi[0], hi[1], hi[2], hi[3]);
-                    st_chunk(blk + rec.o_dl, TC_D_FEATS / 8, row, hf, lo[0], lo[1], lo[2], lo[3]);
+                    st_chunk(blk, rec, rec.o_dh, TC_D_FEATS / 8, row, hf, hi[0], hi[1], hi[2], hi[3]);
+                    st_chunk(blk, rec, rec.o_dl, TC_D_FEATS / 8, row, hf, lo[0], lo[1], lo[2], lo[3]);
                 }
                 tc_fence_before();
                 __syncthreads();
@@ -348,7 +348,7 @@ mlp_tc_adj_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 mbar_wait(&mbar[hf], par_half);
                 par_half ^= 1;
                 tc_fence_after();
-                adj_epilogue_bwd(R0, c2_lo, c2_hi, row, blk + rec.o_z2h, blk + rec.o_z2l, rec.nch2, true, m2[st]);
+                adj_epilogue_bwd(R0, c2_lo, c2_hi, row, blk, rec, rec.o_z2h, rec.o_z2l, rec.nch2, m2[st]);
                 tc_wait_st();
                 tc_fence_before();
                 __syncthreads();
@@ -363,7 +363,7 @@ mlp_tc_adj_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 mbar_wait(&mbar[hf], par_half);
                 par_half ^= 1;
                 tc_fence_after();
-                adj_epilogue_bwd(R1, c1_lo, c1_hi, row, blk + rec.o_z1h, blk + rec.o_z1l, rec.nch1, true, m1[st]);
+                adj_epilogue_bwd(R1, c1_lo, c1_hi, row, blk, rec, rec.o_z1h, rec.o_z1l, rec.nch1, m1[st]);
                 tc_wait_st();
                 tc_fence_before();
                 __syncthreads();
@@ -429,13 +429,9 @@ mlp_tc_adj_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
 
 // ---- the weight-gradient GEMM over the records ------------------------------------------------------------------------
 #define WG_THREADS 192       // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue (TMEM lane quadrants 2,3,0,1)
-#define WG_ROWS 32           // rows (K of the GEMM) per pipeline stage: a quarter of a record block
-#define WG_STAGES 2
+#define WG_ROWS 16           // rows (K of the GEMM) per pipeline stage: one MMA K-step, an eighth of a record block
+#define WG_STAGES 4          // 4 x 56 kB: deep enough to keep the TMA loads ahead of the MMAs (2 x 112 kB ran at 2 TB/s)
 // TMEM columns: dW2 [0, 416): M-tile 0 -> [0, n1), M-tile 1 -> [208, 208 + n1);  dW1 [416, 480): 2 x 32;  dW3^T [480, 512): 2 x 16
-
-struct WgStage {  // byte offsets of the parts inside one pipeline stage buffer
-    unsigned h1h, h1l, z1h, z1l, h2h, h2l, z2h, z2l, gh, gl, dh, dl, bytes;
-};
 
 __device__ __forceinline__ void tc_mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -463,7 +459,7 @@ __device__ __forceinline__ void wg_issue(uint32_t d_tmem, uint32_t a_hi, uint32_
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-mlp_tc_wgrad_kernel(TcNet net, TcRec rec, WgStage sg, const unsigned char* __restrict__ records, const int* __restrict__ tile_nsteps,
+mlp_tc_wgrad_kernel(TcNet net, TcRec rec, const unsigned char* __restrict__ records, const int* __restrict__ tile_nsteps,
                     int ntiles, float* __restrict__ partials /* [grid][n2*n1 + n1*32 + n2*16] */) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t full_bar[WG_STAGES], empty_bar[WG_STAGES], done_bar;
@@ -479,7 +475,7 @@ mlp_tc_wgrad_kernel(TcNet net, TcRec rec, WgStage sg, const unsigned char* __res
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     // the tail a second M-tile reads past the last part of the last stage must be finite: zero the slack once
-    for (int i = tid; i < 1024 / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem + (size_t)WG_STAGES * sg.bytes)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 1024 / 16; i += WG_THREADS) reinterpret_cast<uint4*>(smem + (size_t)WG_STAGES * rec.slice_bytes)[i] = make_uint4(0, 0, 0, 0);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tc_fence_before();
     __syncthreads();
@@ -489,66 +485,57 @@ mlp_tc_wgrad_kernel(TcNet net, TcRec rec, WgStage sg, const unsigned char* __res
     const int quarters = TC_ROWS / WG_ROWS;
 
     // items of this CTA: (tile, step, stage, quarter), blocks dealt round-robin over the grid
-    if (warp == 0 && lane == 0) {
-        // ===== TMA producer =====
+    if (warp == 0) {
+        // ===== TMA producer: the whole warp.  One bulk copy is served as a single stream (a 56 kB copy per stage ran at
+        // 2.1 TB/s, twelve smaller ones at 2.6 TB/s): every lane issues 1/32 of the slice, 32 copies in flight per stage =====
         int it = 0;
-        long long blk_lin = 0;
+        unsigned base = 0;  // linear index of this tile's first block, modulo the grid
+        const uint32_t piece = rec.slice_bytes / 32;   // the slice size is a multiple of 512 bytes
         for (int tile = 0; tile < ntiles; ++tile) {
-            const int ns = tile_nsteps[tile];
-            for (int n = 0; n < ns; ++n)
-                for (int st = 0; st < 7; ++st, ++blk_lin) {
-                    if ((int)(blk_lin % gridDim.x) != (int)blockIdx.x) continue;
-                    const unsigned char* blk = records + (((size_t)tile * rec.nsteps + n) * 7 + st) * rec.block_bytes;
-                    for (int q = 0; q < quarters; ++q, ++it) {
-                        const int s = it % WG_STAGES;
-                        const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
+            const unsigned nb = (unsigned)tile_nsteps[tile] * 7u;   // blocks of this tile: (step, stage) pairs
+            // blocks are dealt round-robin over the grid: this CTA owns those with (base + j) % grid == blockIdx.x
+            for (unsigned j = (blockIdx.x + gridDim.x - base) % gridDim.x; j < nb; j += gridDim.x) {
+                const unsigned char* blk = records + ((size_t)tile * rec.nsteps * 7 + j) * rec.block_bytes;
+                for (int q = 0; q < quarters; ++q, ++it) {
+                    const int s = it % WG_STAGES;
+                    const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
+                    if (lane == 0) {
                         mbar_wait(&empty_bar[s], ph ^ 1);
-                        unsigned char* dst = smem + (size_t)s * sg.bytes;
-                        mbar_expect_tx(&full_bar[s], sg.bytes);
-                        const uint32_t q1 = (uint32_t)q * (WG_ROWS / 8) * g1, q2 = (uint32_t)q * (WG_ROWS / 8) * g2;
-                        const uint32_t b1 = (WG_ROWS / 8) * g1, b2 = (WG_ROWS / 8) * g2, bg = (WG_ROWS / 8) * gg, bd = (WG_ROWS / 8) * gd;
-                        bulk_g2s(dst + sg.h1h, blk + rec.o_h1h + q1, b1, &full_bar[s]);
-                        bulk_g2s(dst + sg.h1l, blk + rec.o_h1l + q1, b1, &full_bar[s]);
-                        bulk_g2s(dst + sg.z1h, blk + rec.o_z1h + q1, b1, &full_bar[s]);
-                        bulk_g2s(dst + sg.z1l, blk + rec.o_z1l + q1, b1, &full_bar[s]);
-                        bulk_g2s(dst + sg.h2h, blk + rec.o_h2h + q2, b2, &full_bar[s]);
-                        bulk_g2s(dst + sg.h2l, blk + rec.o_h2l + q2, b2, &full_bar[s]);
-                        bulk_g2s(dst + sg.z2h, blk + rec.o_z2h + q2, b2, &full_bar[s]);
-                        bulk_g2s(dst + sg.z2l, blk + rec.o_z2l + q2, b2, &full_bar[s]);
-                        bulk_g2s(dst + sg.gh, blk + rec.o_gh + (uint32_t)q * bg, bg, &full_bar[s]);
-                        bulk_g2s(dst + sg.gl, blk + rec.o_gl + (uint32_t)q * bg, bg, &full_bar[s]);
-                        bulk_g2s(dst + sg.dh, blk + rec.o_dh + (uint32_t)q * bd, bd, &full_bar[s]);
-                        bulk_g2s(dst + sg.dl, blk + rec.o_dl + (uint32_t)q * bd, bd, &full_bar[s]);
+                        mbar_expect_tx(&full_bar[s], rec.slice_bytes);
                     }
+                    __syncwarp();
+                    bulk_g2s(smem + (size_t)s * rec.slice_bytes + lane * piece, blk + (size_t)q * rec.slice_bytes + lane * piece, piece,
+                             &full_bar[s]);
                 }
+            }
+            base = (base + nb) % gridDim.x;
         }
     } else if (warp == 1 && lane == 0) {
         // ===== MMA issuer =====
         int it = 0;
-        long long blk_lin = 0;
+        unsigned base = 0;
         for (int tile = 0; tile < ntiles; ++tile) {
-            const int ns = tile_nsteps[tile];
-            for (int n = 0; n < ns; ++n)
-                for (int st = 0; st < 7; ++st, ++blk_lin) {
-                    if ((int)(blk_lin % gridDim.x) != (int)blockIdx.x) continue;
-                    for (int q = 0; q < quarters; ++q, ++it) {
-                        const int s = it % WG_STAGES;
-                        const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
-                        mbar_wait(&full_bar[s], ph);
-                        tc_fence_after();
-                        const uint32_t base = smem_u32(smem + (size_t)s * sg.bytes);
-                        const bool first = it == 0;
-                        for (int mt = 0; mt < 2; ++mt) {
-                            // dW2[n2 feature, n1 feature] += dz2^T h1
-                            wg_issue(tmem_base + mt * TC_MAXW, base + sg.z2h, base + sg.z2l, g2, mt * 128, base + sg.h1h, base + sg.h1l, g1, net.n1, first);
-                            // dW1[n1 feature, g feature | 1] += dz1^T [g 1]
-                            wg_issue(tmem_base + 416 + mt * TC_G_FEATS, base + sg.z1h, base + sg.z1l, g1, mt * 128, base + sg.gh, base + sg.gl, gg, TC_G_FEATS, first);
-                            // dW3^T[n2 feature | 1, state component] += h2^T kbar
-                            wg_issue(tmem_base + 480 + mt * TC_D_FEATS, base + sg.h2h, base + sg.h2l, g2, mt * 128, base + sg.dh, base + sg.dl, gd, TC_D_FEATS, first);
-                        }
-                        tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
+            const unsigned nb = (unsigned)tile_nsteps[tile] * 7u;
+            for (unsigned j = (blockIdx.x + gridDim.x - base) % gridDim.x; j < nb; j += gridDim.x) {
+                for (int q = 0; q < quarters; ++q, ++it) {
+                    const int s = it % WG_STAGES;
+                    const uint32_t ph = (uint32_t)((it / WG_STAGES) & 1);
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t base_s = smem_u32(smem + (size_t)s * rec.slice_bytes);
+                    const bool first = it == 0;
+                    for (int mt = 0; mt < 2; ++mt) {
+                        // dW2[n2 feature, n1 feature] += dz2^T h1
+                        wg_issue(tmem_base + mt * TC_MAXW, base_s + rec.o_z2h, base_s + rec.o_z2l, g2, mt * 128, base_s + rec.o_h1h, base_s + rec.o_h1l, g1, net.n1, first);
+                        // dW1[n1 feature, g feature | 1] += dz1^T [g 1]
+                        wg_issue(tmem_base + 416 + mt * TC_G_FEATS, base_s + rec.o_z1h, base_s + rec.o_z1l, g1, mt * 128, base_s + rec.o_gh, base_s + rec.o_gl, gg, TC_G_FEATS, first);
+                        // dW3^T[n2 feature | 1, state component] += h2^T kbar
+                        wg_issue(tmem_base + 480 + mt * TC_D_FEATS, base_s + rec.o_h2h, base_s + rec.o_h2l, g2, mt * 128, base_s + rec.o_dh, base_s + rec.o_dl, gd, TC_D_FEATS, first);
                     }
+                    tc_commit(&empty_bar[s]);  // frees the stage once these MMAs have read it
                 }
+            }
+            base = (base + nb) % gridDim.x;
         }
         tc_commit(&done_bar);
         if (it == 0) {  // no work for this CTA: nothing was accumulated
@@ -557,9 +544,9 @@ mlp_tc_wgrad_kernel(TcNet net, TcRec rec, WgStage sg, const unsigned char* __res
     }
     // ===== epilogue: accumulators -> this CTA's partial gradient =====
     // does this CTA own any block at all?  (same enumeration, cheap)
-    long long nblocks = 0;
-    for (int tile = 0; tile < ntiles; ++tile) nblocks += (long long)tile_nsteps[tile] * 7;
-    const bool has_work = nblocks > (long long)blockIdx.x;
+    unsigned nblocks = 0;
+    for (int tile = 0; tile < ntiles && nblocks <= blockIdx.x; ++tile) nblocks += (unsigned)tile_nsteps[tile] * 7u;
+    const bool has_work = nblocks > blockIdx.x;
     if (warp >= 2) {
         if (has_work) {
             mbar_wait(&done_bar, 0);
@@ -635,24 +622,16 @@ int ldeq_mlp_tc_backward(ldeq_handle* h, const int32_t* dims, int n_layers, cons
     const int tiles = (B + TC_ROWS - 1) / TC_ROWS;
     TcRec rec;
     rec.nch1 = net.n1 / 8; rec.nch2 = net.n2 / 8;
-    rec.p1 = 16u * rec.nch1 * 128; rec.p2 = 16u * rec.nch2 * 128; rec.pg = 16u * (TC_G_FEATS / 8) * 128; rec.pd = 16u * (TC_D_FEATS / 8) * 128;
-    unsigned off = 0;
-    rec.o_h1h = off; off += rec.p1; rec.o_h1l = off; off += rec.p1; rec.o_z1h = off; off += rec.p1; rec.o_z1l = off; off += rec.p1;
-    rec.o_h2h = off; off += rec.p2; rec.o_h2l = off; off += rec.p2; rec.o_z2h = off; off += rec.p2; rec.o_z2l = off; off += rec.p2;
-    rec.o_gh = off; off += rec.pg; rec.o_gl = off; off += rec.pg; rec.o_dh = off; off += rec.pd; rec.o_dl = off; off += rec.pd;
-    rec.block_bytes = off;
-    rec.nsteps = max_na > 0 ? max_na : 1;
-    WgStage sg;
     {
-        const unsigned q1 = (WG_ROWS / 8) * rec.nch1 * 128, q2 = (WG_ROWS / 8) * rec.nch2 * 128, qg = (WG_ROWS / 8) * (TC_G_FEATS / 8) * 128,
-                       qd = (WG_ROWS / 8) * (TC_D_FEATS / 8) * 128;
+        const unsigned q1 = 2u * rec.nch1 * 128, q2 = 2u * rec.nch2 * 128, qg = 2u * (TC_G_FEATS / 8) * 128, qd = 2u * (TC_D_FEATS / 8) * 128;
         unsigned o = 0;
-        // A operands whose second M-tile reads past their own part come first; the small B operands last
-        sg.z2h = o; o += q2; sg.z2l = o; o += q2; sg.z1h = o; o += q1; sg.z1l = o; o += q1; sg.h2h = o; o += q2; sg.h2l = o; o += q2;
-        sg.h1h = o; o += q1; sg.h1l = o; o += q1; sg.gh = o; o += qg; sg.gl = o; o += qg; sg.dh = o; o += qd; sg.dl = o; o += qd;
-        sg.bytes = o;
+        rec.o_z2h = o; o += q2; rec.o_z2l = o; o += q2; rec.o_z1h = o; o += q1; rec.o_z1l = o; o += q1; rec.o_h2h = o; o += q2; rec.o_h2l = o; o += q2;
+        rec.o_h1h = o; o += q1; rec.o_h1l = o; o += q1; rec.o_gh = o; o += qg; rec.o_gl = o; o += qg; rec.o_dh = o; o += qd; rec.o_dl = o; o += qd;
+        rec.slice_bytes = o;
     }
-    const size_t wg_smem = (size_t)WG_STAGES * sg.bytes + 1024;
+    rec.block_bytes = (TC_ROWS / TC_SLICE_ROWS) * rec.slice_bytes;
+    rec.nsteps = max_na > 0 ? max_na : 1;
+    const size_t wg_smem = (size_t)WG_STAGES * rec.slice_bytes + 1024;
     if (wg_smem > 227 * 1024) return set_err(h, LDEQ_ERR_UNSUPPORTED, "bf16x3 tensor-core reverse pass: record tiles do not fit in shared memory");
     const size_t rec_bytes = (size_t)tiles * rec.nsteps * 7 * rec.block_bytes;
     const int wg_grid = h->sm_count;
@@ -673,7 +652,7 @@ int ldeq_mlp_tc_backward(ldeq_handle* h, const int32_t* dims, int n_layers, cons
     mlp_tc_adj_kernel<<<grid, TC_THREADS, net.smem_bytes, s>>>(net, img, d_tgrid, B, T, dtraj, tv, ret, na, dz0, rec, records, tile_nsteps);
     LDEQ_CUDA(cudaGetLastError());
     LDEQ_CUDA(cudaFuncSetAttribute(mlp_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg_smem));
-    mlp_tc_wgrad_kernel<<<wg_grid, WG_THREADS, wg_smem, s>>>(net, rec, sg, records, tile_nsteps, tiles, partials);
+    mlp_tc_wgrad_kernel<<<wg_grid, WG_THREADS, wg_smem, s>>>(net, rec, records, tile_nsteps, tiles, partials);
     LDEQ_CUDA(cudaGetLastError());
     const int total = H1 * D + H1 + H2 * H1 + H2 + D * H2 + D;
     mlp_tc_wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, s>>>(net, D, H1, H2, partials, wg_grid, dparams);

@@ -17,7 +17,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t lbo, uint3
 extern "C" __global__ void __launch_bounds__(128, 1)
 umma_probe_kernel(const unsigned char* a_img, int a_bytes, const unsigned char* b_img, int b_bytes, int N, int ksteps,
                   uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kadv, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kadv,
-                  uint32_t idesc, float* out /* 128 x N */) {
+                  uint32_t idesc, float* out /* 128 x N */, int reps, long long* cycles) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_base_s;
@@ -39,16 +39,22 @@ umma_probe_kernel(const unsigned char* a_img, int a_bytes, const unsigned char* 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = tmem_base_s;
     if (threadIdx.x == 0) {
+        const long long c0 = clock64();
+        for (int rep = 0; rep < reps; ++rep)
         for (int kk = 0; kk < ksteps; ++kk) {
             const uint64_t da = make_desc(smem_u32(sa) + kk * a_kadv, a_lbo, a_sbo);
             const uint64_t db = make_desc(smem_u32(sb) + kk * b_kadv, b_lbo, b_sbo);
-            const uint32_t acc = kk > 0;
+            const uint32_t acc = (kk > 0) || (rep > 0 && rep + 1 < reps);  // last repetition restarts the accumulation: out = one clean product
             asm volatile(
                 "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc)
                 : "memory");
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tW2: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE2;\n\tbra W2;\n\tDONE2:\n\t}\n" ::"r"(smem_u32(&bar))
+            : "memory");
+        if (cycles) *cycles = clock64() - c0;
     }
     asm volatile(
         "{\n\t.reg .pred p;\n\tW: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra DONE;\n\tbra W;\n\tDONE:\n\t}\n" ::"r"(smem_u32(&bar))
@@ -73,10 +79,10 @@ umma_probe_kernel(const unsigned char* a_img, int a_bytes, const unsigned char* 
 
 extern "C" int umma_probe(const unsigned char* a_img, int a_bytes, const unsigned char* b_img, int b_bytes, int N, int ksteps,
                           uint32_t a_lbo, uint32_t a_sbo, uint32_t a_kadv, uint32_t b_lbo, uint32_t b_sbo, uint32_t b_kadv,
-                          uint32_t idesc, float* out) {
+                          uint32_t idesc, float* out, int reps, long long* cycles) {
     const int smem = ((a_bytes + 1023) / 1024) * 1024 + b_bytes + 1024;
     cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    umma_probe_kernel<<<1, 128, smem>>>(a_img, a_bytes, b_img, b_bytes, N, ksteps, a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv, idesc, out);
+    umma_probe_kernel<<<1, 128, smem>>>(a_img, a_bytes, b_img, b_bytes, N, ksteps, a_lbo, a_sbo, a_kadv, b_lbo, b_sbo, b_kadv, idesc, out, reps, cycles);
     cudaError_t e = cudaDeviceSynchronize();
     return (int)e;
 }

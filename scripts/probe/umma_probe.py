@@ -33,26 +33,28 @@ def mnmajor(X):
 def idesc(n, a_mn, b_mn):
     return (1 << 4) | (1 << 7) | (1 << 10) | (int(a_mn) << 15) | (int(b_mn) << 16) | ((n >> 3) << 17) | ((128 >> 4) << 24)
 
-def run(a_img, b_img, da, db, idc):
+def run(a_img, b_img, da, db, idc, reps=64, n=None):
+    n = n or N
     a = a_img.view(torch.uint8).to(dev); b = b_img.view(torch.uint8).to(dev)
-    out = torch.full((M, N), float("nan"), device=dev)
-    rc = lib.umma_probe(C.c_void_p(a.data_ptr()), a.numel(), C.c_void_p(b.data_ptr()), b.numel(), N, K // 16,
-                        da["lbo"], da["sbo"], da["kadv"], db["lbo"], db["sbo"], db["kadv"], idc, C.c_void_p(out.data_ptr()))
+    out = torch.full((M, n), float("nan"), device=dev)
+    cyc = torch.zeros(1, dtype=torch.int64, device=dev)
+    rc = lib.umma_probe(C.c_void_p(a.data_ptr()), a.numel(), C.c_void_p(b.data_ptr()), b.numel(), n, K // 16,
+                        da["lbo"], da["sbo"], da["kadv"], db["lbo"], db["sbo"], db["kadv"], idc, C.c_void_p(out.data_ptr()), reps,
+                        C.c_void_p(cyc.data_ptr()))
     if rc != 0:
         return f"cuda error {rc}"
-    err = np.abs(out.cpu().numpy() - ref).max()
-    return float(err)
+    err = np.abs(out.cpu().numpy() - ref[:, :n]).max()
+    return {"err": float(err), "cycles_per_mma": int(cyc.item()) / (reps * (K // 16))}
 
 ak, dak = kmajor(A); bk, dbk = kmajor(B)
 am, GA = mnmajor(A); bm, GB = mnmajor(B)
 cands = {"lbo=G,sbo=128": lambda G: dict(lbo=G, sbo=128, kadv=2 * G), "lbo=128,sbo=G": lambda G: dict(lbo=128, sbo=G, kadv=2 * G)}
-tests = [("A K-major, B K-major", lambda: run(ak, bk, dak, dbk, idesc(N, 0, 0)))]
-for na, fa in cands.items():
-    tests.append((f"A MN-major ({na}), B K-major", lambda fa=fa: run(am, bk, fa(GA), dbk, idesc(N, 1, 0))))
-for nb, fb in cands.items():
-    tests.append((f"A K-major, B MN-major ({nb})", lambda fb=fb: run(ak, bm, dak, fb(GB), idesc(N, 0, 1))))
-for na, fa in cands.items():
-    tests.append((f"A MN-major ({na}), B MN-major (same)", lambda fa=fa: run(am, bm, fa(GA), fa(GB), idesc(N, 1, 1))))
+good = lambda G: dict(lbo=G, sbo=128, kadv=2 * G)
+tests = [("SS  A K-major, B K-major, N=208", lambda: run(ak, bk, dak, dbk, idesc(N, 0, 0))),
+         ("SS  A MN-major, B MN-major, N=208", lambda: run(am, bm, good(GA), good(GB), idesc(N, 1, 1))),
+         ("SS  A K-major, B K-major, N=16", lambda: run(ak, bk, dak, dbk, idesc(16, 0, 0), n=16)),
+         ("SS  A MN-major, B MN-major, N=16", lambda: run(am, bm, good(GA), good(GB), idesc(16, 1, 1), n=16)),
+         ("SS  A MN-major, B MN-major, N=208, 1 rep", lambda: run(am, bm, good(GA), good(GB), idesc(N, 1, 1), reps=1))]
 if len(sys.argv) > 1:
     name, fn = tests[int(sys.argv[1])]
     print(json.dumps({name: fn()}))
