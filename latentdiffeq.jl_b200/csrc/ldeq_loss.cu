@@ -40,7 +40,11 @@ struct KlHeads {
     int n_heads;
 };
 
-__global__ void __launch_bounds__(ELBO_THREADS) elbo_kl_kernel(KlHeads hd, int B, float gscale_beta, float* loss) {
+// KL term and its gradients, grid-strided over the heads' elements; block b leaves its partial sum in kl_partials[b]
+// (summed in index order by the last block of elbo_mse_kernel: deterministic).  One block used to do all of it: 0.53 ms
+// at B = 8192 (ncu, profiles/r2_loss_kernels_summary.txt) -- as long as the 1.3 GB reconstruction term next to it.
+#define ELBO_KL_BLOCKS 64
+__global__ void __launch_bounds__(ELBO_THREADS) elbo_kl_kernel(KlHeads hd, int B, float gscale_beta, double* __restrict__ kl_partials) {
     __shared__ double sh[ELBO_THREADS / 32];
     double acc = 0.0;
     const float invB = 1.0f / (float)B;
@@ -48,7 +52,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_kl_kernel(KlHeads hd, int B
         const float* __restrict__ mu = hd.mu[hI];
         const float* __restrict__ lv = hd.lv[hI];
         float part = 0.f;
-        for (int i = threadIdx.x; i < hd.n[hI]; i += blockDim.x) {
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hd.n[hI]; i += gridDim.x * blockDim.x) {
             const float m = mu[i], l = lv[i];
             const float e = expf(l);
             part += (e + m * m - l - 1.0f) * 0.5f;
@@ -63,7 +67,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_kl_kernel(KlHeads hd, int B
     if (threadIdx.x == 0) {
         double t = 0.0;
         for (int w = 0; w < ELBO_THREADS / 32; ++w) t += sh[w];
-        loss[2] = (float)t;
+        kl_partials[blockIdx.x] = t;
     }
 }
 
@@ -71,7 +75,7 @@ template <bool GRAD>
 __global__ void __launch_bounds__(ELBO_THREADS)
 elbo_mse_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* __restrict__ dxhat, size_t n,
                 float inv_bt, float gscale, float beta, double* __restrict__ partials, unsigned int* __restrict__ counter,
-                float* __restrict__ loss) {
+                const double* __restrict__ kl_partials, int n_kl, float* __restrict__ loss) {
     __shared__ float shw[ELBO_THREADS / 32];
     __shared__ bool is_last;
     const size_t n4 = n >> 2;
@@ -118,8 +122,12 @@ elbo_mse_kernel(const float* __restrict__ x, const float* __restrict__ xhat, flo
             double r = 0.0;
             for (int w = 0; w < ELBO_THREADS / 32; ++w) r += shd[w];
             const float rec = (float)(r * (double)inv_bt);
+            double klsum = 0.0;
+            for (int i = 0; i < n_kl; ++i) klsum += __ldcg(kl_partials + i);   // written by the preceding elbo_kl_kernel
+            const float klf = (float)klsum;
             loss[1] = rec;
-            loss[0] = rec + beta * loss[2];
+            loss[2] = klf;
+            loss[0] = rec + beta * klf;
             *counter = 0u;  // ready for the next call
         }
     }
@@ -275,7 +283,7 @@ int ldeq_elbo_fwd_bwd(ldeq_handle* h, const float* x, const float* xhat, const f
     LDEQ_CUDA(cudaSetDevice(h->device));
     const int max_blocks = h->sm_count * 8;
     if (!h->d_partials) {
-        LDEQ_CUDA(cudaMalloc((void**)&h->d_partials, sizeof(double) * max_blocks));
+        LDEQ_CUDA(cudaMalloc((void**)&h->d_partials, sizeof(double) * (max_blocks + ELBO_KL_BLOCKS)));
         LDEQ_CUDA(cudaMalloc((void**)&h->d_counter, sizeof(unsigned int)));
         LDEQ_CUDA(cudaMemset(h->d_counter, 0, sizeof(unsigned int)));
         h->n_partials = max_blocks;
@@ -291,16 +299,20 @@ int ldeq_elbo_fwd_bwd(ldeq_handle* h, const float* x, const float* xhat, const f
         hd.dlv[i] = dlogvar_host ? dlogvar_host[i] : nullptr;
         hd.n[i] = head_dims_host[i] * B;
     }
-    elbo_kl_kernel<<<1, ELBO_THREADS, 0, s>>>(hd, B, grad_scale * beta, loss);
+    double* kl_partials = h->d_partials + max_blocks;
+    int kl_grid = 1;
+    for (int i = 0; i < n_heads; ++i) { const int w = (hd.n[i] + 4 * ELBO_THREADS - 1) / (4 * ELBO_THREADS); if (w > kl_grid) kl_grid = w; }
+    if (kl_grid > ELBO_KL_BLOCKS) kl_grid = ELBO_KL_BLOCKS;
+    elbo_kl_kernel<<<kl_grid, ELBO_THREADS, 0, s>>>(hd, B, grad_scale * beta, kl_partials);
     LDEQ_CUDA(cudaGetLastError());
     const size_t n = (size_t)P * B * T;
     size_t want = ((n >> 2) + ELBO_THREADS - 1) / ELBO_THREADS;
     int grid = (int)(want < (size_t)max_blocks ? (want ? want : 1) : (size_t)max_blocks);
     const float inv_bt = 1.0f / ((float)B * (float)T);
     if (dxhat)
-        elbo_mse_kernel<true><<<grid, ELBO_THREADS, 0, s>>>(x, xhat, dxhat, n, inv_bt, grad_scale, beta, h->d_partials, h->d_counter, loss);
+        elbo_mse_kernel<true><<<grid, ELBO_THREADS, 0, s>>>(x, xhat, dxhat, n, inv_bt, grad_scale, beta, h->d_partials, h->d_counter, kl_partials, kl_grid, loss);
     else
-        elbo_mse_kernel<false><<<grid, ELBO_THREADS, 0, s>>>(x, xhat, nullptr, n, inv_bt, grad_scale, beta, h->d_partials, h->d_counter, loss);
+        elbo_mse_kernel<false><<<grid, ELBO_THREADS, 0, s>>>(x, xhat, nullptr, n, inv_bt, grad_scale, beta, h->d_partials, h->d_counter, kl_partials, kl_grid, loss);
     LDEQ_CUDA(cudaGetLastError());
     h->launches += 2;
     return LDEQ_OK;

@@ -498,8 +498,17 @@ mlp_fwd_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ z0, co
                 if (threadIdx.x < TB) {
                     const int b = threadIdx.x;
                     double e = 0.0;
-                    if (ts->active[b])
+                    if (ts->active[b]) {
                         for (int d = 0; d < D; ++d) e += (double)G[d * TB + b];
+                        if (GLOBAL) {
+                            // one integrator for the whole matrix state (LatentODE.jl:70-72): a non-finite entry anywhere fails
+                            // the WHOLE solve.  The flag travels inside the grid-wide sum (NaN), so every CTA takes the same
+                            // decision in the same iteration and none is left waiting at a grid barrier.
+                            bool fin = true;
+                            for (int d = 0; d < D; ++d) fin = fin && s_finite<S>(UN[d * TB + b]);
+                            if (!fin) e = __longlong_as_double(0x7ff8000000000000LL);
+                        }
+                    }
                     ts->esum[b] = e;
                 }
                 __syncthreads();

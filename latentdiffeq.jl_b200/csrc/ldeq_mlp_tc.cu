@@ -322,6 +322,9 @@ mlp_tc_fwd_kernel(TcNet net, const unsigned char* __restrict__ img_global, const
                 if (o.adaptive) {
                     double e2 = e2f, n = D;
                     if (GLOBAL) {
+                        // a non-finite row fails the WHOLE matrix solve (one integrator, LatentODE.jl:70-72): the NaN rides in the
+                        // grid-wide sum, so every CTA decides the same in the same iteration (no CTA left at a grid barrier)
+                        if (active && !finite) e2 = __longlong_as_double(0x7ff8000000000000LL);
                         double v = (active && writer) ? e2 : 0.0;
                         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
                         if (writer && (tid & 31) == 0) red_s[quad] = v;
