@@ -157,12 +157,13 @@ static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj,
     GridInfo gi{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld};
     KOpts kov = tape->kopts;
     const int32_t* ret = tape->retcode;
+    const int32_t* key = tape->naccept;  // lanes re-dealt by the primal step count (ldeq_fwdsens.cuh)
     const int grid = (B + 127) / 128;
     const int base = tape->dtype == LDEQ_F32 ? 6 : 8;
-    void* args_p[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &dtraj, &ret, &dtheta};
+    void* args_p[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &key, &dtraj, &ret, &dtheta};
     cudaError_t e = cudaLaunchKernel(tape->rhs->fn[base], dim3(grid), dim3(128), args_p, 0, s);
     if (e != cudaSuccess) return e;
-    void* args_u[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &dtraj, &ret, &dz0};
+    void* args_u[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &key, &dtraj, &ret, &dz0};
     return cudaLaunchKernel(tape->rhs->fn[base + 1], dim3(grid), dim3(128), args_u, 0, s);
 }
 

@@ -4,6 +4,7 @@
 // (~7x cheaper, equal to this within the solver tolerance).
 #include "ldeq_internal.h"
 #include "ldeq_fwdsens.cuh"
+#include <cstdlib>
 
 namespace ldeq {
 
@@ -25,20 +26,23 @@ template <bool FRICTION> struct PendulumDualRHS {
 };
 
 template <class S, int NP, bool FRICTION, bool SEED_P>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(LDEQ_FWDSENS_THREADS, 512 / LDEQ_FWDSENS_THREADS)
 tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
-                     KOpts o, int norm_partials, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
+                     KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                      S* __restrict__ dout) {
-    tsit5_fwdsens_body<PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, gi, T, o, norm_partials, dtraj, primal_ret, dout);
+    tsit5_fwdsens_body<PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, gi, T, o, norm_partials, sort_key, dtraj, primal_ret, dout);
 }
 
 template <class S, bool FR>
 static cudaError_t launch_fwdsens_t(const ldeq_tape* tp, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
-    const int B = tp->B, grid = (B + 127) / 128;
+    const int B = tp->B, grid = (B + LDEQ_FWDSENS_THREADS - 1) / LDEQ_FWDSENS_THREADS;
     const GridInfo gi{tp->grid_t0, tp->grid_h, tp->grid_uniform, ld};
-    tsit5_fwdsens_kernel<S, 1, FR, true><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, gi, tp->T, tp->kopts, 1,
+    // LDEQ_FWDSENS_SORT=0 keeps the trajectory -> lane assignment of the batch order (A/B switch; the results are identical)
+    static const bool sort = [] { const char* e = getenv("LDEQ_FWDSENS_SORT"); return !(e && e[0] == '0'); }();
+    const int* key = sort ? tp->naccept : nullptr;
+    tsit5_fwdsens_kernel<S, 1, FR, true><<<grid, LDEQ_FWDSENS_THREADS, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, gi, tp->T, tp->kopts, 1, key,
                                                              (const S*)dtraj, tp->retcode, (S*)dtheta);
-    tsit5_fwdsens_kernel<S, 2, FR, false><<<grid, 128, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, gi, tp->T, tp->kopts, 1,
+    tsit5_fwdsens_kernel<S, 2, FR, false><<<grid, LDEQ_FWDSENS_THREADS, 0, s>>>((const S*)tp->u, (const S*)tp->theta, tp->tgrid, B, gi, tp->T, tp->kopts, 1, key,
                                                               (const S*)dtraj, tp->retcode, (S*)dz0);
     return cudaGetLastError();
 }

@@ -63,75 +63,99 @@ template <class S, int N> __device__ __forceinline__ S dual_rms(const Dual<S, N>
 #ifndef LDEQ_FWDSENS_PREFETCH_ROWS
 #define LDEQ_FWDSENS_PREFETCH_ROWS 24
 #endif
+#ifndef LDEQ_FWDSENS_THREADS
+#define LDEQ_FWDSENS_THREADS 128
+#endif
+
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // SEED_P: partials seeded on theta (NP = PD) -> dout = dtheta (p,B);  else on u0 (NP = ZD) -> dout = dz0 (z,B)
 template <class RHS, class S, int NP, bool SEED_P>
 __device__ __forceinline__ void
 tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
-                   KOpts o, int norm_partials, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
+                   KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                    S* __restrict__ dout) {
     constexpr int Z = RHS::ZD, PD = RHS::PD;
     using D = Dual<S, NP>;
     using Tb = Tab<S>;
     using Td = Tab<double>;
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int ld = gi.ld;
     // save times of a verified-uniform grid are one DFMA (bit-identical to the table, ldeq_api.cu::upload_tgrid), not a load
     auto tgrid = [&](int k) -> double { return gi.uniform ? fma((double)k, gi.h, gi.t0) : tg[k]; };
     const bool wp = norm_partials != 0;
+    // Lanes of a warp run until the slowest trajectory finishes.  The primal solve has already counted every trajectory's
+    // accepted steps (sort_key = the tape's naccept): the CTA ranks its trajectories by that count and re-deals them, so a
+    // warp holds 32 neighbours in step count.  Only the assignment of trajectories to lanes changes -- every trajectory's
+    // arithmetic and its output slot are the same.
+    if (sort_key) {
+        __shared__ int s_key[LDEQ_FWDSENS_THREADS];
+        __shared__ short s_order[LDEQ_FWDSENS_THREADS];
+        const int tid = threadIdx.x, nt = blockDim.x;
+        const int key = b < B ? sort_key[b] : 0x7fffffff;  // dead lanes go last
+        s_key[tid] = key;
+        __syncthreads();
+        int rank = 0;
+        for (int j = 0; j < nt; ++j) {
+            const int kj = s_key[j];
+            rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
+        }
+        s_order[rank] = (short)tid;
+        __syncthreads();
+        b = blockIdx.x * blockDim.x + s_order[tid];
+    }
+    if (b >= B) return;
     D u[Z], k[7][Z], unew[Z], tmp[Z], sum, L[PD];
-    for (int i = 0; i < Z; ++i) {
-        u[i] = D(z0[(size_t)b * Z + i]);
-        if (!SEED_P) u[i].d[i] = (S)1;
-    }
-    for (int i = 0; i < PD; ++i) {
-        L[i] = D(theta[(size_t)b * PD + i]);
-        if (SEED_P) L[i].d[i] = (S)1;
-    }
-
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
     const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
     const S abstol = (S)o.abstol, reltol = (S)o.reltol;
     double acc[NP];
+    double t = t0, dt = o.dt;
+    {
+        {
+            for (int i = 0; i < Z; ++i) {
+                u[i] = D(z0[(size_t)b * Z + i]);
+                if (!SEED_P) u[i].d[i] = (S)1;
+            }
+            for (int i = 0; i < PD; ++i) {
+                L[i] = D(theta[(size_t)b * PD + i]);
+                if (SEED_P) L[i].d[i] = (S)1;
+            }
+            RHS::f(k[0], u, L, t0);  // fsalfirst
+            if (o.adaptive && !(o.dt > 0.0)) {
+                // Hairer initial step on the dual state
+                S sk[Z];
+                for (int i = 0; i < Z; ++i) {
+                    sk[i] = abstol + dual_absnorm(u[i], wp) * reltol;
+                    tmp[i] = dual_div_s(u[i], sk[i]);
+                }
+                const double d0 = (double)dual_rms(tmp, Z, wp);
+                for (int i = 0; i < Z; ++i) tmp[i] = dual_div_s(k[0][i], sk[i]);
+                const double d1 = (double)dual_rms(tmp, Z, wp);
+                double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
+                dt0 = fmin(dt0, dtmax);
+                if (dt0 < 10.0 * 2.220446049250313e-16) {
+                    dt = fmax(1e-6, dtmin);
+                } else {
+                    D u1[Z], f1[Z];
+                    for (int i = 0; i < Z; ++i) u1[i] = dual_axpy_time(u[i], dt0, k[0][i]);
+                    RHS::f(f1, u1, L, t0 + dt0);
+                    for (int i = 0; i < Z; ++i) tmp[i] = dual_div_s(f1[i] - k[0][i], sk[i]);
+                    const double d2 = (double)dual_rms(tmp, Z, wp) / dt0;
+                    const double m = fmax(d1, d2);
+                    const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : ::pow(10.0, -(2.0 + log10(m)) / 5.0);
+                    dt = fmax(dtmin, fmin(100.0 * dt0, fmin(dt1, dtmax)));
+                }
+            }
+        }
+    }
 #pragma unroll
     for (int q = 0; q < NP; ++q) acc[q] = 0.0;
     // save point 0 is u0 itself
     for (int i = 0; i < Z; ++i)
 #pragma unroll
         for (int q = 0; q < NP; ++q) acc[q] += (double)u[i].d[q] * (double)dtraj[(size_t)b * Z + i];
-
-    RHS::f(k[0], u, L, t0);  // fsalfirst
-    double t = t0, dt;
-    if (o.adaptive && !(o.dt > 0.0)) {
-        // Hairer initial step on the dual state
-        S sk[Z];
-        for (int i = 0; i < Z; ++i) {
-            sk[i] = abstol + dual_absnorm(u[i], wp) * reltol;
-            tmp[i] = dual_div_s(u[i], sk[i]);
-        }
-        const double d0 = (double)dual_rms(tmp, Z, wp);
-        for (int i = 0; i < Z; ++i) tmp[i] = dual_div_s(k[0][i], sk[i]);
-        const double d1 = (double)dual_rms(tmp, Z, wp);
-        double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
-        dt0 = fmin(dt0, dtmax);
-        if (dt0 < 10.0 * 2.220446049250313e-16) {
-            dt = fmax(1e-6, dtmin);
-        } else {
-            D u1[Z], f1[Z];
-            for (int i = 0; i < Z; ++i) u1[i] = dual_axpy_time(u[i], dt0, k[0][i]);
-            RHS::f(f1, u1, L, t0 + dt0);
-            for (int i = 0; i < Z; ++i) tmp[i] = dual_div_s(f1[i] - k[0][i], sk[i]);
-            const double d2 = (double)dual_rms(tmp, Z, wp) / dt0;
-            const double m = fmax(d1, d2);
-            const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : ::pow(10.0, -(2.0 + log10(m)) / 5.0);
-            dt = fmax(dtmin, fmin(100.0 * dt0, fmin(dt1, dtmax)));
-        }
-    } else {
-        dt = o.dt;
-    }
     PiState pst = pi_init(o);
     int ks = 1, ret = RET_SUCCESS;
     long long iters = 0;
@@ -139,6 +163,10 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
     // The cotangent rows this lane will consume are requested into L1 a few steps ahead (one prefetch per row, 8 sectors
     // per warp instruction): without it the save loop below waits ~600 cycles on every row (ncu: 45 % of all stall samples).
     int kpf = 1;
+    // dvn always holds the cotangent row of the next pending save point: its load is in flight during the stages
+    S dvn[Z];
+#pragma unroll
+    for (int i = 0; i < Z; ++i) dvn[i] = T > 1 ? dtraj[((size_t)ld + b) * Z + i] : (S)0;
     while (ks < T && ret == RET_SUCCESS) {
         if (iters >= o.maxiters) { ret = RET_MAXITERS; break; }
         ++iters;
@@ -216,7 +244,11 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
             while (ks < T && tsv <= tnew) {
                 S dv[Z];
 #pragma unroll
-                for (int i = 0; i < Z; ++i) dv[i] = dtraj[((size_t)ks * ld + b) * Z + i];
+                for (int i = 0; i < Z; ++i) dv[i] = dvn[i];
+                if (ks + 1 < T) {
+#pragma unroll
+                    for (int i = 0; i < Z; ++i) dvn[i] = dtraj[((size_t)(ks + 1) * ld + b) * Z + i];
+                }
                 if (tsv == tnew) {
 #pragma unroll
                     for (int i = 0; i < Z; ++i)
