@@ -714,6 +714,14 @@ def run_latentode(args):
             res[name]["roofline"] = {"bound": "tensor", "achieved": issued, "peak": peak_bf16, "unit": "TFLOP/s",
                                      "frac": issued / peak_bf16, "traffic": None,
                                      "note": "bf16 flops issued to tcgen05 (3 passes, padded widths) / measured cuBLAS bf16 peak"}
+            # reverse pass (ldeq_mlp_tc_bwd.cu): per accepted step and stage one recomputed evaluation, one transposed
+            # (input-gradient) evaluation and one weight-gradient contraction of the same shape, each in 3 bf16 passes
+            na = float(st.naccept.float().mean())
+            issued_b = B * na * 7 * 3 * 3 * 2 * (16 * 208 + 208 * 208 + 208 * 16) / (max(ms2 - ms, 1e-6) * 1e-3) / 1e12
+            res[name]["roofline_reverse_pass"] = {"bound": "tensor", "achieved": issued_b, "peak": peak_bf16, "unit": "TFLOP/s",
+                                                  "frac": issued_b / peak_bf16, "ms": ms2 - ms, "traffic": None,
+                                                  "note": "adjoint kernel (recompute + transposed products) + split-K weight-gradient "
+                                                          "GEMM + reduce, all tcgen05; bf16 flops issued / measured cuBLAS bf16 peak"}
     best = max((v["traj_steps_per_s"], k) for k, v in res.items() if "ms" in v)
     line = {"metric": "latent trajectory-steps/sec (LatentODE forward solve)", "value": best[0], "unit": UNIT, "n_gpus": 1,
             "steps": K, "warmup": W, "ms_per_step": res[best[1]]["ms"], "higher_is_better": True, "scaling": "weak",

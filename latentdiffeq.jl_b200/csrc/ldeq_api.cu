@@ -167,29 +167,35 @@ static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj,
     return cudaLaunchKernel(tape->rhs->fn[base + 1], dim3(grid), dim3(128), args_u, 0, s);
 }
 
-static bool slot_get(ldeq_handle* h, ldeq_tape* tape) {
+// Pinned two-int mirrors + events come from a per-handle pool: cudaMallocHost / cudaFreeHost cost milliseconds of host time
+// (and the free synchronises the device), far more than a small solve.
+bool slot_acquire(ldeq_handle* h, int32_t** h_info, cudaEvent_t* ev) {
     if (h->free_slots.empty()) {
         const int n = 64;
         int32_t* blk = nullptr;
         if (cudaMallocHost((void**)&blk, n * 2 * sizeof(int32_t)) != cudaSuccess) return false;
         h->pinned_blocks.push_back(blk);
         for (int i = 0; i < n; ++i) {
-            cudaEvent_t ev;
-            if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
-            h->free_slots.push_back({blk + 2 * i, ev});
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return false;
+            h->free_slots.push_back({blk + 2 * i, e});
         }
     }
     ldeq_handle::Slot sl = h->free_slots.back();
     h->free_slots.pop_back();
-    tape->h_info = sl.h_info;
-    tape->ready = sl.ev;
+    *h_info = sl.h_info;
+    *ev = sl.ev;
     return true;
 }
-static void slot_put(ldeq_handle* h, ldeq_tape* tape) {
-    if (tape->h_info && tape->ready) {
-        cudaEventSynchronize(tape->ready);  // the async copy into the slot must have landed before reuse
-        if (h) h->free_slots.push_back({tape->h_info, tape->ready});
+void slot_release(ldeq_handle* h, int32_t* h_info, cudaEvent_t ev) {
+    if (h_info && ev) {
+        cudaEventSynchronize(ev);  // the async copy into the slot must have landed before reuse
+        if (h) h->free_slots.push_back({h_info, ev});
     }
+}
+static bool slot_get(ldeq_handle* h, ldeq_tape* tape) { return slot_acquire(h, &tape->h_info, &tape->ready); }
+static void slot_put(ldeq_handle* h, ldeq_tape* tape) {
+    slot_release(h, tape->h_info, tape->ready);
     tape->h_info = nullptr;
     tape->ready = nullptr;
 }

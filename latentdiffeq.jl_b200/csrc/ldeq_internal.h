@@ -84,6 +84,9 @@ int set_err(ldeq_handle* h, int code, const char* what, cudaError_t ce = cudaSuc
 int upload_tgrid(ldeq_handle* h, const double* t_host, int T, cudaStream_t s);
 int ensure_scratch(ldeq_handle* h, int slot, size_t bytes);
 KOpts to_kopts(const ldeq_opts* o);
+// pooled pinned {int32 x 2} mirror + event (ldeq_api.cu)
+bool slot_acquire(ldeq_handle* h, int32_t** h_info, cudaEvent_t* ev);
+void slot_release(ldeq_handle* h, int32_t* h_info, cudaEvent_t ev);
 // ldeq_fwdsens.cu: the reference's ForwardDiffSensitivity pullback (two dual-number re-solves per trajectory)
 cudaError_t launch_fwdsens(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s);
 

@@ -519,9 +519,7 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
         tape->naccept = (int32_t*)(bp + o_na); tape->nreject = (int32_t*)(bp + o_nr);
         tape->info = (int32_t*)(bp + o_info);
         cudaMemsetAsync(tape->info, 0, 4, s);
-        if (cudaMallocHost((void**)&tape->h_info, 8) != cudaSuccess ||
-            cudaEventCreateWithFlags(&tape->ready, cudaEventDisableTiming) != cudaSuccess) {
-            if (tape->h_info) cudaFreeHost(tape->h_info);
+        if (!slot_acquire(h, &tape->h_info, &tape->ready)) {
             cudaFreeAsync(tape->base, s);
             delete tape;
             return set_err(h, LDEQ_ERR_NOMEM, "mlp tape host mirror");
@@ -541,7 +539,7 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
     else
         rc = mlp_fwd_dispatch<double>(h, net, params_flat, z0, h->d_tgrid, B, T, ko, opts->norm_mode, traj_out, d_ret, d_na, d_nr, tape, s);
     if (rc) {
-        if (tape) { cudaFreeAsync(tape->base, s); cudaFreeHost(tape->h_info); cudaEventDestroy(tape->ready); delete tape; }
+        if (tape) { cudaFreeAsync(tape->base, s); cudaEventRecord(tape->ready, s); slot_release(h, tape->h_info, tape->ready); delete tape; }
         return rc;
     }
     if (tape) {
@@ -639,8 +637,7 @@ void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream)
     if (!tape) return;
     if (h) cudaSetDevice(h->device);
     if (tape->base) cudaFreeAsync(tape->base, (cudaStream_t)stream);
-    if (tape->ready) { cudaEventSynchronize(tape->ready); cudaEventDestroy(tape->ready); }
-    if (tape->h_info) cudaFreeHost(tape->h_info);
+    slot_release(h, tape->h_info, tape->ready);
     delete tape;
 }
 
