@@ -675,7 +675,10 @@ def run_latentode(args):
     res = {}
     launches = 0
     for name, kw in (("tcgen05_bf16x3_global", dict(norm_mode=0, mlp_math=1)), ("tcgen05_bf16x3_per_traj", dict(norm_mode=1, mlp_math=1)),
-                     ("exact_fp32_global", dict(norm_mode=0)), ("exact_fp32_per_traj", dict(norm_mode=1))):
+                     ("exact_fp32_global", dict(norm_mode=0)), ("exact_fp32_per_traj", dict(norm_mode=1)),
+                     # the reference's own reverse pass (NeuralODE default InterpolatingAdjoint): continuous adjoint on
+                     # [lambda; mu], ~700 backward steps at C2 against 12 taped forward steps
+                     ("exact_fp32_global_interpolating_adjoint", dict(norm_mode=0, sensealg=ldeq.SENSE_INTERPOLATING_ADJOINT))):
         o = ldeq.default_opts(**kw)
 
         def fwd_bwd():

@@ -94,8 +94,13 @@ enum ldeq_mlp_math {
  *   LDEQ_SENSE_DISCRETE_ADJOINT  reverse sweep over the taped accepted steps of the primal solve: the exact derivative of
  *        the primal discretisation (step sizes frozen), one kernel, ~the cost of the forward solve, ~3x cheaper than
  *        the dual solves.  An explicit opt-in (Python: `sensealg = DiscreteAdjoint()`): it agrees with the reference's
- *        gradient only within the solver tolerance (2e-2 at reltol 1e-3), exactly in fixed-step mode. */
-typedef enum { LDEQ_SENSE_DISCRETE_ADJOINT = 0, LDEQ_SENSE_FORWARD_DUAL = 1 } ldeq_sensealg;
+ *        gradient only within the solver tolerance (2e-2 at reltol 1e-3), exactly in fixed-step mode.
+ *   LDEQ_SENSE_INTERPOLATING_ADJOINT  (ldeq_mlp_* only) the reference's algorithm for the LatentODE path: DiffEqFlux's
+ *        NeuralODE default `InterpolatingAdjoint(autojacvec = ZygoteVJP())` (LatentODE.jl:70 under Zygote) -- the continuous
+ *        adjoint ODE on [lambda; mu] solved backwards by adaptive Tsit5 with the forward dense output and a callback at
+ *        every save time (csrc/ldeq_mlp_cadj.cuh).  Needs the batch-global norm and the exact arithmetic path; any other
+ *        value makes ldeq_mlp_solve_bwd run the discrete adjoint of the taped steps.  The GOKU entry points refuse it. */
+typedef enum { LDEQ_SENSE_DISCRETE_ADJOINT = 0, LDEQ_SENSE_FORWARD_DUAL = 1, LDEQ_SENSE_INTERPOLATING_ADJOINT = 2 } ldeq_sensealg;
 
 /* The diffeq struct's `solver` field (pendulum.jl:11,58: Tsit5()).  Anything else is refused with
  * LDEQ_ERR_UNSUPPORTED rather than silently replaced. */
@@ -196,6 +201,12 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
                        int32_t* nreject, ldeq_mlp_tape** tape_out, ldeq_stream stream);
 int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0,
                        void* dparams_flat, ldeq_stream stream);
+/* {accepted steps, rejected steps, retcode} of the backward solve that LDEQ_SENSE_INTERPOLATING_ADJOINT ran for this
+ * tape (zeros before ldeq_mlp_solve_bwd or in the discrete-adjoint mode); synchronises `stream`. */
+int ldeq_mlp_bwd_stats(ldeq_handle* h, ldeq_mlp_tape* tape, int32_t* out3_host, ldeq_stream stream);
+/* debugging aid: with LDEQ_CADJ_TRACE=1 in the environment, the first n attempted steps of that backward solve as
+ * (t, dt, EEst, accepted) quadruples of doubles; synchronises the device. */
+int ldeq_debug_cadj_trace(ldeq_handle* h, ldeq_mlp_tape* tape, double* out_host, int n);
 void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream);
 
 /* ---- reparameterised sample: z = mu + eps * exp(logvar/2), eps ~ N(0,1) drawn on the device ---- */

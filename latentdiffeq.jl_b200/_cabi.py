@@ -26,12 +26,12 @@ SYMBOLS = [
     "ldeq_rhs_builtin", "ldeq_rhs_from_source", "ldeq_rhs_dims", "ldeq_rhs_free",
     "ldeq_solve_fwd", "ldeq_solve_bwd", "ldeq_tape_overflow", "ldeq_tape_free",
     "ldeq_solve_fwd_host", "ldeq_solve_bwd_host", "ldeq_solve_fwd_bwd_host", "ldeq_debug_trig",
-    "ldeq_mlp_solve_fwd", "ldeq_mlp_solve_bwd", "ldeq_mlp_tape_free",
+    "ldeq_mlp_solve_fwd", "ldeq_mlp_solve_bwd", "ldeq_mlp_tape_free", "ldeq_mlp_bwd_stats", "ldeq_debug_cadj_trace",
     "ldeq_sample", "ldeq_elbo_fwd_bwd", "ldeq_adamw_step", "ldeq_allreduce_adamw_step",
     "ldeq_comm_unique_id", "ldeq_comm_init", "ldeq_allreduce_grads", "ldeq_comm_destroy",
 ]
 COMM_ID_BYTES = 128
-SENSE_DISCRETE_ADJOINT, SENSE_FORWARD_DUAL = 0, 1
+SENSE_DISCRETE_ADJOINT, SENSE_FORWARD_DUAL, SENSE_INTERPOLATING_ADJOINT = 0, 1, 2
 
 
 class Opts(C.Structure):
@@ -94,6 +94,8 @@ def load() -> C.CDLL:
     lib.ldeq_debug_trig.argtypes = [vp, i32, vp, vp, vp, i64, vp]
     lib.ldeq_mlp_solve_fwd.argtypes = [vp, i32, vp, vp, vp, i32, vp, i32, i32, C.POINTER(Opts), vp, vp, vp, vp, pvp, vp]
     lib.ldeq_mlp_solve_bwd.argtypes = [vp, vp, vp, vp, vp, vp]
+    lib.ldeq_mlp_bwd_stats.argtypes = [vp, vp, vp, vp]
+    lib.ldeq_debug_cadj_trace.argtypes = [vp, vp, vp, C.c_int]
     lib.ldeq_mlp_tape_free.argtypes = [vp, vp, vp]
     lib.ldeq_mlp_tape_free.restype = None
     lib.ldeq_sample.argtypes = [vp, vp, vp, vp, vp, i64, C.c_uint64, C.c_uint64, vp]

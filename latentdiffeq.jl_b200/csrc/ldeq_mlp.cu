@@ -315,6 +315,10 @@ template <class S> __global__ void mlp_reduce_grads_kernel(const S* __restrict__
     }
 }
 
+}  // namespace ldeq
+#include "ldeq_mlp_cadj.cuh"
+namespace ldeq {
+
 template <class S, int TB> static size_t bwd_smem(const MlpNet& net) {
     const size_t D = net.dims[0], HW = net.max_width;
     size_t n = (21 * D + 4 * D + (net.n_layers - 1) * HW + 2 * HW + MLP_THREADS) * TB * sizeof(S);
@@ -338,6 +342,8 @@ int ldeq_mlp_tc_forward(ldeq_handle* h, const int32_t* dims, int n_layers, const
 struct ldeq_mlp_tape {
     int dtype = 0, B = 0, T = 0, cap = 0, tb = 0;
     int math = 0;  // ldeq_mlp_math of the forward solve: its reverse pass runs on the same arithmetic
+    int sense = 0, norm_mode = 0;  // ldeq_sensealg / ldeq_norm_mode of the forward solve
+    ldeq::KOpts kopts;             // the solve's options: the continuous adjoint integrates with the same tolerances
     MlpNet net;
     void* base = nullptr;
     double* t = nullptr;
@@ -495,6 +501,7 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
     if (tape_out) {
         tape = new ldeq_mlp_tape();
         tape->dtype = dtype; tape->B = B; tape->T = T; tape->net = net; tape->math = opts->mlp_math;
+        tape->sense = opts->sensealg; tape->norm_mode = opts->norm_mode; tape->kopts = ko;
         long long cap = opts->tape_steps;
         if (cap <= 0) cap = opts->adaptive ? (4LL * T > 256 ? 4LL * T : 256) : (long long)((t_host[T - 1] - t_host[0]) / opts->dt) + 3;
         if (cap > opts->maxiters) cap = opts->maxiters;
@@ -518,7 +525,7 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
         tape->params_t = bp + o_pt; tape->tgrid = (double*)(bp + o_tg); tape->retcode = (int32_t*)(bp + o_r);
         tape->naccept = (int32_t*)(bp + o_na); tape->nreject = (int32_t*)(bp + o_nr);
         tape->info = (int32_t*)(bp + o_info);
-        cudaMemsetAsync(tape->info, 0, 4, s);
+        cudaMemsetAsync(tape->info, 0, 32, s);
         if (!slot_acquire(h, &tape->h_info, &tape->ready)) {
             cudaFreeAsync(tape->base, s);
             delete tape;
@@ -593,6 +600,66 @@ static int launch_mlp_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj
     return LDEQ_OK;
 }
 
+// LDEQ_SENSE_INTERPOLATING_ADJOINT (ldeq_mlp_cadj.cuh): one cooperative launch, a tile of TB trajectories per CTA.
+// Returns LDEQ_ERR_UNSUPPORTED (quietly) when the tiles of this TB cannot all be resident.
+template <class S, int TB>
+static int launch_mlp_cadj(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0, void* dparams, cudaStream_t s) {
+    const MlpNet& net = tape->net;
+    const int B = tape->B, grid = (B + TB - 1) / TB;
+    const size_t smem = cadj_smem<S, TB>(net);
+    auto kern = mlp_cadj_kernel<S, TB>;
+    if (smem > 227 * 1024 || grid > GRID_SUM_HALF) return LDEQ_ERR_UNSUPPORTED;
+    LDEQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    LDEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MLP_THREADS, smem));
+    if (per_sm * h->sm_count < grid) return LDEQ_ERR_UNSUPPORTED;
+    const size_t NP = net.n_params, D = net.dims[0];
+    const int na = tape->h_info[0] > 0 ? tape->h_info[0] : 1;
+    int rc;
+    if ((rc = ensure_scratch(h, 0, sizeof(double) * 4096))) return rc;
+    if ((rc = ensure_scratch(h, 1, (size_t)grid * 2 * NP * sizeof(S)))) return rc;
+    if ((rc = ensure_scratch(h, 3, (size_t)na * 7 * D * grid * TB * sizeof(S)))) return rc;
+    const size_t mu_bytes = (3 * NP * sizeof(S) + 255) & ~(size_t)255;
+    const int trace_cap = getenv("LDEQ_CADJ_TRACE") ? 4096 : 0;  // debugging aid: (t, dt, EEst, accept) of every attempt
+    if ((rc = ensure_scratch(h, 2, mu_bytes + (size_t)trace_cap * 32 + 256))) return rc;
+    mlp_transpose_kernel<S><<<64, 256, 0, s>>>(net, (const S*)tape->params, (S*)tape->params_t);
+    LDEQ_CUDA(cudaGetLastError());
+    MlpNet netv = net;
+    const S* Pp = (const S*)tape->params;
+    const S* Pt = (const S*)tape->params_t;
+    const double* tg = tape->tgrid;
+    int Bv = B, Tv = tape->T;
+    KOpts kov = tape->kopts;
+    const S* dt_ = (const S*)dtraj;
+    MlpTapeView<S> tv{tape->t, tape->dt, (S*)tape->u, tape->cap};
+    const int* ret = tape->retcode;
+    const int* nacc = tape->naccept;
+    S* dense = (S*)h->scratch[3];
+    S* gscr = (S*)h->scratch[1];
+    S* mubuf = (S*)h->scratch[2];
+    double* partials = (double*)h->scratch[0];
+    S* dz = (S*)dz0;
+    S* dp = (S*)dparams;
+    int* status = tape->info + 4;
+    double* trace = trace_cap ? (double*)((char*)h->scratch[2] + mu_bytes) : nullptr;
+    int tcap = trace_cap;
+    void* args[] = {&netv, &Pp, &Pt, &tg, &Bv, &Tv, &kov, &dt_, &tv, &ret, &nacc, &dense, &gscr, &mubuf, &partials, &dz, &dp, &status, &trace, &tcap};
+    LDEQ_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(MLP_THREADS), args, smem, s));
+    h->launches += 2;
+    return LDEQ_OK;
+}
+
+template <class S>
+static int mlp_cadj_dispatch(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0, void* dparams, cudaStream_t s) {
+    int rc = launch_mlp_cadj<S, 2>(h, tape, dtraj, dz0, dparams, s);
+    if (rc == LDEQ_ERR_UNSUPPORTED) rc = launch_mlp_cadj<S, 8>(h, tape, dtraj, dz0, dparams, s);
+    if (rc == LDEQ_ERR_UNSUPPORTED) rc = launch_mlp_cadj<S, 32>(h, tape, dtraj, dz0, dparams, s);
+    if (rc == LDEQ_ERR_UNSUPPORTED)
+        return set_err(h, LDEQ_ERR_UNSUPPORTED, "interpolating adjoint: batch too large (all tiles must be co-resident for the "
+                                                "error norm over the augmented state); use LDEQ_SENSE_DISCRETE_ADJOINT");
+    return rc;
+}
+
 extern "C" {
 
 int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0, void* dparams_flat,
@@ -609,6 +676,15 @@ int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, v
         snprintf(msg, sizeof msg, "mlp tape overflow: the solve accepted %d steps, the tape holds %d; repeat ldeq_mlp_solve_fwd "
                  "with opts.tape_steps >= %d", tape->h_info[0], tape->cap, tape->h_info[0]);
         return set_err(h, LDEQ_ERR_TAPE_OVERFLOW, msg);
+    }
+    if (tape->sense == LDEQ_SENSE_INTERPOLATING_ADJOINT) {
+        if (tape->norm_mode != LDEQ_NORM_GLOBAL)
+            return set_err(h, LDEQ_ERR_UNSUPPORTED, "interpolating adjoint: the reference's backward solve has one step size for the "
+                                                    "whole batch; it needs norm_mode = LDEQ_NORM_GLOBAL");
+        if (tape->math != LDEQ_MLP_MATH_FP32)
+            return set_err(h, LDEQ_ERR_UNSUPPORTED, "interpolating adjoint: exact arithmetic path only (mlp_math = LDEQ_MLP_MATH_FP32)");
+        return tape->dtype == LDEQ_F32 ? mlp_cadj_dispatch<float>(h, tape, dtraj, dz0, dparams_flat, s)
+                                       : mlp_cadj_dispatch<double>(h, tape, dtraj, dz0, dparams_flat, s);
     }
     if (tape->math == LDEQ_MLP_MATH_BF16X3 && !getenv("LDEQ_MLP_TC_BWD_OFF")) {
         // the tensor-core tape: adjoint sweep + weight-gradient GEMM on tcgen05 (ldeq_mlp_tc_bwd.cu)
@@ -631,6 +707,27 @@ int ldeq_mlp_solve_bwd(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, v
                      : launch_mlp_bwd<float, 8>(h, tape, dtraj, dz0, dparams_flat, s);
     return small ? launch_mlp_bwd<double, 2>(h, tape, dtraj, dz0, dparams_flat, s)
                  : launch_mlp_bwd<double, 8>(h, tape, dtraj, dz0, dparams_flat, s);
+}
+
+// debugging aid (LDEQ_CADJ_TRACE=1): the first n attempts of the last interpolating-adjoint solve as (t, dt, EEst, accept)
+int ldeq_debug_cadj_trace(ldeq_handle* h, ldeq_mlp_tape* tape, double* out_host, int n) {
+    if (!h || !tape || !out_host) return LDEQ_ERR_INVALID;
+    if (!getenv("LDEQ_CADJ_TRACE")) return set_err(h, LDEQ_ERR_INVALID, "set LDEQ_CADJ_TRACE=1 before the backward call");
+    const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
+    const size_t mu_bytes = (3 * (size_t)tape->net.n_params * es + 255) & ~(size_t)255;
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    LDEQ_CUDA(cudaDeviceSynchronize());
+    LDEQ_CUDA(cudaMemcpy(out_host, (char*)h->scratch[2] + mu_bytes, (size_t)(n < 4096 ? n : 4096) * 32, cudaMemcpyDeviceToHost));
+    return LDEQ_OK;
+}
+
+int ldeq_mlp_bwd_stats(ldeq_handle* h, ldeq_mlp_tape* tape, int32_t* out3_host, ldeq_stream stream) {
+    if (!h) return LDEQ_ERR_INVALID;
+    if (!tape || !out3_host) return set_err(h, LDEQ_ERR_INVALID, "null argument");
+    LDEQ_CUDA(cudaSetDevice(h->device));
+    LDEQ_CUDA(cudaMemcpyAsync(out3_host, tape->info + 4, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LDEQ_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return LDEQ_OK;
 }
 
 void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream) {

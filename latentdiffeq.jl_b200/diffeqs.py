@@ -49,9 +49,12 @@ class DiscreteAdjoint:
 
 
 class InterpolatingAdjoint:
-    """DiffEqFlux's ``NeuralODE`` default for the LatentODE path.  The LatentODE reverse pass here is the
-    discrete adjoint of the taped steps (``ldeq_mlp_solve_bwd``); it agrees with the continuous adjoint within the
-    solver tolerance."""
+    """DiffEqFlux's ``NeuralODE`` default for the LatentODE path: ``LDEQ_SENSE_INTERPOLATING_ADJOINT`` --
+    the continuous adjoint ODE on ``[lambda; mu]`` solved backwards by adaptive Tsit5 with the forward dense output and a
+    callback at every save time (``csrc/ldeq_mlp_cadj.cuh``).  The default of :class:`NODE` whenever the solve uses the
+    reference's batch-global error norm and the exact arithmetic path; ``DiscreteAdjoint()`` is the ~30x cheaper opt-in
+    (it agrees within the solver tolerance)."""
+    code = _cabi.SENSE_INTERPOLATING_ADJOINT
 
     def __repr__(self):
         return "InterpolatingAdjoint()"
@@ -129,7 +132,7 @@ class NODE(nn.Module):
     Appendix C.2) the MLP weights are registered parameters here and receive gradients.
     """
 
-    def __init__(self, latent_dim_in: int, hidden_dim: int = 200, augment_dim: int = 0, **kwargs):
+    def __init__(self, latent_dim_in: int, hidden_dim: int = 200, augment_dim: int = 0, sensealg=None, **kwargs):
         super().__init__()
         d = latent_dim_in + augment_dim
         self.dims = [d, hidden_dim, hidden_dim, d]
@@ -145,6 +148,13 @@ class NODE(nn.Module):
         self.latent_dim_out = latent_dim_in + augment_dim
         self.augment_dim = augment_dim
         self.kwargs = dict(kwargs)
+        # NeuralODE's default sensitivity algorithm is InterpolatingAdjoint (DiffEqFlux 1.52); it needs the reference's
+        # batch-global norm and exact arithmetic -- with the per-trajectory norm or the bf16x3 tensor-core path (both
+        # documented performance deviations) the reverse pass is the discrete adjoint
+        if sensealg is None:
+            ref = self.kwargs.get("norm_mode", _cabi.NORM_GLOBAL) == _cabi.NORM_GLOBAL and self.kwargs.get("mlp_math", 0) == 0
+            sensealg = InterpolatingAdjoint() if ref else DiscreteAdjoint()
+        self.sensealg = sensealg
 
     @property
     def dudt(self):

@@ -276,7 +276,7 @@ def _opts_from_kwargs(kwargs: dict, sensealg=None, solver=None) -> _cabi.Opts:
     if sensealg is not None:
         code = getattr(sensealg, "code", None)
         if code is None:
-            raise TypeError(f"sensealg {sensealg!r}: ForwardDiffSensitivity() (the reference's) or DiscreteAdjoint()")
+            raise TypeError(f"sensealg {sensealg!r}: ForwardDiffSensitivity() / InterpolatingAdjoint() (the reference's) or DiscreteAdjoint()")
         kw["sensealg"] = code
     if solver is not None:
         code = getattr(solver, "code", None)
@@ -304,8 +304,8 @@ def diffeq_layer(decoder, l_hat, t, stats_out=None):
     if diffeq.augment_dim:
         # AugmentedNDELayer (LatentODE.jl:71): zero-pad augment_dim extra state rows
         z0 = torch.cat([z0, z0.new_zeros(z0.shape[0], diffeq.augment_dim)], dim=1)
-    z = mlp_solve(z0, diffeq.flat_params(), diffeq.dims, t, _opts_from_kwargs(diffeq.kwargs, None, getattr(diffeq, 'solver', None)),
-                  stats_out)
+    z = mlp_solve(z0, diffeq.flat_params(), diffeq.dims, t, _opts_from_kwargs(diffeq.kwargs, getattr(diffeq, 'sensealg', None),
+                                                                          getattr(diffeq, 'solver', None)), stats_out)
     return transform_after_diffeq(z, diffeq)
 
 

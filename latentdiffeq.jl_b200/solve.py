@@ -307,6 +307,15 @@ def mlp_bwd_raw(tape: _Tape, dtraj: torch.Tensor):
     return dz0, dp
 
 
+def mlp_bwd_stats(tape: _Tape):
+    """``(naccept, nreject, retcode)`` of the backward solve ``LDEQ_SENSE_INTERPOLATING_ADJOINT`` ran for this tape."""
+    import ctypes
+    out = (ctypes.c_int32 * 3)()
+    h = tape.h
+    h.check(h._lib.ldeq_mlp_bwd_stats(h.ptr, tape.ptr, out, _stream()))
+    return int(out[0]), int(out[1]), int(out[2])
+
+
 class _MlpSolve(torch.autograd.Function):
     @staticmethod
     def forward(ctx, z0, params_flat, tg, dims, opts, stats_out):

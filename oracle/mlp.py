@@ -352,59 +352,133 @@ def _forward_dense(z0, p_flat, dims, t, opts):
     return rec, layers
 
 
-def interpolating_adjoint(z0, p_flat, dims, t, dtraj, opts: Opts | None = None):
+def _dense_from_tape(tape: Tape, layers):
+    """The dense forward solution rebuilt from a step tape (t_n, dt_n, u_n): the stage derivatives k_1..k_7 of every
+    accepted step are recomputed from u_n (what the CUDA kernel does: the tape holds no stages)."""
+    f = lambda U: mlp(layers, U)  # noqa: E731
+    rec = {"t": [], "dt": [], "u": [], "k": []}
+    for tn, dtn, un in zip(tape.t, tape.dt, tape.u):
+        u = un.astype(np.float64)
+        kk = [f(u)]
+        for j in range(1, 7):
+            kk.append(f(u + dtn * sum(A[j][i] * kk[i] for i in range(j))))
+        rec["t"].append(tn); rec["dt"].append(dtn); rec["u"].append(u); rec["k"].append(kk)
+    rec["t"].append(tape.t[-1] + tape.dt[-1])
+    rec["t"] = np.array(rec["t"])
+    return rec
+
+
+def interpolating_adjoint(z0, p_flat, dims, t, dtraj, opts: Opts | None = None, tape: Tape | None = None, stats=None):
     """Gradients the way the REFERENCE computes them for LatentODE: DiffEqFlux's NeuralODE default
-    ``InterpolatingAdjoint(autojacvec = ZygoteVJP())`` -- the continuous adjoint ODE
+    ``InterpolatingAdjoint(autojacvec = ZygoteVJP())`` [3P SciMLSensitivity 7.10, restated from the published algorithm]
+    -- the continuous adjoint
         lambda' = -(df/du)^T lambda,   mu' = -(df/dp)^T lambda
-    integrated backwards from t_end to t_0 with adaptive Tsit5 at the solve's abstol/reltol, u(t) taken from the forward
-    solution's dense output, and a jump ``lambda += dtraj[k]`` at every save time.  Float64 throughout.
-    Returns ``(dz0[B,D], dparams_flat)``.  This is NOT what the product computes (it uses the discrete adjoint of the
-    accepted steps); the two agree to the solver tolerance, and tests quantify by how much."""
+    solved as ONE ODE on the augmented state [lambda (D*B); mu (n_params)] from t_end back to t_0 with adaptive Tsit5 at
+    the solve's abstol / reltol: RMS error norm over the whole augmented vector, Hairer initial step, PI controller (the
+    same OrdinaryDiffEq machinery as the forward solve, ``solve`` above), u(t) from the forward solution's dense output,
+    and a ``PresetTimeCallback`` at every save time: the step is clipped to the next save time (tstop), there
+    ``lambda += dtraj[k]`` and the FSAL derivative is re-evaluated.  Float64 throughout.
+
+    ``tape``: accepted steps of the forward solve to interpolate (``solve(..., record=True)``); without it a Float64
+    forward solve is made here.  Returns ``(dz0[B,D], dparams_flat)``; ``stats`` (a dict) receives naccept / nreject.
+    The product offers this as LDEQ_SENSE_INTERPOLATING_ADJOINT next to the discrete adjoint of the accepted steps; the
+    two agree to the solver tolerance, and tests quantify by how much."""
     opts = opts or Opts()
-    rec, layers = _forward_dense(z0, p_flat, dims, t, opts)
     t = np.asarray(t, dtype=np.float64)
+    if tape is None:
+        rec, layers = _forward_dense(z0, p_flat, dims, t, opts)
+    else:
+        layers = [(W.astype(np.float64), b.astype(np.float64)) for W, b in unpack_params(p_flat, dims)]
+        rec = _dense_from_tape(tape, layers)
     T = len(t)
-    lam = dtraj[T - 1].astype(np.float64).copy()
     npar = n_params(dims)
+    lam = np.asarray(dtraj[T - 1], dtype=np.float64).copy()
     mu = np.zeros(npar)
+    nall = lam.size + npar
 
     def rhs(tq, lam_):
-        u = _dense_eval(rec, tq)
-        gu, gp = mlp_vjp(layers, u, lam_)
-        return -gu, -pack_params(gp)
+        gu, gp = mlp_vjp(layers, _dense_eval(rec, tq), lam_)
+        return -gu, -pack_params(gp).astype(np.float64)
 
-    # segments between consecutive save times, each integrated with adaptive Tsit5 (time runs backwards: s = -t)
-    for kseg in range(T - 1, 0, -1):
-        ta, tb = t[kseg], t[kseg - 1]
-        tc, y_l, y_m = ta, lam, mu
-        span = ta - tb
-        dl, dm = rhs(tc, y_l)
-        dt = min(span, 0.01 if not opts.adaptive else span / 2)
-        qold = opts.qoldinit
-        while tc > tb + 1e-15:
-            dts = min(dt, tc - tb)
-            kl, km = [dl], [dm]
-            for j in range(1, 7):
-                gl = y_l - dts * sum(A[j][i] * kl[i] for i in range(j))
-                a, b_ = rhs(tc - CS[j] * dts, gl)
-                kl.append(a); km.append(b_)
-            new_l = gl
-            new_m = y_m - dts * sum(A[6][i] * km[i] for i in range(6))
-            el = dts * sum(BT[i] * kl[i] for i in range(7))
-            em = dts * sum(BT[i] * km[i] for i in range(7))
-            res = np.concatenate([(el / (opts.abstol + np.maximum(np.abs(y_l), np.abs(new_l)) * opts.reltol)).ravel(),
-                                  em / (opts.abstol + np.maximum(np.abs(y_m), np.abs(new_m)) * opts.reltol)])
-            EEst = float(np.sqrt(np.mean(res * res)))
-            q11 = EEst ** opts.beta1 if EEst > 0 else 1.0
-            q = max(1 / opts.qmax, min(1 / opts.qmin, (q11 / qold ** opts.beta2) / opts.gamma)) if EEst > 0 else 1 / opts.qmax
-            if EEst <= 1:
-                tc = tb if tc - dts - tb < 1e-13 else tc - dts
-                y_l, y_m = new_l, new_m
-                dl, dm = kl[6], km[6]
-                qold = max(EEst, opts.qoldinit)
-                dt = min(span, dts / q)
+    def rms(a_l, a_m):
+        return float(np.sqrt((np.sum(a_l * a_l) + np.sum(a_m * a_m)) / nall))
+
+    t0, tend = t[0], t[-1]
+    dtmax = opts.dtmax if opts.dtmax > 0 else tend - t0
+    dtmin = opts.dtmin if opts.dtmin > 0 else max(np.finfo(np.float64).eps, np.spacing(abs(tend)))
+    pw = fastpow if opts.controller_pow == 0 else (lambda x, y: x ** y)
+    tc, ks = tend, T - 2
+    kl, km = rhs(tc, lam)
+    if opts.adaptive and not opts.dt > 0:
+        # ode_determine_initdt on the augmented state, time running backwards (tdir = -1)
+        sl, sm = opts.abstol + np.abs(lam) * opts.reltol, opts.abstol + np.abs(mu) * opts.reltol
+        d0, d1 = rms(lam / sl, mu / sm), rms(kl / sl, km / sm)
+        dt0 = 1e-6 if (d0 < 1e-5 or d1 < 1e-5) else 0.01 * d0 / d1
+        dt0 = min(dt0, dtmax)
+        fl, fm = rhs(tc - dt0, lam - dt0 * kl)
+        d2 = rms((fl - kl) / sl, (fm - km) / sm) / dt0
+        m = max(d1, d2)
+        dt1 = max(1e-6, dt0 * 1e-3) if m <= 1e-15 else 10.0 ** (-(2.0 + np.log10(m)) / 5.0)
+        dt = max(dtmin, min(100 * dt0, dt1, dtmax))
+    else:
+        dt = opts.dt
+    qold = opts.qoldinit
+    na = nr = iters = 0
+    while ks >= 0:
+        if iters >= opts.maxiters:
+            lam[:], mu[:] = np.nan, np.nan
+            break
+        iters += 1
+        tstop = t[ks]
+        dts = min(dt, tc - tstop)
+        tnew = tc - dts
+        if abs(tnew - tstop) < 100 * np.spacing(max(abs(tc), abs(tstop))):
+            tnew = tstop
+        kls, kms = [kl], [km]
+        for j in range(1, 7):
+            gl = lam - dts * sum(A[j][i] * kls[i] for i in range(j))
+            a, b_ = rhs(tc - CS[j] * dts, gl)
+            kls.append(a); kms.append(b_)
+        new_l = gl
+        new_m = mu - dts * sum(A[6][i] * kms[i] for i in range(6))
+        accept, q, q11 = True, 1.0, 1.0
+        if opts.adaptive:
+            el = dts * sum(BT[i] * kls[i] for i in range(7))
+            em = dts * sum(BT[i] * kms[i] for i in range(7))
+            EEst = rms(el / (opts.abstol + np.maximum(np.abs(lam), np.abs(new_l)) * opts.reltol),
+                       em / (opts.abstol + np.maximum(np.abs(mu), np.abs(new_m)) * opts.reltol))
+            if not np.isfinite(EEst):
+                lam[:], mu[:] = np.nan, np.nan
+                break
+            if EEst == 0:
+                q = 1 / opts.qmax
             else:
-                dt = dts / min(1 / opts.qmin, q11 / opts.gamma)
-        lam = y_l + dtraj[kseg - 1]
-        mu = y_m
+                q11 = pw(EEst, opts.beta1)
+                q = max(1 / opts.qmax, min(1 / opts.qmin, (q11 / pw(qold, opts.beta2)) / opts.gamma))
+            accept = EEst <= 1
+            if stats is not None:
+                stats.setdefault("trace", []).append((tc, dts, EEst, float(accept)))
+            if accept:
+                if opts.qsteady_min <= q <= opts.qsteady_max:
+                    q = 1.0
+                qold = max(EEst, opts.qoldinit)
+        if accept:
+            na += 1
+            tc, lam, mu = tnew, new_l, new_m
+            kl, km = kls[6], kms[6]
+            if tc == tstop:
+                lam = lam + dtraj[ks]      # the callback: cotangent of save point ks, then f is re-evaluated
+                ks -= 1
+                if ks >= 0:
+                    kl, km = rhs(tc, lam)
+            if opts.adaptive:
+                dt = min(dtmax, dts / q)
+        else:
+            nr += 1
+            dt = dts / min(1 / opts.qmin, q11 / opts.gamma)
+        if ks >= 0 and opts.adaptive and not (abs(dt) > dtmin and np.isfinite(dt)):
+            lam[:], mu[:] = np.nan, np.nan
+            break
+    if stats is not None:
+        stats["naccept"], stats["nreject"] = na, nr
     return lam, mu

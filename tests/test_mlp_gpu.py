@@ -342,3 +342,92 @@ def test_tensor_core_path_refuses_unsupported_shapes(ldeq):
     with pytest.raises(ldeq.LdeqError):
         _solve(ldeq, z0.astype(np.float64), np.zeros(om.n_params([16, 200, 200, 16])), [16, 200, 200, 16], 0.05 * np.arange(5),
                mlp_math=ldeq.MLP_MATH_BF16X3)
+
+
+# ---- row a13: the reference's own reverse pass (InterpolatingAdjoint) ------------------------------------------------
+def _cadj(ldeq, z0, p, dims, t, d, trace=0, **kw):
+    import ctypes
+    opts = ldeq.default_opts(sensealg=ldeq.SENSE_INTERPOLATING_ADJOINT, **kw)
+    z = torch.from_numpy(z0).to(DEV)
+    pp = torch.from_numpy(p).to(DEV)
+    traj, st, tape = ldeq.mlp_solve_raw(z, pp, dims, t, opts, want_tape=True)
+    gz, gp = ldeq.mlp_bwd_raw(tape, torch.from_numpy(d).to(DEV))
+    stats = ldeq.mlp_bwd_stats(tape)
+    tr = None
+    if trace:
+        buf = (ctypes.c_double * (4 * trace))()
+        tape.h.check(tape.h._lib.ldeq_debug_cadj_trace(tape.h.ptr, tape.ptr, buf, trace))
+        tr = np.array(buf).reshape(trace, 4)
+    tape.free()
+    return traj.cpu().numpy(), gz.cpu().numpy(), gp.cpu().numpy(), stats, tr
+
+
+@pytest.mark.parametrize("adaptive", [True, False])
+def test_interpolating_adjoint_fp64_follows_the_oracle_step_for_step(ldeq, adaptive, monkeypatch):
+    # fp64: kernel and oracle interpolate the same forward steps and integrate [lambda; mu] backwards with the same
+    # controller.  Fixed step: identical steps, gradients equal to rounding.  Adaptive: the device controller proposes dt
+    # through Float32 arithmetic (1e-7 relative), and the relu right-hand side makes the error estimate jump wherever a mask
+    # flips inside a step, so the sequences agree attempt by attempt at first (asserted on the first 16: time, dt, EEst,
+    # accept/reject) and drift apart at borderline decisions later; the gradients then agree to the solver tolerance.
+    monkeypatch.setenv("LDEQ_CADJ_TRACE", "1")
+    dims, p, rng = _net(dtype="float64", bias_scale=0.1)
+    B, T = 24, 20
+    z0 = 0.5 * rng.standard_normal((B, 16))
+    t = 0.05 * np.arange(T)
+    d = rng.standard_normal((T, B, 16))
+    kw = dict(controller_pow=1) if adaptive else dict(adaptive=False, dt=0.02)
+    okw = og.Opts(controller_pow=1) if adaptive else og.Opts(adaptive=False, dt=0.02)
+    tr, gz, gp, (na, nr, ret), trace = _cadj(ldeq, z0, p, dims, t, d, trace=16 if adaptive else 0, **kw)
+    otr, _, _, tape = om.solve(z0, p, dims, t, okw, record=True)
+    st = {}
+    oz, op = om.interpolating_adjoint(z0, p, dims, t, d, okw, tape=tape, stats=st)
+    ez, ep = np.abs(gz - oz).max() / np.abs(oz).max(), np.abs(gp - op).max() / np.abs(op).max()
+    print("backward solve", na, nr, ret, "oracle", st["naccept"], st["nreject"], "dz0", ez, "dp", ep)
+    assert ret == ldeq.RET_SUCCESS
+    assert np.abs(tr - otr).max() <= 1e-8 * np.abs(otr).max()
+    if adaptive:
+        otrace = np.array(st["trace"][:16])
+        assert np.array_equal(trace[:, 3], otrace[:, 3])
+        assert np.allclose(trace[:, :2], otrace[:, :2], rtol=1e-5, atol=0)
+        assert np.allclose(trace[:, 2], otrace[:, 2], rtol=1e-3, atol=1e-12)
+        assert abs(na - st["naccept"]) <= 0.1 * st["naccept"] and ez <= 5e-3 and ep <= 1e-2
+        # and it is NOT the discrete adjoint: the two differ by the discretisation error (row a13's point)
+        dz, dp = om.discrete_adjoint(p, dims, t, tape, d)
+        assert np.abs(gp - dp).max() > 10 * np.abs(gp - op).max()
+    else:
+        assert (na, nr) == (st["naccept"], st["nreject"]) and ez <= 1e-9 and ep <= 1e-9
+
+
+def test_interpolating_adjoint_fp32_c2_shape(ldeq):
+    # C2 (B = 256, T = 50, glorot weights): fp32 kernel vs the fp64 oracle on the kernel's own forward steps
+    dims, p, rng = _net()
+    B, T = 256, 50
+    z0 = (0.5 * rng.standard_normal((B, 16))).astype(np.float32)
+    t = 0.05 * np.arange(T)
+    d = rng.standard_normal((T, B, 16)).astype(np.float32)
+    tr, gz, gp, (na, nr, ret), _ = _cadj(ldeq, z0, p, dims, t, d)
+    otr, _, _, tape = om.solve(z0, p, dims, t, og.Opts(), record=True)
+    st = {}
+    oz, op = om.interpolating_adjoint(z0, p, dims, t, d, og.Opts(), tape=tape, stats=st)
+    ez, ep = np.abs(gz - oz).max() / np.abs(oz).max(), np.abs(gp - op).max() / np.abs(op).max()
+    print("backward solve", na, nr, "oracle", st["naccept"], st["nreject"], "dz0", ez, "dp", ep)
+    assert abs(na - st["naccept"]) <= 0.05 * st["naccept"] + 2
+    assert ez <= 5e-3 and ep <= 5e-3
+
+
+def test_interpolating_adjoint_needs_the_reference_configuration(ldeq):
+    dims, p, rng = _net()
+    z = torch.from_numpy((0.5 * rng.standard_normal((8, 16))).astype(np.float32)).to(DEV)
+    pp = torch.from_numpy(p).to(DEV)
+    t = 0.05 * np.arange(10)
+    d = torch.zeros(10, 8, 16, device=DEV)
+    for kw in (dict(norm_mode=1), dict(mlp_math=1)):
+        _, _, tape = ldeq.mlp_solve_raw(z, pp, dims, t, ldeq.default_opts(sensealg=ldeq.SENSE_INTERPOLATING_ADJOINT, **kw),
+                                        want_tape=True)
+        with pytest.raises(ldeq.LdeqError, match="interpolating adjoint"):
+            ldeq.mlp_bwd_raw(tape, d)
+        tape.free()
+    # and the GOKU entry points refuse it
+    with pytest.raises(ldeq.LdeqError):
+        ldeq.goku_solve_raw(torch.zeros(4, 2, device=DEV), torch.ones(4, 1, device=DEV), t, 0,
+                            ldeq.default_opts(sensealg=ldeq.SENSE_INTERPOLATING_ADJOINT), want_tape=True)
