@@ -82,6 +82,22 @@ def profile_traffic(kernel):
         return None
 
 
+def issue_roofline(kernels, launch_ms, sm_mhz, sms=148):
+    """The instruction-issue roofline of kernels that are bound by it: warp instructions per launch (counted by ncu,
+    profiles/traffic.json `issue_model`; the count is a property of the code and the inputs, not of the run) over the
+    live launch time, against one warp instruction per SM sub-partition per cycle at the sampled SM clock."""
+    model = profile_traffic("issue_model") or {}
+    try:
+        inst = sum(model[k]["warp_inst"] for k in kernels)
+        peak = sms * 4 * float(sm_mhz) * 1e6
+        ach = inst / (launch_ms * 1e-3)
+        return {"bound": "issue", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "T warp-inst/s", "frac": ach / peak,
+                "warp_inst_per_launch": inst, "lanes_per_inst": [model[k]["lanes"] for k in kernels],
+                "source": "instruction counts from profiles/traffic.json (ncu), time and clock measured live"}
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 
@@ -409,6 +425,8 @@ def run_ours(args):
                          "achieved": fdp_gbs, "peak": peak, "unit": "GB/s", "frac": fdp_gbs / peak,
                          "peak_source": peak_src, "launch_ms": fd["bwd_ms"], "algorithmic_bytes_per_launch": alg_fd,
                          "traffic": profile_traffic("tsit5_fwdsens_kernels"),
+                         "issue": issue_roofline(("tsit5_fwdsens_kernel_theta", "tsit5_fwdsens_kernel_u0"), fd["bwd_ms"],
+                                                 fd["clocks"].get("sm_mhz")),
                          "note": "the dominant kernels of the headline step; the dual solves restate the reference's arithmetic "
                                  "literally (Float64-promoted stage updates, Julia's Float32 sin/cos in Float64): ~1e5 issued "
                                  "instructions per trajectory for 1.6 kB of cotangent -- instruction-issue bound, not HBM bound; "
@@ -416,10 +434,12 @@ def run_ours(args):
             "kernels": {
                 "tsit5_fwd_kernel<PendulumRHS<float,0>,float,TAPE=1>": {
                     "bound": "hbm", "achieved": fwd_gbs, "peak": peak, "unit": "GB/s", "frac": fwd_gbs / peak, "launch_ms": fd["fwd_ms"],
-                    "algorithmic_bytes_per_launch": alg_fwd, "traffic": profile_traffic("tsit5_fwd_kernel_tape")},
+                    "algorithmic_bytes_per_launch": alg_fwd, "traffic": profile_traffic("tsit5_fwd_kernel_tape"),
+                    "issue": issue_roofline(("tsit5_fwd_kernel_tape",), fd["fwd_ms"], fd["clocks"].get("sm_mhz"))},
                 "tsit5_bwd_kernel<PendulumRHS<float,0>,float>": {
                     "bound": "hbm", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak, "launch_ms": da["bwd_ms"],
-                    "algorithmic_bytes_per_launch": alg_bwd, "traffic": profile_traffic("tsit5_bwd_kernel")}},
+                    "algorithmic_bytes_per_launch": alg_bwd, "traffic": profile_traffic("tsit5_bwd_kernel"),
+                    "issue": issue_roofline(("tsit5_bwd_kernel",), da["bwd_ms"], fd["clocks"].get("sm_mhz"))}},
             "issue_model": profile_traffic("issue_model"),
             "discrete_adjoint": {
                 "sensealg": "LDEQ_SENSE_DISCRETE_ADJOINT (explicit opt-in: exact derivative of the primal discretisation; equals the "

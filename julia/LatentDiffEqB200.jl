@@ -46,6 +46,7 @@ struct DiscreteAdjoint end
 function sensealg_code(s)
     s isa DiscreteAdjoint && return Int32(0)
     nameof(typeof(s)) === :ForwardDiffSensitivity && return Int32(1)   # SciMLSensitivity / DiffEqSensitivity, whichever is loaded
+    nameof(typeof(s)) === :InterpolatingAdjoint && return Int32(2)     # LatentODE path only (ldeq_mlp_*): NeuralODE's default
     error("sensealg $(typeof(s)) not supported by libldeq: use ForwardDiffSensitivity() (the reference's) or LatentDiffEqB200.DiscreteAdjoint()")
 end
 solver_code(s) = nameof(typeof(s)) === :Tsit5 ? Int32(0) : error("solver $(typeof(s)) not supported by libldeq: the hot path implements Tsit5()")
@@ -188,6 +189,12 @@ function mlp_fwd(diffeq, ẑ₀::CuMatrix{T}, t; tape::Bool) where {T}
     tt = collect(Float64, t)
     ẑ = CUDA.zeros(T, D, B, length(tt))
     opts = Ref(Opts(diffeq))                          # kwargs + solver (a NODE struct has no sensealg field, nODE.jl:3-12)
+    # NeuralODE's default sensitivity algorithm is InterpolatingAdjoint (DiffEqFlux 1.52): LDEQ_SENSE_INTERPOLATING_ADJOINT
+    # whenever the solve runs in the reference's configuration (batch-global norm, exact arithmetic); the per-trajectory
+    # norm and the bf16x3 tensor-core path are performance deviations whose reverse pass is the discrete adjoint
+    if !hasproperty(diffeq, :sensealg)
+        opts[].sensealg = (opts[].norm_mode == 0 && opts[].mlp_math == 0) ? Int32(2) : Int32(0)
+    end
     tp = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:ldeq_mlp_solve_fwd, libldeq), Cint,
                (Ptr{Cvoid}, Cint, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Int32}, Cint, Ptr{Cdouble}, Cint, Cint, Ref{Opts}, CuPtr{Cvoid},
@@ -198,7 +205,8 @@ function mlp_fwd(diffeq, ẑ₀::CuMatrix{T}, t; tape::Bool) where {T}
     return ẑ, Tape(tp[], true)
 end
 
-# reverse pass of the LatentODE method (replaces DiffEqFlux's InterpolatingAdjoint pullback, LatentODE.jl:70-72 under Zygote):
+# reverse pass of the LatentODE method (replaces DiffEqFlux's InterpolatingAdjoint pullback, LatentODE.jl:70-72 under Zygote;
+# the tape remembers the sensealg of the forward call: the continuous adjoint kernel or the discrete adjoint of the taped steps):
 # ldeq_mlp_solve_bwd -> (dẑ₀ (D,B), dparams_flat in Flux.destructure order), the latter restructured into a tangent of `dudt`
 function ChainRulesCore.rrule(::typeof(diffeq_layer), decoder::Decoder{LatentODE}, ẑ₀::CuMatrix{T}, t) where {T}
     diffeq = decoder.diffeq

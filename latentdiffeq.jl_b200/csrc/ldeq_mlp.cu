@@ -651,8 +651,12 @@ static int launch_mlp_cadj(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtra
 
 template <class S>
 static int mlp_cadj_dispatch(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0, void* dparams, cudaStream_t s) {
-    int rc = launch_mlp_cadj<S, 2>(h, tape, dtraj, dz0, dparams, s);
-    if (rc == LDEQ_ERR_UNSUPPORTED) rc = launch_mlp_cadj<S, 8>(h, tape, dtraj, dz0, dparams, s);
+    const char* force = getenv("LDEQ_CADJ_TB");  // tuning aid: 2, 8 or 32 rows per CTA
+    const int ftb = force ? atoi(force) : 0;
+    int rc = LDEQ_ERR_UNSUPPORTED;
+    if (ftb == 0 || ftb == 2) rc = launch_mlp_cadj<S, 2>(h, tape, dtraj, dz0, dparams, s);
+    if (rc == LDEQ_ERR_UNSUPPORTED && (ftb == 0 || ftb == 8)) rc = launch_mlp_cadj<S, 8>(h, tape, dtraj, dz0, dparams, s);
+    if (ftb == 2 || ftb == 8) { if (rc == LDEQ_ERR_UNSUPPORTED) return set_err(h, rc, "LDEQ_CADJ_TB: does not fit"); return rc; }
     if (rc == LDEQ_ERR_UNSUPPORTED) rc = launch_mlp_cadj<S, 32>(h, tape, dtraj, dz0, dparams, s);
     if (rc == LDEQ_ERR_UNSUPPORTED)
         return set_err(h, LDEQ_ERR_UNSUPPORTED, "interpolating adjoint: batch too large (all tiles must be co-resident for the "
