@@ -102,9 +102,13 @@ enum ldeq_mlp_math {
  *        value makes ldeq_mlp_solve_bwd run the discrete adjoint of the taped steps.  The GOKU entry points refuse it. */
 typedef enum { LDEQ_SENSE_DISCRETE_ADJOINT = 0, LDEQ_SENSE_FORWARD_DUAL = 1, LDEQ_SENSE_INTERPOLATING_ADJOINT = 2 } ldeq_sensealg;
 
-/* The diffeq struct's `solver` field (pendulum.jl:11,58: Tsit5()).  Anything else is refused with
- * LDEQ_ERR_UNSUPPORTED rather than silently replaced. */
-typedef enum { LDEQ_SOLVER_TSIT5 = 0 } ldeq_solver;
+/* The diffeq struct's `solver` field, handed to `solve` at GOKU.jl:121.  The reference's structs use Tsit5()
+ * (pendulum.jl:11,58); the field is the user's to set, so OrdinaryDiffEq's DP5(), BS3() and RK4() are built as well
+ * (csrc/ldeq_erk.cuh: the same integrator kernels with a table-driven method, dense output as
+ * OrdinaryDiffEq defines it -- dopri5's contd5 for DP5, cubic Hermite for BS3 / RK4).  GOKU entry points only: the
+ * LatentODE kernels are Tsit5.  RK4 is accepted with adaptive = 0 only (OrdinaryDiffEq's adaptive RK4 is a defect-control
+ * estimate that is not restated).  Anything unsupported is refused with LDEQ_ERR_UNSUPPORTED, never silently replaced. */
+typedef enum { LDEQ_SOLVER_TSIT5 = 0, LDEQ_SOLVER_DP5 = 1, LDEQ_SOLVER_BS3 = 2, LDEQ_SOLVER_RK4 = 3 } ldeq_solver;
 
 /* The keyword arguments the diffeq struct's `kwargs` field forwards to `solve` (pendulum.jl:11,43;
  * GOKU.jl:108,121).  ldeq_opts_default fills OrdinaryDiffEq's defaults for Tsit5. */
@@ -136,6 +140,9 @@ typedef struct ldeq_opts {
 
 int ldeq_version(void);
 void ldeq_opts_default(ldeq_opts* opts);
+/* The same with `solver` set and the PI-controller exponents OrdinaryDiffEq gives that algorithm (beta2 = 2/(5 order),
+ * beta1 = 7/(10 order); DP5: beta2 = 4/100, beta1 = 1/5 - 3 beta2/4).  Returns LDEQ_ERR_INVALID for an unknown solver. */
+int ldeq_opts_default_solver(ldeq_opts* opts, int solver);
 
 /* ---- handle ------------------------------------------------------------------------------------ */
 int ldeq_create(ldeq_handle** out, int device);

@@ -34,7 +34,7 @@ Base.@kwdef mutable struct Opts
     norm_mode::Int32 = 0
     mlp_math::Int32 = 0
     sensealg::Int32 = 1   # 1 = LDEQ_SENSE_FORWARD_DUAL, the reference's dual-number re-solves (default); 0 = discrete adjoint
-    solver::Int32 = 0     # 0 = LDEQ_SOLVER_TSIT5
+    solver::Int32 = 0     # ldeq_solver: 0 = Tsit5 (the reference's structs), 1 = DP5, 2 = BS3, 3 = RK4 (fixed step only)
     reserved_::Int32 = 0
 end
 
@@ -49,7 +49,10 @@ function sensealg_code(s)
     nameof(typeof(s)) === :InterpolatingAdjoint && return Int32(2)     # LatentODE path only (ldeq_mlp_*): NeuralODE's default
     error("sensealg $(typeof(s)) not supported by libldeq: use ForwardDiffSensitivity() (the reference's) or LatentDiffEqB200.DiscreteAdjoint()")
 end
-solver_code(s) = nameof(typeof(s)) === :Tsit5 ? Int32(0) : error("solver $(typeof(s)) not supported by libldeq: the hot path implements Tsit5()")
+const SOLVER_CODES = Dict(:Tsit5 => Int32(0), :DP5 => Int32(1), :BS3 => Int32(2), :RK4 => Int32(3))
+solver_code(s) = get(SOLVER_CODES, nameof(typeof(s))) do
+    error("solver $(typeof(s)) not supported by libldeq: Tsit5(), DP5(), BS3() and RK4() (fixed step) are built")
+end
 
 # the `kwargs` field of the diffeq struct is splatted into `solve` by the reference (GOKU.jl:108,121)
 function Opts(kwargs::Union{NamedTuple,Base.Pairs,Dict})
@@ -62,11 +65,20 @@ function Opts(kwargs::Union{NamedTuple,Base.Pairs,Dict})
     return o
 end
 
-# everything the reference reads from a GOKU diffeq struct (GOKU.jl:105-108): kwargs, sensealg, solver
+# everything the reference reads from a GOKU diffeq struct (GOKU.jl:105-108): kwargs, sensealg, solver.  The solver comes
+# first: the PI-controller exponents OrdinaryDiffEq defaults to depend on the algorithm (ldeq_opts_default_solver), and
+# the struct's kwargs then override them like they override OrdinaryDiffEq's defaults in `solve`.
 function Opts(diffeq)
-    o = Opts(diffeq.kwargs)
+    base = Ref(Opts())
+    code = hasproperty(diffeq, :solver) ? solver_code(diffeq.solver) : Int32(0)
+    ccall((:ldeq_opts_default_solver, libldeq), Cint, (Ptr{Opts}, Cint), base, code) == 0 || error("ldeq_opts_default_solver($code)")
+    o = base[]
+    for (k, v) in pairs(diffeq.kwargs)
+        k === :saveat && continue
+        hasproperty(o, k) || error("solver option $k is not supported by libldeq")
+        setproperty!(o, k, convert(fieldtype(Opts, k), v))
+    end
     hasproperty(diffeq, :sensealg) && (o.sensealg = sensealg_code(diffeq.sensealg))
-    hasproperty(diffeq, :solver) && (o.solver = solver_code(diffeq.solver))
     return o
 end
 

@@ -18,11 +18,11 @@ RET_SUCCESS, RET_MAXITERS, RET_DTLESSTHANMIN, RET_UNSTABLE = 0, 1, 2, 3
 NORM_GLOBAL, NORM_PER_TRAJ = 0, 1
 MLP_MATH_FP32, MLP_MATH_BF16X3 = 0, 1
 OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM, ERR_COMPILE, ERR_TAPE_OVERFLOW = 0, -1, -2, -3, -4, -5, -6
-SOLVER_TSIT5 = 0
+SOLVER_TSIT5, SOLVER_DP5, SOLVER_BS3, SOLVER_RK4 = 0, 1, 2, 3
 
 # every symbol include/ldeq.h declares (tests check the library exports exactly these)
 SYMBOLS = [
-    "ldeq_version", "ldeq_opts_default", "ldeq_create", "ldeq_destroy", "ldeq_last_error", "ldeq_launch_count",
+    "ldeq_version", "ldeq_opts_default", "ldeq_opts_default_solver", "ldeq_create", "ldeq_destroy", "ldeq_last_error", "ldeq_launch_count",
     "ldeq_rhs_builtin", "ldeq_rhs_from_source", "ldeq_rhs_dims", "ldeq_rhs_free",
     "ldeq_solve_fwd", "ldeq_solve_bwd", "ldeq_tape_overflow", "ldeq_tape_free",
     "ldeq_solve_fwd_host", "ldeq_solve_bwd_host", "ldeq_solve_fwd_bwd_host", "ldeq_debug_trig",
@@ -71,6 +71,7 @@ def load() -> C.CDLL:
     lib.ldeq_version.restype = i32
     lib.ldeq_opts_default.argtypes = [C.POINTER(Opts)]
     lib.ldeq_opts_default.restype = None
+    lib.ldeq_opts_default_solver.argtypes = [C.POINTER(Opts), i32]
     lib.ldeq_create.argtypes = [pvp, i32]
     lib.ldeq_destroy.argtypes = [vp]
     lib.ldeq_destroy.restype = None
@@ -111,9 +112,12 @@ def load() -> C.CDLL:
 
 
 def default_opts(**kw) -> Opts:
-    """OrdinaryDiffEq's Tsit5 defaults, overridden by keyword (same names as ``solve`` kwargs)."""
+    """OrdinaryDiffEq's defaults for ``solver`` (Tsit5 unless given: the controller exponents depend on the algorithm),
+    overridden by keyword (same names as ``solve`` kwargs)."""
     o = Opts()
-    load().ldeq_opts_default(C.byref(o))
+    rc = load().ldeq_opts_default_solver(C.byref(o), int(kw.get("solver", SOLVER_TSIT5)))
+    if rc != OK:
+        raise LdeqError(rc, f"unknown solver code {kw.get('solver')!r}")
     for k, v in kw.items():
         if not hasattr(o, k):
             raise TypeError(f"unknown solver option {k!r}")

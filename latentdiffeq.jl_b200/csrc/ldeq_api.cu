@@ -13,6 +13,11 @@
 
 namespace ldeq {
 
+// ldeq_erk.cu: the forward kernel for solver = DP5 / BS3 / RK4 (built-in right-hand sides)
+cudaError_t launch_erk_fwd(int solver, int dtype, bool friction, bool with_tape, const void* z0, const void* theta, const double* tg, int B,
+                           int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr, const TapeView<float>& tv,
+                           const GridInfo& gi, cudaStream_t s);
+
 int set_err(ldeq_handle* h, int code, const char* what, cudaError_t ce) {
     if (h) {
         h->err = what ? what : "";
@@ -120,7 +125,7 @@ static size_t ring_smem(int z_dim, size_t es, int threads, int T) {
 
 // kernels of an NVRTC-compiled user right-hand side (ldeq_user_rhs.cu): fn[] = {fwd f32, fwd f32 tape, fwd f64,
 // fwd f64 tape, bwd f32, bwd f64}; same signatures as the built-in instantiations
-static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg,
+static cudaError_t launch_user_fwd(void* const* fn, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg,
                                    int B, int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
                                    const ldeq_tape* tape, const GridInfo& gi, cudaStream_t s) {
     TapeView<float> tv{nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};  // identical layout for float and double
@@ -130,10 +135,10 @@ static cudaError_t launch_user_fwd(const ldeq_rhs* rhs, int dtype, const void* z
     void* args[] = {&z0, &theta, &tg, &B, &T, &kov, &traj, &ret, &na, &nr, &tv, &giv};
     const int grid = (B + LDEQ_FWD_THREADS - 1) / LDEQ_FWD_THREADS;
     const size_t es = dtype == LDEQ_F32 ? 4 : 8;
-    void* fn = rhs->fn[(dtype == LDEQ_F32 ? 0 : 2) + (tape ? 1 : 0)];
-    return cudaLaunchKernel(fn, dim3(grid), dim3(LDEQ_FWD_THREADS), args, ring_smem(rhs->z_dim, es, LDEQ_FWD_THREADS, T), s);
+    void* kfn = fn[(dtype == LDEQ_F32 ? 0 : 2) + (tape ? 1 : 0)];
+    return cudaLaunchKernel(kfn, dim3(grid), dim3(LDEQ_FWD_THREADS), args, ring_smem(rhs->z_dim, es, LDEQ_FWD_THREADS, T), s);
 }
-static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
+static cudaError_t launch_user_bwd(void* const* fn, const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     TapeView<float> tv{tape->t, (float*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
     const void* theta = tape->theta;
     const double* tg = tape->tgrid;
@@ -144,12 +149,12 @@ static cudaError_t launch_user_bwd(const ldeq_tape* tape, const void* dtraj, int
     void* args[] = {&theta, &tg, &B, &T, &dtraj, &tv, &ret, &na, &dz0, &dtheta, &giv};
     const int grid = (B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
     const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;
-    void* fn = tape->rhs->fn[tape->dtype == LDEQ_F32 ? 4 : 5];
-    return cudaLaunchKernel(fn, dim3(grid), dim3(LDEQ_BWD_THREADS), args, ring_smem(tape->z_dim, es, LDEQ_BWD_THREADS, T), s);
+    void* kfn = fn[tape->dtype == LDEQ_F32 ? 4 : 5];
+    return cudaLaunchKernel(kfn, dim3(grid), dim3(LDEQ_BWD_THREADS), args, ring_smem(tape->z_dim, es, LDEQ_BWD_THREADS, T), s);
 }
 
 // fn[6..9] = forward-dual pullback {theta-seeded f32, u0-seeded f32, theta-seeded f64, u0-seeded f64}
-static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
+static cudaError_t launch_user_fwdsens(void* const* fn, const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     const void* z0 = tape->u;
     const void* theta = tape->theta;
     const double* tg = tape->tgrid;
@@ -161,10 +166,10 @@ static cudaError_t launch_user_fwdsens(const ldeq_tape* tape, const void* dtraj,
     const int grid = (B + 127) / 128;
     const int base = tape->dtype == LDEQ_F32 ? 6 : 8;
     void* args_p[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &key, &dtraj, &ret, &dtheta};
-    cudaError_t e = cudaLaunchKernel(tape->rhs->fn[base], dim3(grid), dim3(128), args_p, 0, s);
+    cudaError_t e = cudaLaunchKernel(fn[base], dim3(grid), dim3(128), args_p, 0, s);
     if (e != cudaSuccess) return e;
     void* args_u[] = {&z0, &theta, &tg, &B, &gi, &T, &kov, &np, &key, &dtraj, &ret, &dz0};
-    return cudaLaunchKernel(tape->rhs->fn[base + 1], dim3(grid), dim3(128), args_u, 0, s);
+    return cudaLaunchKernel(fn[base + 1], dim3(grid), dim3(128), args_u, 0, s);
 }
 
 // Pinned two-int mirrors + events come from a per-handle pool: cudaMallocHost / cudaFreeHost cost milliseconds of host time
@@ -226,11 +231,20 @@ static int tape_alloc(ldeq_handle* h, ldeq_tape* tape, int cap, cudaStream_t s) 
     return LDEQ_OK;
 }
 
-static cudaError_t dispatch_fwd(const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta, const double* tg, int B,
-                                int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
+static cudaError_t dispatch_fwd(ldeq_handle* h, int solver, const ldeq_rhs* rhs, int dtype, const void* z0, const void* theta,
+                                const double* tg, int B, int T, const KOpts& ko, void* traj, int32_t* ret, int32_t* na, int32_t* nr,
                                 const ldeq_tape* tape, const GridInfo& gi, cudaStream_t s) {
-    if (rhs->kind < 0) return launch_user_fwd(rhs, dtype, z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s);
+    if (rhs->kind < 0) {
+        void* const* fn = user_rhs_kernels(h, rhs, solver);
+        if (!fn) return cudaErrorLaunchFailure;  // h->err holds the NVRTC log
+        return launch_user_fwd(fn, rhs, dtype, z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s);
+    }
     const bool friction = rhs->kind == LDEQ_RHS_PENDULUM_FRICTION;
+    if (solver != LDEQ_SOLVER_TSIT5) {
+        TapeView<float> tv{nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, nullptr, nullptr};
+        if (tape) tv = fwd_tape_view<float>(tape, theta, tg);
+        return launch_erk_fwd(solver, dtype, friction, tape != nullptr, z0, theta, tg, B, T, ko, traj, ret, na, nr, tv, gi, s);
+    }
 #define LDEQ_DISPATCH_FWD(S)                                                                              \
     (tape ? (friction ? launch_fwd<S, true, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s)    \
                       : launch_fwd<S, false, true>(z0, theta, tg, B, T, ko, traj, ret, na, nr, tape, gi, s))  \
@@ -256,7 +270,7 @@ static int tape_heal(ldeq_handle* h, ldeq_tape* tape, cudaStream_t s) {
     cudaMemcpyAsync(tape->theta, old.theta, (size_t)tape->B * tape->p_dim * es, cudaMemcpyDeviceToDevice, s);
     cudaMemcpyAsync(tape->tgrid, old.tgrid, (size_t)tape->T * 8, cudaMemcpyDeviceToDevice, s);
     // step 0 of the old tape holds u0 for every trajectory (capacity is always >= 1)
-    cudaError_t e = dispatch_fwd(tape->rhs, tape->dtype, old.u, tape->theta,
+    cudaError_t e = dispatch_fwd(h, tape->solver, tape->rhs, tape->dtype, old.u, tape->theta,
                                  tape->tgrid, tape->B, tape->T, tape->kopts, nullptr, nullptr, nullptr,
                                  nullptr, tape, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform, tape->B}, s);
     h->launches += 1;
@@ -281,6 +295,21 @@ void ldeq_opts_default(ldeq_opts* o) {
     o->norm_mode = LDEQ_NORM_GLOBAL; o->mlp_math = LDEQ_MLP_MATH_FP32;
     o->sensealg = LDEQ_SENSE_FORWARD_DUAL;  // what the reference's diffeq structs ask for (pendulum.jl:11,58)
     o->solver = LDEQ_SOLVER_TSIT5;
+}
+
+int ldeq_opts_default_solver(ldeq_opts* o, int solver) {
+    if (!o || solver < LDEQ_SOLVER_TSIT5 || solver > LDEQ_SOLVER_RK4) return LDEQ_ERR_INVALID;
+    ldeq_opts_default(o);
+    o->solver = solver;
+    // OrdinaryDiffEq alg_utils.jl [3P]: beta2_default = 2/(5 order), beta1_default = 7/(10 order); DP5 has its own pair
+    const double order = solver == LDEQ_SOLVER_BS3 ? 3.0 : solver == LDEQ_SOLVER_RK4 ? 4.0 : 5.0;
+    o->beta2 = 2.0 / (5.0 * order);
+    o->beta1 = 7.0 / (10.0 * order);
+    if (solver == LDEQ_SOLVER_DP5) {
+        o->beta2 = 4.0 / 100.0;
+        o->beta1 = 1.0 / 5.0 - 3.0 * o->beta2 / 4.0;
+    }
+    return LDEQ_OK;
 }
 
 int ldeq_create(ldeq_handle** out, int device) {
@@ -368,6 +397,7 @@ static int solve_fwd_slab(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const 
         tape->grid_t0 = h->grid_t0; tape->grid_h = h->grid_h; tape->grid_uniform = h->grid_uniform;
         long long cap = opts->tape_steps;
         tape->sense = opts->sensealg;
+        tape->solver = opts->solver;
         if (fwd_dual) {
             cap = 1;  // the dual re-solves need only u0 (record 0), theta, the grid and the options
         } else if (cap <= 0) {
@@ -390,11 +420,12 @@ static int solve_fwd_slab(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const 
         }
         // theta, the grid, the statistics and u0 (record 0) reach the tape through the forward kernel itself (TapeView)
     }
-    cudaError_t e = dispatch_fwd(rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, retcode, naccept, nreject, tape,
+    cudaError_t e = dispatch_fwd(h, opts->solver, rhs, dtype, z0, theta, h->d_tgrid, B, T, ko, traj_out, retcode, naccept, nreject, tape,
                                  GridInfo{h->grid_t0, h->grid_h, h->grid_uniform, ld}, s);
     h->launches += 1;
     if (e != cudaSuccess) {
         if (tape) { cudaFreeAsync(tape->base, s); cudaEventRecord(tape->ready, s); slot_put(h, tape); delete tape; }
+        if (rhs->kind < 0 && e == cudaErrorLaunchFailure && !h->err.empty() && h->err.compare(0, 5, "NVRTC") == 0) return LDEQ_ERR_COMPILE;
         return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwd_kernel launch", e);
     }
     if (tape) {
@@ -407,8 +438,10 @@ static int solve_fwd_slab(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const 
 
 // reverse pass of one slab (a single-part tape); dtraj / dz0 / dtheta already offset, ld = row stride of dtraj
 static int solve_bwd_slab(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
+    void* const* ufn = nullptr;
+    if (tape->rhs_kind < 0 && !(ufn = user_rhs_kernels(h, tape->rhs, tape->solver))) return LDEQ_ERR_COMPILE;
     if (tape->sense == LDEQ_SENSE_FORWARD_DUAL) {
-        const cudaError_t e2 = tape->rhs_kind < 0 ? launch_user_fwdsens(tape, dtraj, ld, dz0, dtheta, s)
+        const cudaError_t e2 = tape->rhs_kind < 0 ? launch_user_fwdsens(ufn, tape, dtraj, ld, dz0, dtheta, s)
                                                   : launch_fwdsens(tape, dtraj, ld, dz0, dtheta, s);
         h->launches += 2;
         if (e2 != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "tsit5_fwdsens_kernel launch", e2);
@@ -419,7 +452,9 @@ static int solve_bwd_slab(ldeq_handle* h, ldeq_tape* tape, const void* dtraj, in
     const bool fr = tape->rhs_kind == LDEQ_RHS_PENDULUM_FRICTION;
     cudaError_t e;
     if (tape->rhs_kind < 0)
-        e = launch_user_bwd(tape, dtraj, ld, dz0, dtheta, s);
+        e = launch_user_bwd(ufn, tape, dtraj, ld, dz0, dtheta, s);
+    else if (tape->solver != LDEQ_SOLVER_TSIT5)
+        e = launch_erk_bwd(tape, dtraj, ld, dz0, dtheta, s);
     else if (tape->dtype == LDEQ_F32)
         e = fr ? launch_bwd<float, true>(tape, dtraj, ld, dz0, dtheta, s) : launch_bwd<float, false>(tape, dtraj, ld, dz0, dtheta, s);
     else
@@ -439,8 +474,10 @@ static int check_solve_args(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, cons
         if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
     if (opts->sensealg != LDEQ_SENSE_DISCRETE_ADJOINT && opts->sensealg != LDEQ_SENSE_FORWARD_DUAL)
         return set_err(h, LDEQ_ERR_INVALID, "sensealg");
-    if (opts->solver != LDEQ_SOLVER_TSIT5)
-        return set_err(h, LDEQ_ERR_UNSUPPORTED, "solver: only LDEQ_SOLVER_TSIT5 is built (the reference's examples use Tsit5(), pendulum.jl:11,58)");
+    if (opts->solver < LDEQ_SOLVER_TSIT5 || opts->solver > LDEQ_SOLVER_RK4)
+        return set_err(h, LDEQ_ERR_UNSUPPORTED, "solver: LDEQ_SOLVER_TSIT5 / DP5 / BS3 / RK4 are built");
+    if (opts->solver == LDEQ_SOLVER_RK4 && opts->adaptive)
+        return set_err(h, LDEQ_ERR_UNSUPPORTED, "solver RK4: fixed step only (adaptive = 0, dt > 0); OrdinaryDiffEq's defect-control estimate of adaptive RK4 is not built");
     return LDEQ_OK;
 }
 
@@ -589,7 +626,7 @@ int ldeq_solve_fwd_host(ldeq_handle* h, const ldeq_rhs* rhs, int dtype, const vo
     if (tape_out) {
         parent = new ldeq_tape();
         parent->dtype = dtype; parent->rhs_kind = rhs->kind; parent->rhs = rhs; parent->B = B; parent->T = T;
-        parent->z_dim = rhs->z_dim; parent->p_dim = rhs->p_dim; parent->sense = opts->sensealg;
+        parent->z_dim = rhs->z_dim; parent->p_dim = rhs->p_dim; parent->sense = opts->sensealg; parent->solver = opts->solver;
     }
     const int ns = slab_count(B);
     for (int i = 0; i < ns; ++i) {

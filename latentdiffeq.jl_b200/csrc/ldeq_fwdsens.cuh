@@ -14,6 +14,7 @@
 #pragma once
 
 #include "ldeq_dual.cuh"
+#include "ldeq_erk.cuh"
 
 namespace ldeq {
 
@@ -69,16 +70,126 @@ template <class S, int N> __device__ __forceinline__ S dual_rms(const Dual<S, N>
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
+// ---- one step on duals, per method ---------------------------------------------------------------------------
+// Tsit5: written out (the arithmetic order is the oracle's tsit5_step, bit for bit); DP5 / BS3 / RK4: the table-driven
+// form of the oracle's erk_step (zero coefficients skipped, first term a product, the rest FMAs).
+struct Tsit5Dual {
+    static constexpr int NS = 7, ORDER = 5;
+    template <class RHS, class S, int NP>
+    __device__ __forceinline__ static void step(const Dual<S, NP>* u, const Dual<S, NP>* L, double t, double dts,
+                                                Dual<S, NP> (*k)[RHS::ZD], Dual<S, NP>* unew) {
+        constexpr int Z = RHS::ZD;
+        using D = Dual<S, NP>;
+        using Tb = Tab<S>;
+        D tmp[Z], sum;
+        for (int i = 0; i < Z; ++i) { sum = dual_scale(Tb::a21, k[0][i]); tmp[i] = dual_axpy_time(u[i], dts, sum); }
+        RHS::f(k[1], tmp, L, t + Tb::c2 * dts);
+        for (int i = 0; i < Z; ++i) {
+            sum = dual_scale(Tb::a31, k[0][i]); sum = dual_fma(Tb::a32, k[1][i], sum);
+            tmp[i] = dual_axpy_time(u[i], dts, sum);
+        }
+        RHS::f(k[2], tmp, L, t + Tb::c3 * dts);
+        for (int i = 0; i < Z; ++i) {
+            sum = dual_scale(Tb::a41, k[0][i]); sum = dual_fma(Tb::a42, k[1][i], sum); sum = dual_fma(Tb::a43, k[2][i], sum);
+            tmp[i] = dual_axpy_time(u[i], dts, sum);
+        }
+        RHS::f(k[3], tmp, L, t + Tb::c4 * dts);
+        for (int i = 0; i < Z; ++i) {
+            sum = dual_scale(Tb::a51, k[0][i]); sum = dual_fma(Tb::a52, k[1][i], sum); sum = dual_fma(Tb::a53, k[2][i], sum);
+            sum = dual_fma(Tb::a54, k[3][i], sum);
+            tmp[i] = dual_axpy_time(u[i], dts, sum);
+        }
+        RHS::f(k[4], tmp, L, t + Tb::c5 * dts);
+        for (int i = 0; i < Z; ++i) {
+            sum = dual_scale(Tb::a61, k[0][i]); sum = dual_fma(Tb::a62, k[1][i], sum); sum = dual_fma(Tb::a63, k[2][i], sum);
+            sum = dual_fma(Tb::a64, k[3][i], sum); sum = dual_fma(Tb::a65, k[4][i], sum);
+            tmp[i] = dual_axpy_time(u[i], dts, sum);
+        }
+        RHS::f(k[5], tmp, L, t + dts);
+        for (int i = 0; i < Z; ++i) {
+            sum = dual_scale(Tb::a71, k[0][i]); sum = dual_fma(Tb::a72, k[1][i], sum); sum = dual_fma(Tb::a73, k[2][i], sum);
+            sum = dual_fma(Tb::a74, k[3][i], sum); sum = dual_fma(Tb::a75, k[4][i], sum); sum = dual_fma(Tb::a76, k[5][i], sum);
+            unew[i] = dual_axpy_time(u[i], dts, sum);
+        }
+        RHS::f(k[6], unew, L, t + dts);
+    }
+    // sum_j btilde_j k_j of one state component
+    template <class S, int NP, int Z>
+    __device__ __forceinline__ static Dual<S, NP> err_sum(Dual<S, NP> (*k)[Z], int i) {
+        using Tb = Tab<S>;
+        Dual<S, NP> sum = dual_scale(Tb::bt1, k[0][i]);
+        sum = dual_fma(Tb::bt2, k[1][i], sum); sum = dual_fma(Tb::bt3, k[2][i], sum);
+        sum = dual_fma(Tb::bt4, k[3][i], sum); sum = dual_fma(Tb::bt5, k[4][i], sum); sum = dual_fma(Tb::bt6, k[5][i], sum);
+        sum = dual_fma(Tb::bt7, k[6][i], sum);
+        return sum;
+    }
+    // the Horner coefficients c_2..c_4 of one partial (c_1 = k_1), contracted in Float64: sum_j r_jm = 0 for m >= 2
+    __device__ __forceinline__ static void dense_c(const double* kk, double* c2, double* c3, double* c4) {
+        using Td = Tab<double>;
+        *c2 = fma(Td::r72, kk[6], fma(Td::r62, kk[5], fma(Td::r52, kk[4], fma(Td::r42, kk[3], fma(Td::r32, kk[2], fma(Td::r22, kk[1], Td::r12 * kk[0]))))));
+        *c3 = fma(Td::r73, kk[6], fma(Td::r63, kk[5], fma(Td::r53, kk[4], fma(Td::r43, kk[3], fma(Td::r33, kk[2], fma(Td::r23, kk[1], Td::r13 * kk[0]))))));
+        *c4 = fma(Td::r74, kk[6], fma(Td::r64, kk[5], fma(Td::r54, kk[4], fma(Td::r44, kk[3], fma(Td::r34, kk[2], fma(Td::r24, kk[1], Td::r14 * kk[0]))))));
+    }
+};
+
+template <class TB> struct ErkDual {
+    static constexpr int NS = TB::NS, ORDER = TB::ORDER;
+    template <class RHS, class S, int NP>
+    __device__ __forceinline__ static void step(const Dual<S, NP>* u, const Dual<S, NP>* L, double t, double dts,
+                                                Dual<S, NP> (*k)[RHS::ZD], Dual<S, NP>* unew) {
+        constexpr int Z = RHS::ZD;
+        using D = Dual<S, NP>;
+        D tmp[Z];
+#pragma unroll
+        for (int j = 1; j < NS; ++j) {
+            for (int i = 0; i < Z; ++i) {
+                D sum = D((S)0);
+                bool first = true;
+#pragma unroll
+                for (int l = 0; l < j; ++l) {
+                    if (TB::a(j, l) == 0.0) continue;
+                    sum = first ? dual_scale((S)TB::a(j, l), k[l][i]) : dual_fma((S)TB::a(j, l), k[l][i], sum);
+                    first = false;
+                }
+                if (j < NS - 1) tmp[i] = dual_axpy_time(u[i], dts, sum);
+                else unew[i] = dual_axpy_time(u[i], dts, sum);
+            }
+            if (j < NS - 1) RHS::f(k[j], tmp, L, t + TB::c(j) * dts);
+            else RHS::f(k[j], unew, L, t + dts);
+        }
+    }
+    template <class S, int NP, int Z>
+    __device__ __forceinline__ static Dual<S, NP> err_sum(Dual<S, NP> (*k)[Z], int i) {
+        Dual<S, NP> sum = Dual<S, NP>((S)0);
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < NS; ++j) {
+            if (TB::bt(j) == 0.0) continue;
+            sum = first ? dual_scale((S)TB::bt(j), k[j][i]) : dual_fma((S)TB::bt(j), k[j][i], sum);
+            first = false;
+        }
+        return sum;
+    }
+    __device__ __forceinline__ static void dense_c(const double* kk, double* c2, double* c3, double* c4) {
+        double c[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+        for (int m = 1; m < 4; ++m)
+#pragma unroll
+            for (int j = 0; j < NS; ++j)
+                if (erk_r<TB>(j, m) != 0.0) c[m - 1] = fma(erk_r<TB>(j, m), kk[j], c[m - 1]);
+        *c2 = c[0]; *c3 = c[1]; *c4 = c[2];
+    }
+};
+
 // SEED_P: partials seeded on theta (NP = PD) -> dout = dtheta (p,B);  else on u0 (NP = ZD) -> dout = dz0 (z,B)
-template <class RHS, class S, int NP, bool SEED_P>
+template <class M, class RHS, class S, int NP, bool SEED_P>
 __device__ __forceinline__ void
-tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
+erk_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
                    KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                    S* __restrict__ dout) {
     constexpr int Z = RHS::ZD, PD = RHS::PD;
     using D = Dual<S, NP>;
-    using Tb = Tab<S>;
-    using Td = Tab<double>;
+    constexpr int NS = M::NS;
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     const int ld = gi.ld;
     // save times of a verified-uniform grid are one DFMA (bit-identical to the table, ldeq_api.cu::upload_tgrid), not a load
@@ -105,7 +216,7 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
         b = blockIdx.x * blockDim.x + s_order[tid];
     }
     if (b >= B) return;
-    D u[Z], k[7][Z], unew[Z], tmp[Z], sum, L[PD];
+    D u[Z], k[NS][Z], unew[Z], tmp[Z], sum, L[PD];
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
     const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
@@ -144,7 +255,7 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
                     for (int i = 0; i < Z; ++i) tmp[i] = dual_div_s(f1[i] - k[0][i], sk[i]);
                     const double d2 = (double)dual_rms(tmp, Z, wp) / dt0;
                     const double m = fmax(d1, d2);
-                    const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : ::pow(10.0, -(2.0 + log10(m)) / 5.0);
+                    const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : ::pow(10.0, -(2.0 + log10(m)) / (double)M::ORDER);
                     dt = fmax(dtmin, fmin(100.0 * dt0, fmin(dt1, dtmax)));
                 }
             }
@@ -177,43 +288,11 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
         const double dts = fmin(dt, tend - t);
         double tnew = t + dts;
         if (::fabs(tnew - tend) < 100.0 * ulp_of(fmax(::fabs(t), ::fabs(tend)))) tnew = tend;
-        // ---- one Tsit5 step on duals ----
-        for (int i = 0; i < Z; ++i) { sum = dual_scale(Tb::a21, k[0][i]); tmp[i] = dual_axpy_time(u[i], dts, sum); }
-        RHS::f(k[1], tmp, L, t + Tb::c2 * dts);
-        for (int i = 0; i < Z; ++i) {
-            sum = dual_scale(Tb::a31, k[0][i]); sum = dual_fma(Tb::a32, k[1][i], sum);
-            tmp[i] = dual_axpy_time(u[i], dts, sum);
-        }
-        RHS::f(k[2], tmp, L, t + Tb::c3 * dts);
-        for (int i = 0; i < Z; ++i) {
-            sum = dual_scale(Tb::a41, k[0][i]); sum = dual_fma(Tb::a42, k[1][i], sum); sum = dual_fma(Tb::a43, k[2][i], sum);
-            tmp[i] = dual_axpy_time(u[i], dts, sum);
-        }
-        RHS::f(k[3], tmp, L, t + Tb::c4 * dts);
-        for (int i = 0; i < Z; ++i) {
-            sum = dual_scale(Tb::a51, k[0][i]); sum = dual_fma(Tb::a52, k[1][i], sum); sum = dual_fma(Tb::a53, k[2][i], sum);
-            sum = dual_fma(Tb::a54, k[3][i], sum);
-            tmp[i] = dual_axpy_time(u[i], dts, sum);
-        }
-        RHS::f(k[4], tmp, L, t + Tb::c5 * dts);
-        for (int i = 0; i < Z; ++i) {
-            sum = dual_scale(Tb::a61, k[0][i]); sum = dual_fma(Tb::a62, k[1][i], sum); sum = dual_fma(Tb::a63, k[2][i], sum);
-            sum = dual_fma(Tb::a64, k[3][i], sum); sum = dual_fma(Tb::a65, k[4][i], sum);
-            tmp[i] = dual_axpy_time(u[i], dts, sum);
-        }
-        RHS::f(k[5], tmp, L, t + dts);
-        for (int i = 0; i < Z; ++i) {
-            sum = dual_scale(Tb::a71, k[0][i]); sum = dual_fma(Tb::a72, k[1][i], sum); sum = dual_fma(Tb::a73, k[2][i], sum);
-            sum = dual_fma(Tb::a74, k[3][i], sum); sum = dual_fma(Tb::a75, k[4][i], sum); sum = dual_fma(Tb::a76, k[5][i], sum);
-            unew[i] = dual_axpy_time(u[i], dts, sum);
-        }
-        RHS::f(k[6], unew, L, t + dts);
+        M::template step<RHS, S, NP>(u, L, t, dts, k, unew);  // one step on duals
         double EEst = 0.0;
         if (o.adaptive) {
             for (int i = 0; i < Z; ++i) {
-                sum = dual_scale(Tb::bt1, k[0][i]); sum = dual_fma(Tb::bt2, k[1][i], sum); sum = dual_fma(Tb::bt3, k[2][i], sum);
-                sum = dual_fma(Tb::bt4, k[3][i], sum); sum = dual_fma(Tb::bt5, k[4][i], sum); sum = dual_fma(Tb::bt6, k[5][i], sum);
-                sum = dual_fma(Tb::bt7, k[6][i], sum);
+                sum = M::template err_sum<S, NP, Z>(k, i);
                 const D ut = dual_scale_time(dts, sum);
                 const S a0 = dual_absnorm(u[i], wp), a1 = dual_absnorm(unew[i], wp);
                 const S sk = abstol + (a0 > a1 ? a0 : a1) * reltol;
@@ -276,17 +355,17 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         // c_m = sum_j r_jm k_j cancels heavily (sum_j r_jm = 0 for m >= 2): contract in Float64
-                        const double k1 = k[0][i].d[q], k2 = k[1][i].d[q], k3 = k[2][i].d[q], k4 = k[3][i].d[q], k5 = k[4][i].d[q],
-                                     k6 = k[5][i].d[q], k7 = k[6][i].d[q];
-                        const double c2 = fma(Td::r72, k7, fma(Td::r62, k6, fma(Td::r52, k5, fma(Td::r42, k4, fma(Td::r32, k3, fma(Td::r22, k2, Td::r12 * k1))))));
-                        const double c3 = fma(Td::r73, k7, fma(Td::r63, k6, fma(Td::r53, k5, fma(Td::r43, k4, fma(Td::r33, k3, fma(Td::r23, k2, Td::r13 * k1))))));
-                        const double c4 = fma(Td::r74, k7, fma(Td::r64, k6, fma(Td::r54, k5, fma(Td::r44, k4, fma(Td::r34, k3, fma(Td::r24, k2, Td::r14 * k1))))));
+                        double kk[NS], c2, c3, c4;
+#pragma unroll
+                        for (int j = 0; j < NS; ++j) kk[j] = (double)k[j][i].d[q];
+                        const double k1 = kk[0];
+                        M::dense_c(kk, &c2, &c3, &c4);
                         acc[q] += (double)u[i].d[q] * (double)wsum[i] +
                                   (k1 * (double)w1[i] + c2 * (double)w2[i] + c3 * (double)w3[i] + c4 * (double)w4[i]);
                     }
             }
             t = tnew;
-            for (int i = 0; i < Z; ++i) { u[i] = unew[i]; k[0][i] = k[6][i]; }
+            for (int i = 0; i < Z; ++i) { u[i] = unew[i]; k[0][i] = k[NS - 1][i]; }
         }
         if (o.adaptive) dt = dt_next;
         if (ks < T && o.adaptive && (!(::fabs(dt) > dtmin) || !isfinite(dt))) { ret = RET_DTLESSTHANMIN; break; }
@@ -295,6 +374,15 @@ tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const 
     const bool ok = ret == RET_SUCCESS && primal_ret[b] == RET_SUCCESS;
 #pragma unroll
     for (int q = 0; q < NP; ++q) dout[(size_t)b * NP + q] = ok ? (S)acc[q] : (S)0;
+}
+
+// the Tsit5 instantiation under its own name (NVRTC wrapper source)
+template <class RHS, class S, int NP, bool SEED_P>
+__device__ __forceinline__ void
+tsit5_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
+                   KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
+                   S* __restrict__ dout) {
+    erk_fwdsens_body<Tsit5Dual, RHS, S, NP, SEED_P>(z0, theta, tg, B, gi, T, o, norm_partials, sort_key, dtraj, primal_ret, dout);
 }
 
 }  // namespace ldeq

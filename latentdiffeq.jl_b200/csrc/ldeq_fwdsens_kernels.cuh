@@ -1,0 +1,50 @@
+// ldeq_fwdsens_kernels.cuh -- kernel entry points of the forward-dual pullback for the built-in right-hand sides, shared by
+// ldeq_fwdsens.cu (Tsit5) and ldeq_erk_fwdsens.cu (DP5 / BS3 / RK4).  Both are compiled with -fmad=false (build.py).
+#pragma once
+#include "ldeq_internal.h"
+#include "ldeq_fwdsens.cuh"
+#include <cstdlib>
+
+namespace ldeq {
+
+// pendulum.jl:19-26 / :65-74 on duals (G, b, m are Float32 literals of the reference, rounded to S)
+template <bool FRICTION> struct PendulumDualRHS {
+    static constexpr int ZD = 2, PD = 1;
+    template <class D> __device__ __forceinline__ static void f(D* du, const D* u, const D* p, double) {
+        typedef typename D::value_type S;
+        const D G((S)10.0f);
+        du[0] = u[1];
+        const D a = (-G / p[0]) * sin(u[0]);
+        if (FRICTION) {
+            const S bm = (S)0.7f / (S)1.0f;
+            du[1] = a - bm * u[1];
+        } else {
+            du[1] = a;
+        }
+    }
+};
+
+template <class S, int NP, bool FRICTION, bool SEED_P>
+__global__ void __launch_bounds__(LDEQ_FWDSENS_THREADS, 512 / LDEQ_FWDSENS_THREADS)
+tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
+                     KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
+                     S* __restrict__ dout) {
+    tsit5_fwdsens_body<PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, gi, T, o, norm_partials, sort_key, dtraj, primal_ret, dout);
+}
+
+// the same for the table-driven methods (MD = ErkDual<TabDP5> ...)
+template <class MD, class S, int NP, bool FRICTION, bool SEED_P>
+__global__ void __launch_bounds__(LDEQ_FWDSENS_THREADS, 512 / LDEQ_FWDSENS_THREADS)
+erk_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
+                   KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
+                   S* __restrict__ dout) {
+    erk_fwdsens_body<MD, PendulumDualRHS<FRICTION>, S, NP, SEED_P>(z0, theta, tg, B, gi, T, o, norm_partials, sort_key, dtraj, primal_ret, dout);
+}
+
+// LDEQ_FWDSENS_SORT=0 keeps the trajectory -> lane assignment of the batch order (A/B switch; the results are identical)
+inline const int* fwdsens_sort_key(const ldeq_tape* tp) {
+    static const bool sort = [] { const char* e = getenv("LDEQ_FWDSENS_SORT"); return !(e && e[0] == '0'); }();
+    return sort ? tp->naccept : nullptr;
+}
+
+}  // namespace ldeq

@@ -51,6 +51,10 @@ struct ldeq_rhs {
     int z_dim = 2, p_dim = 1;
     void* module = nullptr;  // CUmodule of a user RHS
     void* fn[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // a user RHS under another `solver`: its own NVRTC module, compiled on first use from the kept source
+    struct PerSolver { void* module = nullptr; void* fn[12] = {}; };
+    PerSolver alt[4];
+    std::string user_src;
 };
 
 struct ldeq_tape {
@@ -72,6 +76,7 @@ struct ldeq_tape {
     double grid_t0 = 0.0, grid_h = 0.0;
     int grid_uniform = 0;
     int sense = 0;  // ldeq_sensealg of the solve that made this tape
+    int solver = 0; // ldeq_solver of that solve
     // a tape recorded slab by slab (ldeq_solve_fwd_host) is a list of single-slab tapes: parts[i] covers trajectories
     // part_b0[i] .. part_b0[i] + parts[i]->B - 1 and owns its own arrays; the parent then owns nothing else
     std::vector<ldeq_tape*> parts;
@@ -89,6 +94,11 @@ bool slot_acquire(ldeq_handle* h, int32_t** h_info, cudaEvent_t* ev);
 void slot_release(ldeq_handle* h, int32_t* h_info, cudaEvent_t ev);
 // ldeq_fwdsens.cu: the reference's ForwardDiffSensitivity pullback (two dual-number re-solves per trajectory)
 cudaError_t launch_fwdsens(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s);
+// ldeq_erk_fwdsens.cu / ldeq_erk.cu: the same kernels for solver = DP5 / BS3 / RK4 (built-in right-hand sides)
+cudaError_t launch_erk_fwdsens(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s);
+cudaError_t launch_erk_bwd(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s);
+// ldeq_user_rhs.cu: kernel table of a user RHS for `solver` (compiles the variant on first use); null + error text on failure
+void* const* user_rhs_kernels(ldeq_handle* h, const ldeq_rhs* rhs, int solver);
 
 #define LDEQ_CUDA(call)                                                    \
     do {                                                                   \

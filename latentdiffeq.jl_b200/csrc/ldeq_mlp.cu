@@ -485,6 +485,8 @@ int ldeq_mlp_solve_fwd(ldeq_handle* h, int dtype, const void* z0, const void* pa
     if (!opts->adaptive && !(opts->dt > 0.0)) return set_err(h, LDEQ_ERR_INVALID, "adaptive = 0 needs dt > 0");
     for (int k = 1; k < T; ++k)
         if (!(t_host[k] > t_host[k - 1])) return set_err(h, LDEQ_ERR_INVALID, "t must be strictly increasing");
+    if (opts->solver != LDEQ_SOLVER_TSIT5)
+        return set_err(h, LDEQ_ERR_UNSUPPORTED, "solver: the LatentODE kernels are Tsit5 (nODE.jl:17); DP5 / BS3 / RK4 exist for the GOKU entry points only");
     if (opts->mlp_math != LDEQ_MLP_MATH_FP32 && opts->mlp_math != LDEQ_MLP_MATH_BF16X3) return set_err(h, LDEQ_ERR_INVALID, "mlp_math");
     if (opts->mlp_math == LDEQ_MLP_MATH_BF16X3 && dtype != LDEQ_F32)
         return set_err(h, LDEQ_ERR_UNSUPPORTED, "mlp_math BF16X3 (tensor cores) needs a Float32 state; Float64 runs on the exact path");

@@ -14,6 +14,7 @@
 #pragma once
 
 #include "ldeq_common.cuh"
+#include "ldeq_erk.cuh"
 
 namespace ldeq {
 
@@ -106,10 +107,10 @@ __device__ __forceinline__ void tsit5_stages(const S* u, const S* p, double t, d
 }
 
 // out of line: the redo of a step whose end points left the fast sine's range (keeps the hot loop's code small)
-template <class RHS, class S, bool KEEP>
-__device__ __forceinline__ void tsit5_stages_safe(const S* u, const S* p, double t, double dts, S (*k)[RHS::ZD], S* un,
-                                               S (*g)[RHS::ZD], typename RHS::Aux* aux) {
-    tsit5_stages<RHS, S, KEEP, true>(u, p, t, dts, k, un, g, aux);
+template <class M, class RHS, class S, bool KEEP>
+__device__ __forceinline__ void erk_stages_safe(const S* u, const S* p, double t, double dts, S (*k)[RHS::ZD], S* un,
+                                                S (*g)[RHS::ZD], typename RHS::Aux* aux) {
+    M::template stages<RHS, S, KEEP, true, KEEP>(u, p, t, dts, k, un, g, aux);
 }
 
 // scaled RMS error estimate
@@ -138,7 +139,7 @@ __device__ __forceinline__ double tsit5_eest(const S* u, const S* un, S (*k)[ZD]
 }
 
 // Hairer initial step (OrdinaryDiffEq ode_determine_initdt)
-template <class RHS, class S>
+template <class RHS, class S, int ORDER = 5>
 __device__ double tsit5_initdt(const S* u0, const S* p, const S* f0, double t0, double dtmax, double dtmin,
                                const KOpts& o) {
     constexpr int ZD = RHS::ZD;
@@ -168,7 +169,7 @@ __device__ double tsit5_initdt(const S* u0, const S* p, const S* f0, double t0, 
     }
     const double d2 = (double)s_sqrt<S>(s2 / (S)ZD) / dt0;
     const double m = fmax(d1, d2);
-    const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(m)) / 5.0);
+    const double dt1 = (m <= 1e-15) ? fmax(1e-6, dt0 * 1e-3) : pow(10.0, -(2.0 + log10(m)) / (double)ORDER);
     return fmax(dtmin, fmin(100.0 * dt0, fmin(dt1, dtmax)));
 }
 
@@ -203,6 +204,87 @@ __device__ __forceinline__ void interp_coeffs_adj(S (*cb)[ZD], S (*kbar)[ZD]) {
     V::axpy(kbar[5], Tb::r62, cb[1]); V::axpy(kbar[5], Tb::r63, cb[2]); V::axpy(kbar[5], Tb::r64, cb[3]);
     V::axpy(kbar[6], Tb::r72, cb[1]); V::axpy(kbar[6], Tb::r73, cb[2]); V::axpy(kbar[6], Tb::r74, cb[3]);
 }
+
+// reverse sweep through the seven stages of one taped step (see ErkM::reverse_sweep for the contract)
+template <class RHS, class S>
+__device__ __forceinline__ void tsit5_reverse_sweep(const S* p, double tn, double dtn, S (*g)[RHS::ZD], const S* un,
+                                                    typename RHS::Aux* aux, const typename RHS::Aux& aux_next,
+                                                    S (*kbar)[RHS::ZD], S* ubn, S* ub, S* pbar) {
+    constexpr int ZD = RHS::ZD;
+    using Tb = Tab<S>;
+    using V = VecOps<S, ZD>;
+    const S h = (S)dtn;
+    // k7 = f(u_{n+1}) (it is also next step's k1, whose adjoint was already folded into ubn)
+    RHS::vjp(ubn, pbar, un, p, tn + dtn, kbar[6], aux_next);
+    // u_{n+1} = u_n + h sum_j a7j k_j
+    S v[ZD];
+    V::scale(v, h, ubn);
+    V::add(ub, ubn);
+    V::axpy(kbar[0], Tb::a71, v); V::axpy(kbar[1], Tb::a72, v); V::axpy(kbar[2], Tb::a73, v);
+    V::axpy(kbar[3], Tb::a74, v); V::axpy(kbar[4], Tb::a75, v); V::axpy(kbar[5], Tb::a76, v);
+    S gb[ZD];
+    // stage 6: g6 = u + h (a61 k1 + ... + a65 k5)
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+    RHS::vjp(gb, pbar, g[5], p, tn + dtn, kbar[5], aux[5]);
+    V::scale(v, h, gb);
+    V::add(ub, gb);
+    V::axpy(kbar[0], Tb::a61, v); V::axpy(kbar[1], Tb::a62, v); V::axpy(kbar[2], Tb::a63, v);
+    V::axpy(kbar[3], Tb::a64, v); V::axpy(kbar[4], Tb::a65, v);
+    // stage 5
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+    RHS::vjp(gb, pbar, g[4], p, tn + Tb::c5 * dtn, kbar[4], aux[4]);
+    V::scale(v, h, gb);
+    V::add(ub, gb);
+    V::axpy(kbar[0], Tb::a51, v); V::axpy(kbar[1], Tb::a52, v); V::axpy(kbar[2], Tb::a53, v);
+    V::axpy(kbar[3], Tb::a54, v);
+    // stage 4
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+    RHS::vjp(gb, pbar, g[3], p, tn + Tb::c4 * dtn, kbar[3], aux[3]);
+    V::scale(v, h, gb);
+    V::add(ub, gb);
+    V::axpy(kbar[0], Tb::a41, v); V::axpy(kbar[1], Tb::a42, v); V::axpy(kbar[2], Tb::a43, v);
+    // stage 3
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+    RHS::vjp(gb, pbar, g[2], p, tn + Tb::c3 * dtn, kbar[2], aux[2]);
+    V::scale(v, h, gb);
+    V::add(ub, gb);
+    V::axpy(kbar[0], Tb::a31, v); V::axpy(kbar[1], Tb::a32, v);
+    // stage 2
+#pragma unroll
+    for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
+    RHS::vjp(gb, pbar, g[1], p, tn + Tb::c2 * dtn, kbar[1], aux[1]);
+    V::add(ub, gb);
+    V::axpy(kbar[0], h * Tb::a21, gb);
+    // stage 1: k1 = f(u_n)
+    RHS::vjp(ub, pbar, g[0], p, tn, kbar[0], aux[0]);
+}
+
+// The method interface of the integrator bodies: the hand-unrolled Tsit5 (the reference's solver, pendulum.jl:11,58).
+// ErkM<...> (ldeq_erk.cuh) supplies the same members for the table-driven DP5 / BS3 / RK4.
+struct Tsit5M {
+    static constexpr int NS = 7, ORDER = 5;
+    template <class RHS, class S, bool KEEP, bool SAFE, bool PACK>
+    __device__ __forceinline__ static void stages(const S* u, const S* p, double t, double dts, S (*k)[RHS::ZD], S* un,
+                                                  S (*g)[RHS::ZD], typename RHS::Aux* aux) {
+        tsit5_stages<RHS, S, KEEP, SAFE, PACK>(u, p, t, dts, k, un, g, aux);
+    }
+    template <class S, int ZD>
+    __device__ __forceinline__ static double eest(const S* u, const S* un, S (*k)[ZD], double dts, S abstol, S reltol) {
+        return tsit5_eest<S, ZD>(u, un, k, dts, abstol, reltol);
+    }
+    template <class S, int ZD> __device__ __forceinline__ static void interp_coeffs(S (*k)[ZD], S (*c)[ZD]) { ldeq::interp_coeffs<S, ZD>(k, c); }
+    template <class S, int ZD> __device__ __forceinline__ static void interp_coeffs_adj(S (*cb)[ZD], S (*kbar)[ZD]) { ldeq::interp_coeffs_adj<S, ZD>(cb, kbar); }
+    template <class RHS, class S>
+    __device__ __forceinline__ static void reverse_sweep(const S* p, double tn, double dtn, S (*g)[RHS::ZD], const S* un,
+                                                         typename RHS::Aux* aux, const typename RHS::Aux& aux_next,
+                                                         S (*kbar)[RHS::ZD], S* ubn, S* ub, S* pbar) {
+        tsit5_reverse_sweep<RHS, S>(p, tn, dtn, g, un, aux, aux_next, kbar, ubn, ub, pbar);
+    }
+};
 
 // The save grid is staged in shared memory (explicit LDS, not a generic load); grids too long for
 // that are read through the global pointer.
@@ -296,9 +378,9 @@ template <class S, int ZD> __device__ __forceinline__ void cp_async_row(S* smem_
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
 // ---- forward ------------------------------------------------------------------------------------
-template <class RHS, class S, bool TAPE>
+template <class M, class RHS, class S, bool TAPE>
 __device__ __forceinline__ void
-tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
+erk_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
                  int T, KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
                  int* __restrict__ nreject, TapeView<S> tape, GridInfo ginfo) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
@@ -312,7 +394,8 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
     const bool live = b < B;
     const int bb = live ? b : B - 1;  // dead lanes of the last warp shadow a valid trajectory and store nothing
 
-    S u[ZD], un[ZD], p[PD], k[7][ZD];
+    constexpr int NS = M::NS;  // stages, the FSAL stage included
+    S u[ZD], un[ZD], p[PD], k[NS][ZD];
     load_vec<S, ZD>(z0 + (size_t)bb * ZD, u);
 #pragma unroll
     for (int i = 0; i < PD; ++i) p[i] = theta[(size_t)bb * PD + i];
@@ -337,7 +420,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
 
     RHS::f(k[0], u, p, t0);  // fsalfirst
     double t = t0;
-    double dt = (o.adaptive && !(o.dt > 0.0)) ? tsit5_initdt<RHS, S>(u, p, k[0], t0, dtmax, dtmin, o) : o.dt;
+    double dt = (o.adaptive && !(o.dt > 0.0)) ? tsit5_initdt<RHS, S, M::ORDER>(u, p, k[0], t0, dtmax, dtmin, o) : o.dt;
     PiState pist = pi_init(o);
     int na = 0, nr = 0, ret = RET_SUCCESS;
     int iters_left = (int)(o.maxiters < 0x7fffffffLL ? o.maxiters : 0x7fffffffLL);
@@ -366,9 +449,9 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                 tnew = t + dts;
                 if (fabs(tnew - tend) < (fabs(t) > abs_tend ? 100.0 * ulp_of(fabs(t)) : snap_end)) tnew = tend;
 
-                tsit5_stages<RHS, S, false, false>(u, p, t, dts, k, un, nullptr, nullptr);
+                M::template stages<RHS, S, false, false, false>(u, p, t, dts, k, un, nullptr, nullptr);
                 if (!(RHS::fast_ok(u) && RHS::fast_ok(un)))  // an end point outside the fast sine's range: libdevice (never for a pendulum)
-                    tsit5_stages_safe<RHS, S, false>(u, p, t, dts, k, un, nullptr, nullptr);
+                    erk_stages_safe<M, RHS, S, false>(u, p, t, dts, k, un, nullptr, nullptr);
 
                 bool finite = true;
 #pragma unroll
@@ -376,7 +459,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
                 bool accept = true;
                 double dt_next = dt;
                 if (o.adaptive) {
-                    const double EEst = tsit5_eest<S, ZD>(u, un, k, dts, abstol, reltol);
+                    const double EEst = M::template eest<S, ZD>(u, un, k, dts, abstol, reltol);
                     if (EEst != EEst) finite = false;
                     accept = pi_controller(o, EEst, dts, dtmax, pist, dt_next);
                 }
@@ -417,7 +500,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
             const int kstop = kint < klim ? kint : klim;
             if (ks < kstop) {
                 S c[4][ZD];
-                interp_coeffs<S, ZD>(k, c);
+                M::template interp_coeffs<S, ZD>(k, c);
                 const S h = (S)dts;
                 const double inv = 1.0 / dts;
                 // Theta of consecutive points of a uniform grid advances by h_grid / dt: one FMA per point, anchored at
@@ -444,7 +527,7 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
             if (ks >= kend) {  // all save points of this step are parked: commit it
                 t = tnew;
 #pragma unroll
-                for (int i = 0; i < ZD; ++i) { u[i] = un[i]; k[0][i] = k[6][i]; }  // FSAL
+                for (int i = 0; i < ZD; ++i) { u[i] = un[i]; k[0][i] = k[NS - 1][i]; }  // FSAL
                 pending = false;
                 if (ks >= T) active = false;
             }
@@ -497,9 +580,9 @@ tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const doub
 // ---- backward: discrete adjoint of the taped steps ----------------------------------------------
 // dtraj (z,B,T) -> dz0 (z,B), dtheta (p,B).  Step sizes are constants of the differentiation, as in
 // the reference's ForwardDiffSensitivity where tspan/dt stay plain Float64.
-template <class RHS, class S>
+template <class M, class RHS, class S>
 __device__ __forceinline__ void
-tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
+erk_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
                  const S* __restrict__ dtraj, TapeView<S> tape, const int* __restrict__ retcode,
                  const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ dtheta, GridInfo ginfo) {
     constexpr int ZD = RHS::ZD, PD = RHS::PD;
@@ -545,8 +628,9 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
     bool hit = false;      // ... and the topmost of them coincides with the step end t_{n+1}
     double tnext = tg[T - 1];  // time after step n; the forward pass ended exactly on tend
     double tn = 0.0, dtn = 0.0;
-    S g[6][ZD], un[ZD], kbar[7][ZD], cb[4][ZD], ub[ZD];
-    typename RHS::Aux aux[6], aux_next;  // aux_next: f's auxiliaries at u_{n+1} (= those of step n+1's k1)
+    constexpr int NS = M::NS;
+    S g[NS - 1][ZD], un[ZD], kbar[NS][ZD], cb[4][ZD], ub[ZD];
+    typename RHS::Aux aux[NS - 1], aux_next;  // aux_next: f's auxiliaries at u_{n+1} (= those of step n+1's k1)
 
     refill(warp_max_i(n >= 0 ? ks : 0));
     // the record of the step a lane will need next is fetched one step ahead (its latency hides behind
@@ -566,7 +650,7 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
         if (!holding && n >= 0) {
             tn = tn_pre;
             dtn = tnext - tn;
-            S u[ZD], k[7][ZD];
+            S u[ZD], k[NS][ZD];
 #pragma unroll
             for (int i = 0; i < ZD; ++i) u[i] = u_pre[i];
             if (n >= 1) {
@@ -574,15 +658,15 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
                 tn_pre = tape.t[r];
                 load_vec<S, ZD>(tape.u + r * ZD, u_pre);
             }
-            tsit5_stages<RHS, S, true, false>(u, p, tn, dtn, k, un, g, aux);
-            if (!(RHS::fast_ok(u) && RHS::fast_ok(un))) tsit5_stages_safe<RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
+            M::template stages<RHS, S, true, false, true>(u, p, tn, dtn, k, un, g, aux);
+            if (!(RHS::fast_ok(u) && RHS::fast_ok(un))) erk_stages_safe<M, RHS, S, true>(u, p, tn, dtn, k, un, g, aux);
             if (first) {  // the last step of the solve: nothing follows it, evaluate f's auxiliaries at u(tend) here
                 S ktmp[ZD];
                 RHS::f(ktmp, un, p, tn + dtn, aux_next);
                 first = false;
             }
 #pragma unroll
-            for (int j = 0; j < 7; ++j)
+            for (int j = 0; j < NS; ++j)
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) kbar[j][i] = (S)0;
 #pragma unroll
@@ -631,54 +715,8 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
             }
             if (ks < klo_step) {
                 // every save point of this step has been consumed: reverse sweep through the stages
-                interp_coeffs_adj<S, ZD>(cb, kbar);
-                // k7 = f(u_{n+1}) (it is also next step's k1, whose adjoint was already folded into ubn)
-                RHS::vjp(ubn, pbar, un, p, tn + dtn, kbar[6], aux_next);
-                // u_{n+1} = u_n + h sum_j a7j k_j
-                S v[ZD];
-                V::scale(v, h, ubn);
-                V::add(ub, ubn);
-                V::axpy(kbar[0], Tb::a71, v); V::axpy(kbar[1], Tb::a72, v); V::axpy(kbar[2], Tb::a73, v);
-                V::axpy(kbar[3], Tb::a74, v); V::axpy(kbar[4], Tb::a75, v); V::axpy(kbar[5], Tb::a76, v);
-                S gb[ZD];
-                // stage 6: g6 = u + h (a61 k1 + ... + a65 k5)
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-                RHS::vjp(gb, pbar, g[5], p, tn + dtn, kbar[5], aux[5]);
-                V::scale(v, h, gb);
-                V::add(ub, gb);
-                V::axpy(kbar[0], Tb::a61, v); V::axpy(kbar[1], Tb::a62, v); V::axpy(kbar[2], Tb::a63, v);
-                V::axpy(kbar[3], Tb::a64, v); V::axpy(kbar[4], Tb::a65, v);
-                // stage 5
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-                RHS::vjp(gb, pbar, g[4], p, tn + Tb::c5 * dtn, kbar[4], aux[4]);
-                V::scale(v, h, gb);
-                V::add(ub, gb);
-                V::axpy(kbar[0], Tb::a51, v); V::axpy(kbar[1], Tb::a52, v); V::axpy(kbar[2], Tb::a53, v);
-                V::axpy(kbar[3], Tb::a54, v);
-                // stage 4
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-                RHS::vjp(gb, pbar, g[3], p, tn + Tb::c4 * dtn, kbar[3], aux[3]);
-                V::scale(v, h, gb);
-                V::add(ub, gb);
-                V::axpy(kbar[0], Tb::a41, v); V::axpy(kbar[1], Tb::a42, v); V::axpy(kbar[2], Tb::a43, v);
-                // stage 3
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-                RHS::vjp(gb, pbar, g[2], p, tn + Tb::c3 * dtn, kbar[2], aux[2]);
-                V::scale(v, h, gb);
-                V::add(ub, gb);
-                V::axpy(kbar[0], Tb::a31, v); V::axpy(kbar[1], Tb::a32, v);
-                // stage 2
-#pragma unroll
-                for (int i = 0; i < ZD; ++i) gb[i] = (S)0;
-                RHS::vjp(gb, pbar, g[1], p, tn + Tb::c2 * dtn, kbar[1], aux[1]);
-                V::add(ub, gb);
-                V::axpy(kbar[0], h * Tb::a21, gb);
-                // stage 1: k1 = f(u_n)
-                RHS::vjp(ub, pbar, g[0], p, tn, kbar[0], aux[0]);
+                M::template interp_coeffs_adj<S, ZD>(cb, kbar);
+                M::template reverse_sweep<RHS, S>(p, tn, dtn, g, un, aux, aux_next, kbar, ubn, ub, pbar);
 #pragma unroll
                 for (int i = 0; i < ZD; ++i) ubn[i] = ub[i];
                 aux_next = aux[0];  // u_n is the end point of step n-1
@@ -711,6 +749,22 @@ tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global
 }
 
 // ---- kernel entry points ---------------------------------------------------------------------------------
+// the Tsit5 instantiations under their own names (NVRTC wrapper source, launch lists in profiles/)
+template <class RHS, class S, bool TAPE>
+__device__ __forceinline__ void
+tsit5_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
+               int T, KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
+               int* __restrict__ nreject, TapeView<S> tape, GridInfo ginfo) {
+    erk_fwd_body<Tsit5M, RHS, S, TAPE>(z0, theta, tg_global, B, T, o, traj, retcode, naccept, nreject, tape, ginfo);
+}
+template <class RHS, class S>
+__device__ __forceinline__ void
+tsit5_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
+               const S* __restrict__ dtraj, TapeView<S> tape, const int* __restrict__ retcode,
+               const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ dtheta, GridInfo ginfo) {
+    erk_bwd_body<Tsit5M, RHS, S>(theta, tg_global, B, T, dtraj, tape, retcode, naccept, dz0, dtheta, ginfo);
+}
+
 template <class RHS, class S, bool TAPE>
 __global__ void __launch_bounds__(LDEQ_FWD_THREADS, LDEQ_FWD_MINBLOCKS)
 tsit5_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
@@ -725,6 +779,23 @@ tsit5_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_glob
                  const S* __restrict__ dtraj, TapeView<S> tape, const int* __restrict__ retcode,
                  const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ dtheta, GridInfo ginfo) {
     tsit5_bwd_body<RHS, S>(theta, tg_global, B, T, dtraj, tape, retcode, naccept, dz0, dtheta, ginfo);
+}
+
+// the same kernels for the table-driven methods (M = DP5M / BS3M / RK4M, ldeq_erk.cuh)
+template <class M, class RHS, class S, bool TAPE>
+__global__ void __launch_bounds__(LDEQ_FWD_THREADS, LDEQ_FWD_MINBLOCKS)
+erk_fwd_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg_global, int B,
+               int T, KOpts o, S* __restrict__ traj, int* __restrict__ retcode, int* __restrict__ naccept,
+               int* __restrict__ nreject, TapeView<S> tape, GridInfo ginfo) {
+    erk_fwd_body<M, RHS, S, TAPE>(z0, theta, tg_global, B, T, o, traj, retcode, naccept, nreject, tape, ginfo);
+}
+
+template <class M, class RHS, class S>
+__global__ void __launch_bounds__(LDEQ_BWD_THREADS, LDEQ_BWD_MINBLOCKS)
+erk_bwd_kernel(const S* __restrict__ theta, const double* __restrict__ tg_global, int B, int T,
+               const S* __restrict__ dtraj, TapeView<S> tape, const int* __restrict__ retcode,
+               const int* __restrict__ naccept, S* __restrict__ dz0, S* __restrict__ dtheta, GridInfo ginfo) {
+    erk_bwd_body<M, RHS, S>(theta, tg_global, B, T, dtraj, tape, retcode, naccept, dz0, dtheta, ginfo);
 }
 
 }  // namespace ldeq

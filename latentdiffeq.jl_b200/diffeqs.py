@@ -19,12 +19,38 @@ from . import _cabi
 
 
 class Tsit5:
-    """``OrdinaryDiffEq.Tsit5()`` -- the solver of the reference's diffeq structs (pendulum.jl:11,58) and the one the hot
-    path implements.  Any other ``solver`` object is refused (``LDEQ_ERR_UNSUPPORTED``), never silently replaced."""
+    """``OrdinaryDiffEq.Tsit5()`` -- the solver of the reference's diffeq structs (pendulum.jl:11,58).  The ``solver``
+    field is the user's to set (it is handed to ``solve`` at GOKU.jl:121): :class:`DP5`, :class:`BS3` and :class:`RK4`
+    are built for the GOKU path as well; any other object is refused, never silently replaced."""
     code = _cabi.SOLVER_TSIT5
 
     def __repr__(self):
         return "Tsit5()"
+
+
+class DP5:
+    """``OrdinaryDiffEq.DP5()``: Dormand-Prince 5(4), dense output in dopri5's ``contd5`` form (``csrc/ldeq_erk.cuh``)."""
+    code = _cabi.SOLVER_DP5
+
+    def __repr__(self):
+        return "DP5()"
+
+
+class BS3:
+    """``OrdinaryDiffEq.BS3()``: Bogacki-Shampine 3(2), cubic Hermite dense output."""
+    code = _cabi.SOLVER_BS3
+
+    def __repr__(self):
+        return "BS3()"
+
+
+class RK4:
+    """``OrdinaryDiffEq.RK4()``: the classical method, Hermite dense output.  Fixed step only (``adaptive=False, dt=...``):
+    OrdinaryDiffEq's adaptive RK4 is a defect-control estimate that is not built (``LDEQ_ERR_UNSUPPORTED``)."""
+    code = _cabi.SOLVER_RK4
+
+    def __repr__(self):
+        return "RK4()"
 
 
 class ForwardDiffSensitivity:

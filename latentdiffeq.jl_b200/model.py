@@ -281,7 +281,7 @@ def _opts_from_kwargs(kwargs: dict, sensealg=None, solver=None) -> _cabi.Opts:
     if solver is not None:
         code = getattr(solver, "code", None)
         if code is None:
-            raise NotImplementedError(f"solver {solver!r}: the hot path implements Tsit5() (pendulum.jl:11,58)")
+            raise NotImplementedError(f"solver {solver!r}: Tsit5() (pendulum.jl:11,58), DP5(), BS3() and RK4() are built")
         kw["solver"] = code
     return _cabi.default_opts(**kw)
 

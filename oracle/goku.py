@@ -23,6 +23,13 @@ PENDULUM_FRICTION = 1   # examples/pendulum_friction-less/pendulum.jl:65-74
 
 RET_SUCCESS, RET_MAXITERS, RET_DTLESSTHANMIN, RET_UNSTABLE = 0, 1, 2, 3
 
+# the diffeq struct's `solver` field (pendulum.jl:11,58 use Tsit5(); SURVEY.md 8(f)4 names DP5 / BS3 / RK4)
+TSIT5, DP5, BS3, RK4 = 0, 1, 2, 3
+# OrdinaryDiffEq's PI-controller defaults per algorithm (beta2_default / beta1_default in alg_utils.jl [3P]):
+# beta2 = 2/(5 order), beta1 = 7/(10 order), except DP5: beta2 = 4/100, beta1 = 1/order - 3 beta2/4
+CONTROLLER_DEFAULTS = {TSIT5: (7.0 / 50.0, 2.0 / 25.0), DP5: (1.0 / 5.0 - 3.0 * 0.04 / 4.0, 0.04), BS3: (7.0 / 30.0, 2.0 / 15.0),
+                       RK4: (7.0 / 40.0, 2.0 / 20.0)}
+
 
 class _COpts(ctypes.Structure):
     _fields_ = [
@@ -31,7 +38,7 @@ class _COpts(ctypes.Structure):
         ("maxiters", ctypes.c_longlong), ("gamma", ctypes.c_double), ("qmin", ctypes.c_double),
         ("qmax", ctypes.c_double), ("beta1", ctypes.c_double), ("beta2", ctypes.c_double),
         ("qoldinit", ctypes.c_double), ("qsteady_min", ctypes.c_double), ("qsteady_max", ctypes.c_double),
-        ("controller_pow", ctypes.c_int),
+        ("controller_pow", ctypes.c_int), ("solver", ctypes.c_int),
     ]
 
 
@@ -54,6 +61,13 @@ class Opts:
     qsteady_min: float = 1.0
     qsteady_max: float = 1.0
     controller_pow: int = 0   # 0: DiffEqBase.fastpow (reference), 1: exact pow
+    solver: int = 0           # TSIT5 / DP5 / BS3 / RK4
+
+    @classmethod
+    def for_solver(cls, solver: int, **kw) -> "Opts":
+        """Options with the controller defaults OrdinaryDiffEq gives ``solver``."""
+        b1, b2 = CONTROLLER_DEFAULTS[solver]
+        return cls(solver=solver, **{"beta1": b1, "beta2": b2, **kw})
 
     def c(self) -> _COpts:
         d = asdict(self)
@@ -163,6 +177,21 @@ def steps(rhs: int, z0, theta, t, opts: Opts | None = None, cap: int = 100000):
     n = lib().oracle_goku_steps_f64(ctypes.c_int(rhs), _ptr(z0), _ptr(theta), _ptr(t), ctypes.c_int(t.shape[0]),
                                     ctypes.byref(co), _ptr(ts), _ptr(dts), ctypes.c_int(cap))
     return ts[:n].copy(), dts[:n].copy()
+
+
+def method_table(solver: int):
+    """``(ns, order, c[7], a[7,7], btilde[7])`` of a table-driven method as the oracle holds it."""
+    c, a, bt = np.zeros(7), np.zeros((7, 7)), np.zeros(7)
+    order = ctypes.c_int(0)
+    ns = lib().oracle_method_table(ctypes.c_int(solver), _ptr(c), _ptr(a), _ptr(bt), ctypes.byref(order))
+    return int(ns), int(order.value), c, a, bt
+
+
+def dense_weights(solver: int, theta: float) -> np.ndarray:
+    """Weights of ``k_1..k_ns`` in ``(u(theta) - u_n)/dt``, probed from the oracle's own dense-output routine."""
+    w = np.zeros(7)
+    lib().oracle_dense_weights(ctypes.c_int(solver), ctypes.c_double(theta), _ptr(w))
+    return w
 
 
 def jl_sincosf(x: np.ndarray):

@@ -276,6 +276,7 @@ struct Opts {
     long long maxiters;
     double gamma, qmin, qmax, beta1, beta2, qoldinit, qsteady_min, qsteady_max;
     int controller_pow;  // 0 fastpow (reference), 1 exact pow
+    int solver;          // SOLVER_* (the diffeq struct's `solver` field, pendulum.jl:11,58)
 };
 
 enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTLESSTHANMIN = 2, RET_UNSTABLE = 3 };
@@ -403,6 +404,134 @@ inline void tsit5_interp(const Dual<S, NP>* uprev, const StepOut<S, NP>& st, dou
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Other values of the diffeq struct's `solver` field (the reference's structs carry
+// `solver = Tsit5()`, pendulum.jl:11,58, and pass it to `solve` at GOKU.jl:121).  OrdinaryDiffEq's DP5, BS3 and RK4
+// [3P, restated from the published methods]: all three are FSAL methods in OrdinaryDiffEq (the last stage is
+// f(u_{n+1}) and becomes k1 of the next step), so one table-driven step serves them:
+//   DP5  Dormand-Prince 5(4), 7 stages, dense output in Hairer's dopri5 form (contd5: update, bspl, ..., sum d_j k_j);
+//        PI controller with beta2 = 4/100, beta1 = 1/5 - 3 beta2/4
+//   BS3  Bogacki-Shampine 3(2), 4 stages, cubic Hermite dense output (OrdinaryDiffEq's default interpolant);
+//        beta2 = 2/(5 order), beta1 = 7/(10 order) like Tsit5
+//   RK4  the classical method + fsallast = f(u_{n+1}), Hermite dense output.  FIXED STEP ONLY here: OrdinaryDiffEq's
+//        adaptive RK4 uses a defect-control estimate that is not restated.
+// The initial step uses the method's order in 10^(-(2 + log10 max(d1,d2))/order).
+// ---------------------------------------------------------------------------------------------
+enum { SOLVER_TSIT5 = 0, SOLVER_DP5 = 1, SOLVER_BS3 = 2, SOLVER_RK4 = 3 };
+
+struct Method {
+    int ns, order;        // stages including the FSAL stage; order of the method
+    double c[7], a[7][7], bt[7], d[7];
+    int dense;            // 1: DP5 (Hairer), 2: Hermite
+};
+
+inline Method make_dp5() {
+    Method m{};
+    m.ns = 7; m.order = 5; m.dense = 1;
+    const double c[7] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1};
+    for (int i = 0; i < 7; ++i) m.c[i] = c[i];
+    m.a[1][0] = 1.0 / 5;
+    m.a[2][0] = 3.0 / 40; m.a[2][1] = 9.0 / 40;
+    m.a[3][0] = 44.0 / 45; m.a[3][1] = -56.0 / 15; m.a[3][2] = 32.0 / 9;
+    m.a[4][0] = 19372.0 / 6561; m.a[4][1] = -25360.0 / 2187; m.a[4][2] = 64448.0 / 6561; m.a[4][3] = -212.0 / 729;
+    m.a[5][0] = 9017.0 / 3168; m.a[5][1] = -355.0 / 33; m.a[5][2] = 46732.0 / 5247; m.a[5][3] = 49.0 / 176; m.a[5][4] = -5103.0 / 18656;
+    m.a[6][0] = 35.0 / 384; m.a[6][2] = 500.0 / 1113; m.a[6][3] = 125.0 / 192; m.a[6][4] = -2187.0 / 6784; m.a[6][5] = 11.0 / 84;
+    m.bt[0] = 71.0 / 57600; m.bt[2] = -71.0 / 16695; m.bt[3] = 71.0 / 1920; m.bt[4] = -17253.0 / 339200; m.bt[5] = 22.0 / 525; m.bt[6] = -1.0 / 40;
+    m.d[0] = -12715105075.0 / 11282082432.0; m.d[2] = 87487479700.0 / 32700410799.0; m.d[3] = -10690763975.0 / 1880347072.0;
+    m.d[4] = 701980252875.0 / 199316789632.0; m.d[5] = -1453857185.0 / 822651844.0; m.d[6] = 69997945.0 / 29380423.0;
+    return m;
+}
+inline Method make_bs3() {
+    Method m{};
+    m.ns = 4; m.order = 3; m.dense = 2;
+    m.c[1] = 1.0 / 2; m.c[2] = 3.0 / 4; m.c[3] = 1;
+    m.a[1][0] = 1.0 / 2; m.a[2][1] = 3.0 / 4;
+    m.a[3][0] = 2.0 / 9; m.a[3][1] = 1.0 / 3; m.a[3][2] = 4.0 / 9;
+    m.bt[0] = -5.0 / 72; m.bt[1] = 1.0 / 12; m.bt[2] = 1.0 / 9; m.bt[3] = -1.0 / 8;
+    return m;
+}
+inline Method make_rk4() {
+    Method m{};
+    m.ns = 5; m.order = 4; m.dense = 2;
+    m.c[1] = 0.5; m.c[2] = 0.5; m.c[3] = 1; m.c[4] = 1;
+    m.a[1][0] = 0.5; m.a[2][1] = 0.5; m.a[3][2] = 1;
+    m.a[4][0] = 1.0 / 6; m.a[4][1] = 1.0 / 3; m.a[4][2] = 1.0 / 3; m.a[4][3] = 1.0 / 6;
+    return m;
+}
+inline const Method& method_of(int solver) {
+    static const Method dp5 = make_dp5(), bs3 = make_bs3(), rk4 = make_rk4();
+    return solver == SOLVER_DP5 ? dp5 : solver == SOLVER_BS3 ? bs3 : rk4;
+}
+inline int order_of(int solver) { return solver == SOLVER_TSIT5 ? 5 : method_of(solver).order; }
+
+// One step of a table-driven FSAL method (OrdinaryDiffEq perform_step! of DP5 / BS3 / RK4 constant caches): the same
+// mixed-precision form as tsit5_step -- stage sums in the state type, `uprev + dt*(...)` promoted through the Float64 dt.
+template <class S, int NP>
+inline void erk_step(const Method& m, int rhs, const Dual<S, NP>* uprev, const Dual<S, NP>* p, double t, double dt,
+                     const Opts& o, bool norm_partials, StepOut<S, NP>& st) {
+    Dual<S, NP> tmp[Z], sum = dmake<S, NP>(S(0));
+    auto& k = st.k;
+    const int ns = m.ns;
+    for (int j = 1; j < ns; ++j) {
+        for (int i = 0; i < Z; ++i) {
+            bool first = true;
+            for (int l = 0; l < j; ++l) {
+                if (m.a[j][l] == 0.0) continue;
+                sum = first ? (S)m.a[j][l] * k[l][i] : dfma((S)m.a[j][l], k[l][i], sum);
+                first = false;
+            }
+            (j == ns - 1 ? st.unew[i] : tmp[i]) = axpy_time(uprev[i], dt, sum);
+        }
+        rhs_eval<S, NP>(rhs, k[j], j == ns - 1 ? st.unew : tmp, p, t + m.c[j] * dt);
+    }
+    st.EEst = 0.0;
+    if (o.adaptive) {
+        Dual<S, NP> atmp[Z];
+        const S abstol = (S)o.abstol, reltol = (S)o.reltol;
+        for (int i = 0; i < Z; ++i) {
+            bool first = true;
+            for (int j = 0; j < ns; ++j) {
+                if (m.bt[j] == 0.0) continue;
+                sum = first ? (S)m.bt[j] * k[j][i] : dfma((S)m.bt[j], k[j][i], sum);
+                first = false;
+            }
+            Dual<S, NP> utilde = scale_time(dt, sum);
+            S a0 = abs_norm(uprev[i], norm_partials), a1 = abs_norm(st.unew[i], norm_partials);
+            S sk = abstol + (a0 > a1 ? a0 : a1) * reltol;
+            atmp[i] = ddiv_s(utilde, sk);
+        }
+        st.EEst = (double)rms_norm(atmp, Z, norm_partials);
+    }
+}
+
+// Dense output of the table-driven methods, in the literal forms OrdinaryDiffEq evaluates (Float64 Theta meets the
+// Float32 k's: promoted, rounded on the store):
+//   DP5      y0 + dt (Theta K1 + Theta(1-Theta) K2 + Theta^2(1-Theta) K3 + Theta^2(1-Theta)^2 K4),
+//            K1 = update = sum b_j k_j, K2 = k1 - update, K3 = update - k7 - K2, K4 = sum d_j k_j   (dopri5 contd5)
+//   Hermite  (1-Theta) y0 + Theta y1 + Theta(Theta-1) ((1-2Theta)(y1-y0) + (Theta-1) dt k1 + Theta dt k_last)
+template <class S, int NP>
+inline void erk_interp(const Method& m, const Dual<S, NP>* uprev, const StepOut<S, NP>& st, double dt, double Th,
+                       Dual<S, NP>* out) {
+    const int ns = m.ns;
+    auto comp = [&](int i, int q) -> double {  // q = -1: value, else partial q
+        auto get = [&](const Dual<S, NP>& x) -> double { return q < 0 ? (double)x.v : (double)x.d[q]; };
+        const double y0 = get(uprev[i]), k1 = get(st.k[0][i]), kl = get(st.k[ns - 1][i]);
+        if (m.dense == 1) {
+            double upd = 0.0, K4 = 0.0;
+            for (int j = 0; j < ns - 1; ++j) upd += m.a[ns - 1][j] * get(st.k[j][i]);
+            for (int j = 0; j < ns; ++j) K4 += m.d[j] * get(st.k[j][i]);
+            const double K2 = k1 - upd, K3 = upd - kl - K2, T1 = 1.0 - Th;
+            return y0 + dt * (Th * upd + Th * T1 * K2 + Th * Th * T1 * K3 + Th * Th * T1 * T1 * K4);
+        }
+        const double y1 = get(st.unew[i]);
+        return (1.0 - Th) * y0 + Th * y1 + Th * (Th - 1.0) * ((1.0 - 2.0 * Th) * (y1 - y0) + (Th - 1.0) * dt * k1 + Th * dt * kl);
+    };
+    for (int i = 0; i < Z; ++i) {
+        out[i].v = (S)comp(i, -1);
+        for (int q = 0; q < NP; ++q) out[i].d[q] = (S)comp(i, q);
+    }
+}
+
 // Hairer initial step (ode_determine_initdt); f0 is supplied by the caller.
 template <class S, int NP>
 inline double initdt(int rhs, const Dual<S, NP>* u0, const Dual<S, NP>* p, const Dual<S, NP>* f0,
@@ -426,7 +555,7 @@ inline double initdt(int rhs, const Dual<S, NP>* u0, const Dual<S, NP>* p, const
     for (int i = 0; i < Z; ++i) tmp[i] = ddiv_s(f1[i] - f0[i], sk[i]);
     double d2 = (double)rms_norm(tmp, Z, norm_partials) / dt0;
     double m = std::fmax(d1, d2);
-    double dt1 = (m <= 1e-15) ? std::fmax(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2.0 + std::log10(m)) / 5.0);
+    double dt1 = (m <= 1e-15) ? std::fmax(1e-6, dt0 * 1e-3) : std::pow(10.0, -(2.0 + std::log10(m)) / (double)order_of(o.solver));
     return std::fmax(dtmin, std::fmin(100.0 * dt0, std::fmin(dt1, dtmax)));
 }
 
@@ -473,7 +602,8 @@ int solve_one(int rhs, const Dual<S, NP>* u0, const Dual<S, NP>* p, const double
         const double ulp = std::nextafter(tmx, std::numeric_limits<double>::infinity()) - tmx;
         const bool last = std::fabs(tnew - tend) < 100.0 * ulp;
         if (last) tnew = tend;
-        tsit5_step<S, NP>(rhs, u, p, t, dts, o, norm_partials, st);
+        if (o.solver == SOLVER_TSIT5) tsit5_step<S, NP>(rhs, u, p, t, dts, o, norm_partials, st);
+        else erk_step<S, NP>(method_of(o.solver), rhs, u, p, t, dts, o, norm_partials, st);
         bool finite = true;
         for (int i = 0; i < Z; ++i) finite = finite && std::isfinite((double)st.unew[i].v);
         if (!finite || std::isnan(st.EEst)) { ret = RET_UNSTABLE; break; }
@@ -510,11 +640,13 @@ int solve_one(int rhs, const Dual<S, NP>* u0, const Dual<S, NP>* p, const double
                     for (int i = 0; i < Z; ++i) out[ksave * Z + i] = st.unew[i];
                 } else {
                     const double Theta = (tg[ksave] - tprev) / dts;
-                    tsit5_interp<S, NP>(u, st, dts, Theta, out + ksave * Z);
+                    if (o.solver == SOLVER_TSIT5) tsit5_interp<S, NP>(u, st, dts, Theta, out + ksave * Z);
+                    else erk_interp<S, NP>(method_of(o.solver), u, st, dts, Theta, out + ksave * Z);
                 }
                 ++ksave;
             }
-            for (int i = 0; i < Z; ++i) { u[i] = st.unew[i]; st.k[0][i] = st.k[6][i]; }  // FSAL
+            const int klast = o.solver == SOLVER_TSIT5 ? 6 : method_of(o.solver).ns - 1;
+            for (int i = 0; i < Z; ++i) { u[i] = st.unew[i]; st.k[0][i] = st.k[klast][i]; }  // FSAL
             if (o.adaptive) dt = std::fmin(dtmax, dts / q);
         } else {
             ++nr;
@@ -618,6 +750,7 @@ struct oracle_opts {
     long long maxiters;
     double gamma, qmin, qmax, beta1, beta2, qoldinit, qsteady_min, qsteady_max;
     int controller_pow;
+    int solver;
 };
 
 // OrdinaryDiffEq defaults for Tsit5
@@ -626,6 +759,7 @@ void oracle_opts_default(oracle_opts* o) {
     o->maxiters = 1000000; o->gamma = 0.9; o->qmin = 0.2; o->qmax = 10.0; o->beta1 = 7.0 / 50.0;
     o->beta2 = 2.0 / 25.0; o->qoldinit = 1e-4; o->qsteady_min = 1.0; o->qsteady_max = 1.0;
     o->controller_pow = 0;
+    o->solver = SOLVER_TSIT5;
 }
 
 static Opts cvt(const oracle_opts* o) {
@@ -633,7 +767,7 @@ static Opts cvt(const oracle_opts* o) {
     r.abstol = o->abstol; r.reltol = o->reltol; r.adaptive = o->adaptive; r.dt = o->dt; r.dtmax = o->dtmax;
     r.dtmin = o->dtmin; r.maxiters = o->maxiters; r.gamma = o->gamma; r.qmin = o->qmin; r.qmax = o->qmax;
     r.beta1 = o->beta1; r.beta2 = o->beta2; r.qoldinit = o->qoldinit; r.qsteady_min = o->qsteady_min;
-    r.qsteady_max = o->qsteady_max; r.controller_pow = o->controller_pow;
+    r.qsteady_max = o->qsteady_max; r.controller_pow = o->controller_pow; r.solver = o->solver;
     return r;
 }
 
@@ -674,6 +808,37 @@ int oracle_goku_steps_f64(int rhs, const double* z0, const double* theta, const 
 }
 
 double oracle_fastpow(double x, double y) { return fastpow(x, y); }
+
+// the table-driven methods' own numbers, for the order-condition pins in tests/test_oracle_pins.py:
+// c[7], a[7][7] (row-major), btilde[7]; returns the number of stages (FSAL stage included), 0 for an unknown solver
+int oracle_method_table(int solver, double* c, double* a, double* bt, int* order) {
+    if (solver != SOLVER_DP5 && solver != SOLVER_BS3 && solver != SOLVER_RK4) return 0;
+    const Method& m = method_of(solver);
+    for (int i = 0; i < 7; ++i) {
+        c[i] = m.c[i];
+        bt[i] = m.bt[i];
+        for (int j = 0; j < 7; ++j) a[i * 7 + j] = m.a[i][j];
+    }
+    *order = m.order;
+    return m.ns;
+}
+// weights w_j(Theta) of k_j in (u(Theta) - u_n)/dt, obtained by probing erk_interp itself with unit slopes
+int oracle_dense_weights(int solver, double theta, double* w) {
+    if (solver != SOLVER_DP5 && solver != SOLVER_BS3 && solver != SOLVER_RK4) return 0;
+    const Method& m = method_of(solver);
+    for (int j = 0; j < m.ns; ++j) {
+        StepOut<double, 0> st;
+        Dual<double, 0> u0[Z], out[Z];
+        for (int i = 0; i < Z; ++i) {
+            u0[i] = dmake<double, 0>(0.0);
+            for (int l = 0; l < 7; ++l) st.k[l][i] = dmake<double, 0>(l == j ? 1.0 : 0.0);
+            st.unew[i] = dmake<double, 0>(j < m.ns - 1 ? m.a[m.ns - 1][j] : 0.0);  // u_{n+1} - u_n = dt sum_j b_j k_j with dt = 1
+        }
+        erk_interp<double, 0>(m, u0, st, 1.0, theta, out);
+        w[j] = out[0].v;
+    }
+    return m.ns;
+}
 
 // Base.sin / Base.cos(::Float32) restatement, for the pins in tests/test_oracle_pins.py and the GPU bit-equality test
 void oracle_jl_sincosf(const float* x, float* s, float* c, int n) {

@@ -127,6 +127,25 @@ int main(void) {
         CHECK(fabs(fd - gp[b]) <= 2e-2 * fmax(fabs(fd), 1e-3), "dL/dtheta[%d]: finite difference %g vs pullback %g", b, fd, gp[b]);
     }
 
+    /* the diffeq struct's `solver` field: DP5 / BS3 adaptive, RK4 fixed step -- same problem, so the trajectories agree with
+       Tsit5's within the solver tolerance, and every solver's pullback is finite and close to Tsit5's */
+    for (int sv = LDEQ_SOLVER_DP5; sv <= LDEQ_SOLVER_RK4; ++sv) {
+        ldeq_opts os;
+        LD(ldeq_opts_default_solver(&os, sv));
+        CHECK(os.solver == sv && os.beta2 > 0.0 && os.sensealg == LDEQ_SENSE_FORWARD_DUAL, "ldeq_opts_default_solver(%d)", sv);
+        if (sv == LDEQ_SOLVER_RK4) {
+            CHECK(ldeq_solve_fwd_host(h, rhs, LDEQ_F32, z0, th, t, B, T, &os, traj2, NULL, NULL, NULL, NULL, NULL) == LDEQ_ERR_UNSUPPORTED,
+                  "adaptive RK4 must be refused");
+            os.adaptive = 0; os.dt = 0.025;
+        }
+        LD(ldeq_solve_fwd_bwd_host(h, rhs, LDEQ_F32, z0, th, t, B, T, &os, w, traj2, gz2, gp2, ret, NULL, NULL, NULL));
+        double dmax = 0, gmax = 0, gden = 0;
+        for (int i = 0; i < T * B * Z; ++i) dmax = fmax(dmax, fabs(traj2[i] - traj[i]));
+        for (int i = 0; i < B * Z; ++i) { gmax = fmax(gmax, fabs(gz2[i] - dz0[i])); gden = fmax(gden, fabs(dz0[i])); }
+        for (int b = 0; b < B; ++b) CHECK(ret[b] == LDEQ_RET_SUCCESS, "solver %d: retcode[%d] = %d", sv, b, ret[b]);
+        CHECK(dmax <= 2e-2 && gmax <= 1e-1 * gden, "solver %d vs Tsit5: trajectories %g, dz0 %g of %g", sv, dmax, gmax, gden);
+    }
+
     /* a trajectory that cannot finish: NaN block, zero gradient, no error code (GOKU.jl:114) */
     o.maxiters = 40;
     th[5] = 1e-4f;

@@ -72,11 +72,19 @@ def test_sensealg_and_solver_map_to_the_solver_options(ldeq):
         model._opts_from_kwargs({}, object())
     with pytest.raises(NotImplementedError):
         model._opts_from_kwargs({}, None, "Rodas5()")
+    # the `solver` field is the user's (GOKU.jl:121): DP5 / BS3 / RK4 carry OrdinaryDiffEq's controller defaults
+    r = ldeq.Pendulum(solver=ldeq.DP5(), reltol=1e-4)
+    o = model._opts_from_kwargs(r.kwargs, r.sensealg, r.solver)
+    assert repr(r.solver) == "DP5()" and o.solver == ldeq.SOLVER_DP5 == 1 and o.beta2 == 0.04 and o.reltol == 1e-4
+    o = model._opts_from_kwargs({"adaptive": False, "dt": 0.01}, None, ldeq.RK4())
+    assert o.solver == ldeq.SOLVER_RK4 == 3 and o.adaptive == 0 and o.beta2 == pytest.approx(0.1)
 
 
-def test_user_rhs_translation_unit_compiles_with_nvrtc():
+@pytest.mark.parametrize("method", ["Tsit5M|Tsit5Dual", "DP5M|ErkDual<TabDP5>", "BS3M|ErkDual<TabBS3>", "RK4M|ErkDual<TabRK4>"])
+def test_user_rhs_translation_unit_compiles_with_nvrtc(method):
     """The text ldeq_rhs_from_source hands to NVRTC (the integrator headers embedded in the library + a user function +
-    the kernel entry points) compiles for sm_100a; NVRTC needs no GPU."""
+    the kernel entry points) compiles for sm_100a -- one variant per value of the diffeq struct's `solver` field; NVRTC
+    needs no GPU."""
     import re
     nvrtc = pytest.importorskip("cuda.bindings.nvrtc")
     csrc = os.path.join(ROOT, "latentdiffeq.jl_b200", "csrc")
@@ -88,8 +96,10 @@ def test_user_rhs_translation_unit_compiles_with_nvrtc():
     wrapper = re.search(r'kWrapper = R"LDEQ\((.*?)\)LDEQ";', open(os.path.join(csrc, "ldeq_user_rhs.cu")).read(), re.S).group(1)
     user = ("template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t) { du[0] = u[1]; "
             "du[1] = -p[0] * sin(u[0]) - S(0.1) * u[1]; du[2] = p[1] * u[0] - u[2] + exp(-t); }")
-    src = ("#define LDEQ_USER_ZD 3\n#define LDEQ_USER_PD 2\n" + "".join(strip(f) for f in (
-        "ldeq_common.cuh", "ldeq_tsit5.cuh", "ldeq_julia_trig.cuh", "ldeq_dual.cuh", "ldeq_fwdsens.cuh")) + "\n" + user + "\n" + wrapper)
+    m, md = method.split("|")
+    assert f"#define LDEQ_USER_M {m}\\n#define LDEQ_USER_MD {md}\\n" in open(os.path.join(csrc, "ldeq_user_rhs.cu")).read()
+    src = (f"#define LDEQ_USER_ZD 3\n#define LDEQ_USER_PD 2\n#define LDEQ_USER_M {m}\n#define LDEQ_USER_MD {md}\n" + "".join(strip(f) for f in (
+        "ldeq_common.cuh", "ldeq_erk.cuh", "ldeq_tsit5.cuh", "ldeq_julia_trig.cuh", "ldeq_dual.cuh", "ldeq_fwdsens.cuh")) + "\n" + user + "\n" + wrapper)
     err, prog = nvrtc.nvrtcCreateProgram(src.encode(), b"u.cu", 0, [], [])
     opts = [b"--gpu-architecture=sm_100a", b"--std=c++17", b"-default-device", b"--fmad=true", b"-DLDEQ_NVRTC=1"]
     err, = nvrtc.nvrtcCompileProgram(prog, len(opts), opts)
