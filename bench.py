@@ -528,8 +528,8 @@ def training_record(ldeq, dev, world, rank, local, steps, warmup, GB=TRAIN_GB, T
     built = {name: make(sym) for name, sym in routes}
     rec = {"metric": "GOKU-net training samples/sec", "unit": "samples/s", "scaling": "strong", "global_batch": GB, "per_gpu_batch": Bl,
            "frames_per_sequence": T, "params": int(built["nccl"][1].n), "gradient": "library default (ForwardDiffSensitivity dual solves)",
-           "layers": "encoder / decoder dense and recurrent layers: stock PyTorch fp32 + cuDNN RNN/LSTM (outside the hot path); solve, "
-                     "pullback, sample, ELBO, all-reduce + AdamW: libldeq.so"}
+           "layers": "encoder / decoder dense layers: stock PyTorch fp32 (outside the hot path); recurrent pattern extractor (forward + "
+                     "back-propagation through time), solve, pullback, sample, ELBO, all-reduce + AdamW: libldeq.so"}
     # ---- multi-rank parity self-test: fused peer-memory route vs NCCL route, one step from identical state ----
     if world > 1:
         torch.manual_seed(1234)

@@ -10,6 +10,7 @@
  *   ldeq_rhs_builtin / _from_source      the user-defined diffeq struct's f!        pendulum.jl:19-26, 65-74
  *   ldeq_mlp_solve_fwd / _bwd            diffeq_layer(::Decoder{LatentODE}, z0, t) src/models/LatentODE.jl:61-78
  *                                        with dudt = Chain(Dense,Dense,Dense)      examples/.../nODE.jl:14-16
+ *   ldeq_pattern_extractor_fwd / _bwd    apply_pattern_extractor(encoder, fe_out)  src/models/GOKU.jl:30-49, 224-234
  *   ldeq_sample                          sample(mu, logvar, model)                src/models/GOKU.jl:155-173,
  *                                                                                  src/models/LatentODE.jl:82-98
  *   ldeq_elbo_fwd_bwd                    loss_batch + vector_kl                   examples/.../model_train.jl:225-238,
@@ -215,6 +216,32 @@ int ldeq_mlp_bwd_stats(ldeq_handle* h, ldeq_mlp_tape* tape, int32_t* out3_host, 
  * (t, dt, EEst, accepted) quadruples of doubles; synchronises the device. */
 int ldeq_debug_cadj_trace(ldeq_handle* h, ldeq_mlp_tape* tape, double* out_host, int n);
 void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream);
+
+/* ---- recurrent pattern extractor ----------------------------------------------------------------
+ * Replaces the body of apply_pattern_extractor (src/models/GOKU.jl:30-49; src/models/LatentODE.jl:20-34): the two-layer
+ * relu-RNN stack on the REVERSED frame sequence and, for GOKU, the two two-layer LSTM stacks (forward and reversed
+ * sequence) of default_layers (GOKU.jl:224-234), each one persistent kernel over all T frames (csrc/ldeq_recurrent.cu);
+ * only the final hidden states leave, and every call starts from the trainable initial states (`Flux.reset!`).
+ *   x            (F,B,T) Float32 device array, the feature extractor's output per frame: element (f,b,k) at (k*B+b)*F+f
+ *   *_params     one flat Float32 vector per stack in `Flux.destructure` order: per layer Wi (rows x in, column-major),
+ *                Wh (rows x H), b (rows), state0 (H) [LSTM: h0 (H), c0 (H)]; rows = H (RNN) or 4H (LSTM, gate order input,
+ *                forget, cell, output); layer 1 has in = F, layer 2 in = H.  ldeq_pattern_extractor_param_count(cell = 0
+ *                RNN / 1 LSTM, F, H) gives the length.  lstm_f_params / lstm_b_params / theta_out may all be NULL (LatentODE).
+ *   z0_out       (H,B): final state of the RNN stack;  theta_out (2H,B): [LSTM forward; LSTM reversed] (GOKU.jl:42)
+ *   tape_out     non-NULL: keep the hidden / cell states of every step for ldeq_pattern_extractor_bwd
+ * Built for H = 16 and F in {16, 32, 64} (defaults F = 32, H = 16, GOKU.jl:200-201); anything else LDEQ_ERR_UNSUPPORTED.
+ * The reverse pass is back-propagation through time: dx (F,B,T) and the three flat parameter gradients are OUTPUTS
+ * (overwritten), x and the parameters must be those of the forward call. */
+typedef struct ldeq_pe_tape ldeq_pe_tape;
+int ldeq_pattern_extractor_param_count(int cell, int F, int H);
+int ldeq_pattern_extractor_fwd(ldeq_handle* h, const float* x, int B, int T, int F, int H, const float* rnn_params,
+                               const float* lstm_f_params, const float* lstm_b_params, float* z0_out, float* theta_out,
+                               ldeq_pe_tape** tape_out, ldeq_stream stream);
+int ldeq_pattern_extractor_bwd(ldeq_handle* h, ldeq_pe_tape* tape, const float* x, const float* rnn_params,
+                               const float* lstm_f_params, const float* lstm_b_params, const float* dz0_out,
+                               const float* dtheta_out, float* dx, float* d_rnn_params, float* d_lstm_f_params,
+                               float* d_lstm_b_params, ldeq_stream stream);
+void ldeq_pe_tape_free(ldeq_handle* h, ldeq_pe_tape* tape, ldeq_stream stream);
 
 /* ---- reparameterised sample: z = mu + eps * exp(logvar/2), eps ~ N(0,1) drawn on the device ---- */
 int ldeq_sample(ldeq_handle* h, const float* mu, const float* logvar, float* z_out, float* eps_out /*opt*/,

@@ -25,7 +25,7 @@ from torch import nn
 
 from . import _cabi
 from .diffeqs import NODE, CudaRHS
-from .solve import goku_solve, mlp_solve, sample_reparam
+from .solve import goku_solve, mlp_solve, sample_reparam, pattern_extractor
 
 
 # ---- model types (src/models/GOKU.jl:6-7, src/models/LatentODE.jl:7) ------------------------------
@@ -212,9 +212,36 @@ def apply_feature_extractor(encoder, x):
     return encoder.feature_extractor(x)
 
 
+def _pe_kernel_ok(fe_out, rnn_chain, lstm_chains=()):
+    """The default architecture's stacks (two layers, 16 hidden units, relu RNN / LSTM; GOKU.jl:224-234) on a CUDA
+    sequence: the shapes ``ldeq_pattern_extractor_fwd`` is built for."""
+    from .solve import PE_HIDDEN, PE_INPUTS
+    if not (PERSISTENT_RECURRENT and fe_out.is_cuda and fe_out.dtype == torch.float32 and fe_out.dim() == 3 and fe_out.shape[-1] in PE_INPUTS):
+        return False
+
+    def stack_ok(chain, cls):
+        layers = list(chain) if isinstance(chain, nn.Sequential) else []
+        if len(layers) != 2 or not all(isinstance(l, cls) for l in layers):
+            return False
+        rows = PE_HIDDEN * (4 if cls is LSTM else 1)
+        return (all(l.Wi.dtype == torch.float32 for l in layers) and tuple(layers[0].Wi.shape) == (rows, fe_out.shape[-1]) and tuple(layers[1].Wi.shape) == (rows, PE_HIDDEN)
+                and (cls is LSTM or all(l.act is F.relu for l in layers)))
+    return stack_ok(rnn_chain, RNN) and all(stack_ok(c, LSTM) for c in lstm_chains)
+
+
+PERSISTENT_RECURRENT = True   # False: the cuDNN / per-step route below (kept for other layer shapes and as a cross-check)
+
+
 def apply_pattern_extractor(encoder, fe_out):
     """GOKU.jl:30-49 / LatentODE.jl:20-34: recurrent layers over the (reversed) sequence; only the
-    final hidden state is used; hidden states start from ``state0`` on every call (``Flux.reset!``)."""
+    final hidden state is used; hidden states start from ``state0`` on every call (``Flux.reset!``).
+    The default architecture runs through the persistent kernels of ``csrc/ldeq_recurrent.cu``."""
+    if isinstance(encoder.model_type, GOKU):
+        pe_z0, pe_th_f, pe_th_b = encoder.pattern_extractor
+        if _pe_kernel_ok(fe_out, pe_z0, (pe_th_f, pe_th_b)):
+            return pattern_extractor(fe_out, list(pe_z0), list(pe_th_f), list(pe_th_b))
+    elif _pe_kernel_ok(fe_out, encoder.pattern_extractor):
+        return pattern_extractor(fe_out, list(encoder.pattern_extractor))
     rev = torch.flip(fe_out, dims=[0])
     if isinstance(encoder.model_type, GOKU):
         pe_z0, pe_th_f, pe_th_b = encoder.pattern_extractor

@@ -344,6 +344,105 @@ def mlp_solve(z0, params_flat, dims, t, opts: _cabi.Opts | None = None, stats_ou
     return _MlpSolve.apply(z0, params_flat, _tgrid(t), list(dims), opts, stats_out)
 
 
+# ---- recurrent pattern extractor ----------------------------------------------------------------
+PE_HIDDEN = 16
+PE_INPUTS = (16, 32, 64)
+
+
+def pe_flat_params(layers, lstm: bool) -> torch.Tensor:
+    """One stack's parameters as the flat vector ``ldeq_pattern_extractor_*`` read -- ``Flux.destructure`` order: per layer
+    ``Wi`` (rows x in, column-major = the row-major ``[in, rows]`` of ``W.t()``), ``Wh``, ``b``, ``state0`` (LSTM: ``h0``,
+    ``c0``).  Built with differentiable torch ops, so autograd routes the flat gradient back to the layers' own tensors."""
+    parts = []
+    for l in layers:
+        parts += [l.Wi.t().reshape(-1), l.Wh.t().reshape(-1), l.b]
+        parts += [l.h0, l.c0] if lstm else [l.state0]
+    return torch.cat(parts).float()
+
+
+class _PeTape:
+    """Owns an ``ldeq_pe_tape``; frees it stream-ordered when dropped."""
+
+    def __init__(self, h: _cabi.Handle, ptr: C.c_void_p):
+        self.h, self.ptr = h, ptr
+
+    def free(self):
+        if self.ptr:
+            try:
+                with torch.cuda.device(self.h.device):
+                    self.h._lib.ldeq_pe_tape_free(self.h.ptr, self.ptr, _stream())
+            finally:
+                self.ptr = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class _PatternExtractor(torch.autograd.Function):
+    """``apply_pattern_extractor`` (GOKU.jl:30-49 / LatentODE.jl:20-34) through the persistent recurrent kernels."""
+
+    @staticmethod
+    def forward(ctx, x, rnn, lstm_f, lstm_b):
+        h = _cabi.handle(x.device.index or 0)
+        T, B, F = x.shape
+        x = _aligned16(x.contiguous().float())
+        rnn = rnn.contiguous()
+        has_lstm = lstm_f is not None
+        lstm_f = lstm_f.contiguous() if has_lstm else None
+        lstm_b = lstm_b.contiguous() if has_lstm else None
+        lib = h._lib
+        if rnn.numel() != lib.ldeq_pattern_extractor_param_count(0, F, PE_HIDDEN) or (
+                has_lstm and lstm_f.numel() != lib.ldeq_pattern_extractor_param_count(1, F, PE_HIDDEN)):
+            raise _cabi.LdeqError(_cabi.ERR_UNSUPPORTED, "pattern extractor: parameter vectors do not match (F, H = 16)")
+        z0 = torch.empty(B, PE_HIDDEN, device=x.device, dtype=torch.float32)
+        th = torch.empty(B, 2 * PE_HIDDEN, device=x.device, dtype=torch.float32) if has_lstm else None
+        need = any(ctx.needs_input_grad)
+        tape = C.c_void_p()
+        with torch.cuda.device(x.device):
+            h.check(lib.ldeq_pattern_extractor_fwd(h.ptr, _p(x), B, T, F, PE_HIDDEN, _p(rnn), _p(lstm_f), _p(lstm_b), _p(z0), _p(th),
+                                                   C.byref(tape) if need else None, _stream()))
+        ctx.h, ctx.tape, ctx.has_lstm = h, (tape if need else None), has_lstm
+        ctx.save_for_backward(x, rnn, *( [lstm_f, lstm_b] if has_lstm else []))
+        if need:
+            ctx.freer = _PeTape(h, tape)
+        return (z0, th) if has_lstm else (z0, torch.empty(0, device=x.device))
+
+    @staticmethod
+    def backward(ctx, dz0, dth):
+        if ctx.tape is None:
+            raise RuntimeError("the tape of this pattern-extractor call was already consumed and freed (backward twice?)")
+        saved = ctx.saved_tensors
+        x, rnn = saved[0], saved[1]
+        lf, lb = (saved[2], saved[3]) if ctx.has_lstm else (None, None)
+        h = ctx.h
+        dz0 = dz0.contiguous().float()
+        dth = dth.contiguous().float() if ctx.has_lstm else None
+        dx = torch.empty_like(x)
+        drnn = torch.empty_like(rnn)
+        dlf = torch.empty_like(lf) if ctx.has_lstm else None
+        dlb = torch.empty_like(lb) if ctx.has_lstm else None
+        with torch.cuda.device(x.device):
+            h.check(h._lib.ldeq_pattern_extractor_bwd(h.ptr, ctx.tape, _p(x), _p(rnn), _p(lf), _p(lb), _p(dz0), _p(dth), _p(dx), _p(drnn),
+                                                      _p(dlf), _p(dlb), _stream()))
+        ctx.freer.free()
+        ctx.tape = None
+        return dx, drnn, dlf, dlb
+
+
+def pattern_extractor(x: torch.Tensor, rnn_layers, lstm_f_layers=None, lstm_b_layers=None):
+    """Final hidden states of the pattern extractor's recurrent stacks over the frame sequence ``x [T, B, F]``:
+    ``(z0_out [B, 16], theta_out [B, 32])`` for GOKU, ``z0_out`` alone for LatentODE (no LSTM stacks).  Differentiable."""
+    if not x.is_cuda:
+        raise RuntimeError("pattern_extractor needs CUDA tensors (no CPU fallback)")
+    rnn = pe_flat_params(rnn_layers, False)
+    if lstm_f_layers is None:
+        return _PatternExtractor.apply(x, rnn, None, None)[0]
+    return _PatternExtractor.apply(x, rnn, pe_flat_params(lstm_f_layers, True), pe_flat_params(lstm_b_layers, True))
+
+
 # ---- reparameterised sample, ELBO, AdamW ------------------------------------------------------------
 def sample_raw(mu: torch.Tensor, logvar: torch.Tensor, seed: int, offset: int = 0, want_eps: bool = True):
     """``ldeq_sample``: ``z = mu + eps * exp(logvar/2)``, ``eps ~ N(0,1)`` drawn on the device (Philox4x32-10)."""
