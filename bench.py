@@ -388,7 +388,28 @@ def run_ours(args):
         barrier()
         return allmax(ms)
 
+    def link_probe(reps=4):
+        """The ceiling of the end-to-end call at this rank count: the step's own byte counts as plain pinned copies, upload
+        and download CONCURRENTLY on two streams, all ranks at once (they share the host's memory system and PCIe root)."""
+        up, down = torch.cuda.Stream(), torch.cuda.Stream()
+        dbuf_in, dbuf_out = torch.empty_like(dtraj), torch.empty_like(dtraj)
+        ms = []
+        for i in range(reps + 1):
+            torch.cuda.synchronize()
+            barrier()
+            w0 = time.perf_counter()
+            with torch.cuda.stream(up):
+                dbuf_in.copy_(hd, non_blocking=True)
+            with torch.cuda.stream(down):
+                htraj.copy_(dbuf_out, non_blocking=True)
+            up.synchronize()
+            down.synchronize()
+            if i:
+                ms.append((time.perf_counter() - w0) * 1e3)
+        return allmax(float(np.median(ms)))
+
     Ke = max(4, min(K, 10))
+    link_ms = link_probe()
     e2e_comb = e2e_leg(opts_fd, True, Ke)
     e2e_sep = e2e_leg(opts_fd, False, Ke)
     e2e_da_comb = e2e_leg(opts_da, True, Ke)
@@ -414,6 +435,12 @@ def run_ours(args):
             "clocks": fd["clocks"],
             "e2e": {"value": world * B * (T - 1) / (e2e_comb * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_comb, "steps": Ke, "host_threads": 1, "numa": numa,
+                    "link_roofline": {"bound": "host link (PCIe + host memory, shared by the ranks of the box)",
+                                      "probe": "the step's cotangent upload and trajectory download as plain pinned cudaMemcpyAsync on two "
+                                               "streams, concurrently, on all ranks at once (max over ranks, median of 4)",
+                                      "probe_ms": link_ms, "peak": world * (h2d + d2h) / (link_ms * 1e-3) / 1e9,
+                                      "achieved": world * (h2d + d2h) / (e2e_comb * 1e-3) / 1e9, "unit": "GB/s (both directions, all ranks)",
+                                      "frac": link_ms / e2e_comb},
                     "path": "ldeq_solve_fwd_bwd_host (one call, one caller thread, pinned host buffers; batch cut into column slabs, "
                             "cotangent upload / trajectory download / kernels overlapped on the library's own streams)",
                     "separate_calls": {"value": world * B * (T - 1) / (e2e_sep * 1e-3), "ms_per_step": e2e_sep,

@@ -17,7 +17,9 @@
 //     recomputes the gates from the taped states, pulls the cotangents through the transposed weights (reduce-scatter
 //     over the 4 lanes), writes d x, and accumulates the weight gradients in REGISTERS across all T steps: after every
 //     step the CTA parks its 32 x (deltas, inputs) in shared memory and each thread adds its 4 x 6 tile of the
-//     (rows x inputs) outer product -- one atomic add per weight and CTA at the very end.
+//     (rows x inputs) outer product; every CTA stores its partial gradient and a second kernel sums the CTAs in a
+//     fixed order (deterministic: no floating-point atomics anywhere);
+//   * the three stacks run in ONE launch per pass (blockIdx.y), each with its own d x buffer, added in a fixed order.
 // Parameters travel as one flat Float32 vector per stack in `Flux.destructure` order: per layer Wi (rows x in,
 // column-major), Wh (rows x H), b (rows), state0 (H) [LSTM: h0 (H), c0 (H)]; rows = H (RNN) or 4H (LSTM, gate-major).
 #include <cstring>
@@ -135,9 +137,9 @@ template <int G> __device__ __forceinline__ const float* pe_state0(const float* 
 // x (F,B,T) = [T][B][F]; reverse: the stack reads frame T-1-s at step s (GOKU.jl:39).  out: final h of layer 2 into
 // out[b * ostride + ooff + unit].  tape (may be null): [T][B][NS] = h1 [c1] h2 [c2] after every step.
 template <int G, int F>
-__global__ void __launch_bounds__(PE_THREADS)
-pe_fwd_kernel(const float* __restrict__ x, int B, int T, int reverse, const float* __restrict__ params, float* __restrict__ out, int ostride,
-              int ooff, float* __restrict__ tape) {
+__device__ __forceinline__ void
+pe_fwd_body(const float* __restrict__ x, int B, int T, int reverse, const float* __restrict__ params, float* __restrict__ out, int ostride,
+            int ooff, float* __restrict__ tape) {
     using D = PeDims<G>;
     using SM = PeSmem<G, F>;
     extern __shared__ __align__(16) float pe_smem[];
@@ -302,7 +304,7 @@ __device__ __forceinline__ void pe_cell_bwd(const float* acc, const float* h_t, 
     }
 }
 
-// add a thread's (G rows x TI inputs) weight-gradient tile to the flat gradient of one layer (Wi | Wh in Flux order)
+// store a thread's (G rows x TI inputs) weight-gradient tile into the CTA's partial of one layer (Wi | Wh in Flux order)
 template <int G, int TI>
 __device__ __forceinline__ void pe_flush_tile(const float (&tile)[G][TI], float* gl, int in, int rg, int ig) {
     using D = PeDims<G>;
@@ -315,19 +317,19 @@ __device__ __forceinline__ void pe_flush_tile(const float (&tile)[G][TI], float*
 #pragma unroll
         for (int i = 0; i < TI; ++i) {
             const int j = ig * TI + i;
-            if (j < in) atomicAdd(gWi + (size_t)j * D::R + row, tile[r][i]);
-            else atomicAdd(gWh + (size_t)(j - in) * D::R + row, tile[r][i]);
+            if (j < in) gWi[(size_t)j * D::R + row] = tile[r][i];      // every (row, input) pair has one owner thread in the CTA
+            else gWh[(size_t)(j - in) * D::R + row] = tile[r][i];
         }
     }
 }
 
-// dx: the stack's cotangent of x.  accumulate_dx = 0: stored; 1: added to what is there (the three stacks of the
-// pattern extractor read the same frames; their launches are ordered on the stream, every element has one owner lane).
-// dparams: flat gradient, atomically added (zeroed by the caller).  dout: cotangent of the final h of layer 2.
+// dx: this stack's own cotangent buffer of x (the three stacks of the pattern extractor read the same frames; their
+// buffers are added in a fixed order afterwards).  gpart: [n_cta][n_params] partial gradients, row blockIdx.x written here.
+// dout: cotangent of the final h of layer 2.
 template <int G, int F>
-__global__ void __launch_bounds__(PE_THREADS, 2)
-pe_bwd_kernel(const float* __restrict__ x, int B, int T, int reverse, const float* __restrict__ params, const float* __restrict__ tape,
-              const float* __restrict__ dout, int ostride, int ooff, float* __restrict__ dx, int accumulate_dx, float* __restrict__ dparams) {
+__device__ __forceinline__ void
+pe_bwd_body(const float* __restrict__ x, int B, int T, int reverse, const float* __restrict__ params, const float* __restrict__ tape,
+            const float* __restrict__ dout, int ostride, int ooff, float* __restrict__ dx, float* __restrict__ gpart) {
     using D = PeDims<G>;
     using SM = PeSmem<G, F>;
     constexpr int IN1 = F + PE_H, IN2 = 2 * PE_H;
@@ -447,11 +449,8 @@ pe_bwd_kernel(const float* __restrict__ x, int B, int T, int reverse, const floa
             float* dp = dx + ((size_t)frame * B + bb) * F;
 #pragma unroll 2
             for (int i = 0; i < F / 4; ++i) {                          // W_i1^T delta1: cotangent of x, columns 4 i + g
-                float v = pe_col_dot<G>(img1, 4 * i + g, dall);
-                if (live) {
-                    if (accumulate_dx) v += dp[4 * i + g];
-                    dp[4 * i + g] = v;
-                }
+                const float v = pe_col_dot<G>(img1, 4 * i + g, dall);
+                if (live) dp[4 * i + g] = v;
             }
         }
 #pragma unroll
@@ -485,43 +484,117 @@ pe_bwd_kernel(const float* __restrict__ x, int B, int T, int reverse, const floa
         // has finished this loop
     }
 
-    // ---- flush: one atomic add per weight and CTA
-    float* g1 = dparams;
-    float* g2 = dparams + pe_layer_params(G, F);
+    // ---- flush: this CTA's partial gradient (plain stores: deterministic); pe_reduce_kernel sums the CTAs in order
+    float* g1 = gpart + (size_t)blockIdx.x * pe_stack_params(G, F);
+    float* g2 = g1 + pe_layer_params(G, F);
     pe_flush_tile<G, TI1>(gw1, g1, F, rg, ig);
     pe_flush_tile<G, TI2>(gw2, g2, PE_H, rg, ig);
-    // biases and initial states: sum over the 8 sequences of the warp (lanes with the same g), then one atomic per warp
+    // biases and initial states: sum over the 8 sequences of the warp (lanes with the same g), park the 4 warps' sums in
+    // shared memory and add them in a fixed order
     auto warp_sum_same_g = [](float v) {
         v += __shfl_xor_sync(0xffffffffu, v, 4);
         v += __shfl_xor_sync(0xffffffffu, v, 8);
         v += __shfl_xor_sync(0xffffffffu, v, 16);
         return v;
     };
+    constexpr int NRED = 2 * D::R + 4 * PE_H;   // db1 | db2 | dh1_0 | dh2_0 | dc1_0 | dc2_0 in Flux row / unit order
+    __syncthreads();                            // the staging rows are free now
+    float* red = stage;                         // [4 warps][NRED]
+    const int warp = threadIdx.x >> 5;
     const bool writer = (threadIdx.x & 31) < 4;
-    float* gb1 = g1 + D::R * F + D::R * PE_H;
-    float* gb2 = g2 + D::R * PE_H + D::R * PE_H;
 #pragma unroll
     for (int r = 0; r < D::RL; ++r) {
         const float v1 = warp_sum_same_g(db1[r]), v2 = warp_sum_same_g(db2[r]);
         if (writer) {
-            atomicAdd(gb1 + pe_flux_row_il<G>(g, r), v1);
-            atomicAdd(gb2 + pe_flux_row_il<G>(g, r), v2);
+            red[warp * NRED + pe_flux_row_il<G>(g, r)] = v1;
+            red[warp * NRED + D::R + pe_flux_row_il<G>(g, r)] = v2;
         }
     }
-    float* gs1 = gb1 + D::R;
-    float* gs2 = gb2 + D::R;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float a = warp_sum_same_g(live ? dh1[k] : 0.f), c = warp_sum_same_g(live ? dh2[k] : 0.f);
         const float e = warp_sum_same_g(live ? dc1[k] : 0.f), f = warp_sum_same_g(live ? dc2[k] : 0.f);
         if (writer) {
-            atomicAdd(gs1 + 4 * k + g, a);
-            atomicAdd(gs2 + 4 * k + g, c);
-            if (G == 4) {
-                atomicAdd(gs1 + PE_H + 4 * k + g, e);
-                atomicAdd(gs2 + PE_H + 4 * k + g, f);
-            }
+            float* rw = red + warp * NRED + 2 * D::R;
+            rw[4 * k + g] = a;
+            rw[PE_H + 4 * k + g] = c;
+            rw[2 * PE_H + 4 * k + g] = e;
+            rw[3 * PE_H + 4 * k + g] = f;
         }
+    }
+    __syncthreads();
+    float* gb1 = g1 + D::R * F + D::R * PE_H;
+    float* gb2 = g2 + D::R * PE_H + D::R * PE_H;
+    for (int i = threadIdx.x; i < NRED; i += PE_THREADS) {
+        const float v = (red[i] + red[NRED + i]) + (red[2 * NRED + i] + red[3 * NRED + i]);
+        if (i < D::R) gb1[i] = v;
+        else if (i < 2 * D::R) gb2[i - D::R] = v;
+        else {
+            const int q = (i - 2 * D::R) / PE_H, u = (i - 2 * D::R) % PE_H;   // q: dh1_0, dh2_0, dc1_0, dc2_0
+            if (q == 0) gb1[D::R + u] = v;
+            else if (q == 1) gb2[D::R + u] = v;
+            else if (G == 4) (q == 2 ? gb1 : gb2)[D::R + PE_H + u] = v;
+        }
+    }
+}
+
+// One launch per pass: blockIdx.y selects the stack (0: relu-RNN on the reversed sequence, 1: LSTM forwards,
+// 2: LSTM on the reversed sequence; GOKU.jl:39-41).  The three stacks are independent, so at one GPU's share of a
+// training batch (B = 8192: 256 CTAs per stack) they fill the machine together instead of one after the other.
+struct PeStackArgs {
+    const float* params[3];
+    float* tape[3];
+    float* out[3];      // forward: final states; reverse pass: cotangents of the final states (read)
+    int ostride[3], ooff[3];
+    float* dx[3];       // reverse pass: one cotangent buffer per stack (summed in a fixed order afterwards)
+    float* gpart[3];    // reverse pass: [n_cta][n_params] partial gradients
+};
+
+template <int F>
+__global__ void __launch_bounds__(PE_THREADS)
+pe_fwd_kernel(const float* __restrict__ x, int B, int T, PeStackArgs a) {
+    const int y = blockIdx.y;
+    if (y == 0) pe_fwd_body<1, F>(x, B, T, 1, a.params[0], a.out[0], a.ostride[0], a.ooff[0], a.tape[0]);
+    else pe_fwd_body<4, F>(x, B, T, y == 2, a.params[y], a.out[y], a.ostride[y], a.ooff[y], a.tape[y]);
+}
+
+template <int F>
+__global__ void __launch_bounds__(PE_THREADS, 2)
+pe_bwd_kernel(const float* __restrict__ x, int B, int T, PeStackArgs a) {
+    const int y = blockIdx.y;
+    if (y == 0) pe_bwd_body<1, F>(x, B, T, 1, a.params[0], a.tape[0], a.out[0], a.ostride[0], a.ooff[0], a.dx[0], a.gpart[0]);
+    else pe_bwd_body<4, F>(x, B, T, y == 2, a.params[y], a.tape[y], a.out[y], a.ostride[y], a.ooff[y], a.dx[y], a.gpart[y]);
+}
+
+// dparams[p] = sum over the CTAs' partials in CTA order (deterministic); blockIdx.y = stack
+struct PeReduceArgs {
+    const float* gpart[3];
+    float* dparams[3];
+    int n[3];
+};
+__global__ void pe_reduce_kernel(PeReduceArgs a, int n_cta) {
+    const int y = blockIdx.y, p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.n[y]) return;
+    const float* src = a.gpart[y] + p;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int c = 0;
+    for (; c + 3 < n_cta; c += 4) {
+        s0 += src[(size_t)c * a.n[y]];
+        s1 += src[(size_t)(c + 1) * a.n[y]];
+        s2 += src[(size_t)(c + 2) * a.n[y]];
+        s3 += src[(size_t)(c + 3) * a.n[y]];
+    }
+    for (; c < n_cta; ++c) s0 += src[(size_t)c * a.n[y]];
+    a.dparams[y][p] = (s0 + s1) + (s2 + s3);
+}
+
+// dx = dx0 + dx1 + dx2 in that order
+__global__ void pe_sum_dx_kernel(float4* __restrict__ dx, const float4* __restrict__ d1, const float4* __restrict__ d2, size_t n4) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 a = dx[i];
+        const float4 b = __ldcs(d1 + i), c = __ldcs(d2 + i);
+        a.x = (a.x + b.x) + c.x; a.y = (a.y + b.y) + c.y; a.z = (a.z + b.z) + c.z; a.w = (a.w + b.w) + c.w;
+        dx[i] = a;
     }
 }
 
@@ -540,37 +613,55 @@ namespace {
 
 template <int F> int pe_fwd_launch(ldeq_handle* h, const float* x, int B, int T, const float* rnn, const float* lf, const float* lb, float* z0o,
                                    float* tho, ldeq_pe_tape* tape, cudaStream_t s) {
-    const int grid = (B + PE_SPB - 1) / PE_SPB;
+    const int grid = (B + PE_SPB - 1) / PE_SPB, ny = lf ? 3 : 1;
+    const size_t smem = lf ? PeSmem<4, F>::fwd_bytes : PeSmem<1, F>::fwd_bytes;
     // per device, a few microseconds: set on every call rather than cached per process
-    cudaFuncSetAttribute(pe_fwd_kernel<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PeSmem<4, F>::fwd_bytes);
-    cudaFuncSetAttribute(pe_fwd_kernel<1, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PeSmem<1, F>::fwd_bytes);
-    pe_fwd_kernel<1, F><<<grid, PE_THREADS, PeSmem<1, F>::fwd_bytes, s>>>(x, B, T, 1, rnn, z0o, PE_H, 0, tape ? tape->rnn : nullptr);
+    cudaFuncSetAttribute(pe_fwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PeSmem<4, F>::fwd_bytes);
+    PeStackArgs a{};
+    a.params[0] = rnn; a.params[1] = lf; a.params[2] = lb;
+    a.tape[0] = tape ? tape->rnn : nullptr; a.tape[1] = tape ? tape->lf : nullptr; a.tape[2] = tape ? tape->lb : nullptr;
+    a.out[0] = z0o; a.out[1] = tho; a.out[2] = tho;
+    a.ostride[0] = PE_H; a.ostride[1] = a.ostride[2] = 2 * PE_H;
+    a.ooff[0] = 0; a.ooff[1] = 0; a.ooff[2] = PE_H;
+    pe_fwd_kernel<F><<<dim3(grid, ny), PE_THREADS, smem, s>>>(x, B, T, a);
     h->launches += 1;
-    if (lf) {
-        pe_fwd_kernel<4, F><<<grid, PE_THREADS, PeSmem<4, F>::fwd_bytes, s>>>(x, B, T, 0, lf, tho, 2 * PE_H, 0, tape ? tape->lf : nullptr);
-        pe_fwd_kernel<4, F><<<grid, PE_THREADS, PeSmem<4, F>::fwd_bytes, s>>>(x, B, T, 1, lb, tho, 2 * PE_H, PE_H, tape ? tape->lb : nullptr);
-        h->launches += 2;
-    }
     LDEQ_CUDA(cudaGetLastError());
     return LDEQ_OK;
 }
 
 template <int F> int pe_bwd_launch(ldeq_handle* h, const ldeq_pe_tape* tape, const float* x, const float* rnn, const float* lf, const float* lb,
                                    const float* dz0o, const float* dtho, float* dx, float* drnn, float* dlf, float* dlb, cudaStream_t s) {
-    const int B = tape->B, T = tape->T, grid = (B + PE_SPB - 1) / PE_SPB;
-    cudaFuncSetAttribute(pe_bwd_kernel<4, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PeSmem<4, F>::bwd_bytes);
-    cudaFuncSetAttribute(pe_bwd_kernel<1, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PeSmem<1, F>::bwd_bytes);
-    LDEQ_CUDA(cudaMemsetAsync(drnn, 0, (size_t)pe_stack_params(1, F) * 4, s));
-    pe_bwd_kernel<1, F><<<grid, PE_THREADS, PeSmem<1, F>::bwd_bytes, s>>>(x, B, T, 1, rnn, tape->rnn, dz0o, PE_H, 0, dx, 0, drnn);
-    h->launches += 1;
-    if (tape->has_lstm) {
-        LDEQ_CUDA(cudaMemsetAsync(dlf, 0, (size_t)pe_stack_params(4, F) * 4, s));
-        LDEQ_CUDA(cudaMemsetAsync(dlb, 0, (size_t)pe_stack_params(4, F) * 4, s));
-        pe_bwd_kernel<4, F><<<grid, PE_THREADS, PeSmem<4, F>::bwd_bytes, s>>>(x, B, T, 0, lf, tape->lf, dtho, 2 * PE_H, 0, dx, 1, dlf);
-        pe_bwd_kernel<4, F><<<grid, PE_THREADS, PeSmem<4, F>::bwd_bytes, s>>>(x, B, T, 1, lb, tape->lb, dtho, 2 * PE_H, PE_H, dx, 1, dlb);
-        h->launches += 2;
+    const int B = tape->B, T = tape->T, grid = (B + PE_SPB - 1) / PE_SPB, ny = tape->has_lstm ? 3 : 1;
+    const size_t smem = tape->has_lstm ? PeSmem<4, F>::bwd_bytes : PeSmem<1, F>::bwd_bytes;
+    cudaFuncSetAttribute(pe_bwd_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PeSmem<4, F>::bwd_bytes);
+    const size_t nr = pe_stack_params(1, F), nl = pe_stack_params(4, F), nx = (size_t)T * B * F;
+    // scratch (stream-ordered): per-CTA partial gradients of every stack, and the two extra cotangent buffers
+    const size_t n_part = (size_t)grid * (nr + (ny == 3 ? 2 * nl : 0)), n_dx = ny == 3 ? 2 * nx : 0;
+    float* scratch = nullptr;
+    cudaError_t e = cudaMallocAsync((void**)&scratch, (n_part + n_dx) * sizeof(float), s);
+    if (e != cudaSuccess) return set_err(h, LDEQ_ERR_NOMEM, "cudaMallocAsync(pattern extractor reverse-pass scratch)", e);
+    PeStackArgs a{};
+    a.params[0] = rnn; a.params[1] = lf; a.params[2] = lb;
+    a.tape[0] = tape->rnn; a.tape[1] = tape->lf; a.tape[2] = tape->lb;
+    a.out[0] = const_cast<float*>(dz0o); a.out[1] = a.out[2] = const_cast<float*>(dtho);
+    a.ostride[0] = PE_H; a.ostride[1] = a.ostride[2] = 2 * PE_H;
+    a.ooff[0] = 0; a.ooff[1] = 0; a.ooff[2] = PE_H;
+    a.gpart[0] = scratch; a.gpart[1] = scratch + (size_t)grid * nr; a.gpart[2] = a.gpart[1] + (size_t)grid * nl;
+    a.dx[0] = dx; a.dx[1] = scratch + n_part; a.dx[2] = a.dx[1] + nx;
+    pe_bwd_kernel<F><<<dim3(grid, ny), PE_THREADS, smem, s>>>(x, B, T, a);
+    PeReduceArgs r{};
+    r.gpart[0] = a.gpart[0]; r.gpart[1] = a.gpart[1]; r.gpart[2] = a.gpart[2];
+    r.dparams[0] = drnn; r.dparams[1] = dlf; r.dparams[2] = dlb;
+    r.n[0] = (int)nr; r.n[1] = r.n[2] = (int)nl;
+    pe_reduce_kernel<<<dim3((unsigned)((nl + 127) / 128), ny), 128, 0, s>>>(r, grid);
+    h->launches += 2;
+    if (ny == 3) {
+        pe_sum_dx_kernel<<<h->sm_count * 8, 256, 0, s>>>((float4*)dx, (const float4*)a.dx[1], (const float4*)a.dx[2], nx / 4);
+        h->launches += 1;
     }
-    LDEQ_CUDA(cudaGetLastError());
+    e = cudaGetLastError();
+    cudaFreeAsync(scratch, s);
+    if (e != cudaSuccess) return set_err(h, LDEQ_ERR_CUDA, "pattern extractor reverse pass launch", e);
     return LDEQ_OK;
 }
 

@@ -51,6 +51,22 @@ def test_forward_and_gradients_match_the_oracle(ldeq, F, B, T):
     assert np.array_equal(z0, z0b) and np.array_equal(th, thb)
 
 
+def test_reverse_pass_is_deterministic(ldeq):
+    # no floating-point atomics: per-CTA partial gradients and the three stacks' dx buffers are added in a fixed order
+    # (the multi-rank self-test of the training bench compares two steps from identical state)
+    rng = np.random.default_rng(11)
+    T, B, F = 50, 2000, 32
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    rnn, lf, lb = orr.init_params(False, F, rng), orr.init_params(True, F, rng), orr.init_params(True, F, rng)
+    dz0 = rng.standard_normal((B, 16)).astype(np.float32)
+    dth = rng.standard_normal((B, 32)).astype(np.float32)
+    a = _raw(ldeq, x, rnn, lf, lb, dz0, dth)
+    b = _raw(ldeq, x, rnn, lf, lb, dz0, dth)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    for ga, gb in zip(a[2], b[2]):
+        assert np.array_equal(ga, gb)
+
+
 def test_latentode_rnn_only(ldeq):
     rng = np.random.default_rng(5)
     T, B, F = 50, 256, 32
