@@ -6,9 +6,9 @@
 # (reference src/models/GOKU.jl:98-130, src/models/LatentODE.jl:61-78, src/models/LatentDiffEqModel.jl:101-113).
 module LatentDiffEqB200
 
-using CUDA, ChainRulesCore, Flux
+using CUDA, ChainRulesCore, Flux, Functors
 import LatentDiffEq
-import LatentDiffEq: diffeq_layer, transform_after_diffeq, Decoder, GOKU, LatentODE
+import LatentDiffEq: diffeq_layer, transform_after_diffeq, apply_pattern_extractor, Encoder, Decoder, GOKU, LatentODE
 
 const libldeq = get(ENV, "LDEQ_LIB", "libldeq.so")
 
@@ -287,6 +287,48 @@ function sample_device(μ::CuMatrix{Float32}, logσ²::CuMatrix{Float32}; seed::
                    (Ptr{Cvoid}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, Int64, UInt64, UInt64, Ptr{Cvoid}),
                    h, μ, logσ², z̃, ε, length(μ), seed, offset, CUDA.stream().handle))
     return z̃, ε
+end
+
+# ---- apply_pattern_extractor (GOKU.jl:30-49): the three recurrent stacks as persistent kernels ----------------------------
+# fe_out is the (F,B,T) CuArray the feature extractor returns.  Flux.destructure of a Chain(RNN, RNN) / Chain(LSTM, LSTM)
+# is exactly the flat layout ldeq_pattern_extractor_* read (per layer Wi column-major, Wh, b, state0 [h0, c0]); `re` of the
+# flat gradients rebuilds the parameter cotangents.  Built for rnn_output_dim = 16 and rnn_input_dim in {16, 32, 64}.
+function pattern_extractor_fwd(fe_out::CuArray{Float32,3}, p_rnn::CuVector{Float32}, p_f::CuVector{Float32}, p_b::CuVector{Float32}; tape::Bool)
+    h = handle()
+    F, B, T = size(fe_out)
+    z0o, θo = CUDA.zeros(Float32, 16, B), CUDA.zeros(Float32, 32, B)
+    tp = Ref{Ptr{Cvoid}}(C_NULL)
+    check(h, ccall((:ldeq_pattern_extractor_fwd, libldeq), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cfloat}, Cint, Cint, Cint, Cint, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat},
+                    Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
+                   h, fe_out, B, T, F, 16, p_rnn, p_f, p_b, z0o, θo, tape ? tp : C_NULL, CUDA.stream().handle))
+    return z0o, θo, tp[]
+end
+
+function apply_pattern_extractor(encoder::Encoder{M}, fe_out::CuArray{Float32,3}) where {M<:GOKU}
+    pe_z₀, pe_f, pe_b = encoder.pattern_extractor
+    z0o, θo, _ = pattern_extractor_fwd(fe_out, Flux.destructure(pe_z₀)[1], Flux.destructure(pe_f)[1], Flux.destructure(pe_b)[1]; tape = false)
+    return z0o, θo
+end
+
+function ChainRulesCore.rrule(::typeof(apply_pattern_extractor), encoder::Encoder{M}, fe_out::CuArray{Float32,3}) where {M<:GOKU}
+    h = handle()
+    pe_z₀, pe_f, pe_b = encoder.pattern_extractor
+    (p_rnn, re_rnn), (p_f, re_f), (p_b, re_b) = Flux.destructure(pe_z₀), Flux.destructure(pe_f), Flux.destructure(pe_b)
+    z0o, θo, tp = pattern_extractor_fwd(fe_out, p_rnn, p_f, p_b; tape = true)
+    function pullback((Δz0, Δθ))
+        dx, g_rnn, g_f, g_b = similar(fe_out), similar(p_rnn), similar(p_f), similar(p_b)
+        check(h, ccall((:ldeq_pattern_extractor_bwd, libldeq), Cint,
+                       (Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat},
+                        CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, CuPtr{Cfloat}, Ptr{Cvoid}),
+                       h, tp, fe_out, p_rnn, p_f, p_b, CuArray{Float32}(unthunk(Δz0)), CuArray{Float32}(unthunk(Δθ)), dx, g_rnn, g_f, g_b,
+                       CUDA.stream().handle))
+        ccall((:ldeq_pe_tape_free, libldeq), Cvoid, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), h, tp, CUDA.stream().handle)
+        # parameter cotangents as structural tangents of the three Chains (Functors.fmapstructure of the rebuilt gradient models)
+        d_pe = map((re, g) -> Functors.fmapstructure(identity, re(g)), (re_rnn, re_f, re_b), (g_rnn, g_f, g_b))
+        return NoTangent(), Tangent{typeof(encoder)}(; pattern_extractor = d_pe), dx
+    end
+    return (z0o, θo), pullback
 end
 
 # loss_batch's reduction + its gradient in one pass: x, x̂ (P,B,T); μs / logσ²s tuples of (d,B) heads
