@@ -608,25 +608,42 @@ template <class S, int TB>
 static int launch_mlp_cadj(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtraj, void* dz0, void* dparams, cudaStream_t s) {
     const MlpNet& net = tape->net;
     const int B = tape->B, grid = (B + TB - 1) / TB;
-    const size_t smem = cadj_smem<S, TB>(net);
-    auto kern = mlp_cadj_kernel<S, TB>;
+    // BATCH (stage records in shared memory, one weight-gradient pass per attempt) whenever the records fit;
+    // LDEQ_CADJ_BATCH=0 keeps the per-stage reduction atomics (A/B switch)
+    static const bool allow_batch = [] { const char* e = getenv("LDEQ_CADJ_BATCH"); return !(e && e[0] == '0'); }();
+    static const bool allow_res = [] { const char* e = getenv("LDEQ_CADJ_RES"); return !(e && e[0] == '0'); }();
+    bool batch = allow_batch && cadj_smem<S, TB>(net, true) <= 227 * 1024;
+    // RES: Float32, the smallest tile, the padded weight image + one working record fit next to the tile state
+    bool res = false;
+    if constexpr (sizeof(S) == 4 && TB == 2)
+        res = allow_res && allow_batch && !getenv("LDEQ_MLP_NO_RESIDENT") && res_layout_ok(net, TB) && net.n_img > 0 &&
+              cadj_smem<S, TB>(net, true, true) <= 227 * 1024 - 1024 && grid <= h->sm_count;
+    if (res) batch = true;
+    const size_t smem = cadj_smem<S, TB>(net, batch, res);
+    const int nthreads = res ? RES_THREADS : MLP_THREADS;
+    void* kern = batch ? (void*)mlp_cadj_kernel<S, TB, true, false> : (void*)mlp_cadj_kernel<S, TB, false, false>;
+    if constexpr (sizeof(S) == 4 && TB == 2) { if (res) kern = (void*)mlp_cadj_kernel<S, TB, true, true>; }
     if (smem > 227 * 1024 || grid > GRID_SUM_HALF) return LDEQ_ERR_UNSUPPORTED;
     LDEQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
-    LDEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, MLP_THREADS, smem));
+    LDEQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem));
     if (per_sm * h->sm_count < grid) return LDEQ_ERR_UNSUPPORTED;
     const size_t NP = net.n_params, D = net.dims[0];
     const int na = tape->h_info[0] > 0 ? tape->h_info[0] : 1;
     int rc;
     if ((rc = ensure_scratch(h, 0, sizeof(double) * 4096))) return rc;
     if ((rc = ensure_scratch(h, 1, (size_t)grid * 2 * NP * sizeof(S)))) return rc;
-    if ((rc = ensure_scratch(h, 3, (size_t)na * 7 * D * grid * TB * sizeof(S)))) return rc;
+    const size_t dense_bytes = ((size_t)na * 7 * D * grid * TB * sizeof(S) + 255) & ~(size_t)255;
+    const size_t grec_bytes = res ? (size_t)grid * 7 * CadjRec<S, TB>::floats(net.dims[0], net.max_width, net.n_layers) * sizeof(S) : 0;
+    if ((rc = ensure_scratch(h, 3, dense_bytes + grec_bytes))) return rc;
     const size_t mu_bytes = (3 * NP * sizeof(S) + 255) & ~(size_t)255;
     const int trace_cap = getenv("LDEQ_CADJ_TRACE") ? 4096 : 0;  // debugging aid: (t, dt, EEst, accept) of every attempt
     if ((rc = ensure_scratch(h, 2, mu_bytes + (size_t)trace_cap * 32 + 256))) return rc;
     mlp_transpose_kernel<S><<<64, 256, 0, s>>>(net, (const S*)tape->params, (S*)tape->params_t);
     LDEQ_CUDA(cudaGetLastError());
     MlpNet netv = net;
+    if (res) res_plan(netv, RES_THREADS);
+    S* grec = res ? (S*)((char*)h->scratch[3] + dense_bytes) : nullptr;
     const S* Pp = (const S*)tape->params;
     const S* Pt = (const S*)tape->params_t;
     const double* tg = tape->tgrid;
@@ -645,8 +662,8 @@ static int launch_mlp_cadj(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtra
     int* status = tape->info + 4;
     double* trace = trace_cap ? (double*)((char*)h->scratch[2] + mu_bytes) : nullptr;
     int tcap = trace_cap;
-    void* args[] = {&netv, &Pp, &Pt, &tg, &Bv, &Tv, &kov, &dt_, &tv, &ret, &nacc, &dense, &gscr, &mubuf, &partials, &dz, &dp, &status, &trace, &tcap};
-    LDEQ_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(MLP_THREADS), args, smem, s));
+    void* args[] = {&netv, &Pp, &Pt, &tg, &Bv, &Tv, &kov, &dt_, &tv, &ret, &nacc, &dense, &gscr, &mubuf, &partials, &dz, &dp, &status, &trace, &tcap, &grec};
+    LDEQ_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(nthreads), args, smem, s));
     h->launches += 2;
     return LDEQ_OK;
 }

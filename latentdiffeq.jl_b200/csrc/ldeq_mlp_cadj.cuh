@@ -104,22 +104,158 @@ template <class S> __device__ __forceinline__ S tab_c(int j) {
     return (S)0;
 }
 
+// ---- BATCH: the weight gradients of an attempt in ONE pass ---------------------------------------------------------------
+// The seven stages of an attempted step add  b_j (df/dp)^T lambda_j  and  btilde_j (df/dp)^T lambda_j  into the CTA's two
+// accumulators.  Doing that per stage costs two reduction atomics per parameter and stage (at C2: 655 k per CTA and
+// attempt, 84 M per attempt over the grid -- the L2's atomic throughput, not the arithmetic, set the time of an attempt).
+// Instead every stage leaves its layer inputs x_l and pre-activation cotangents dy_l in a shared-memory record, and one
+// pass after the last stage forms  gA = sum_j b_j dy_j x_j^T,  gB = sum_j btilde_j dy_j x_j^T  with plain stores:
+// 2 stores per parameter and attempt instead of 14 atomics.
+template <class S, int TB> struct CadjRec {
+    // one stage's record: x (D) | kbar (D) | acts [(L-1) HW] | dys [(L-1) HW], each x TB
+    __host__ __device__ static size_t floats(int D, int HW, int L) { return (size_t)(2 * D + 2 * (L - 1) * HW) * TB; }
+};
+
+// forward + input-VJP through the MLP, leaving the record of this stage in `rec` (no parameter accumulation)
+template <class S, int TB>
+__device__ void mlp_vjp_rec(const MlpNet& net, const S* __restrict__ P, const S* __restrict__ Pt, S* rec, S* gbar, S* ytmp, S* red, int HW) {
+    // (general kernels: MLP_THREADS threads, weights through L1 / L2)
+    const int D = net.dims[0], L = net.n_layers;
+    S* xs = rec;
+    S* kb = rec + D * TB;
+    S* acts = kb + D * TB;
+    S* dys = acts + (size_t)(L - 1) * HW * TB;
+    const S* in = xs;
+    for (int l = 0; l < L; ++l) {
+        const bool last = l + 1 == L;
+        S* out = last ? ytmp : acts + (size_t)l * HW * TB;
+        dense_fwd<S, TB>(P + net.w_off[l], P + net.b_off[l], in, out, red, net.dims[l], net.dims[l + 1], !last);
+        in = out;
+    }
+    const S* dy = kb;
+    for (int l = L - 1; l >= 0; --l) {
+        const int K = net.dims[l], N = net.dims[l + 1];
+        const S* xin = l == 0 ? xs : acts + (size_t)(l - 1) * HW * TB;
+        S* dx = l == 0 ? gbar : dys + (size_t)(l - 1) * HW * TB;
+        dense_bwd_input<S, TB>(Pt + net.w_off[l], dy, dx, red, K, N);
+        if (l > 0) {
+            for (int i = threadIdx.x; i < K * TB; i += MLP_THREADS) dx[i] = xin[i] > (S)0 ? dx[i] : (S)0;
+            __syncthreads();
+        }
+        dy = dx;
+    }
+}
+
+// the same from the shared-memory-resident weight image (ldeq_mlp_common.cuh: dense_res, RES_THREADS threads, Float32):
+// forward and transposed products read the one image, the relu mask is applied in the transposed product's epilogue
+template <int TB>
+__device__ void mlp_vjp_rec_res(const MlpNet& net, const float* img, float* rec, float* gbar, float* ytmp, int HW) {
+    const int D = net.dims[0], L = net.n_layers;
+    float* xs = rec;
+    float* kb = rec + D * TB;
+    float* acts = kb + D * TB;
+    float* dys = acts + (size_t)(L - 1) * HW * TB;
+    const float* in = xs;
+    for (int l = 0; l < L; ++l) {
+        const bool last = l + 1 == L;
+        float* out = last ? ytmp : acts + (size_t)l * HW * TB;
+        dense_res<TB>(net, img, l, 0, in, out, !last, nullptr);
+        in = out;
+    }
+    const float* dy = kb;
+    for (int l = L - 1; l >= 0; --l) {
+        const float* xin = l == 0 ? xs : acts + (size_t)(l - 1) * HW * TB;
+        float* dx = l == 0 ? gbar : dys + (size_t)(l - 1) * HW * TB;
+        dense_res<TB>(net, img, l, 1, dy, dx, false, l > 0 ? xin : nullptr);
+        dy = dx;
+    }
+}
+
+// gA = sum_j wa[j] dy_j x_j^T, gB = sum_j wb[j] dy_j x_j^T over the stages in `jmask`, for every layer; plain stores
+template <class S, int TB, int NT>
+__device__ void cadj_param_pass(const MlpNet& net, const S* recs, size_t rec_stride, unsigned jmask, const S* wa, const S* wb,
+                                S* __restrict__ gA, S* __restrict__ gB, int HW) {
+    const int D = net.dims[0], L = net.n_layers;
+    for (int l = 0; l < L; ++l) {
+        const int K = net.dims[l], N = net.dims[l + 1];
+        // offsets of this layer's input and cotangent inside a record
+        const size_t o_x = l == 0 ? 0 : (size_t)(2 * D + (size_t)(l - 1) * HW) * TB;
+        const size_t o_dy = l == L - 1 ? (size_t)D * TB : (size_t)(2 * D + (size_t)(L - 1) * HW + (size_t)l * HW) * TB;
+        S* gWa = gA + net.w_off[l];
+        S* gWb = gB + net.w_off[l];
+        int SL = 1;
+        while (SL * 2 * N <= NT && SL < 16 && SL * 2 <= K) SL *= 2;
+        const int kper = (K + SL - 1) / SL;
+        for (int w = threadIdx.x; w < N * SL; w += NT) {
+            const int sl = w / N, n = w - sl * N;
+            const int k0 = sl * kper, k1 = min(K, k0 + kper);
+            S da[7][TB], db[7][TB];
+            S sa = (S)0, sb = (S)0;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+#pragma unroll
+                for (int b = 0; b < TB; ++b) { da[j][b] = (S)0; db[j][b] = (S)0; }
+                if (!((jmask >> j) & 1u)) continue;
+                const S* dy = recs + j * rec_stride + o_dy;
+#pragma unroll
+                for (int b = 0; b < TB; ++b) {
+                    const S d = dy[n * TB + b];
+                    da[j][b] = wa[j] * d;
+                    db[j][b] = wb[j] * d;
+                    sa += da[j][b];
+                    sb += db[j][b];
+                }
+            }
+#pragma unroll 2
+            for (int k = k0; k < k1; ++k) {
+                S a = (S)0, bsum = (S)0;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                    if (!((jmask >> j) & 1u)) continue;
+                    const S* x = recs + j * rec_stride + o_x + (size_t)k * TB;
+#pragma unroll
+                    for (int b = 0; b < TB; ++b) {
+                        const S xv = x[b];
+                        a = s_fma<S>(da[j][b], xv, a);
+                        bsum = s_fma<S>(db[j][b], xv, bsum);
+                    }
+                }
+                gWa[(size_t)k * N + n] = a;
+                gWb[(size_t)k * N + n] = bsum;
+            }
+            if (sl == 0) {
+                gA[net.b_off[l] + n] = sa;
+                gB[net.b_off[l] + n] = sb;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 struct CadjShared {
     double tc, dt, dts, tnew, tq, th, dtn, sum;
     int n, ks, accept, ret;
 };
 
 // status[0..3] = {accepted, rejected, retcode, -} of the backward solve
-template <class S, int TB>
-__global__ void __launch_bounds__(MLP_THREADS)
+// BATCH: stage records + one weight-gradient pass per attempt (above).  RES (Float32, implies BATCH): the weights are staged
+// once into shared memory (the padded image of ldeq_mlp_res.cu) and every dense product reads them from there with
+// RES_THREADS threads; the image leaves room for ONE working record, so the seven records of an attempt live in `grec`
+// (global scratch, L2-resident: 47 kB per CTA written and read once per attempt).
+template <class S, int TB, bool BATCH, bool RES>
+__global__ void __launch_bounds__(RES ? RES_THREADS : MLP_THREADS)
 mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, const double* __restrict__ tg, int B, int T, KOpts o,
                 const S* __restrict__ dtraj, MlpTapeView<S> tape, const int* __restrict__ retcode, const int* __restrict__ naccept,
                 S* __restrict__ dense, S* __restrict__ gscr, S* __restrict__ mubuf, double* __restrict__ partials,
-                S* __restrict__ dz0, S* __restrict__ dparams, int* __restrict__ status, double* __restrict__ trace, int trace_cap) {
+                S* __restrict__ dz0, S* __restrict__ dparams, int* __restrict__ status, double* __restrict__ trace, int trace_cap,
+                S* __restrict__ grec) {
+    constexpr int NT = RES ? RES_THREADS : MLP_THREADS;
+    static_assert(!RES || (BATCH && sizeof(S) == 4), "the resident variant is Float32 and keeps stage records");
     cg::grid_group grid = cg::this_grid();
     const int D = net.dims[0], HW = net.max_width, DT = D * TB, NP = net.n_params;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    S* Y = reinterpret_cast<S*>(smem_raw);  // lambda of this tile, feature-major [D][TB]
+    S* Wimg = reinterpret_cast<S*>(smem_raw);                      // RES: the padded weight image
+    S* Y = Wimg + (RES ? ((net.n_img + 3) & ~3) : 0);  // lambda of this tile, feature-major [D][TB]
     S* KL = Y + DT;                          // [7][D][TB] stage derivatives of lambda
     S* G = KL + 7 * DT;                      // stage input / candidate
     S* X = G + DT;                           // u(t) from the dense output
@@ -128,9 +264,14 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
     S* acts = ytmp + DT;
     S* dbuf0 = acts + (size_t)(net.n_layers - 1) * HW * TB;
     S* dbuf1 = dbuf0 + HW * TB;
-    S* red = dbuf1 + HW * TB;                // [MLP_THREADS][TB]
+    S* red = dbuf1 + HW * TB;                // [NT][TB] (general kernels only)
+    S* recs = red + (RES ? 0 : NT * TB);     // BATCH: [7] stage records (CadjRec); RES: one working record
+    const size_t rec_stride = CadjRec<S, TB>::floats(D, HW, net.n_layers);
+    S* grecs = RES ? grec + (size_t)blockIdx.x * 7 * rec_stride : recs;   // where the attempt's seven records are read from
+    if constexpr (RES) stage_weight_image<NT>(net, reinterpret_cast<const float*>(P), reinterpret_cast<float*>(Wimg));
     __shared__ CadjShared sh;
-    __shared__ double s_red[MLP_THREADS / 32];
+    __shared__ S s_wa[7], s_wb[7];
+    __shared__ double s_red[NT / 32];
 
     const int b0 = blockIdx.x * TB;
     const int ncta = gridDim.x;
@@ -153,7 +294,7 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
         __syncthreads();
         double r = 0.0;
         if (threadIdx.x == 0) {
-            for (int i = 0; i < MLP_THREADS / 32; ++i) r += s_red[i];
+            for (int i = 0; i < NT / 32; ++i) r += s_red[i];
             sh.sum = r;
         }
         __syncthreads();
@@ -162,16 +303,16 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
         return r;
     };
     auto finish = [&](bool nan_out) {
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+        for (int i = threadIdx.x; i < DT; i += NT) {
             const int d = i / TB, b = i - d * TB;
             if (b0 + b < B) dz0[(size_t)(b0 + b) * D + d] = nan_out ? s_nan<S>() : Y[i];
         }
-        for (int p = p_lo + threadIdx.x; p < p_hi; p += MLP_THREADS) dparams[p] = nan_out ? s_nan<S>() : mu[p];
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += NT) dparams[p] = nan_out ? s_nan<S>() : mu[p];
     };
 
     if (!fwd_ok) {  // a failed forward solve contributes no gradient (GOKU.jl:114 convention, uniform over the batch)
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) Y[i] = (S)0;
-        for (int p = p_lo + threadIdx.x; p < p_hi; p += MLP_THREADS) mu[p] = (S)0;
+        for (int i = threadIdx.x; i < DT; i += NT) Y[i] = (S)0;
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += NT) mu[p] = (S)0;
         __syncthreads();
         finish(false);
         if (blockIdx.x == 0 && threadIdx.x == 0) { status[0] = 0; status[1] = 0; status[2] = RET_SUCCESS; }
@@ -182,26 +323,28 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
     const size_t Bld = (size_t)ncta * TB;
     for (int n = 0; n < na_f; ++n) {
         const double dtn = tape.dt[(size_t)n * B];
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+        for (int i = threadIdx.x; i < DT; i += NT) {
             const int d = i / TB, b = i - d * TB;
             Y[i] = b0 + b < B ? tape.u[((size_t)n * B + b0 + b) * D + d] : (S)0;
         }
         __syncthreads();
         for (int j = 0; j < 7; ++j) {
             if (j == 0) {
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) G[i] = Y[i];
+                for (int i = threadIdx.x; i < DT; i += NT) G[i] = Y[i];
             } else {
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                for (int i = threadIdx.x; i < DT; i += NT) {
                     S acc = tab_a<S>(j, 0) * KL[i];
                     for (int q = 1; q < j; ++q) acc = s_fma<S>(tab_a<S>(j, q), KL[q * DT + i], acc);
                     G[i] = s_fma<S>((S)dtn, acc, Y[i]);
                 }
             }
             __syncthreads();
-            mlp_fwd<S, TB>(net, P, G, KL + j * DT, dbuf0, dbuf1, red);
+            if constexpr (RES) mlp_fwd_res<TB>(net, reinterpret_cast<const float*>(Wimg), reinterpret_cast<const float*>(G), reinterpret_cast<float*>(KL + j * DT),
+                                               reinterpret_cast<float*>(dbuf0), reinterpret_cast<float*>(dbuf1), nullptr);
+            else mlp_fwd<S, TB>(net, P, G, KL + j * DT, dbuf0, dbuf1, red);
             __syncthreads();
         }
-        for (int i = threadIdx.x; i < 7 * DT; i += MLP_THREADS) {
+        for (int i = threadIdx.x; i < 7 * DT; i += NT) {
             const int j = i / DT, r = i - j * DT, d = r / TB, b = r - d * TB;
             dense[(((size_t)n * 7 + j) * D + d) * Bld + b0 + b] = KL[i];
         }
@@ -224,7 +367,7 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
             const S dtn = (S)sh.dtn;
             S bw[7];
             interp_weights<S>((S)sh.th, bw);
-            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+            for (int i = threadIdx.x; i < DT; i += NT) {
                 const int d = i / TB, b = i - d * TB;
                 S v = (S)0;
                 if (b0 + b < B) {
@@ -233,13 +376,30 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
                     for (int q = 0; q < 7; ++q) acc = s_fma<S>(bw[q], dense[(((size_t)n * 7 + q) * D + d) * Bld + b0 + b], acc);
                     v = s_fma<S>(dtn, acc, tape.u[((size_t)n * B + b0 + b) * D + d]);
                 }
-                X[i] = v;
+                if (BATCH) {
+                    S* rec = recs + (RES ? 0 : (size_t)j * rec_stride);
+                    rec[i] = v;               // x of this stage
+                    rec[DT + i] = lam[i];     // the stage's lambda (cotangent of f's output)
+                } else {
+                    X[i] = v;
+                }
             }
         }
         __syncthreads();
-        mlp_vjp2<S, TB>(net, P, Pt, gA, gB, wa, wb, store, X, lam, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+        if constexpr (RES) {
+            if (threadIdx.x == 0) { s_wa[j] = wa; s_wb[j] = wb; }
+            mlp_vjp_rec_res<TB>(net, reinterpret_cast<const float*>(Wimg), reinterpret_cast<float*>(recs), reinterpret_cast<float*>(GB),
+                                reinterpret_cast<float*>(ytmp), HW);
+            S* dst = grecs + (size_t)j * rec_stride;     // park the record (read back by this CTA only, after its barriers)
+            for (int i = threadIdx.x; i < (int)rec_stride; i += NT) dst[i] = recs[i];
+        } else if (BATCH) {
+            if (threadIdx.x == 0) { s_wa[j] = wa; s_wb[j] = wb; }
+            mlp_vjp_rec<S, TB>(net, P, Pt, recs + (size_t)j * rec_stride, GB, ytmp, red, HW);
+        } else {
+            mlp_vjp2<S, TB>(net, P, Pt, gA, gB, wa, wb, store, X, lam, GB, acts, dbuf0, dbuf1, ytmp, red, HW);
+        }
         __syncthreads();
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) KL[j * DT + i] = -GB[i];
+        for (int i = threadIdx.x; i < DT; i += NT) KL[j * DT + i] = -GB[i];
         __syncthreads();
     };
     // sum over all CTAs of accumulator `which` (0: gA, 1: gB) at parameter p, in CTA order
@@ -259,26 +419,27 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
     const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(tend));
-    for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+    for (int i = threadIdx.x; i < DT; i += NT) {
         const int d = i / TB, b = i - d * TB;
         Y[i] = b0 + b < B ? dtraj[((size_t)(T - 1) * B + b0 + b) * D + d] : (S)0;
     }
-    for (int p = p_lo + threadIdx.x; p < p_hi; p += MLP_THREADS) mu[p] = (S)0;
+    for (int p = p_lo + threadIdx.x; p < p_hi; p += NT) mu[p] = (S)0;
     if (threadIdx.x == 0) { sh.n = na_f - 1; sh.tc = tend; sh.ks = T - 2; sh.ret = RET_SUCCESS; sh.dt = o.dt; }
     __syncthreads();
 
     if (o.adaptive && !(o.dt > 0.0)) {
         // ode_determine_initdt on the augmented state, time running backwards
         eval(tend, Y, 0, (S)1, (S)0, true);
+        if (BATCH) cadj_param_pass<S, TB, NT>(net, grecs, rec_stride, 1u, s_wa, s_wb, gA, gB, HW);
         grid.sync();
         double a0 = 0.0, a1 = 0.0;
-        for (int p = p_lo + threadIdx.x; p < p_hi; p += MLP_THREADS) {
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += NT) {
             const S f0 = -acc_sum(0, p);  // mu' = -(df/dp)^T lambda; mu = 0: sk = abstol
             mu_f0[p] = f0;
             const S r = f0 / abstol;
             a1 += (double)(r * r);
         }
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+        for (int i = threadIdx.x; i < DT; i += NT) {
             if (b0 + (i % TB) < B) {
                 const S sk = s_fma<S>(s_abs<S>(Y[i]), reltol, abstol);
                 const S r0 = Y[i] / sk, r1 = KL[i] / sk;
@@ -292,16 +453,17 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
         const double d1 = sqrt(grid_sum(a1, partials, grid, gs_parity) / nall);
         double dt0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * (d0 / d1);
         dt0 = fmin(dt0, dtmax);
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) G[i] = s_fma<S>(-(S)dt0, KL[i], Y[i]);
+        for (int i = threadIdx.x; i < DT; i += NT) G[i] = s_fma<S>(-(S)dt0, KL[i], Y[i]);
         __syncthreads();
         eval(tend - dt0, G, 1, (S)1, (S)0, true);
+        if (BATCH) cadj_param_pass<S, TB, NT>(net, grecs, rec_stride, 2u, s_wa, s_wb, gA, gB, HW);
         grid.sync();
         double a2 = 0.0;
-        for (int p = p_lo + threadIdx.x; p < p_hi; p += MLP_THREADS) {
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += NT) {
             const S r = (-acc_sum(0, p) - mu_f0[p]) / abstol;
             a2 += (double)(r * r);
         }
-        for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+        for (int i = threadIdx.x; i < DT; i += NT) {
             if (b0 + (i % TB) < B) {
                 const S sk = s_fma<S>(s_abs<S>(Y[i]), reltol, abstol);
                 const S r = (KL[DT + i] - KL[i]) / sk;
@@ -333,7 +495,7 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
         // seven stages; f is re-evaluated at the start of every step (after a callback it has to be, otherwise it equals k_7)
         eval(tc, Y, 0, tab_b<S>(0), tab_bt<S>(0), true);
         for (int j = 1; j < 7; ++j) {
-            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+            for (int i = threadIdx.x; i < DT; i += NT) {
                 S acc = tab_a<S>(j, 0) * KL[i];
                 for (int q = 1; q < j; ++q) acc = s_fma<S>(tab_a<S>(j, q), KL[q * DT + i], acc);
                 G[i] = s_fma<S>(-(S)dts, acc, Y[i]);
@@ -342,9 +504,10 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
             eval(tc - (double)tab_c<double>(j) * dts, G, j, j < 6 ? tab_b<S>(j) : (S)0, tab_bt<S>(j), false);
         }
         // G = lambda candidate (a_7j = b_j).  Every tile's weight gradients must be complete before the parameter slices are summed.
+        if (BATCH) cadj_param_pass<S, TB, NT>(net, grecs, rec_stride, 0x7fu, s_wa, s_wb, gA, gB, HW);
         grid.sync();
         double e2 = 0.0;
-        for (int p = p_lo + threadIdx.x; p < p_hi; p += MLP_THREADS) {
+        for (int p = p_lo + threadIdx.x; p < p_hi; p += NT) {
             // k_j^mu = -sum_rows (df/dp)^T lambda_j:  mu_new = mu - dts sum b_j k_j^mu = mu + dts * sum_cta gA
             const S m_old = mu[p];
             const S m_new = s_fma<S>((S)dts, acc_sum(0, p), m_old);
@@ -356,7 +519,7 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
             }
         }
         if (o.adaptive) {
-            for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+            for (int i = threadIdx.x; i < DT; i += NT) {
                 if (b0 + (i % TB) < B) {
                     S acc = tab_bt<S>(0) * KL[i];
                     for (int q = 1; q < 7; ++q) acc = s_fma<S>(tab_bt<S>(q), KL[q * DT + i], acc);
@@ -383,16 +546,16 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
         if (accept) {
             ++na;
             tc = tnew;
-            for (int p = p_lo + threadIdx.x; p < p_hi; p += MLP_THREADS) mu[p] = mu_new[p];
+            for (int p = p_lo + threadIdx.x; p < p_hi; p += NT) mu[p] = mu_new[p];
             if (tc == tstop) {
                 // the callback: cotangent of save point ks
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) {
+                for (int i = threadIdx.x; i < DT; i += NT) {
                     const int d = i / TB, b = i - d * TB;
                     Y[i] = G[i] + (b0 + b < B ? dtraj[((size_t)ks * B + b0 + b) * D + d] : (S)0);
                 }
                 --ks;
             } else {
-                for (int i = threadIdx.x; i < DT; i += MLP_THREADS) Y[i] = G[i];
+                for (int i = threadIdx.x; i < DT; i += NT) Y[i] = G[i];
             }
             __syncthreads();
         } else {
@@ -406,9 +569,12 @@ mlp_cadj_kernel(MlpNet net, const S* __restrict__ P, const S* __restrict__ Pt, c
     if (blockIdx.x == 0 && threadIdx.x == 0) { status[0] = na; status[1] = nr; status[2] = ret; }
 }
 
-template <class S, int TB> static size_t cadj_smem(const MlpNet& net) {
+template <class S, int TB> static size_t cadj_smem(const MlpNet& net, bool batch, bool res = false) {
     const size_t D = net.dims[0], HW = net.max_width;
-    return ((12 * D + (net.n_layers - 1) * HW + 2 * HW + MLP_THREADS) * TB * sizeof(S) + 15) & ~(size_t)15;
+    size_t n = (12 * D + (net.n_layers - 1) * HW + 2 * HW + (res ? 0 : MLP_THREADS)) * TB;
+    if (res) n += ((size_t)net.n_img + 3) & ~(size_t)3;
+    if (batch) n += (res ? 1 : 7) * CadjRec<S, TB>::floats(net.dims[0], net.max_width, net.n_layers);
+    return (n * sizeof(S) + 15) & ~(size_t)15;
 }
 
 }  // namespace ldeq

@@ -39,6 +39,31 @@ if which in ("all", "goku"):
         ldeq.goku_fwd_bwd_host(torch.from_numpy(z0), torch.from_numpy(th), tt, dd, 0, o)
     for w in (0, 1, 2):
         ldeq.debug_trig(torch.linspace(-20, 20, 1001, device=dev), w)
+if which in ("all", "solvers"):
+    # the diffeq struct's other solver values (csrc/ldeq_erk.cuh): forward, tape overflow + healing, both pullbacks, user RHS
+    for dtype in ("float32", "float64"):
+        z0, th = pendulum_inputs(131, dtype=dtype)
+        for sv in (1, 2, 3):
+            for kw in ((dict(adaptive=False, dt=0.07),) if sv == 3 else (dict(), dict(tape_steps=2), dict(adaptive=False, dt=0.07))):
+                for sense in (0, 1):
+                    z = torch.from_numpy(z0).to(dev).requires_grad_(True); p = torch.from_numpy(th).to(dev).requires_grad_(True)
+                    tr = ldeq.goku_solve(z, p, 0.05 * np.arange(23), 1, ldeq.default_opts(solver=sv, sensealg=sense, **kw)); tr.backward(torch.ones_like(tr))
+    h = ldeq.handle(0)
+    rhs = h.rhs_from_source("template <class S> __device__ void ldeq_user_rhs(S* du, const S* u, const S* p, S t) { du[0] = u[1]; du[1] = -p[0]*sin(u[0]); du[2] = p[1]*u[0] - u[2]; }", 3, 2)
+    for sv in (1, 2):
+        for sense in (0, 1):
+            z = torch.randn(37, 3, device=dev, requires_grad=True); p = (1 + torch.rand(37, 2, device=dev)).requires_grad_(True)
+            tr = ldeq.goku_solve(z, p, 0.05 * np.arange(30), rhs, ldeq.default_opts(solver=sv, sensealg=sense)); tr.backward(torch.ones_like(tr))
+if which in ("all", "recurrent"):
+    from oracle import recurrent as orr
+    from latentdiffeq_jl_b200.solve import _PatternExtractor
+    rng = np.random.default_rng(0)
+    for F in (16, 32, 64):
+        for B, T in ((37, 7), (1, 1), (70, 3)):
+            x = torch.randn(T, B, F, device=dev, requires_grad=True)
+            ps = [torch.from_numpy(orr.init_params(l, F, rng)).to(dev).requires_grad_(True) for l in (False, True, True)]
+            z0, th = _PatternExtractor.apply(x, *ps); (z0.sum() + th.sum()).backward()
+            z0, _ = _PatternExtractor.apply(x, ps[0], None, None); z0.sum().backward()
 if which in ("all", "mlp"):
     from oracle import mlp as om
     rng = np.random.Generator(np.random.PCG64(1)); dims = [16, 200, 200, 16]
@@ -51,6 +76,13 @@ if which in ("all", "mlp"):
         for kw in (dict(norm_mode=0), dict(norm_mode=1), dict(norm_mode=1, mlp_math=1), dict(norm_mode=0, mlp_math=1), dict(adaptive=False, dt=0.05, mlp_math=1)):
             z = (0.5 * torch.randn(B, 16, device=dev)).requires_grad_(True); q = pp.clone().requires_grad_(True)
             tr = ldeq.mlp_solve(z, q, dims, 0.05 * np.arange(12), ldeq.default_opts(**kw)); tr.backward(torch.ones_like(tr))
+    # the reference's continuous adjoint (LDEQ_SENSE_INTERPOLATING_ADJOINT): resident-weights variant (Float32, TB = 2),
+    # general variant with stage records (Float64) and without (LDEQ_CADJ_BATCH=0 is exercised by the A/B runs)
+    for dt_, dims2 in ((torch.float32, [8, 24, 24, 8]), (torch.float64, [6, 20, 20, 6])):
+        q = (0.3 * torch.randn(om.n_params(dims2), device=dev, dtype=dt_)).requires_grad_(True)
+        z = (0.5 * torch.randn(5, dims2[0], device=dev, dtype=dt_)).requires_grad_(True)
+        tr = ldeq.mlp_solve(z, q, dims2, 0.05 * np.arange(6), ldeq.default_opts(norm_mode=0, sensealg=ldeq.SENSE_INTERPOLATING_ADJOINT))
+        tr.backward(torch.ones_like(tr))
     z = torch.randn(9, 5, device=dev, dtype=torch.float64, requires_grad=True)
     q = torch.randn(om.n_params([5, 33, 5]), device=dev, dtype=torch.float64).mul_(0.1).requires_grad_(True)
     tr = ldeq.mlp_solve(z, q, [5, 33, 5], 0.05 * np.arange(8)); tr.backward(torch.ones_like(tr))
