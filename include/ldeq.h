@@ -229,7 +229,8 @@ void ldeq_mlp_tape_free(ldeq_handle* h, ldeq_mlp_tape* tape, ldeq_stream stream)
  *                RNN / 1 LSTM, F, H) gives the length.  lstm_f_params / lstm_b_params / theta_out may all be NULL (LatentODE).
  *   z0_out       (H,B): final state of the RNN stack;  theta_out (2H,B): [LSTM forward; LSTM reversed] (GOKU.jl:42)
  *   tape_out     non-NULL: keep the hidden / cell states of every step for ldeq_pattern_extractor_bwd
- * Built for H = 16 and F in {16, 32, 64} (defaults F = 32, H = 16, GOKU.jl:200-201); anything else LDEQ_ERR_UNSUPPORTED.
+ * Built for H = 16 with F in {16, 32, 64} (defaults F = 32, H = 16, GOKU.jl:200-201) and, for the RNN stack alone, H = 32
+ * with F in {32, 64} (LatentODE's defaults F = 32, H = 32, LatentODE.jl:101-102); anything else LDEQ_ERR_UNSUPPORTED.
  * The reverse pass is back-propagation through time: dx (F,B,T) and the three flat parameter gradients are OUTPUTS
  * (overwritten), x and the parameters must be those of the forward call. */
 typedef struct ldeq_pe_tape ldeq_pe_tape;

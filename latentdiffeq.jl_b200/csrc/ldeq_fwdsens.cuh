@@ -9,8 +9,8 @@
 // meets the Float64 dt: `uprev + dt*(...)` is evaluated in Float64 and rounded on the store; the dense-output
 // polynomials are evaluated in Float64), so that its step sequences are the oracle's (oracle/ldeq_oracle.cpp::solve_one
 // with NP > 0).  One thread per trajectory, two launches (theta-seeded NP = p_dim, u0-seeded NP = z_dim); the
-// cotangent is consumed on the fly, nothing is stored.  RHS: ZD, PD and  template <class D> f(D* du, const D* u,
-// const D* p, double t)  on duals -- the built-in pendulums (ldeq_fwdsens.cu) or a user's NVRTC function.
+// cotangent is consumed on the fly, nothing is stored.  RHS: ZD, PD, NPRE + prepare(D* p) (per-trajectory constants kept
+// in p[PD..PD+NPRE)) and  template <class D> f(D* du, const D* u, const D* p, double t)  on duals -- the built-in pendulums (ldeq_fwdsens.cu) or a user's NVRTC function.
 #pragma once
 
 #include "ldeq_dual.cuh"
@@ -216,7 +216,7 @@ erk_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const do
         b = blockIdx.x * blockDim.x + s_order[tid];
     }
     if (b >= B) return;
-    D u[Z], k[NS][Z], unew[Z], tmp[Z], sum, L[PD];
+    D u[Z], k[NS][Z], unew[Z], tmp[Z], sum, L[PD + RHS::NPRE];   // NPRE: slots for per-trajectory constants of the right-hand side
     const double t0 = tg[0], tend = tg[T - 1];
     const double dtmax = o.dtmax > 0.0 ? o.dtmax : (tend - t0);
     const double dtmin = o.dtmin > 0.0 ? o.dtmin : fmax(2.220446049250313e-16, ulp_of(t0));
@@ -233,6 +233,7 @@ erk_fwdsens_body(const S* __restrict__ z0, const S* __restrict__ theta, const do
                 L[i] = D(theta[(size_t)b * PD + i]);
                 if (SEED_P) L[i].d[i] = (S)1;
             }
+            RHS::prepare(L);
             RHS::f(k[0], u, L, t0);  // fsalfirst
             if (o.adaptive && !(o.dt > 0.0)) {
                 // Hairer initial step on the dual state

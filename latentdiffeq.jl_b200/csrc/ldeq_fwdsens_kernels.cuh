@@ -10,11 +10,19 @@ namespace ldeq {
 // pendulum.jl:19-26 / :65-74 on duals (G, b, m are Float32 literals of the reference, rounded to S)
 template <bool FRICTION> struct PendulumDualRHS {
     static constexpr int ZD = 2, PD = 1;
-    template <class D> __device__ __forceinline__ static void f(D* du, const D* u, const D* p, double) {
+    // -G/L is a constant of the trajectory: the dual quotient (1 + NP IEEE divisions) is taken ONCE and kept in an extra
+    // parameter slot instead of in each of the ~7 right-hand-side evaluations of every step -- the same bits, 21 divisions
+    // per attempted step fewer
+    static constexpr int NPRE = 1;
+    template <class D> __device__ __forceinline__ static void prepare(D* p) {
         typedef typename D::value_type S;
         const D G((S)10.0f);
+        p[PD] = -G / p[0];
+    }
+    template <class D> __device__ __forceinline__ static void f(D* du, const D* u, const D* p, double) {
+        typedef typename D::value_type S;
         du[0] = u[1];
-        const D a = (-G / p[0]) * sin(u[0]);
+        const D a = p[PD] * sin(u[0]);
         if (FRICTION) {
             const S bm = (S)0.7f / (S)1.0f;
             du[1] = a - bm * u[1];

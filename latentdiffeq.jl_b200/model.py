@@ -215,18 +215,21 @@ def apply_feature_extractor(encoder, x):
 def _pe_kernel_ok(fe_out, rnn_chain, lstm_chains=()):
     """The default architecture's stacks (two layers, 16 hidden units, relu RNN / LSTM; GOKU.jl:224-234) on a CUDA
     sequence: the shapes ``ldeq_pattern_extractor_fwd`` is built for."""
-    from .solve import PE_HIDDEN, PE_INPUTS
+    from .solve import PE_HIDDEN, PE_HIDDEN_RNN_ONLY, PE_INPUTS
     if not (PERSISTENT_RECURRENT and fe_out.is_cuda and fe_out.dtype == torch.float32 and fe_out.dim() == 3 and fe_out.shape[-1] in PE_INPUTS):
         return False
 
-    def stack_ok(chain, cls):
+    def stack_ok(chain, cls, hidden):
         layers = list(chain) if isinstance(chain, nn.Sequential) else []
         if len(layers) != 2 or not all(isinstance(l, cls) for l in layers):
             return False
-        rows = PE_HIDDEN * (4 if cls is LSTM else 1)
-        return (all(l.Wi.dtype == torch.float32 for l in layers) and tuple(layers[0].Wi.shape) == (rows, fe_out.shape[-1]) and tuple(layers[1].Wi.shape) == (rows, PE_HIDDEN)
+        rows = hidden * (4 if cls is LSTM else 1)
+        return (all(l.Wi.dtype == torch.float32 for l in layers) and tuple(layers[0].Wi.shape) == (rows, fe_out.shape[-1]) and tuple(layers[1].Wi.shape) == (rows, hidden)
                 and (cls is LSTM or all(l.act is F.relu for l in layers)))
-    return stack_ok(rnn_chain, RNN) and all(stack_ok(c, LSTM) for c in lstm_chains)
+    if lstm_chains:     # GOKU: all three stacks with 16 hidden units
+        return stack_ok(rnn_chain, RNN, PE_HIDDEN) and all(stack_ok(c, LSTM, PE_HIDDEN) for c in lstm_chains)
+    # LatentODE: the RNN stack alone, 16 or 32 hidden units (LatentODE.jl:102 defaults to 32, input 32 or 64)
+    return stack_ok(rnn_chain, RNN, PE_HIDDEN) or (fe_out.shape[-1] in (32, 64) and stack_ok(rnn_chain, RNN, PE_HIDDEN_RNN_ONLY))
 
 
 PERSISTENT_RECURRENT = True   # False: the cuDNN / per-step route below (kept for other layer shapes and as a cross-check)

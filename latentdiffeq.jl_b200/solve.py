@@ -345,7 +345,8 @@ def mlp_solve(z0, params_flat, dims, t, opts: _cabi.Opts | None = None, stats_ou
 
 
 # ---- recurrent pattern extractor ----------------------------------------------------------------
-PE_HIDDEN = 16
+PE_HIDDEN = 16            # GOKU's stacks (GOKU.jl:201): relu-RNN + two LSTM stacks
+PE_HIDDEN_RNN_ONLY = 32   # LatentODE's relu-RNN stack (LatentODE.jl:102)
 PE_INPUTS = (16, 32, 64)
 
 
@@ -394,15 +395,16 @@ class _PatternExtractor(torch.autograd.Function):
         lstm_f = lstm_f.contiguous() if has_lstm else None
         lstm_b = lstm_b.contiguous() if has_lstm else None
         lib = h._lib
-        if rnn.numel() != lib.ldeq_pattern_extractor_param_count(0, F, PE_HIDDEN) or (
-                has_lstm and lstm_f.numel() != lib.ldeq_pattern_extractor_param_count(1, F, PE_HIDDEN)):
-            raise _cabi.LdeqError(_cabi.ERR_UNSUPPORTED, "pattern extractor: parameter vectors do not match (F, H = 16)")
-        z0 = torch.empty(B, PE_HIDDEN, device=x.device, dtype=torch.float32)
-        th = torch.empty(B, 2 * PE_HIDDEN, device=x.device, dtype=torch.float32) if has_lstm else None
+        H = next((hh for hh in ((PE_HIDDEN,) if has_lstm else (PE_HIDDEN, PE_HIDDEN_RNN_ONLY))
+                  if rnn.numel() == lib.ldeq_pattern_extractor_param_count(0, F, hh)), None)
+        if H is None or (has_lstm and lstm_f.numel() != lib.ldeq_pattern_extractor_param_count(1, F, H)):
+            raise _cabi.LdeqError(_cabi.ERR_UNSUPPORTED, "pattern extractor: the parameter vectors match no built size (H = 16, or H = 32 for the RNN stack alone)")
+        z0 = torch.empty(B, H, device=x.device, dtype=torch.float32)
+        th = torch.empty(B, 2 * H, device=x.device, dtype=torch.float32) if has_lstm else None
         need = any(ctx.needs_input_grad)
         tape = C.c_void_p()
         with torch.cuda.device(x.device):
-            h.check(lib.ldeq_pattern_extractor_fwd(h.ptr, _p(x), B, T, F, PE_HIDDEN, _p(rnn), _p(lstm_f), _p(lstm_b), _p(z0), _p(th),
+            h.check(lib.ldeq_pattern_extractor_fwd(h.ptr, _p(x), B, T, F, H, _p(rnn), _p(lstm_f), _p(lstm_b), _p(z0), _p(th),
                                                    C.byref(tape) if need else None, _stream()))
         ctx.h, ctx.tape, ctx.has_lstm = h, (tape if need else None), has_lstm
         ctx.save_for_backward(x, rnn, *( [lstm_f, lstm_b] if has_lstm else []))

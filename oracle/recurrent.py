@@ -17,24 +17,24 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-H = 16
+H = 16     # rnn_output_dim of GOKU's default stacks (GOKU.jl:201); LatentODE's RNN stack has 32 (LatentODE.jl:102)
 
 
-def layer_sizes(lstm: bool, fan_in: int):
+def layer_sizes(lstm: bool, fan_in: int, H: int = H):
     rows = 4 * H if lstm else H
     return rows, [rows * fan_in, rows * H, rows, H] + ([H] if lstm else [])
 
 
-def param_count(lstm: bool, F: int) -> int:
-    return sum(layer_sizes(lstm, F)[1]) + sum(layer_sizes(lstm, H)[1])
+def param_count(lstm: bool, F: int, H: int = H) -> int:
+    return sum(layer_sizes(lstm, F, H)[1]) + sum(layer_sizes(lstm, H, H)[1])
 
 
-def init_params(lstm: bool, F: int, rng: np.random.Generator, scale: float = 0.3) -> np.ndarray:
+def init_params(lstm: bool, F: int, rng: np.random.Generator, scale: float = 0.3, H: int = H) -> np.ndarray:
     """Random parameters in flat ``Flux.destructure`` order (forget-gate bias 1 like Flux's LSTMCell; random state0 so
     that their gradients are exercised)."""
     out = []
     for fan_in in (F, H):
-        rows, sizes = layer_sizes(lstm, fan_in)
+        rows, sizes = layer_sizes(lstm, fan_in, H)
         wi = rng.uniform(-1, 1, sizes[0]) * scale
         wh = rng.uniform(-1, 1, sizes[1]) * scale
         b = rng.uniform(-0.1, 0.1, rows)
@@ -44,10 +44,10 @@ def init_params(lstm: bool, F: int, rng: np.random.Generator, scale: float = 0.3
     return np.concatenate(out).astype(np.float32)
 
 
-def _split(flat: torch.Tensor, lstm: bool, F: int):
+def _split(flat: torch.Tensor, lstm: bool, F: int, H: int = H):
     layers, off = [], 0
     for fan_in in (F, H):
-        rows, sizes = layer_sizes(lstm, fan_in)
+        rows, sizes = layer_sizes(lstm, fan_in, H)
         parts = []
         for n in sizes:
             parts.append(flat[off:off + n])
@@ -59,10 +59,10 @@ def _split(flat: torch.Tensor, lstm: bool, F: int):
     return layers
 
 
-def stack_final(x: torch.Tensor, flat: torch.Tensor, lstm: bool, reverse: bool) -> torch.Tensor:
+def stack_final(x: torch.Tensor, flat: torch.Tensor, lstm: bool, reverse: bool, H: int = H) -> torch.Tensor:
     """Final hidden state ``[B, H]`` of one two-layer stack over ``x [T, B, F]``."""
     T, B, F = x.shape
-    layers = _split(flat, lstm, F)
+    layers = _split(flat, lstm, F, H)
     hs = [l[3].expand(B, H) for l in layers]
     cs = [l[4].expand(B, H) for l in layers] if lstm else None
     order = range(T - 1, -1, -1) if reverse else range(T)
@@ -82,14 +82,14 @@ def stack_final(x: torch.Tensor, flat: torch.Tensor, lstm: bool, reverse: bool) 
 
 
 def pattern_extractor(x: np.ndarray, rnn: np.ndarray, lstm_f: np.ndarray | None = None, lstm_b: np.ndarray | None = None,
-                      dz0: np.ndarray | None = None, dth: np.ndarray | None = None):
+                      dz0: np.ndarray | None = None, dth: np.ndarray | None = None, H: int = H):
     """``(z0_out [B,H], theta_out [B,2H] or None)``; with cotangents also ``(dx, d_rnn, d_lstm_f, d_lstm_b)``."""
     xt = torch.tensor(x, dtype=torch.float64, requires_grad=dz0 is not None)
     ps = [None if p is None else torch.tensor(p, dtype=torch.float64, requires_grad=dz0 is not None) for p in (rnn, lstm_f, lstm_b)]
-    z0 = stack_final(xt, ps[0], False, True)
+    z0 = stack_final(xt, ps[0], False, True, H)
     th = None
     if lstm_f is not None:
-        th = torch.cat([stack_final(xt, ps[1], True, False), stack_final(xt, ps[2], True, True)], dim=1)
+        th = torch.cat([stack_final(xt, ps[1], True, False, H), stack_final(xt, ps[2], True, True, H)], dim=1)
     if dz0 is None:
         return z0.detach().numpy(), None if th is None else th.detach().numpy()
     loss = (z0 * torch.tensor(dz0, dtype=torch.float64)).sum()

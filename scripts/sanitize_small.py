@@ -64,6 +64,9 @@ if which in ("all", "recurrent"):
             ps = [torch.from_numpy(orr.init_params(l, F, rng)).to(dev).requires_grad_(True) for l in (False, True, True)]
             z0, th = _PatternExtractor.apply(x, *ps); (z0.sum() + th.sum()).backward()
             z0, _ = _PatternExtractor.apply(x, ps[0], None, None); z0.sum().backward()
+            if F >= 32:    # LatentODE's RNN stack with 32 hidden units
+                q = torch.from_numpy(orr.init_params(False, F, rng, H=32)).to(dev).requires_grad_(True)
+                z0, _ = _PatternExtractor.apply(x, q, None, None); z0.sum().backward()
 if which in ("all", "mlp"):
     from oracle import mlp as om
     rng = np.random.Generator(np.random.PCG64(1)); dims = [16, 200, 200, 16]

@@ -79,6 +79,55 @@ def test_latentode_rnn_only(ldeq):
     assert _rel(g[0], og_[0]) < 2e-4 and _rel(g[1], og_[1]) < 2e-4
 
 
+@pytest.mark.parametrize("F", [32, 64])
+@pytest.mark.parametrize("B,T", [(300, 50), (19, 5)])
+def test_latentode_default_rnn_stack_32_hidden_units(ldeq, F, B, T):
+    # LatentODE's default pattern extractor: Chain(RNN(32,32,relu), RNN(32,32,relu)) on the reversed sequence (LatentODE.jl:100-124)
+    rng = np.random.default_rng(F + B)
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    rnn = orr.init_params(False, F, rng, H=32)
+    assert rnn.size == orr.param_count(False, F, 32)
+    dz0 = rng.standard_normal((B, 32)).astype(np.float32)
+    z0, th, g = _raw(ldeq, x, rnn, None, None, dz0)
+    oz0, _, og_ = orr.pattern_extractor(x, rnn, None, None, dz0, H=32)
+    assert z0.shape == (B, 32) and _rel(z0, oz0) < 2e-5
+    assert _rel(g[0], og_[0]) < 2e-4 and _rel(g[1], og_[1]) < 2e-4
+    a = _raw(ldeq, x, rnn, None, None, dz0)
+    assert np.array_equal(a[2][0], g[0]) and np.array_equal(a[2][1], g[1])      # deterministic
+    # the LSTM stacks are built for 16 hidden units only: refused, not replaced
+    from latentdiffeq_jl_b200.solve import _PatternExtractor
+    with pytest.raises(ldeq.LdeqError):
+        _PatternExtractor.apply(torch.from_numpy(x).to(DEV), torch.from_numpy(rnn).to(DEV),
+                                torch.zeros(orr.param_count(True, F, 32), device=DEV), torch.zeros(orr.param_count(True, F, 32), device=DEV))
+
+
+def test_latentode_model_route(ldeq):
+    # the LatentODE encoder of default_layers goes through the kernels (no cuDNN call) and matches the per-step route
+    import latentdiffeq_jl_b200 as L
+    model_mod = __import__(L.__name__ + ".model", fromlist=["x"]) if hasattr(L, "__path__") else L.model
+    torch.manual_seed(0)
+    enc, dec = ldeq.default_layers(ldeq.LatentODE(), 28 * 28, ldeq.NODE(16), device=DEV)
+    model = ldeq.LatentDiffEqModel(ldeq.LatentODE(), enc, dec)
+    fe = torch.randn(50, 64, 32, device=DEV, requires_grad=True)
+    assert model_mod._pe_kernel_ok(fe, model.encoder.pattern_extractor)
+    w = torch.randn(64, 32, device=DEV)
+    outs = {}
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    for flag in (True, False):
+        model_mod.PERSISTENT_RECURRENT = flag
+        model.zero_grad(); fe.grad = None
+        out = ldeq.apply_pattern_extractor(model.encoder, fe)
+        (out * w).sum().backward()
+        outs[flag] = (out.detach().clone(), fe.grad.clone(), [p.grad.clone() for p in model.encoder.pattern_extractor.parameters()])
+    model_mod.PERSISTENT_RECURRENT = True
+    torch.backends.cudnn.allow_tf32 = tf32
+    a, b = outs[True], outs[False]
+    assert torch.allclose(a[0], b[0], rtol=1e-4, atol=1e-5) and (a[1] - b[1]).abs().max() <= 2e-4 * b[1].abs().max()
+    for ga, gb in zip(a[2], b[2]):
+        assert (ga - gb).abs().max() <= 5e-4 * max(gb.abs().max().item(), 1e-3)
+
+
 def test_model_route_equals_the_cudnn_route(ldeq):
     # the default GOKU encoder: apply_pattern_extractor through the kernels vs the cuDNN / per-step route, values and
     # gradients of every recurrent parameter and of the frames
