@@ -15,6 +15,7 @@ sys.path.insert(0, os.path.dirname(HERE))
 from conftest import pendulum_inputs  # noqa: E402
 from oracle import goku as og  # noqa: E402
 from oracle import mlp as om  # noqa: E402
+from oracle import recurrent as orr  # noqa: E402
 
 
 def main():
@@ -55,6 +56,35 @@ def main():
     np.savez_compressed(os.path.join(HERE, "c2_latentode_mlp.npz"), z0=z0, params=p, dims=np.array(dims), t=t, dtraj=d,
                         traj_f32_adaptive_global=tr32, naccept_f32=np.array(na32), traj_f64_fixed=tr64,
                         dz0_f64_fixed=gz, dparams_f64_fixed=gp.astype(np.float32))
+    # Other solvers of the diffeq struct: C3's right-hand side, first 32 trajectories, Float64, per solver
+    # adaptive (DP5, BS3) and fixed step off the save grid (all three), with the ForwardDiff-semantics gradient
+    z0, th = pendulum_inputs(1024, seed=333, dtype="float64")
+    z0, th = z0[:32], th[:32]
+    d = np.random.default_rng(336).standard_normal((50, 32, 2))
+    out = dict(z0=z0, theta=th, t=t, dtraj=d)
+    for name, sv in (("dp5", og.DP5), ("bs3", og.BS3), ("rk4", og.RK4)):
+        of = og.Opts.for_solver(sv, adaptive=False, dt=0.08)
+        out[f"traj_{name}_fixed"] = og.solve(og.PENDULUM_FRICTION, z0, th, t, of)[0]
+        out[f"dz0_{name}_fixed"], out[f"dtheta_{name}_fixed"] = og.grad(og.PENDULUM_FRICTION, z0, th, t, d, of)
+        if sv != og.RK4:
+            oa = og.Opts.for_solver(sv)
+            tr, _, na, nr = og.solve(og.PENDULUM_FRICTION, z0, th, t, oa)
+            out[f"traj_{name}_adaptive"], out[f"naccept_{name}_adaptive"], out[f"nreject_{name}_adaptive"] = tr, na, nr
+            out[f"dz0_{name}_adaptive_fwddiff"], out[f"dtheta_{name}_adaptive_fwddiff"] = og.grad(og.PENDULUM_FRICTION, z0, th, t, d, oa)
+    np.savez_compressed(os.path.join(HERE, "solvers_goku_friction_f64.npz"), **out)
+    # Recurrent pattern extractor: GOKU's three stacks (F = 32, H = 16) and LatentODE's RNN stack (H = 32),
+    # 12 sequences of 20 frames, seed 1; final states and all gradients (float64 restatement of the Flux cells)
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((20, 12, 32)).astype(np.float32)
+    rnn, lf, lb = orr.init_params(False, 32, rng), orr.init_params(True, 32, rng), orr.init_params(True, 32, rng)
+    rnn32 = orr.init_params(False, 32, rng, H=32)
+    dz0, dth, dz32 = (rng.standard_normal((12, 16)).astype(np.float32), rng.standard_normal((12, 32)).astype(np.float32),
+                      rng.standard_normal((12, 32)).astype(np.float32))
+    zo, tho, g = orr.pattern_extractor(x, rnn, lf, lb, dz0, dth)
+    zo32, _, g32 = orr.pattern_extractor(x, rnn32, None, None, dz32, H=32)
+    np.savez_compressed(os.path.join(HERE, "pattern_extractor.npz"), x=x, rnn=rnn, lstm_f=lf, lstm_b=lb, rnn32=rnn32, dz0=dz0, dtheta=dth,
+                        dz0_32=dz32, z0_out=zo, theta_out=tho, dx=g[0], d_rnn=g[1], d_lstm_f=g[2], d_lstm_b=g[3], z0_out_32=zo32,
+                        dx_32=g32[0], d_rnn32=g32[1])
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print(f, os.path.getsize(os.path.join(HERE, f)))

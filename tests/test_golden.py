@@ -36,6 +36,62 @@ def test_oracle_reproduces_latentode_golden():
     assert na == int(g["naccept_f32"]) and np.allclose(tr, g["traj_f32_adaptive_global"], rtol=0, atol=1e-5)
 
 
+def test_oracle_reproduces_solver_and_recurrent_golden():
+    from oracle import recurrent as orr
+    g = _load("solvers_goku_friction_f64.npz")
+    for name, sv in (("dp5", og.DP5), ("bs3", og.BS3), ("rk4", og.RK4)):
+        of = og.Opts.for_solver(sv, adaptive=False, dt=0.08)
+        assert np.allclose(og.solve(og.PENDULUM_FRICTION, g["z0"], g["theta"], g["t"], of)[0], g[f"traj_{name}_fixed"], rtol=0, atol=1e-13)
+        if sv != og.RK4:
+            tr, _, na, nr = og.solve(og.PENDULUM_FRICTION, g["z0"], g["theta"], g["t"], og.Opts.for_solver(sv))
+            assert np.array_equal(na, g[f"naccept_{name}_adaptive"]) and np.allclose(tr, g[f"traj_{name}_adaptive"], rtol=0, atol=1e-12)
+    g = _load("pattern_extractor.npz")
+    zo, tho, gr = orr.pattern_extractor(g["x"], g["rnn"], g["lstm_f"], g["lstm_b"], g["dz0"], g["dtheta"])
+    assert np.allclose(zo, g["z0_out"], rtol=0, atol=1e-13) and np.allclose(tho, g["theta_out"], rtol=0, atol=1e-13)
+    assert np.allclose(gr[0], g["dx"], rtol=0, atol=1e-12) and np.allclose(gr[2], g["d_lstm_f"], rtol=0, atol=1e-11)
+
+
+@pytest.mark.gpu
+def test_cuda_matches_solver_golden(ldeq):
+    dev = "cuda:0"
+    g = _load("solvers_goku_friction_f64.npz")
+    d = torch.from_numpy(g["dtraj"]).to(dev)
+    for name, sv in (("dp5", ldeq.SOLVER_DP5), ("bs3", ldeq.SOLVER_BS3), ("rk4", ldeq.SOLVER_RK4)):
+        for mode in (("fixed", dict(adaptive=False, dt=0.08)),) + ((("adaptive", dict()),) if name != "rk4" else ()):
+            z = torch.from_numpy(g["z0"]).to(dev).requires_grad_(True)
+            p = torch.from_numpy(g["theta"]).to(dev).requires_grad_(True)
+            st = []
+            tr = ldeq.goku_solve(z, p, g["t"], ldeq.RHS_PENDULUM_FRICTION, ldeq.default_opts(solver=sv, **mode[1]), st)
+            tr.backward(d)          # library default: the reference's dual-number re-solves
+            ref = g[f"traj_{name}_{mode[0]}"]
+            assert np.abs(tr.detach().cpu().numpy() - ref).max() <= 1e-5 * np.abs(ref).max()      # north star: fp64 rtol 1e-5
+            if mode[0] == "adaptive":
+                assert np.array_equal(st[0].naccept.cpu().numpy(), g[f"naccept_{name}_adaptive"])
+            gz = g[f"dz0_{name}_{'fixed' if mode[0] == 'fixed' else 'adaptive_fwddiff'}"]
+            gp = g[f"dtheta_{name}_{'fixed' if mode[0] == 'fixed' else 'adaptive_fwddiff'}"]
+            assert np.abs(z.grad.cpu().numpy() - gz).max() <= 1e-4 * np.abs(gz).max()              # north star: gradients 1e-4
+            assert np.abs(p.grad.cpu().numpy() - gp).max() <= 1e-4 * np.abs(gp).max()
+
+
+@pytest.mark.gpu
+def test_cuda_matches_pattern_extractor_golden(ldeq):
+    from latentdiffeq_jl_b200.solve import _PatternExtractor
+    dev = "cuda:0"
+    g = _load("pattern_extractor.npz")
+    t = lambda k: torch.from_numpy(g[k]).to(dev).requires_grad_(True)
+    x, rnn, lf, lb = t("x"), t("rnn"), t("lstm_f"), t("lstm_b")
+    z0, th = _PatternExtractor.apply(x, rnn, lf, lb)
+    ((z0 * torch.from_numpy(g["dz0"]).to(dev)).sum() + (th * torch.from_numpy(g["dtheta"]).to(dev)).sum()).backward()
+    rel = lambda a, b: np.abs(a.detach().cpu().numpy() - b).max() / np.abs(b).max()
+    assert rel(z0, g["z0_out"]) < 2e-5 and rel(th, g["theta_out"]) < 2e-5
+    for got, key in ((x.grad, "dx"), (rnn.grad, "d_rnn"), (lf.grad, "d_lstm_f"), (lb.grad, "d_lstm_b")):
+        assert rel(got, g[key]) < 2e-4, key
+    x2, r32 = t("x"), t("rnn32")          # LatentODE's stack: 32 hidden units
+    z32, _ = _PatternExtractor.apply(x2, r32, None, None)
+    (z32 * torch.from_numpy(g["dz0_32"]).to(dev)).sum().backward()
+    assert rel(z32, g["z0_out_32"]) < 2e-5 and rel(x2.grad, g["dx_32"]) < 2e-4 and rel(r32.grad, g["d_rnn32"]) < 2e-4
+
+
 @pytest.mark.gpu
 def test_cuda_matches_goku_golden(ldeq):
     dev = "cuda:0"
