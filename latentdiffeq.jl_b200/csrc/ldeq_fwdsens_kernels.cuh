@@ -5,6 +5,12 @@
 #include "ldeq_fwdsens.cuh"
 #include <cstdlib>
 
+#ifndef LDEQ_FWDSENS_MINBLOCKS
+// 5 CTAs of 128 threads per SM (<= 102 registers; the u0-seeded Float32 kernel spills 80 bytes): measured 6.20 -> 5.93 ms for
+// the pair of pullback launches at 2^20 x 200 against 4 CTAs / 128 registers (6 CTAs: 5.90 ms with 3x the spills)
+#define LDEQ_FWDSENS_MINBLOCKS 5
+#endif
+
 namespace ldeq {
 
 // pendulum.jl:19-26 / :65-74 on duals (G, b, m are Float32 literals of the reference, rounded to S)
@@ -33,7 +39,7 @@ template <bool FRICTION> struct PendulumDualRHS {
 };
 
 template <class S, int NP, bool FRICTION, bool SEED_P>
-__global__ void __launch_bounds__(LDEQ_FWDSENS_THREADS, 512 / LDEQ_FWDSENS_THREADS)
+__global__ void __launch_bounds__(LDEQ_FWDSENS_THREADS, LDEQ_FWDSENS_MINBLOCKS)
 tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
                      KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                      S* __restrict__ dout) {
@@ -42,7 +48,7 @@ tsit5_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, cons
 
 // the same for the table-driven methods (MD = ErkDual<TabDP5> ...)
 template <class MD, class S, int NP, bool FRICTION, bool SEED_P>
-__global__ void __launch_bounds__(LDEQ_FWDSENS_THREADS, 512 / LDEQ_FWDSENS_THREADS)
+__global__ void __launch_bounds__(LDEQ_FWDSENS_THREADS, LDEQ_FWDSENS_MINBLOCKS)
 erk_fwdsens_kernel(const S* __restrict__ z0, const S* __restrict__ theta, const double* __restrict__ tg, int B, GridInfo gi, int T,
                    KOpts o, int norm_partials, const int* __restrict__ sort_key, const S* __restrict__ dtraj, const int* __restrict__ primal_ret,
                    S* __restrict__ dout) {
