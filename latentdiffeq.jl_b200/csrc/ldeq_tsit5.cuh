@@ -434,6 +434,7 @@ erk_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const double
     bool active = live && T > 1 && ret == RET_SUCCESS;  // still has steps to take
     bool pending = false;   // an accepted step whose save points are not all parked yet
     int kend = 1;           // save points ks .. kend-1 fall into the pending step
+    int kanchor = 1;        // ... the first of them: Theta of the step's points is anchored there
     bool hit = false;       // ... and the last of them coincides with the step end (stored as u_{n+1} itself)
     double dts = 0.0, tnew = t0;
 
@@ -479,6 +480,7 @@ erk_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const double
                         pending = true;
                         // saveat: every pending grid time <= tnew belongs to this step
                         kend = tg.count_le(tnew, ks);
+                        kanchor = ks;
                         hit = kend > ks && tg[kend - 1] == tnew;
                     } else {
                         ++nr;
@@ -504,10 +506,13 @@ erk_fwd_body(const S* __restrict__ z0, const S* __restrict__ theta, const double
                 const S h = (S)dts;
                 const double inv = 1.0 / dts;
                 // Theta of consecutive points of a uniform grid advances by h_grid / dt: one FMA per point, anchored at
-                // the first point of this visit (|Theta| <= 1, so the anchor's rounding is the only error that matters)
-                const S th0 = (S)((tg[ks] - t) * inv);
+                // the first save point of the STEP (|Theta| <= 1, so the anchor's rounding is the only error that matters).
+                // Anchoring at the step, not at this visit, keeps the arithmetic of a trajectory independent of how the
+                // ring splits its save points into visits, i.e. of the other lanes of its warp: a solve commutes bit for
+                // bit with any split or permutation of the batch (tests/test_properties_gpu.py).
+                const S th0 = (S)((tg[kanchor] - t) * inv);
                 const S dth = (S)(tg.h * inv);
-                S fk = (S)0;
+                S fk = (S)(ks - kanchor);
                 do {
                     const S th = tg.uniform ? s_fma<S>(fk, dth, th0) : (S)((tg[ks] - t) * inv);
                     S pl[ZD], out[ZD];
@@ -625,6 +630,7 @@ erk_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, 
     int ks = T - 1;        // next save point of this lane (descending); row 0 is handled at the end
     bool holding = false;  // a step whose stages are recomputed and whose save points are being consumed
     int klo_step = T;      // save points klo_step .. ks fall into the step being held
+    int kanchor = T;       // ... the topmost interior one: Theta of the step's points is anchored there
     bool hit = false;      // ... and the topmost of them coincides with the step end t_{n+1}
     double tnext = tg[T - 1];  // time after step n; the forward pass ended exactly on tend
     double tn = 0.0, dtn = 0.0;
@@ -679,6 +685,7 @@ erk_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, 
             klo_step = tg.count_le_down(tn, ks + 1);
             klo_step = klo_step < 1 ? 1 : klo_step;
             hit = ks >= klo_step && tg[ks] == tnext;
+            kanchor = hit ? ks - 1 : ks;
             holding = true;
         }
         cp_async_wait_all();  // rows fetched at the end of the previous iteration have landed by now
@@ -695,9 +702,10 @@ erk_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, 
                 int kstop = klo_step > kload ? klo_step : kload;  // consume ks, ks-1, ..., kstop
                 if (ks >= kstop) {
                     const double inv = 1.0 / dtn;
-                    const S th0 = (S)((tg[ks] - tn) * inv);
+                    // anchored at the step's topmost interior save point, not at this visit (see the forward kernel)
+                    const S th0 = (S)((tg[kanchor] - tn) * inv);
                     const S dth = (S)(tg.h * inv);
-                    S fk = (S)0;
+                    S fk = (S)(kanchor - ks);
                     do {
                         S d[ZD];
                         load_vec<S, ZD>(ring.at(ks), d);
