@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define LDEQ_VERSION 200
+#define LDEQ_VERSION 210
 
 typedef struct ldeq_handle ldeq_handle;
 typedef struct ldeq_rhs ldeq_rhs;

@@ -48,7 +48,7 @@ def test_opts_layout_and_defaults(ldeq):
 
 def test_version_and_clean_failure_without_a_device(ldeq):
     lib = ldeq._cabi.load()
-    assert lib.ldeq_version() == 200
+    assert lib.ldeq_version() == 210      # round 2: + ldeq_opts_default_solver, ldeq_pattern_extractor_*, solver enum DP5 / BS3 / RK4
     import torch
     if not torch.cuda.is_available():
         # the product path must fail loudly, not fall back to the CPU
