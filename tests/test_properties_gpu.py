@@ -115,3 +115,37 @@ def test_c5_share_pattern_extractor_split_and_linearity(ldeq):
     assert float((dx3 - (0.5 * dx - 2.0 * dx2)).abs().max()) <= 1e-5 * float(dx3.abs().max())
     for a, b, c in zip(dps, dps2, dps3):
         assert float((c - (0.5 * a - 2.0 * b)).abs().max()) <= 2e-5 * float(c.abs().max())
+
+
+@pytest.mark.parametrize("path", ["resident_fp32", "tensor_core_bf16x3", "general_fp64"])
+def test_latentode_per_trajectory_mode_split_invariance(ldeq, path):
+    # LDEQ_NORM_PER_TRAJ (the documented deviation for sharded batches): every row has its own controller, so the rows of a
+    # solve are independent problems here too -- trajectories and dz0 commute bit for bit with a ragged split of the batch
+    # on every kernel family (rows share a tile / an MMA with other rows, never an arithmetic result)
+    from oracle import mlp as om
+    rng = np.random.Generator(np.random.PCG64(1))
+    dims = [16, 200, 200, 16]
+    dt_ = np.float64 if path == "general_fp64" else np.float32
+    p = om.pack_params([(om.glorot_uniform(rng, dims[i + 1], dims[i]), np.zeros(dims[i + 1], np.float32)) for i in range(3)]).astype(dt_)
+    B, T = (300, 50) if path != "tensor_core_bf16x3" else (1000, 50)
+    z0 = (0.5 * rng.standard_normal((B, 16))).astype(dt_)
+    d = rng.standard_normal((T, B, 16)).astype(dt_)
+    t = 0.05 * np.arange(T)
+    kw = dict(norm_mode=ldeq.NORM_PER_TRAJ, sensealg=ldeq.SENSE_DISCRETE_ADJOINT)
+    if path == "tensor_core_bf16x3":
+        kw["mlp_math"] = ldeq.MLP_MATH_BF16X3
+
+    def run(lo, hi):
+        z = torch.from_numpy(z0[lo:hi]).to(DEV).requires_grad_(True)
+        q = torch.from_numpy(p).to(DEV).requires_grad_(True)
+        tr = ldeq.mlp_solve(z, q, dims, t, ldeq.default_opts(**kw))
+        tr.backward(torch.from_numpy(np.ascontiguousarray(d[:, lo:hi])).to(DEV))
+        return tr.detach(), z.grad, q.grad
+    tr, gz, gq = run(0, B)
+    acc = torch.zeros_like(gq)
+    for lo, hi in ((0, 101), (101, B)):
+        tr2, gz2, gq2 = run(lo, hi)
+        assert torch.equal(tr2, tr[:, lo:hi]), path
+        assert torch.equal(gz2, gz[lo:hi]), path
+        acc += gq2
+    assert float((acc - gq).abs().max()) <= (1e-12 if path == "general_fp64" else 2e-5) * float(gq.abs().max())
