@@ -12,7 +12,10 @@ mode, which is the reference's own: ``ForwardDiffSensitivity`` = two dual-number
 HBM; ``e2e`` = the same through ``ldeq_solve_fwd_bwd_host`` from ONE caller thread with pinned host buffers, copies
 inside the timed region.  The cheaper discrete adjoint (explicit opt-in) is reported under ``discrete_adjoint``; a C5
 data-parallel training step (samples/s, gradient all-reduce measured, fused-vs-NCCL parity self-test) under
-``training``.  ``--impl reference`` times the CPU oracle (the reference is pure Julia, which this image does not have:
+``training``; the LatentODE configurations (BASELINE.json configs[1] at batch 256 on the resident exact path -- forward,
+forward + discrete adjoint, forward + the reference's InterpolatingAdjoint -- and the tcgen05 path at batch 18 944)
+under ``latentode``; ``e2e.link_roofline`` is the host link's ceiling measured in the same run (the step's byte counts as
+plain concurrent pinned copies).  ``--impl reference`` times the CPU oracle (the reference is pure Julia, which this image does not have:
 the oracle port is the reference arm) on the host cores, same workload, same sizes, same gradient semantics.
 
 One JSON line on stdout (rank 0).
@@ -489,6 +492,14 @@ def run_ours(args):
         tr = training_record(ldeq, dev, world, rank, local, steps=max(3, min(K, 8)), warmup=3)
         if rank == 0:
             line["training"] = tr
+            # ---- the LatentODE configurations (BASELINE.json configs[1] and the tcgen05 batch): rank 0, a few seconds ------
+            try:
+                torch.cuda.empty_cache()
+                line["latentode"] = latentode_subrecord(dev)
+            except Exception as e:  # the headline record must survive a failure of this appendix
+                line["latentode"] = {"unavailable": repr(e)}
+        if world > 1:
+            dist.barrier()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
@@ -698,21 +709,21 @@ def run_latentode_reference(args):
     print(json.dumps(line))
 
 
-def run_latentode(args):
-    """`--workload c2` (BASELINE.json configs[1]: LatentODE, small-MLP RHS 16-200-200-16, batch 256, T = 50) and
-    `--workload mlp` (the same network at batch 18 944 = 128 trajectories per SM: where batch x hidden is a genuine
-    dense contraction).  Adaptive Tsit5, per-trajectory and global (reference) error norm, exact CUDA-core path vs the
-    tcgen05 path; forward solve and forward + adjoint.  Unit: trajectory-steps/s (and accepted RK steps per trajectory
-    per second, SURVEY.md 8(d) C2)."""
+LATENTODE_VARIANTS = (("tcgen05_bf16x3_global", dict(norm_mode=0, mlp_math=1)), ("tcgen05_bf16x3_per_traj", dict(norm_mode=1, mlp_math=1)),
+                      ("exact_fp32_global", dict(norm_mode=0)), ("exact_fp32_per_traj", dict(norm_mode=1)),
+                      # the reference's own reverse pass (NeuralODE default InterpolatingAdjoint): continuous adjoint on
+                      # [lambda; mu], ~700 backward steps at C2 against 12 taped forward steps
+                      ("exact_fp32_global_interpolating_adjoint", dict(norm_mode=0, sensealg="interpolating_adjoint")))
+
+
+def latentode_variants(workload, dev, K, W, only=None):
+    """Times the LatentODE solve (forward; forward + reverse pass) for the kernel variants of `workload` ('c2' | 'mlp')."""
     import torch
 
     import latentdiffeq_jl_b200 as ldeq
 
-    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    torch.cuda.set_device(dev)
-    B, T, dims, p_np, z_np, d_np, t = _latentode_inputs(args.workload)
+    B, T, dims, p_np, z_np, d_np, t = _latentode_inputs(workload)
     p, z, d = (torch.from_numpy(a).to(dev) for a in (p_np, z_np, d_np))
-    K, W = args.steps, max(args.warmup, 3)
     peak_bf16 = 1634.1
     try:
         peak_bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
@@ -721,11 +732,12 @@ def run_latentode(args):
     h = ldeq.handle(dev.index or 0)
     res = {}
     launches = 0
-    for name, kw in (("tcgen05_bf16x3_global", dict(norm_mode=0, mlp_math=1)), ("tcgen05_bf16x3_per_traj", dict(norm_mode=1, mlp_math=1)),
-                     ("exact_fp32_global", dict(norm_mode=0)), ("exact_fp32_per_traj", dict(norm_mode=1)),
-                     # the reference's own reverse pass (NeuralODE default InterpolatingAdjoint): continuous adjoint on
-                     # [lambda; mu], ~700 backward steps at C2 against 12 taped forward steps
-                     ("exact_fp32_global_interpolating_adjoint", dict(norm_mode=0, sensealg=ldeq.SENSE_INTERPOLATING_ADJOINT))):
+    for name, kw in LATENTODE_VARIANTS:
+        if only is not None and name not in only:
+            continue
+        kw = dict(kw)
+        if kw.get("sensealg") == "interpolating_adjoint":
+            kw["sensealg"] = ldeq.SENSE_INTERPOLATING_ADJOINT
         o = ldeq.default_opts(**kw)
 
         def fwd_bwd():
@@ -772,6 +784,39 @@ def run_latentode(args):
                                                   "frac": issued_b / peak_bf16, "ms": ms2 - ms, "traffic": None,
                                                   "note": "adjoint kernel (recompute + transposed products) + split-K weight-gradient "
                                                           "GEMM + reduce, all tcgen05; bf16 flops issued / measured cuBLAS bf16 peak"}
+    return B, T, res, launches
+
+
+def latentode_subrecord(dev):
+    """The LatentODE configurations in the default bench line (rank 0): C2 (BASELINE.json configs[1], B = 256) on the exact
+    resident path -- forward, forward + discrete adjoint, forward + the reference's InterpolatingAdjoint -- and the same
+    network at B = 18 944 on tcgen05 (forward, forward + tcgen05 reverse pass)."""
+    out = {"metric": "LatentODE solve, MLP right-hand side 16-200-200-16, T = 50, adaptive Tsit5 (abstol 1e-6, reltol 1e-3), batch-global norm"}
+    _, _, c2, _ = latentode_variants("c2", dev, 5, 3, only=("exact_fp32_global", "exact_fp32_global_interpolating_adjoint"))
+    ex, ia = c2.get("exact_fp32_global", {}), c2.get("exact_fp32_global_interpolating_adjoint", {})
+    out["c2_batch_256"] = {"forward_ms": ex.get("ms"), "forward_discrete_adjoint_ms": ex.get("fwd_bwd_ms"),
+                           "forward_interpolating_adjoint_ms": ia.get("fwd_bwd_ms", ia.get("unavailable")),
+                           "traj_steps_per_s": ex.get("traj_steps_per_s")}
+    _, _, big, _ = latentode_variants("mlp", dev, 5, 3, only=("tcgen05_bf16x3_global",))
+    tc = big.get("tcgen05_bf16x3_global", {})
+    out["batch_18944_tcgen05"] = {"forward_ms": tc.get("ms"), "forward_reverse_pass_ms": tc.get("fwd_bwd_ms", tc.get("unavailable")),
+                                  "traj_steps_per_s": tc.get("traj_steps_per_s"), "roofline": tc.get("roofline"),
+                                  "roofline_reverse_pass": tc.get("roofline_reverse_pass")}
+    return out
+
+
+def run_latentode(args):
+    """`--workload c2` (BASELINE.json configs[1]: LatentODE, small-MLP RHS 16-200-200-16, batch 256, T = 50) and
+    `--workload mlp` (the same network at batch 18 944 = 128 trajectories per SM: where batch x hidden is a genuine
+    dense contraction).  Adaptive Tsit5, per-trajectory and global (reference) error norm, exact CUDA-core path vs the
+    tcgen05 path; forward solve and forward + adjoint.  Unit: trajectory-steps/s (and accepted RK steps per trajectory
+    per second, SURVEY.md 8(d) C2)."""
+    import torch
+
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    K, W = args.steps, max(args.warmup, 3)
+    B, T, res, launches = latentode_variants(args.workload, dev, K, W)
     best = max((v["traj_steps_per_s"], k) for k, v in res.items() if "ms" in v)
     line = {"metric": "latent trajectory-steps/sec (LatentODE forward solve)", "value": best[0], "unit": UNIT, "n_gpus": 1,
             "steps": K, "warmup": W, "ms_per_step": res[best[1]]["ms"], "higher_is_better": True, "scaling": "weak",
