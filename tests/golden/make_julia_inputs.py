@@ -35,8 +35,13 @@ def main():
     rng = np.random.default_rng(7)
     trig = np.concatenate([rng.uniform(-1, 1, 1024), rng.uniform(-8, 8, 2048), rng.uniform(-1e3, 1e3, 1024)]).astype(np.float32)
     fp_x = np.concatenate([10.0 ** rng.uniform(-8, 2, 512), [1e-4, 1.0, 0.5]])
+    # the pattern-extractor fixture (tests/golden/pattern_extractor.npz): frames as the (F,B,T) array the feature extractor
+    # returns, the three stacks' parameters as Flux.destructure vectors, the cotangents of the final states as (H,B) arrays
+    g = np.load(os.path.join(HERE, "pattern_extractor.npz"))
+    pe = dict(x=np.ascontiguousarray(g["x"].transpose(2, 1, 0)), rnn=g["rnn"], lstm_f=g["lstm_f"], lstm_b=g["lstm_b"], rnn32=g["rnn32"],
+              dz0=np.ascontiguousarray(g["dz0"].T), dtheta=np.ascontiguousarray(g["dtheta"].T), dz0_32=np.ascontiguousarray(g["dz0_32"].T))
     bson_io.save(os.path.join(HERE, "julia_inputs.bson"), c1=c1, c3=c3, trig_x=trig, fastpow_x=fp_x,
-                 fastpow_y=np.array([7 / 50, 2 / 25]))
+                 fastpow_y=np.array([7 / 50, 2 / 25]), pe=pe)
     print(os.path.getsize(os.path.join(HERE, "julia_inputs.bson")), "bytes")
 
 

@@ -211,6 +211,38 @@ def test_oracle_against_julia_golden(ldeq):
             assert np.abs(gp - np.asarray(ref["dtheta"]).T).max() <= 1e-4 * np.abs(ref["dtheta"]).max(), (case, mode)
 
 
+def test_oracle_solvers_and_recurrent_against_julia_golden(ldeq):
+    """The round-2 restatements vs the REFERENCE (when julia_golden.bson carries them): DP5 / BS3 / RK4 solves and gradients,
+    the Flux RNN / LSTM stacks of the pattern extractor."""
+    from oracle import recurrent as orr
+    gold, inp = _julia_golden(ldeq)
+    if "c3_f64_dp5" not in gold or "pe" not in gold:
+        pytest.skip("julia_golden.bson predates the other solvers / pattern extractor: re-run julia/make_golden.jl")
+    c_in = inp["c3"]
+    z0, th, t = c_in["z0"].T.astype(np.float64), c_in["theta"].T.astype(np.float64), np.asarray(c_in["t"])
+    d = c_in["dtraj"].transpose(2, 1, 0).astype(np.float64)
+    for key, sv in (("c3_f64_dp5", og.DP5), ("c3_f64_bs3", og.BS3), ("c3_f64_rk4", og.RK4)):
+        for mode, kw in (("fixed", dict(adaptive=False, dt=0.08)),) + ((("adaptive", dict()),) if sv != og.RK4 else ()):
+            ref, o = gold[key][mode], og.Opts.for_solver(sv, **kw)
+            tr, ret, na, nr = og.solve(og.PENDULUM_FRICTION, z0, th, t, o)
+            rtr = np.asarray(ref["traj"]).transpose(2, 1, 0)
+            assert np.abs(tr - rtr).max() <= (1e-11 if mode == "fixed" else 1e-5) * np.abs(rtr).max(), (key, mode)
+            assert np.array_equal(na, np.asarray(ref["naccept"])), (key, mode)
+            gz, gp = og.grad(og.PENDULUM_FRICTION, z0, th, t, d, o, norm_partials=True)
+            assert np.abs(gz - np.asarray(ref["dz0"]).T).max() <= 1e-4 * np.abs(ref["dz0"]).max(), (key, mode)
+            assert np.abs(gp - np.asarray(ref["dtheta"]).T).max() <= 1e-4 * np.abs(ref["dtheta"]).max(), (key, mode)
+    pe, ref = inp["pe"], gold["pe"]
+    x = np.ascontiguousarray(np.asarray(pe["x"]).transpose(2, 1, 0))
+    zo, tho, g = orr.pattern_extractor(x, pe["rnn"], pe["lstm_f"], pe["lstm_b"], np.asarray(pe["dz0"]).T, np.asarray(pe["dtheta"]).T)
+    rel = lambda a, b: np.abs(a - np.asarray(b)).max() / np.abs(np.asarray(b)).max()
+    assert rel(zo, np.asarray(ref["z0_out"]).T) < 2e-5 and rel(tho, np.asarray(ref["theta_out"]).T) < 2e-5
+    assert rel(g[0], np.asarray(ref["dx"]).transpose(2, 1, 0)) < 2e-4
+    for got, key in ((g[1], "d_rnn"), (g[2], "d_lstm_f"), (g[3], "d_lstm_b")):
+        assert rel(got, ref[key]) < 2e-4, key
+    z32, _, g32 = orr.pattern_extractor(x, pe["rnn32"], None, None, np.asarray(pe["dz0_32"]).T, H=32)
+    assert rel(z32, np.asarray(ref["z0_out_32"]).T) < 2e-5 and rel(g32[1], ref["d_rnn32"]) < 2e-4
+
+
 @pytest.mark.gpu
 def test_cuda_against_julia_golden(ldeq):
     """The CUDA path (through the C ABI) vs the REFERENCE itself at the north star's tolerances."""
