@@ -4,6 +4,7 @@
 // diffeq_layer(::Decoder{<:GOKU}, l, t) (reference src/models/GOKU.jl:98-130) and its pullback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ldeq_internal.h"
@@ -102,6 +103,13 @@ static cudaError_t launch_fwd(const void* z0, const void* theta, const double* t
     return cudaGetLastError();
 }
 
+// LDEQ_BWD_SORT=1 re-deals the trajectories of a CTA to lanes by their accepted-step count in the discrete-adjoint kernels
+// (A/B switch; the results are identical).  Off until measured on the device.
+int bwd_sort_lanes() {
+    static const int on = [] { const char* e = getenv("LDEQ_BWD_SORT"); return (e && e[0] == '1') ? 1 : 0; }();
+    return on;
+}
+
 template <class S, bool FRICTION>
 static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, int ld, void* dz0, void* dtheta, cudaStream_t s) {
     TapeView<S> tv{tape->t, (S*)tape->u, tape->info, tape->cap, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -110,7 +118,7 @@ static cudaError_t launch_bwd(const ldeq_tape* tape, const void* dtraj, int ld, 
         Ring<S, 2>::bytes(LDEQ_BWD_THREADS) + (tape->T <= LDEQ_TGRID_SMEM_MAX ? (size_t)tape->T * sizeof(double) : 0);
     tsit5_bwd_kernel<PendulumRHS<S, FRICTION>, S><<<grid, LDEQ_BWD_THREADS, smem, s>>>(
         (const S*)tape->theta, tape->tgrid, tape->B, tape->T, (const S*)dtraj, tv, tape->retcode, tape->naccept,
-        (S*)dz0, (S*)dtheta, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld});
+        (S*)dz0, (S*)dtheta, GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld, bwd_sort_lanes()});
     return cudaGetLastError();
 }
 
@@ -145,7 +153,7 @@ static cudaError_t launch_user_bwd(void* const* fn, const ldeq_tape* tape, const
     int B = tape->B, T = tape->T;
     const int32_t* ret = tape->retcode;
     const int32_t* na = tape->naccept;
-    GridInfo giv{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld};
+    GridInfo giv{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld, bwd_sort_lanes()};
     void* args[] = {&theta, &tg, &B, &T, &dtraj, &tv, &ret, &na, &dz0, &dtheta, &giv};
     const int grid = (B + LDEQ_BWD_THREADS - 1) / LDEQ_BWD_THREADS;
     const size_t es = tape->dtype == LDEQ_F32 ? 4 : 8;

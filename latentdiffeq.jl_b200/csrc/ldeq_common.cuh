@@ -71,6 +71,7 @@ struct GridInfo {
     double t0, h;
     int uniform;
     int ld;  // row stride (in trajectories) of the (z,B,T) arrays: the kernel may work on a column slab of a wider batch
+    int sort;  // reverse pass: re-deal the CTA's trajectories to lanes by their accepted-step count (0: batch order)
 };
 
 enum { RET_SUCCESS = 0, RET_MAXITERS = 1, RET_DTLESSTHANMIN = 2, RET_UNSTABLE = 3 };

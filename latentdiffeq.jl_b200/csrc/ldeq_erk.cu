@@ -55,7 +55,7 @@ static cudaError_t bwd_t(const ldeq_tape* tape, const void* dtraj, int ld, void*
     const size_t smem = Ring<S, 2>::bytes(LDEQ_BWD_THREADS) + (tape->T <= LDEQ_TGRID_SMEM_MAX ? (size_t)tape->T * sizeof(double) : 0);
     erk_bwd_kernel<M, PendulumRHS<S, FRICTION>, S><<<grid, LDEQ_BWD_THREADS, smem, s>>>(
         (const S*)tape->theta, tape->tgrid, tape->B, tape->T, (const S*)dtraj, tv, tape->retcode, tape->naccept, (S*)dz0, (S*)dtheta,
-        GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld});
+        GridInfo{tape->grid_t0, tape->grid_h, tape->grid_uniform, ld, bwd_sort_lanes()});
     return cudaGetLastError();
 }
 

@@ -89,6 +89,7 @@ int set_err(ldeq_handle* h, int code, const char* what, cudaError_t ce = cudaSuc
 int upload_tgrid(ldeq_handle* h, const double* t_host, int T, cudaStream_t s);
 int ensure_scratch(ldeq_handle* h, int slot, size_t bytes);
 KOpts to_kopts(const ldeq_opts* o);
+int bwd_sort_lanes();  // ldeq_api.cu: lane re-deal of the discrete-adjoint kernels (LDEQ_BWD_SORT)
 // pooled pinned {int32 x 2} mirror + event (ldeq_api.cu)
 bool slot_acquire(ldeq_handle* h, int32_t** h_info, cudaEvent_t* ev);
 void slot_release(ldeq_handle* h, int32_t* h_info, cudaEvent_t ev);

@@ -598,7 +598,27 @@ erk_bwd_body(const S* __restrict__ theta, const double* __restrict__ tg_global, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RingT ring{reinterpret_cast<S*>(smem_raw) + threadIdx.x * ZD, (int)blockDim.x * ZD};
     const TGrid tg = stage_tgrid(tg_global, T, reinterpret_cast<double*>(smem_raw + RingT::bytes(blockDim.x)), ginfo);
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    // Lanes of a warp run until the trajectory with the most taped steps is done.  The forward pass has counted every
+    // trajectory's accepted steps: the CTA ranks its trajectories by that count and re-deals them, so a warp holds 32
+    // neighbours in step count (the same re-deal as the forward-dual kernels, ldeq_fwdsens.cuh).  Only the assignment of
+    // trajectories to lanes changes -- every trajectory's arithmetic and its output slots are the same.
+    if (ginfo.sort) {
+        __shared__ int s_key[LDEQ_BWD_THREADS];
+        __shared__ short s_order[LDEQ_BWD_THREADS];
+        const int tid = threadIdx.x, nt = blockDim.x;
+        const int key = b < B ? naccept[b] : 0x7fffffff;  // dead lanes go last
+        s_key[tid] = key;
+        __syncthreads();
+        int rank = 0;
+        for (int j = 0; j < nt; ++j) {
+            const int kj = s_key[j];
+            rank += (kj < key || (kj == key && j < tid)) ? 1 : 0;
+        }
+        s_order[rank] = (short)tid;
+        __syncthreads();
+        b = blockIdx.x * blockDim.x + s_order[tid];
+    }
     const bool live = b < B;
     const int bb = live ? b : B - 1;  // dead lanes of the last warp read a valid column and write nothing
 
