@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for v in 0 1; do
-  LDEQ_BWD_SORT=$v timeout 600 python bench.py --no-cpu --no-training --steps 20 > gpurun_out/s27_bench_$v.json 2>/dev/null
+for v in 0 1; do export LDEQ_BWD_SORT=$v;
+  timeout 600 python bench.py --no-cpu --no-training --steps 20 > gpurun_out/s27_bench_$v.json 2>/dev/null
   python - $v <<'PY'
 import json,sys
 d=json.loads(open(f"gpurun_out/s27_bench_{sys.argv[1]}.json").read().strip().splitlines()[-1])
@@ -9,5 +9,5 @@ da=d["discrete_adjoint"]
 print("sort",sys.argv[1],"DA ms",round(da["ms_per_step"],4),"fwd",round(da["fwd_ms"],4),"bwd",round(da["bwd_ms"],4))
 PY
 done
-timeout 1200 python -m pytest tests/test_properties_gpu.py tests/test_goku_gpu.py tests/test_solvers_gpu.py tests/test_user_rhs_gpu.py -q -m gpu > gpurun_out/s27_tests.log 2>&1; tail -3 gpurun_out/s27_tests.log
-timeout 600 compute-sanitizer --tool racecheck python scripts/sanitize_small.py goku > gpurun_out/s27_race.log 2>&1; tail -1 gpurun_out/s27_race.log
+LDEQ_BWD_SORT=1 timeout 1200 python -m pytest tests/test_properties_gpu.py tests/test_goku_gpu.py tests/test_solvers_gpu.py tests/test_user_rhs_gpu.py -q -m gpu > gpurun_out/s27_tests.log 2>&1; tail -3 gpurun_out/s27_tests.log
+LDEQ_BWD_SORT=1 timeout 600 compute-sanitizer --tool racecheck python scripts/sanitize_small.py goku > gpurun_out/s27_race.log 2>&1; tail -1 gpurun_out/s27_race.log
