@@ -103,10 +103,10 @@ static cudaError_t launch_fwd(const void* z0, const void* theta, const double* t
     return cudaGetLastError();
 }
 
-// LDEQ_BWD_SORT=1 re-deals the trajectories of a CTA to lanes by their accepted-step count in the discrete-adjoint kernels
-// (A/B switch; the results are identical).  Off until measured on the device.
+// The discrete-adjoint kernels re-deal the trajectories of a CTA to lanes by their accepted-step count (measured at
+// 2^20 x 200: 1.135 -> 1.095 ms); LDEQ_BWD_SORT=0 keeps the batch order (A/B switch; the results are identical bit for bit).
 int bwd_sort_lanes() {
-    static const int on = [] { const char* e = getenv("LDEQ_BWD_SORT"); return (e && e[0] == '1') ? 1 : 0; }();
+    static const int on = [] { const char* e = getenv("LDEQ_BWD_SORT"); return (e && e[0] == '0') ? 0 : 1; }();
     return on;
 }
 
