@@ -256,6 +256,13 @@ int ldeq_elbo_fwd_bwd(ldeq_handle* h, const float* x, const float* xhat, const f
                       const float* const* logvar_host, const int32_t* head_dims_host, int n_heads, float beta,
                       int B, int T, int P, float grad_scale, float* loss, float* dxhat, float* const* dmu_host,
                       float* const* dlogvar_host, ldeq_stream stream);
+/* The same with the reconstructor's sigmoid output activation folded in (GOKU.jl:265-268: the last Dense layer has
+ * output_activation = sigma): `logits` (P,B,T) are that layer's pre-activations a, xhat = 1/(1+exp(-a)) is formed inside and
+ * `dlogits` is the gradient with respect to a -- no xhat array, no separate activation passes. */
+int ldeq_elbo_logits_fwd_bwd(ldeq_handle* h, const float* x, const float* logits, const float* const* mu_host,
+                      const float* const* logvar_host, const int32_t* head_dims_host, int n_heads, float beta,
+                      int B, int T, int P, float grad_scale, float* loss, float* dlogits, float* const* dmu_host,
+                      float* const* dlogvar_host, ldeq_stream stream);
 
 /* ---- fused multi-tensor AdamW with Flux semantics:
  * m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2; x -= lr * m/(1-b1^t) / (sqrt(v/(1-b2^t)) + eps) + decay * x

@@ -348,6 +348,24 @@ function elbo_fwd_bwd(x::CuArray{Float32,3}, x̂::CuArray{Float32,3}, μs::Tuple
     return loss, dx̂, dμs, dlvs
 end
 
+# the same with the reconstructor's sigmoid output activation folded into the kernel: `a` are the pre-activations of its last
+# Dense layer (GOKU.jl:265-268); returns the gradient with respect to `a`
+function elbo_logits_fwd_bwd(x::CuArray{Float32,3}, a::CuArray{Float32,3}, μs::Tuple, logσ²s::Tuple, β::Real; grad_scale::Real = 1)
+    h = handle()
+    P, B, T = size(x)
+    nh = length(μs)
+    loss = CUDA.zeros(Float32, 3)
+    da = similar(a)
+    dμs, dlvs = map(similar, μs), map(similar, logσ²s)
+    ptrs(xs) = Ptr{Cvoid}[reinterpret(Ptr{Cvoid}, pointer(v)) for v in xs]
+    check(h, ccall((:ldeq_elbo_logits_fwd_bwd, libldeq), Cint,
+                   (Ptr{Cvoid}, CuPtr{Cfloat}, CuPtr{Cfloat}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Cint, Cfloat, Cint, Cint, Cint,
+                    Cfloat, CuPtr{Cfloat}, CuPtr{Cfloat}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Cvoid}),
+                   h, x, a, ptrs(μs), ptrs(logσ²s), Int32[size(m, 1) for m in μs], nh, β, B, T, P, grad_scale, loss, da,
+                   ptrs(dμs), ptrs(dlvs), CUDA.stream().handle))
+    return loss, da, dμs, dlvs
+end
+
 # Flux ADAMW(η, (β₁, β₂), decay) on the flat parameter vector of Flux.destructure(model); `step` is 1-based
 adamw_step!(p::CuVector{Float32}, g::CuVector{Float32}, m::CuVector{Float32}, v::CuVector{Float32}, step::Integer;
             η = 1e-3, β = (0.9, 0.999), ϵ = 1e-8, decay = 1f-3, grad_scale = 1f0) =

@@ -71,7 +71,12 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_kl_kernel(KlHeads hd, int B
     }
 }
 
-template <bool GRAD>
+// LOGITS: `xhat` holds the pre-activations a of a sigmoid output layer (the reconstructor's last layer, GOKU.jl:265-268):
+// xhat = 1 / (1 + exp(-a)) is formed here and the gradient is taken with respect to a -- the activation's forward pass,
+// its backward pass and the x-hat round trip through HBM between them and the loss never exist.
+__device__ __forceinline__ float elbo_sigmoid(float a) { return 1.0f / (1.0f + expf(-a)); }
+
+template <bool GRAD, bool LOGITS>
 __global__ void __launch_bounds__(ELBO_THREADS)
 elbo_mse_kernel(const float* __restrict__ x, const float* __restrict__ xhat, float* __restrict__ dxhat, size_t n,
                 float inv_bt, float gscale, float beta, double* __restrict__ partials, unsigned int* __restrict__ counter,
@@ -86,17 +91,24 @@ elbo_mse_kernel(const float* __restrict__ x, const float* __restrict__ xhat, flo
     float4* __restrict__ d4 = reinterpret_cast<float4*>(dxhat);
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
-        const float4 a = __ldcs(x4 + i), b = __ldcs(h4 + i);
+        const float4 a = __ldcs(x4 + i);
+        float4 b = __ldcs(h4 + i);
+        if (LOGITS) { b.x = elbo_sigmoid(b.x); b.y = elbo_sigmoid(b.y); b.z = elbo_sigmoid(b.z); b.w = elbo_sigmoid(b.w); }
         const float e0 = b.x - a.x, e1 = b.y - a.y, e2 = b.z - a.z, e3 = b.w - a.w;
         acc = fmaf(e0, e0, acc); acc = fmaf(e1, e1, acc); acc = fmaf(e2, e2, acc); acc = fmaf(e3, e3, acc);
-        if (GRAD) __stcs(d4 + i, make_float4(g2 * e0, g2 * e1, g2 * e2, g2 * e3));
+        if (GRAD) {
+            if (LOGITS) __stcs(d4 + i, make_float4(g2 * e0 * b.x * (1.0f - b.x), g2 * e1 * b.y * (1.0f - b.y), g2 * e2 * b.z * (1.0f - b.z),
+                                                   g2 * e3 * b.w * (1.0f - b.w)));
+            else __stcs(d4 + i, make_float4(g2 * e0, g2 * e1, g2 * e2, g2 * e3));
+        }
     }
     // tail (n not a multiple of 4)
     if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
         const size_t i = (n4 << 2) + threadIdx.x;
-        const float e = xhat[i] - x[i];
+        const float bh = LOGITS ? elbo_sigmoid(xhat[i]) : xhat[i];
+        const float e = bh - x[i];
         acc = fmaf(e, e, acc);
-        if (GRAD) dxhat[i] = g2 * e;
+        if (GRAD) dxhat[i] = LOGITS ? g2 * e * bh * (1.0f - bh) : g2 * e;
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) shw[threadIdx.x >> 5] = acc;
@@ -270,10 +282,10 @@ using namespace ldeq;
 
 extern "C" {
 
-int ldeq_elbo_fwd_bwd(ldeq_handle* h, const float* x, const float* xhat, const float* const* mu_host,
-                      const float* const* logvar_host, const int32_t* head_dims_host, int n_heads, float beta, int B,
-                      int T, int P, float grad_scale, float* loss, float* dxhat, float* const* dmu_host,
-                      float* const* dlogvar_host, ldeq_stream stream) {
+static int elbo_impl(bool logits, ldeq_handle* h, const float* x, const float* xhat, const float* const* mu_host,
+                     const float* const* logvar_host, const int32_t* head_dims_host, int n_heads, float beta, int B,
+                     int T, int P, float grad_scale, float* loss, float* dxhat, float* const* dmu_host,
+                     float* const* dlogvar_host, ldeq_stream stream) {
     if (!h) return LDEQ_ERR_INVALID;
     if (!x || !xhat || !loss || n_heads < 0 || n_heads > 4 || B <= 0 || T <= 0 || P <= 0)
         return set_err(h, LDEQ_ERR_INVALID, "elbo: bad argument (n_heads <= 4)");
@@ -309,13 +321,29 @@ int ldeq_elbo_fwd_bwd(ldeq_handle* h, const float* x, const float* xhat, const f
     size_t want = ((n >> 2) + ELBO_THREADS - 1) / ELBO_THREADS;
     int grid = (int)(want < (size_t)max_blocks ? (want ? want : 1) : (size_t)max_blocks);
     const float inv_bt = 1.0f / ((float)B * (float)T);
-    if (dxhat)
-        elbo_mse_kernel<true><<<grid, ELBO_THREADS, 0, s>>>(x, xhat, dxhat, n, inv_bt, grad_scale, beta, h->d_partials, h->d_counter, kl_partials, kl_grid, loss);
-    else
-        elbo_mse_kernel<false><<<grid, ELBO_THREADS, 0, s>>>(x, xhat, nullptr, n, inv_bt, grad_scale, beta, h->d_partials, h->d_counter, kl_partials, kl_grid, loss);
+#define LDEQ_ELBO_LAUNCH(G, L) elbo_mse_kernel<G, L><<<grid, ELBO_THREADS, 0, s>>>(x, xhat, dxhat, n, inv_bt, grad_scale, beta, h->d_partials, h->d_counter, kl_partials, kl_grid, loss)
+    if (dxhat) { if (logits) LDEQ_ELBO_LAUNCH(true, true); else LDEQ_ELBO_LAUNCH(true, false); }
+    else { if (logits) LDEQ_ELBO_LAUNCH(false, true); else LDEQ_ELBO_LAUNCH(false, false); }
+#undef LDEQ_ELBO_LAUNCH
     LDEQ_CUDA(cudaGetLastError());
     h->launches += 2;
     return LDEQ_OK;
+}
+
+int ldeq_elbo_fwd_bwd(ldeq_handle* h, const float* x, const float* xhat, const float* const* mu_host,
+                      const float* const* logvar_host, const int32_t* head_dims_host, int n_heads, float beta, int B,
+                      int T, int P, float grad_scale, float* loss, float* dxhat, float* const* dmu_host,
+                      float* const* dlogvar_host, ldeq_stream stream) {
+    return elbo_impl(false, h, x, xhat, mu_host, logvar_host, head_dims_host, n_heads, beta, B, T, P, grad_scale, loss, dxhat, dmu_host,
+                     dlogvar_host, stream);
+}
+
+int ldeq_elbo_logits_fwd_bwd(ldeq_handle* h, const float* x, const float* logits, const float* const* mu_host,
+                             const float* const* logvar_host, const int32_t* head_dims_host, int n_heads, float beta, int B,
+                             int T, int P, float grad_scale, float* loss, float* dlogits, float* const* dmu_host,
+                             float* const* dlogvar_host, ldeq_stream stream) {
+    return elbo_impl(true, h, x, logits, mu_host, logvar_host, head_dims_host, n_heads, beta, B, T, P, grad_scale, loss, dlogits, dmu_host,
+                     dlogvar_host, stream);
 }
 
 int ldeq_adamw_step(ldeq_handle* h, float* params, const float* grads, float* m, float* v, int64_t n, double lr,

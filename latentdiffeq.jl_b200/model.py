@@ -344,6 +344,20 @@ def apply_reconstructor(decoder, z_hat):
     return decoder.reconstructor(z_hat)
 
 
+def reconstructor_logits(decoder, z_hat):
+    """The reconstructor up to the pre-activations of its last layer, when that layer is a ``Dense`` with the sigmoid output
+    activation of ``default_layers`` (GOKU.jl:265-268); ``None`` otherwise.  ``ldeq_elbo_logits_fwd_bwd`` applies the sigmoid
+    inside the loss kernel."""
+    rec = decoder.reconstructor
+    layers = list(rec) if isinstance(rec, nn.Sequential) else []
+    if not layers or not isinstance(layers[-1], Dense) or layers[-1].act is not torch.sigmoid:
+        return None
+    h = z_hat
+    for l in layers[:-1]:
+        h = l(h)
+    return F.linear(h, layers[-1].weight, layers[-1].bias)
+
+
 # ---- containers (src/models/LatentDiffEqModel.jl) --------------------------------------------------
 class Encoder(nn.Module):
     def __init__(self, model_type, encoder_layers):
@@ -384,6 +398,18 @@ class LatentDiffEqModel(nn.Module):
         l_tilde = sample(mu, logvar, self) if variational else mu
         X_hat = self.decoder(l_tilde, t)
         return X_hat, mu, logvar
+
+    def forward_logits(self, x, t, variational=False):
+        """``forward`` with the reconstruction left as the pre-activations of the sigmoid output layer: returns
+        ``((logits, z_hat, l_hat), mu, logvar)``, or ``None`` when the reconstructor does not end in such a layer."""
+        mu, logvar = self.encoder(x)
+        l_tilde = sample(mu, logvar, self) if variational else mu
+        l_hat = apply_latent_out(self.decoder, l_tilde)
+        z_hat = diffeq_layer(self.decoder, l_hat, t)
+        logits = reconstructor_logits(self.decoder, z_hat)
+        if logits is None:
+            return None
+        return (logits, z_hat, l_hat), mu, logvar
 
 
 def _resnet(d_in, hidden, d_out, act, out_act, init):

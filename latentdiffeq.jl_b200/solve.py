@@ -478,9 +478,11 @@ def sample_reparam(mu, logvar, seed: int, offset: int = 0):
 
 
 def elbo_raw(x: torch.Tensor, xhat: torch.Tensor, mus, logvars, beta: float, want_grad: bool = True,
-             grad_scale: float = 1.0):
+             grad_scale: float = 1.0, logits: bool = False):
     """``ldeq_elbo_fwd_bwd``: ``x, xhat`` are ``[T, B, P]``; ``mus/logvars`` lists of ``[B, d_h]`` heads.
-    Returns ``(loss3 = [total, reconstruction, kl], dxhat, dmus, dlogvars)``."""
+    Returns ``(loss3 = [total, reconstruction, kl], dxhat, dmus, dlogvars)``.  ``logits=True``
+    (``ldeq_elbo_logits_fwd_bwd``): ``xhat`` holds the pre-activations of a sigmoid output layer; the gradient returned in
+    ``dxhat``'s place is with respect to them."""
     h = _cabi.handle(x.device.index or 0)
     x = _aligned16(x.contiguous().float())
     xhat = _aligned16(xhat.contiguous().float())
@@ -499,18 +501,20 @@ def elbo_raw(x: torch.Tensor, xhat: torch.Tensor, mus, logvars, beta: float, wan
     dlv_a = PA(*[l.data_ptr() for l in dlvs]) if want_grad else None
     hd = (C.c_int32 * max(nh, 1))(*[m.shape[1] for m in mus])
     with torch.cuda.device(x.device):
-        h.check(h._lib.ldeq_elbo_fwd_bwd(h.ptr, _p(x), _p(xhat), mu_a, lv_a, hd, nh, C.c_float(beta), B, T, P,
-                                         C.c_float(grad_scale), _p(loss), _p(dxhat), dmu_a, dlv_a, _stream()))
+        fn = h._lib.ldeq_elbo_logits_fwd_bwd if logits else h._lib.ldeq_elbo_fwd_bwd
+        h.check(fn(h.ptr, _p(x), _p(xhat), mu_a, lv_a, hd, nh, C.c_float(beta), B, T, P,
+                   C.c_float(grad_scale), _p(loss), _p(dxhat), dmu_a, dlv_a, _stream()))
     return loss, dxhat, dmus, dlvs
 
 
 class _Elbo(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, xhat, beta, nh, *heads):
+    def forward(ctx, x, xhat, beta, nh, logits, unit_cotangent, grad_scale, *heads):
         mus, lvs = list(heads[:nh]), list(heads[nh:])
-        loss, dxhat, dmus, dlvs = elbo_raw(x, xhat, mus, lvs, beta, want_grad=True)
+        loss, dxhat, dmus, dlvs = elbo_raw(x, xhat, mus, lvs, beta, want_grad=True, logits=logits, grad_scale=grad_scale)
         ctx.save_for_backward(dxhat, *dmus, *dlvs)
         ctx.nh = nh
+        ctx.unit = unit_cotangent
         ctx.parts = loss
         return loss[0]
 
@@ -518,15 +522,23 @@ class _Elbo(torch.autograd.Function):
     def backward(ctx, g):
         saved = ctx.saved_tensors
         dxhat, rest = saved[0], saved[1:]
-        return (None, g * dxhat, None, None, *[g * r for r in rest])
+        if ctx.unit:
+            # the caller differentiates the loss itself (`loss.backward()`): the cotangent is 1 and the (P,B,T) gradient
+            # the kernel already wrote is handed on as it is (scaling it would be one more pass over 1.3 GB at B = 8192)
+            return (None, dxhat, None, None, None, None, None, *rest)
+        return (None, g * dxhat, None, None, None, None, None, *[g * r for r in rest])
 
 
-def elbo_loss(x, xhat, mu, logvar, beta: float):
+def elbo_loss(x, xhat, mu, logvar, beta: float, logits: bool = False, unit_cotangent: bool = False, grad_scale: float = 1.0):
     """``loss_batch``'s reduction (reference ``examples/pendulum_friction-less/model_train.jl:225-238``):
-    ``sum(mean((x - xhat)^2, dims=(2,3))) + beta * vector_kl(mu, logvar)`` as one fused forward+gradient pass."""
+    ``sum(mean((x - xhat)^2, dims=(2,3))) + beta * vector_kl(mu, logvar)`` as one fused forward+gradient pass.
+    ``logits=True``: ``xhat`` are the pre-activations of the reconstructor's sigmoid output layer (folded into the kernel).
+    ``unit_cotangent=True``: the result is differentiated directly (``loss.backward()``), never scaled further; a constant
+    factor on the gradients (the data-parallel ``B_local / B_global``) then goes in as ``grad_scale`` -- the kernel writes the
+    gradients already multiplied by it, the returned loss value stays unscaled."""
     mus = list(mu) if isinstance(mu, (tuple, list)) else [mu]
     lvs = list(logvar) if isinstance(logvar, (tuple, list)) else [logvar]
-    return _Elbo.apply(x, xhat, float(beta), len(mus), *mus, *lvs)
+    return _Elbo.apply(x, xhat, float(beta), len(mus), bool(logits), bool(unit_cotangent), float(grad_scale), *mus, *lvs)
 
 
 def adamw_step(params: torch.Tensor, grads: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step: int, lr=1e-3,

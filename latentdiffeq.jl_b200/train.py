@@ -14,13 +14,20 @@ import torch.distributed as dist
 from .solve import adamw_step, allreduce_adamw_step, elbo_loss
 
 
-def loss_batch(model, x, t, beta, variational):
-    """model_train.jl:225-238.  ``x`` is ``[T, B, P]``."""
-    X_hat, mu, logvar = model(x, t, variational)
-    x_hat, z_hat, l_hat = X_hat
+def loss_batch(model, x, t, beta, variational, fused_output: bool = True, unit_cotangent: bool = False, grad_scale: float = 1.0):
+    """model_train.jl:225-238.  ``x`` is ``[T, B, P]``.  With ``fused_output`` (default) the sigmoid of the reconstructor's
+    output layer (GOKU.jl:265-268) is evaluated inside the loss kernel (``ldeq_elbo_logits_fwd_bwd``): same loss, same
+    gradients, no x-hat array.  ``unit_cotangent``: the caller differentiates the returned loss directly (``grad_scale``: constant
+    factor the kernel applies to the gradients, see ``elbo_loss``)."""
     if not x.is_cuda:
         raise RuntimeError("loss_batch runs in libldeq.so on a CUDA device (no CPU fallback)")
-    return elbo_loss(x, x_hat, mu, logvar, beta)
+    out = model.forward_logits(x, t, variational) if fused_output and hasattr(model, "forward_logits") else None
+    if out is not None:
+        (logits, z_hat, l_hat), mu, logvar = out
+        return elbo_loss(x, logits, mu, logvar, beta, logits=True, unit_cotangent=unit_cotangent, grad_scale=grad_scale)
+    X_hat, mu, logvar = model(x, t, variational)
+    x_hat, z_hat, l_hat = X_hat
+    return elbo_loss(x, x_hat, mu, logvar, beta, unit_cotangent=unit_cotangent, grad_scale=grad_scale)
 
 
 def shard_bounds(n: int, rank: int, world: int):
@@ -128,9 +135,11 @@ def train_step(model, flat: FlatParams, opt: ADAMW, x_local, t, beta, variationa
             timers[name] = ev
     mark("start")
     flat.zero_grad()
-    loss = loss_batch(model, x_local, t, beta, variational)
+    # the loss is a mean over the GLOBAL batch: the factor B_local / B_global rides inside the loss kernel's gradients
+    # (grad_scale), the loss itself is differentiated with a unit cotangent -- no extra pass over the (P,B,T) gradient
+    loss = loss_batch(model, x_local, t, beta, variational, unit_cotangent=True, grad_scale=B_local / B_global)
     mark("loss")
-    (loss * (B_local / B_global)).backward()
+    loss.backward()
     mark("backward")
     if flat.symm is not None:
         opt.fused_allreduce_step()

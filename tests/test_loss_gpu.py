@@ -43,6 +43,58 @@ def test_elbo_matches_oracle(ldeq, B, T, P, heads):
     assert torch.allclose(txh2.grad, 2 * (txh - tx) / (B * T), rtol=1e-5, atol=1e-9) and ref > 0
 
 
+@pytest.mark.parametrize("B,T,P", [(64, 50, 784), (7, 3, 5)])
+def test_elbo_with_the_sigmoid_output_layer_folded_in(ldeq, B, T, P):
+    # ldeq_elbo_logits_fwd_bwd: x-hat = sigmoid(a) formed inside the loss kernel, gradient with respect to the pre-activations a
+    # (GOKU.jl:265-268: the reconstructor's last Dense layer has output_activation = sigmoid); oracle: the loss of sigmoid(a)
+    # and its gradient chained through sigmoid' in float64
+    rng = np.random.default_rng(5)
+    x = rng.random((T, B, P), dtype=np.float32)
+    a = (3.0 * rng.standard_normal((T, B, P))).astype(np.float32)
+    mu = [rng.standard_normal((B, 16)).astype(np.float32), rng.standard_normal((B, 16)).astype(np.float32)]
+    lv = [(0.3 * rng.standard_normal((B, 16))).astype(np.float32) for _ in range(2)]
+    beta, gs = 0.37, 0.125
+    tx, ta = torch.from_numpy(x).to(DEV), torch.from_numpy(a).to(DEV)
+    tmu, tlv = [torch.from_numpy(v).to(DEV) for v in mu], [torch.from_numpy(v).to(DEV) for v in lv]
+    loss, da, dmu, dlv = ldeq.elbo_raw(tx, ta, tmu, tlv, beta, logits=True, grad_scale=gs)
+    sig = 1.0 / (1.0 + np.exp(-a.astype(np.float64)))
+    tot, rec, k = ol.loss_batch(x, sig.astype(np.float32), tuple(mu), tuple(lv), beta)
+    l3 = loss.cpu().numpy()
+    assert abs(l3[1] - rec) <= 2e-5 * abs(rec) and abs(l3[0] - tot) <= 2e-5 * abs(tot)
+    oda = gs * 2.0 * (sig - x) / (B * T) * sig * (1.0 - sig)
+    assert np.abs(da.cpu().numpy() - oda).max() <= 2e-6 * np.abs(oda).max()
+    odx, odmu, odlv = ol.loss_batch_grads(x, sig.astype(np.float32), tuple(mu), tuple(lv), beta)
+    for got, want in zip(dmu + dlv, odmu + odlv):
+        assert np.abs(got.cpu().numpy() - gs * want).max() <= 2e-6 * np.abs(gs * want).max()
+    # the autograd routes agree: logits + unit cotangent + grad_scale  ==  sigmoid in torch, then the plain loss, scaled
+    a1 = ta.clone().requires_grad_(True)
+    ldeq.elbo_loss(tx, a1, tuple(tmu), tuple(tlv), beta, logits=True, unit_cotangent=True, grad_scale=gs).backward()
+    a2 = ta.clone().requires_grad_(True)
+    l2 = ldeq.elbo_loss(tx, torch.sigmoid(a2), tuple(tmu), tuple(tlv), beta)
+    (l2 * gs).backward()
+    assert torch.allclose(a1.grad, a2.grad, rtol=1e-4, atol=1e-12)
+
+
+def test_loss_batch_fused_output_equals_the_plain_route(ldeq):
+    # train.loss_batch on the default GOKU model: sigmoid folded into the loss kernel vs model(x) -> x-hat -> loss;
+    # same loss, same parameter gradients
+    torch.manual_seed(0)
+    enc, dec = ldeq.default_layers(ldeq.GOKU(), 28 * 28, ldeq.Pendulum(), device=DEV)
+    model = ldeq.LatentDiffEqModel(ldeq.GOKU(), enc, dec)
+    x = torch.rand(20, 32, 784, device=DEV)
+    t = 0.05 * np.arange(20)
+    grads = {}
+    for fused in (True, False):
+        model.zero_grad()
+        loss = ldeq.loss_batch(model, x, t, 0.5, False, fused_output=fused, unit_cotangent=fused, grad_scale=0.25 if fused else 1.0)
+        (loss if fused else loss * 0.25).backward()
+        grads[fused] = (float(loss), [p.grad.clone() for p in model.parameters() if p.grad is not None])
+    assert abs(grads[True][0] - grads[False][0]) <= 1e-5 * abs(grads[False][0])
+    assert len(grads[True][1]) == len(grads[False][1])
+    for ga, gb in zip(grads[True][1], grads[False][1]):
+        assert (ga - gb).abs().max() <= 2e-4 * max(float(gb.abs().max()), 1e-6)
+
+
 def test_adamw_matches_flux_semantics(ldeq):
     rng = np.random.default_rng(0)
     n = 503387 + 46816  # default GOKU + NODE parameter count (not a multiple of 4)
