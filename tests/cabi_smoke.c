@@ -156,6 +156,69 @@ int main(void) {
     for (int k = 0; k < T; ++k) CHECK(isnan(traj2[(k * B + 5) * 2]) && !isnan(traj2[(k * B + 6) * 2]), "NaN block rule at k = %d", k);
     CHECK(gz[10] == 0.0f && gz[11] == 0.0f && gp[5] == 0.0f && gz[12] != 0.0f, "failed trajectory must have a zero gradient");
 
+    /* the recurrent pattern extractor (GOKU.jl:30-49) and the loss with the sigmoid output layer folded in, through the header
+       alone: final states, reverse pass checked by a finite difference on one frame entry; loss(logits) == loss(sigmoid) */
+    {
+        enum { PB = 40, PT = 9, PF = 32, PH = 16 };
+        const int nr = ldeq_pattern_extractor_param_count(0, PF, PH), nl = ldeq_pattern_extractor_param_count(1, PF, PH);
+        CHECK(nr == 1344 && nl == 5312, "pattern extractor parameter counts %d %d", nr, nl);
+        float *hx = (float*)malloc(sizeof(float) * PT * PB * PF), *hp = (float*)malloc(sizeof(float) * (nr + 2 * nl));
+        for (int i = 0; i < PT * PB * PF; ++i) { s = s * 1664525u + 1013904223u; hx[i] = ((s >> 8) / 16777216.0f - 0.5f) * 2.0f; }
+        for (int i = 0; i < nr + 2 * nl; ++i) { s = s * 1664525u + 1013904223u; hp[i] = ((s >> 8) / 16777216.0f - 0.5f) * 0.5f; }
+        float *dx_, *dp_, *dz_, *dt_, *dgx, *dgp, *dcz, *dct;
+        CHECK(cudaMalloc((void**)&dx_, sizeof(float) * PT * PB * PF) == cudaSuccess && cudaMalloc((void**)&dp_, sizeof(float) * (nr + 2 * nl)) == cudaSuccess &&
+              cudaMalloc((void**)&dz_, sizeof(float) * PB * PH) == cudaSuccess && cudaMalloc((void**)&dt_, sizeof(float) * PB * 2 * PH) == cudaSuccess &&
+              cudaMalloc((void**)&dgx, sizeof(float) * PT * PB * PF) == cudaSuccess && cudaMalloc((void**)&dgp, sizeof(float) * (nr + 2 * nl)) == cudaSuccess &&
+              cudaMalloc((void**)&dcz, sizeof(float) * PB * PH) == cudaSuccess && cudaMalloc((void**)&dct, sizeof(float) * PB * 2 * PH) == cudaSuccess, "cudaMalloc");
+        cudaMemcpy(dp_, hp, sizeof(float) * (nr + 2 * nl), cudaMemcpyHostToDevice);
+        static float hz[PB * PH], ht[PB * 2 * PH], ones_z[PB * PH], ones_t[PB * 2 * PH], hgx[PT * PB * PF];
+        for (int i = 0; i < PB * PH; ++i) ones_z[i] = 1.0f;
+        for (int i = 0; i < PB * 2 * PH; ++i) ones_t[i] = 1.0f;
+        cudaMemcpy(dcz, ones_z, sizeof ones_z, cudaMemcpyHostToDevice);
+        cudaMemcpy(dct, ones_t, sizeof ones_t, cudaMemcpyHostToDevice);
+        double L[3];
+        const int probe = (4 * PB + 7) * PF + 11;   /* frame 4, sequence 7, feature 11 */
+        for (int pass = 0; pass < 3; ++pass) {       /* 0: base (+ reverse pass), 1: +eps, 2: -eps */
+            const float keep = hx[probe];
+            hx[probe] = keep + (pass == 1 ? 1e-2f : pass == 2 ? -1e-2f : 0.0f);
+            cudaMemcpy(dx_, hx, sizeof(float) * PT * PB * PF, cudaMemcpyHostToDevice);
+            hx[probe] = keep;
+            ldeq_pe_tape* pt = NULL;
+            LD(ldeq_pattern_extractor_fwd(h, dx_, PB, PT, PF, PH, dp_, dp_ + nr, dp_ + nr + nl, dz_, dt_, pass == 0 ? &pt : NULL, NULL));
+            if (pass == 0) {
+                CHECK(pt != NULL, "no pattern-extractor tape");
+                LD(ldeq_pattern_extractor_bwd(h, pt, dx_, dp_, dp_ + nr, dp_ + nr + nl, dcz, dct, dgx, dgp, dgp + nr, dgp + nr + nl, NULL));
+                ldeq_pe_tape_free(h, pt, NULL);
+                cudaMemcpy(hgx, dgx, sizeof hgx, cudaMemcpyDeviceToHost);
+            }
+            cudaMemcpy(hz, dz_, sizeof hz, cudaMemcpyDeviceToHost);
+            cudaMemcpy(ht, dt_, sizeof ht, cudaMemcpyDeviceToHost);
+            L[pass] = 0.0;
+            for (int i = 0; i < PB * PH; ++i) L[pass] += hz[i];
+            for (int i = 0; i < PB * 2 * PH; ++i) L[pass] += ht[i];
+        }
+        const double fd = (L[1] - L[2]) / 2e-2;
+        CHECK(isfinite(L[0]) && fabs(fd - hgx[probe]) <= 2e-2 * fmax(fabs(fd), 1e-3), "pattern extractor: finite difference %g vs dx %g", fd, hgx[probe]);
+        CHECK(ldeq_pattern_extractor_fwd(h, dx_, PB, PT, 24, PH, dp_, NULL, NULL, dz_, NULL, NULL, NULL) == LDEQ_ERR_UNSUPPORTED, "F = 24 must be refused");
+        /* ELBO on pre-activations: reuse dx_ (PT*PB*PF values) as logits a and dgx as the data x in [0,1) */
+        const int EP = PF, EB = PB, ET = PT;
+        float* hxx = (float*)malloc(sizeof(float) * ET * EB * EP);
+        float* hsig = (float*)malloc(sizeof(float) * ET * EB * EP);
+        for (int i = 0; i < ET * EB * EP; ++i) { s = s * 1664525u + 1013904223u; hxx[i] = (s >> 8) / 16777216.0f; hsig[i] = 1.0f / (1.0f + expf(-hx[i])); }
+        cudaMemcpy(dx_, hx, sizeof(float) * ET * EB * EP, cudaMemcpyHostToDevice);
+        cudaMemcpy(dgx, hxx, sizeof(float) * ET * EB * EP, cudaMemcpyHostToDevice);
+        float *dl, *dsig;
+        CHECK(cudaMalloc((void**)&dl, 6 * sizeof(float)) == cudaSuccess && cudaMalloc((void**)&dsig, sizeof(float) * ET * EB * EP) == cudaSuccess, "cudaMalloc");
+        cudaMemcpy(dsig, hsig, sizeof(float) * ET * EB * EP, cudaMemcpyHostToDevice);
+        LD(ldeq_elbo_logits_fwd_bwd(h, dgx, dx_, NULL, NULL, NULL, 0, 0.5f, EB, ET, EP, 1.0f, dl, NULL, NULL, NULL, NULL));
+        LD(ldeq_elbo_fwd_bwd(h, dgx, dsig, NULL, NULL, NULL, 0, 0.5f, EB, ET, EP, 1.0f, dl + 3, NULL, NULL, NULL, NULL));
+        float hl[6];
+        cudaMemcpy(hl, dl, sizeof hl, cudaMemcpyDeviceToHost);
+        CHECK(hl[0] > 0.0f && fabsf(hl[0] - hl[3]) <= 1e-5f * hl[3], "elbo on logits %g vs elbo on sigmoid(logits) %g", hl[0], hl[3]);
+        free(hx); free(hp); free(hxx); free(hsig);
+        cudaFree(dx_); cudaFree(dp_); cudaFree(dz_); cudaFree(dt_); cudaFree(dgx); cudaFree(dgp); cudaFree(dcz); cudaFree(dct); cudaFree(dl); cudaFree(dsig);
+    }
+
     /* usage errors come back as codes with a message, never as a crash */
     CHECK(ldeq_solve_fwd(h, rhs, LDEQ_F32, NULL, d_th, t, B, T, &o, d_traj, NULL, NULL, NULL, NULL, NULL) == LDEQ_ERR_INVALID, "null z0");
     CHECK(strlen(ldeq_last_error(h)) > 0, "no error text");
