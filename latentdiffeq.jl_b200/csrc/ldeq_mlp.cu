@@ -612,7 +612,9 @@ static int launch_mlp_cadj(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtra
     // LDEQ_CADJ_BATCH=0 keeps the per-stage reduction atomics (A/B switch)
     static const bool allow_batch = [] { const char* e = getenv("LDEQ_CADJ_BATCH"); return !(e && e[0] == '0'); }();
     static const bool allow_res = [] { const char* e = getenv("LDEQ_CADJ_RES"); return !(e && e[0] == '0'); }();
-    bool batch = allow_batch && cadj_smem<S, TB>(net, true) <= 227 * 1024;
+    // (stage records are instantiated for the smallest tile only: seven records of a wider tile do not fit next to the tile
+    // state for the reference's network, and the unrolled 7 x TB pass would dominate the build time)
+    bool batch = TB == 2 && allow_batch && cadj_smem<S, TB>(net, true) <= 227 * 1024;
     // RES: Float32, the smallest tile, the padded weight image + one working record fit next to the tile state
     bool res = false;
     if constexpr (sizeof(S) == 4 && TB == 2)
@@ -621,7 +623,8 @@ static int launch_mlp_cadj(ldeq_handle* h, ldeq_mlp_tape* tape, const void* dtra
     if (res) batch = true;
     const size_t smem = cadj_smem<S, TB>(net, batch, res);
     const int nthreads = res ? RES_THREADS : MLP_THREADS;
-    void* kern = batch ? (void*)mlp_cadj_kernel<S, TB, true, false> : (void*)mlp_cadj_kernel<S, TB, false, false>;
+    void* kern = (void*)mlp_cadj_kernel<S, TB, false, false>;
+    if constexpr (TB == 2) { if (batch) kern = (void*)mlp_cadj_kernel<S, TB, true, false>; }
     if constexpr (sizeof(S) == 4 && TB == 2) { if (res) kern = (void*)mlp_cadj_kernel<S, TB, true, true>; }
     if (smem > 227 * 1024 || grid > GRID_SUM_HALF) return LDEQ_ERR_UNSUPPORTED;
     LDEQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

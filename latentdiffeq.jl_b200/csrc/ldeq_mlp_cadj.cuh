@@ -68,9 +68,12 @@ __device__ void dense_bwd_params2(S* __restrict__ gWa, S* __restrict__ gba, S* _
     __syncthreads();
 }
 
-// mlp_vjp (ldeq_mlp.cu) with the two weighted accumulators
+// mlp_vjp (ldeq_mlp.cu) with the two weighted accumulators.  (The VJP helpers of the general variants are __noinline__: the
+// kernel evaluates them at four call sites, and nine kernel variants with every dense product inlined four times took the
+// translation unit to five minutes of compile time.  The resident variant -- the default at the reference's network --
+// keeps its helpers inlined: out of line it lost 87 -> 116 ms, the network descriptor then lives behind a pointer.)
 template <class S, int TB>
-__device__ void mlp_vjp2(const MlpNet& net, const S* __restrict__ P, const S* __restrict__ Pt, S* __restrict__ gA, S* __restrict__ gB,
+__device__ __noinline__ void mlp_vjp2(const MlpNet& net, const S* __restrict__ P, const S* __restrict__ Pt, S* __restrict__ gA, S* __restrict__ gB,
                          S wa, S wb, bool store, const S* x, const S* kbar, S* gbar, S* acts, S* dbuf0, S* dbuf1, S* ytmp,
                          S* red, int HW) {
     const S* in = x;
@@ -118,7 +121,7 @@ template <class S, int TB> struct CadjRec {
 
 // forward + input-VJP through the MLP, leaving the record of this stage in `rec` (no parameter accumulation)
 template <class S, int TB>
-__device__ void mlp_vjp_rec(const MlpNet& net, const S* __restrict__ P, const S* __restrict__ Pt, S* rec, S* gbar, S* ytmp, S* red, int HW) {
+__device__ __noinline__ void mlp_vjp_rec(const MlpNet& net, const S* __restrict__ P, const S* __restrict__ Pt, S* rec, S* gbar, S* ytmp, S* red, int HW) {
     // (general kernels: MLP_THREADS threads, weights through L1 / L2)
     const int D = net.dims[0], L = net.n_layers;
     S* xs = rec;
