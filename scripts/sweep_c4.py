@@ -15,14 +15,15 @@ for dtype in (torch.float32, torch.float64):
         z0, th = pendulum_inputs(B)
         z = torch.from_numpy(z0).to(dev, dtype); p = torch.from_numpy(th).to(dev, dtype)
         d = torch.randn(T, B, 2, device=dev, dtype=dtype)
-        opts = ldeq.default_opts()
+        opts = ldeq.default_opts()                                             # library default: the reference's dual-number pullback
+        opts_da = ldeq.default_opts(sensealg=ldeq.SENSE_DISCRETE_ADJOINT)     # the explicit opt-in
         def fwd():
             return ldeq.goku_solve_raw(z, p, t, 0, opts, want_tape=False, want_stats=False)
-        def fwdbwd():
-            tr, st, tape = ldeq.goku_solve_raw(z, p, t, 0, opts, want_tape=True, want_stats=False); tape.p_dim = 1
+        def fwdbwd(o):
+            tr, st, tape = ldeq.goku_solve_raw(z, p, t, 0, o, want_tape=True, want_stats=False); tape.p_dim = 1
             g = ldeq.goku_bwd_raw(tape, d); tape.free(); return g
         res = {}
-        for name, fn in (("forward", fwd), ("forward+adjoint", fwdbwd)):
+        for name, fn in (("forward", fwd), ("forward+adjoint", lambda: fwdbwd(opts_da)), ("forward+forward_dual", lambda: fwdbwd(opts))):
             n = 200 if lg <= 13 else 50 if lg <= 16 else 20
             for _ in range(5): fn()
             torch.cuda.synchronize()
