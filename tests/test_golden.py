@@ -147,7 +147,7 @@ def test_cuda_matches_latentode_golden(ldeq):
     dims = g["dims"].tolist()
     tr, st, _ = ldeq.mlp_solve_raw(torch.from_numpy(g["z0"]).to(dev), torch.from_numpy(g["params"]).to(dev), dims, g["t"])
     # the step count is a discontinuous function of Float32 rounding (a different summation order inside the dense
-    # layers moves the last step across tend in ~1 of 6 seeds, scripts/debug_res_vs_general.py): one step of slack
+    # layers moves the last step across tend in ~1 of 6 seeds): one step of slack
     na = st.naccept.cpu().numpy()
     assert (na == na[0]).all() and abs(int(na[0]) - int(g["naccept_f32"])) <= 1
     ref = g["traj_f32_adaptive_global"]
